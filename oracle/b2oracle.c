@@ -1,0 +1,1124 @@
+/*
+ * b2oracle.c — CPU restatement of the reference's env.step() hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (libb2env.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the arithmetic of the reference path lives in the third-party `pybullet`
+ * wheel (Bullet3 C++; un-pinned in the reference's requirements.txt:2, `pybullet==2.5.0` hinted at
+ * setup.py:35), which is not vendored in /root/reference and not installable here, and the
+ * reference ships no tests or golden vectors.  This file therefore restates
+ * (a) the Python wrapper semantics, which ARE in the reference and are followed line by line, and
+ * (b) the published structure of Bullet's btMultiBodyDynamicsWorld step as recalled in SURVEY.md
+ * Appendix D — Featherstone ABA, velocity-level motor/limit/contact rows, projected Gauss-Seidel
+ * in delta-velocity space with M^-1 J^T obtained by an O(n) ABA-style pass.  It is pinned by the
+ * first-principles known-answer vectors of SURVEY.md Appendix C (tests/test_oracle_kat.py) and by
+ * closed-form checks, not by PyBullet output.
+ *
+ * Reference call sites restated (paths relative to pybullet_robot_envs/envs/):
+ *   step()                      panda_envs/panda_push_gym_env.py:244-255, panda_reach_gym_env.py:228-239
+ *   apply_action() (task)       panda_push_gym_env.py:189-242
+ *   apply_action() (robot)      panda_envs/panda_env.py:293-310 (joint mode), :229-291 (IK mode)
+ *   p.stepSimulation            panda_push_gym_env.py:236       [Bullet, EXT-recalled]
+ *   get_observation() (robot)   panda_env.py:141-193
+ *   get_observation() (world)   world_envs/world_env.py:109-126
+ *   get_extended_observation()  panda_push_gym_env.py:150-187
+ *   scale_gym_data()            utils.py:78-91
+ *   _termination()              panda_push_gym_env.py:301-316, panda_reach_gym_env.py:285-301
+ *   _compute_reward()           panda_push_gym_env.py:318-331, panda_reach_gym_env.py:303-313
+ *
+ * Build: see oracle/Makefile.  `real` is float by default (to compare against the fp32 GPU
+ * path); -DB2O_DOUBLE computes in double (used to bound the fp32 error).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/b2env.h"
+
+#ifdef B2O_DOUBLE
+typedef double real;
+#define RSQRT sqrt
+#define RSIN sin
+#define RCOS cos
+#define RATAN2 atan2
+#define RASIN asin
+#define RFABS fabs
+#else
+typedef float real;
+#define RSQRT sqrtf
+#define RSIN sinf
+#define RCOS cosf
+#define RATAN2 atan2f
+#define RASIN asinf
+#define RFABS fabsf
+#endif
+
+#define NL B2E_MAX_LINKS
+#define ND B2E_MAX_DOF
+#define NV (B2E_MAX_DOF + 6)
+#define MAXC B2E_MAX_CONTACTS
+#define MAXROWS (B2E_MAX_DOF + B2E_MAX_LIMROWS + 3 * B2E_MAX_CONTACTS)
+
+typedef struct b2o_state {
+  int32_t B;
+  float* q;          /* [B][n_dof] */
+  float* qd;         /* [B][n_dof] */
+  float* obj_pose;   /* [B][7] */
+  float* obj_vel;    /* [B][6] */
+  float* target;     /* [B][3] */
+  float* mtarget;    /* [B][n_dof] */
+  int32_t* counters; /* [B][2] */
+  int32_t* cache_key;/* [B][16] */
+  float* cache_lam;  /* [B][16][3] */
+  float* hand_pose;  /* [B][6] */
+  int32_t* status;   /* [B][4] */
+  float* raw_obs;    /* [B][n_obs] */
+  float* contacts;   /* [B][12][8] */
+} b2o_state;
+
+/* ------------------------------------------------------------------ small math */
+static void m3_mul(const real* a, const real* b, real* c) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+static void m3_vec(const real* a, const real* v, real* o) {
+  real x = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
+  real y = a[3] * v[0] + a[4] * v[1] + a[5] * v[2];
+  real z = a[6] * v[0] + a[7] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static void m3t_vec(const real* a, const real* v, real* o) {
+  real x = a[0] * v[0] + a[3] * v[1] + a[6] * v[2];
+  real y = a[1] * v[0] + a[4] * v[1] + a[7] * v[2];
+  real z = a[2] * v[0] + a[5] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static void cross3(const real* a, const real* b, real* o) {
+  real x = a[1] * b[2] - a[2] * b[1];
+  real y = a[2] * b[0] - a[0] * b[2];
+  real z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* Rodrigues rotation about unit axis by angle */
+static void axis_angle(const real* ax, real ang, real* R) {
+  real c = RCOS(ang), s = RSIN(ang), t = 1 - c;
+  real x = ax[0], y = ax[1], z = ax[2];
+  R[0] = t * x * x + c;     R[1] = t * x * y - s * z; R[2] = t * x * z + s * y;
+  R[3] = t * x * y + s * z; R[4] = t * y * y + c;     R[5] = t * y * z - s * x;
+  R[6] = t * x * z - s * y; R[7] = t * y * z + s * x; R[8] = t * z * z + c;
+}
+
+/* quaternion xyzw */
+static void quat_to_mat(const real* q, real* R) {
+  real x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z);     R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y);     R[7] = 2 * (y * z + w * x);     R[8] = 1 - 2 * (x * x + y * y);
+}
+static void mat_to_quat(const real* R, real* q) {
+  real tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    real s = RSQRT(tr + 1) * 2;
+    q[3] = s / 4; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    real s = RSQRT(1 + R[0] - R[4] - R[8]) * 2;
+    q[3] = (R[7] - R[5]) / s; q[0] = s / 4; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    real s = RSQRT(1 + R[4] - R[0] - R[8]) * 2;
+    q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = s / 4; q[2] = (R[5] + R[7]) / s;
+  } else {
+    real s = RSQRT(1 + R[8] - R[0] - R[4]) * 2;
+    q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = s / 4;
+  }
+}
+static void quat_mul(const real* a, const real* b, real* o) { /* o = a*b */
+  real x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  real y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  real z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  real w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+static void quat_rot(const real* q, const real* v, real* o) {
+  real R[9];
+  quat_to_mat(q, R);
+  m3_vec(R, v, o);
+}
+/* p.getEulerFromQuaternion (btQuaternion::getEulerZYX) [EXT-recalled]; used at panda_env.py:160,
+ * world_env.py:119, panda_push_gym_env.py:176 */
+static void quat_to_euler(const real* q, real* e) {
+  real x = q[0], y = q[1], z = q[2], w = q[3];
+  real sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+  real sarg = -2 * (x * z - w * y);
+  if (sarg <= (real)-0.99999) {
+    e[0] = 0; e[1] = (real)(-0.5 * M_PI); e[2] = 2 * RATAN2(x, -y);
+  } else if (sarg >= (real)0.99999) {
+    e[0] = 0; e[1] = (real)(0.5 * M_PI); e[2] = 2 * RATAN2(-x, y);
+  } else {
+    e[0] = RATAN2(2 * (y * z + w * x), sqw - sqx - sqy + sqz);
+    e[1] = RASIN(sarg);
+    e[2] = RATAN2(2 * (x * y + w * z), sqw + sqx - sqy - sqz);
+  }
+}
+/* p.getQuaternionFromEuler (btQuaternion::setEulerZYX) [EXT-recalled]; panda_push_gym_env.py:169,172 */
+static void euler_to_quat(const real* e, real* q) {
+  real hr = e[0] * (real)0.5, hp = e[1] * (real)0.5, hy = e[2] * (real)0.5;
+  real cr = RCOS(hr), sr = RSIN(hr), cp = RCOS(hp), sp = RSIN(hp), cy = RCOS(hy), sy = RSIN(hy);
+  q[0] = sr * cp * cy - cr * sp * sy;
+  q[1] = cr * sp * cy + sr * cp * sy;
+  q[2] = cr * cp * sy - sr * sp * cy;
+  q[3] = cr * cp * cy + sr * sp * sy;
+}
+
+/* ------------------------------------------------------------------ kinematics */
+typedef struct {
+  real R[NL][9]; /* world <- link rotation */
+  real p[NL][3]; /* link origin in world    */
+  real E[NL][9]; /* parent <- link rotation (local) */
+  real r[NL][3]; /* link origin in parent frame      */
+} fk_t;
+
+static void joint_local(const b2e_model* m, int i, real qi, real* Rl, real* rl) {
+  real jr[9], ax[3];
+  for (int k = 0; k < 9; k++) jr[k] = m->jrot[i][k];
+  for (int k = 0; k < 3; k++) { ax[k] = m->axis[i][k]; rl[k] = m->jpos[i][k]; }
+  if (m->jtype[i] == B2E_JOINT_REVOLUTE) {
+    real Rq[9];
+    axis_angle(ax, qi, Rq);
+    m3_mul(jr, Rq, Rl);
+  } else if (m->jtype[i] == B2E_JOINT_PRISMATIC) {
+    real t[3] = {ax[0] * qi, ax[1] * qi, ax[2] * qi}, o[3];
+    m3_vec(jr, t, o);
+    for (int k = 0; k < 3; k++) { rl[k] += o[k]; }
+    memcpy(Rl, jr, sizeof(jr));
+  } else {
+    memcpy(Rl, jr, sizeof(jr));
+  }
+}
+
+static void forward_kinematics(const b2e_model* m, const real* q, fk_t* fk) {
+  real Rb[9], pb[3];
+  for (int k = 0; k < 9; k++) Rb[k] = m->base_rot[k];
+  for (int k = 0; k < 3; k++) pb[k] = m->base_pos[k];
+  for (int i = 0; i < m->n_links; i++) {
+    real qi = m->dof[i] >= 0 ? q[m->dof[i]] : 0;
+    joint_local(m, i, qi, fk->E[i], fk->r[i]);
+    const real* Rp = m->parent[i] < 0 ? Rb : fk->R[m->parent[i]];
+    const real* pp = m->parent[i] < 0 ? pb : fk->p[m->parent[i]];
+    m3_mul(Rp, fk->E[i], fk->R[i]);
+    real o[3];
+    m3_vec(Rp, fk->r[i], o);
+    for (int k = 0; k < 3; k++) fk->p[i][k] = pp[k] + o[k];
+  }
+}
+
+static int is_ancestor_or_self(const b2e_model* m, int a, int link) {
+  while (link >= 0) {
+    if (link == a) return 1;
+    link = m->parent[link];
+  }
+  return 0;
+}
+
+/* world-frame point Jacobian: velocity of world point `pt` rigidly attached to `link`.
+ * Jl[d] (3) linear, Ja[d] (3) angular, for every dof d */
+static void point_jacobian(const b2e_model* m, const fk_t* fk, int link, const real* pt, real Jl[][3], real Ja[][3]) {
+  for (int d = 0; d < m->n_dof; d++)
+    for (int k = 0; k < 3; k++) { Jl[d][k] = 0; Ja[d][k] = 0; }
+  for (int j = 0; j < m->n_links; j++) {
+    int d = m->dof[j];
+    if (d < 0 || !is_ancestor_or_self(m, j, link)) continue;
+    real ax[3] = {m->axis[j][0], m->axis[j][1], m->axis[j][2]}, aw[3];
+    m3_vec(fk->R[j], ax, aw);
+    if (m->jtype[j] == B2E_JOINT_REVOLUTE) {
+      real rel[3] = {pt[0] - fk->p[j][0], pt[1] - fk->p[j][1], pt[2] - fk->p[j][2]};
+      cross3(aw, rel, Jl[d]);
+      for (int k = 0; k < 3; k++) Ja[d][k] = aw[k];
+    } else {
+      for (int k = 0; k < 3; k++) Jl[d][k] = aw[k];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ spatial algebra (link coordinates)
+ * motion vector [w; v], force vector [n; f]; transform parent->child given E (parent<-child) and r. */
+static void xform_motion(const real* E, const real* r, const real* vp, real* vc) {
+  /* w_c = E^T w_p ; v_c = E^T (v_p - r x w_p) */
+  real t[3], u[3];
+  cross3(r, vp, t);
+  for (int k = 0; k < 3; k++) u[k] = vp[3 + k] - t[k];
+  m3t_vec(E, vp, vc);
+  m3t_vec(E, u, vc + 3);
+}
+static void xform_force_T(const real* E, const real* r, const real* fc, real* fp) {
+  /* child -> parent: f_p = E f_c ; n_p = E n_c + r x (E f_c) */
+  real f[3], n[3], t[3];
+  m3_vec(E, fc + 3, f);
+  m3_vec(E, fc, n);
+  cross3(r, f, t);
+  for (int k = 0; k < 3; k++) { fp[k] = n[k] + t[k]; fp[3 + k] = f[k]; }
+}
+static void x6(const real* E, const real* r, real X[36]) {
+  /* 6x6 motion transform parent->child: [Et 0; -Et rx, Et] */
+  real Et[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Et[3 * i + j] = E[3 * j + i];
+  real rx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+  real Etrx[9];
+  m3_mul(Et, rx, Etrx);
+  memset(X, 0, 36 * sizeof(real));
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      X[6 * i + j] = Et[3 * i + j];
+      X[6 * (i + 3) + j] = -Etrx[3 * i + j];
+      X[6 * (i + 3) + 3 + j] = Et[3 * i + j];
+    }
+}
+static void crm(const real* v, const real* m, real* o) { /* motion cross: v x m */
+  real a[3], b[3], c[3];
+  cross3(v, m, a);
+  cross3(v, m + 3, b);
+  cross3(v + 3, m, c);
+  for (int k = 0; k < 3; k++) { o[k] = a[k]; o[3 + k] = b[k] + c[k]; }
+}
+static void crf(const real* v, const real* f, real* o) { /* force cross: v x* f */
+  real a[3], b[3], c[3];
+  cross3(v, f, a);
+  cross3(v + 3, f + 3, b);
+  cross3(v, f + 3, c);
+  for (int k = 0; k < 3; k++) { o[k] = a[k] + b[k]; o[3 + k] = c[k]; }
+}
+static void link_inertia6(const b2e_model* m, int i, real I[36]) {
+  real ms = m->mass[i], c[3] = {m->com[i][0], m->com[i][1], m->com[i][2]};
+  real cx[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0}, cxcx[9];
+  m3_mul(cx, cx, cxcx);
+  memset(I, 0, 36 * sizeof(real));
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      I[6 * a + b] = m->inertia[i][3 * a + b] - ms * cxcx[3 * a + b];
+      I[6 * a + 3 + b] = ms * cx[3 * a + b];
+      I[6 * (a + 3) + b] = -ms * cx[3 * a + b];
+    }
+  for (int a = 0; a < 3; a++) I[6 * (a + 3) + 3 + a] = ms;
+}
+static void mv6(const real* A, const real* x, real* y) {
+  for (int i = 0; i < 6; i++) {
+    real s = 0;
+    for (int j = 0; j < 6; j++) s += A[6 * i + j] * x[j];
+    y[i] = s;
+  }
+}
+static real dot6(const real* a, const real* b) {
+  real s = 0;
+  for (int k = 0; k < 6; k++) s += a[k] * b[k];
+  return s;
+}
+
+/* Articulated-body workspace kept after the forward-dynamics pass so that M^-1 * tau products
+ * (Bullet: calcAccelerationDeltasMultiDof) cost one O(n) sweep each.                         */
+typedef struct {
+  real S[NL][6];
+  real U[NL][6];
+  real Dinv[NL];
+  real IA[NL][36];
+  real pA[NL][6];
+  real v[NL][6];
+  real c[NL][6];
+  real u[NL];
+} aba_t;
+
+/* Featherstone ABA (RBDA Table 7.1) = Bullet computeAccelerationsArticulatedBodyAlgorithmMultiDof. */
+static void aba(const b2e_model* m, const fk_t* fk, const real* qd, const real* tau, const real* grav, aba_t* w, real* qdd) {
+  int n = m->n_links;
+  for (int i = 0; i < n; i++) {
+    int d = m->dof[i];
+    real vp[6] = {0, 0, 0, 0, 0, 0};
+    if (m->parent[i] >= 0) xform_motion(fk->E[i], fk->r[i], w->v[m->parent[i]], vp);
+    for (int k = 0; k < 6; k++) w->S[i][k] = 0;
+    if (d >= 0) {
+      int off = m->jtype[i] == B2E_JOINT_REVOLUTE ? 0 : 3;
+      for (int k = 0; k < 3; k++) w->S[i][off + k] = m->axis[i][k];
+    }
+    real vj[6];
+    for (int k = 0; k < 6; k++) { vj[k] = d >= 0 ? w->S[i][k] * qd[d] : 0; w->v[i][k] = vp[k] + vj[k]; }
+    crm(w->v[i], vj, w->c[i]);
+    link_inertia6(m, i, w->IA[i]);
+    real Iv[6];
+    mv6(w->IA[i], w->v[i], Iv);
+    crf(w->v[i], Iv, w->pA[i]);
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    int d = m->dof[i];
+    real Ia[36], pa[6];
+    memcpy(Ia, w->IA[i], sizeof(Ia));
+    real Ic[6];
+    mv6(w->IA[i], w->c[i], Ic);
+    if (d >= 0) {
+      mv6(w->IA[i], w->S[i], w->U[i]);
+      real D = dot6(w->S[i], w->U[i]);
+      w->Dinv[i] = 1 / D;
+      w->u[i] = tau[d] - dot6(w->S[i], w->pA[i]);
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) Ia[6 * a + b] -= w->U[i][a] * w->Dinv[i] * w->U[i][b];
+      real Iac[6];
+      mv6(Ia, w->c[i], Iac);
+      for (int k = 0; k < 6; k++) pa[k] = w->pA[i][k] + Iac[k] + w->U[i][k] * w->Dinv[i] * w->u[i];
+    } else {
+      for (int k = 0; k < 6; k++) pa[k] = w->pA[i][k] + Ic[k];
+    }
+    int p = m->parent[i];
+    if (p >= 0) {
+      real X[36], T[36];
+      x6(fk->E[i], fk->r[i], X);
+      /* IA_p += X^T Ia X */
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+          real s = 0;
+          for (int k = 0; k < 6; k++) s += Ia[6 * a + k] * X[6 * k + b];
+          T[6 * a + b] = s;
+        }
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+          real s = 0;
+          for (int k = 0; k < 6; k++) s += X[6 * k + a] * T[6 * k + b];
+          w->IA[p][6 * a + b] += s;
+        }
+      real fp[6];
+      xform_force_T(fk->E[i], fk->r[i], pa, fp);
+      for (int k = 0; k < 6; k++) w->pA[p][k] += fp[k];
+    }
+  }
+  real a[NL][6];
+  real gb[3], g3[3] = {grav[0], grav[1], grav[2]}, Rb[9];
+  for (int k = 0; k < 9; k++) Rb[k] = m->base_rot[k];
+  m3t_vec(Rb, g3, gb);
+  real a0[6] = {0, 0, 0, -gb[0], -gb[1], -gb[2]};
+  for (int i = 0; i < n; i++) {
+    int d = m->dof[i], p = m->parent[i];
+    real ap[6];
+    if (p >= 0) {
+      xform_motion(fk->E[i], fk->r[i], a[p], ap);
+    } else {
+      /* link frame vs base frame: base is the parent with transform (E,r) */
+      xform_motion(fk->E[i], fk->r[i], a0, ap);
+    }
+    for (int k = 0; k < 6; k++) ap[k] += w->c[i][k];
+    if (d >= 0) {
+      qdd[d] = w->Dinv[i] * (w->u[i] - dot6(w->U[i], ap));
+      for (int k = 0; k < 6; k++) a[i][k] = ap[k] + w->S[i][k] * qdd[d];
+    } else {
+      for (int k = 0; k < 6; k++) a[i][k] = ap[k];
+    }
+  }
+}
+
+/* y = M^-1 * tau using the stored articulated inertias (Bullet calcAccelerationDeltasMultiDof). */
+static void minv_mul(const b2e_model* m, const fk_t* fk, const aba_t* w, const real* tau, real* y) {
+  int n = m->n_links;
+  real p[NL][6], u[NL], a[NL][6];
+  memset(p, 0, sizeof(p));
+  for (int i = n - 1; i >= 0; i--) {
+    int d = m->dof[i];
+    real pa[6];
+    if (d >= 0) {
+      u[i] = tau[d] - dot6(w->S[i], p[i]);
+      for (int k = 0; k < 6; k++) pa[k] = p[i][k] + w->U[i][k] * w->Dinv[i] * u[i];
+    } else {
+      u[i] = 0;
+      for (int k = 0; k < 6; k++) pa[k] = p[i][k];
+    }
+    int pr = m->parent[i];
+    if (pr >= 0) {
+      real fp[6];
+      xform_force_T(fk->E[i], fk->r[i], pa, fp);
+      for (int k = 0; k < 6; k++) p[pr][k] += fp[k];
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    int d = m->dof[i], pr = m->parent[i];
+    real ap[6] = {0, 0, 0, 0, 0, 0};
+    if (pr >= 0) xform_motion(fk->E[i], fk->r[i], a[pr], ap);
+    if (d >= 0) {
+      y[d] = w->Dinv[i] * (u[i] - dot6(w->U[i], ap));
+      for (int k = 0; k < 6; k++) a[i][k] = ap[k] + w->S[i][k] * y[d];
+    } else {
+      for (int k = 0; k < 6; k++) a[i][k] = ap[k];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ collision */
+#define CT_CUBE_STATIC 0
+#define CT_SPHERE_CUBE 1
+#define CT_SPHERE_STATIC 2
+#define KEY_CUBE_TABLE 0
+#define KEY_CUBE_PLANE 8
+#define KEY_SPHERE_CUBE 16
+#define KEY_SPHERE_TABLE 32
+
+typedef struct {
+  int key, type, link;
+  real pA[3], pB[3], n[3]; /* n points from B towards A; A = cube (cube-static) or the arm sphere */
+  real dist, mu, erp, cfm;
+} contact_t;
+
+static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, const real* cpos, const real* cquat,
+                   contact_t* out, int* overflow) {
+  int nc = 0;
+  *overflow = 0;
+  real Rc[9];
+  quat_to_mat(cquat, Rc);
+  real a = P->cube_half, margin = P->contact_margin;
+  /* cube vertices vs table-top slab / ground plane (vertex-face manifold; equals Bullet's
+   * box-box face clipping result for a face-down cube) */
+  for (int k = 0; k < 8; k++) {
+    real l[3] = {(k & 1) ? a : -a, (k & 2) ? a : -a, (k & 4) ? a : -a}, v[3];
+    m3_vec(Rc, l, v);
+    for (int j = 0; j < 3; j++) v[j] += cpos[j];
+    int over_table = v[0] >= P->table_min[0] && v[0] <= P->table_max[0] && v[1] >= P->table_min[1] &&
+                     v[1] <= P->table_max[1] && v[2] > P->table_min[2];
+    real dist, mu;
+    int key;
+    real top;
+    if (over_table) { top = P->table_max[2]; mu = P->cube_mu * P->table_mu; key = KEY_CUBE_TABLE + k; }
+    else { top = 0; mu = P->cube_mu * P->plane_mu; key = KEY_CUBE_PLANE + k; }
+    dist = v[2] - top;
+    if (dist < margin) {
+      if (nc >= MAXC) { *overflow = 1; continue; }
+      contact_t* c = &out[nc++];
+      c->key = key; c->type = CT_CUBE_STATIC; c->link = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = v[j]; c->pB[j] = v[j]; }
+      c->pB[2] = top;
+      c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
+      c->dist = dist; c->mu = mu; c->erp = P->erp; c->cfm = 0;
+    }
+  }
+  /* robot spheres vs cube */
+  real sc[B2E_MAX_SPHERES][3];
+  for (int s = 0; s < m->n_spheres; s++) {
+    int li = m->sph_link[s];
+    real lc[3] = {m->sph_c[s][0], m->sph_c[s][1], m->sph_c[s][2]}, o[3];
+    m3_vec(fk->R[li], lc, o);
+    for (int j = 0; j < 3; j++) sc[s][j] = fk->p[li][j] + o[j];
+  }
+  for (int s = 0; s < m->n_spheres; s++) {
+    real rel[3] = {sc[s][0] - cpos[0], sc[s][1] - cpos[1], sc[s][2] - cpos[2]}, l[3], cl[3];
+    m3t_vec(Rc, rel, l);
+    int inside = 1;
+    for (int j = 0; j < 3; j++) {
+      cl[j] = l[j] < -a ? -a : (l[j] > a ? a : l[j]);
+      if (cl[j] != l[j]) inside = 0;
+    }
+    real nl[3], dist, r = m->sph_r[s];
+    if (!inside) {
+      real dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+      real d = RSQRT(dot3(dv, dv));
+      dist = d - r;
+      if (!(dist < margin)) continue;
+      for (int j = 0; j < 3; j++) nl[j] = dv[j] / d;
+    } else {
+      /* centre inside the box: push out through the nearest face */
+      int ax = 0;
+      real best = a - RFABS(l[0]);
+      for (int j = 1; j < 3; j++) {
+        real pen = a - RFABS(l[j]);
+        if (pen < best) { best = pen; ax = j; }
+      }
+      nl[0] = nl[1] = nl[2] = 0;
+      nl[ax] = l[ax] >= 0 ? 1 : -1;
+      cl[ax] = nl[ax] * a;
+      dist = -best - r;
+    }
+    if (nc >= MAXC) { *overflow = 1; continue; }
+    contact_t* c = &out[nc++];
+    c->key = KEY_SPHERE_CUBE + s; c->type = CT_SPHERE_CUBE; c->link = m->sph_link[s];
+    real nw[3], pw[3];
+    m3_vec(Rc, nl, nw);
+    m3_vec(Rc, cl, pw);
+    for (int j = 0; j < 3; j++) {
+      c->n[j] = nw[j];
+      c->pB[j] = cpos[j] + pw[j];
+      c->pA[j] = sc[s][j] - nw[j] * r;
+    }
+    c->dist = dist; c->mu = P->cube_mu * m->sph_mu[s];
+    c->erp = m->sph_erp[s] >= 0 ? m->sph_erp[s] : P->erp;
+    c->cfm = m->sph_cfm[s];
+  }
+  /* robot spheres vs table top */
+  for (int s = 0; s < m->n_spheres; s++) {
+    real r = m->sph_r[s];
+    if (!(sc[s][0] >= P->table_min[0] && sc[s][0] <= P->table_max[0] && sc[s][1] >= P->table_min[1] &&
+          sc[s][1] <= P->table_max[1] && sc[s][2] > P->table_min[2]))
+      continue;
+    real dist = sc[s][2] - r - P->table_max[2];
+    if (!(dist < margin)) continue;
+    if (nc >= MAXC) { *overflow = 1; continue; }
+    contact_t* c = &out[nc++];
+    c->key = KEY_SPHERE_TABLE + s; c->type = CT_SPHERE_STATIC; c->link = m->sph_link[s];
+    c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
+    for (int j = 0; j < 3; j++) { c->pA[j] = sc[s][j]; c->pB[j] = sc[s][j]; }
+    c->pA[2] = sc[s][2] - r;
+    c->pB[2] = P->table_max[2];
+    c->dist = dist; c->mu = P->table_mu * m->sph_mu[s];
+    c->erp = m->sph_erp[s] >= 0 ? m->sph_erp[s] : P->erp;
+    c->cfm = m->sph_cfm[s];
+  }
+  return nc;
+}
+
+/* btPlaneSpace1 [EXT-recalled]: deterministic tangent basis of a unit normal */
+static void plane_space(const real* n, real* p, real* q) {
+  if (RFABS(n[2]) > (real)0.7071067811865475244) {
+    real a = n[1] * n[1] + n[2] * n[2];
+    real k = 1 / RSQRT(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    real a = n[0] * n[0] + n[1] * n[1];
+    real k = 1 / RSQRT(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+/* ------------------------------------------------------------------ constraint rows */
+#define ROW_MOTOR 0
+#define ROW_LIMIT 1
+#define ROW_NORMAL 2
+#define ROW_FRICTION 3
+#define ISL_ARM 0
+#define ISL_CUBE 1
+
+typedef struct {
+  int type, island, nrow; /* nrow: index of the normal row (friction rows) */
+  real J[NV], W[NV];
+  real rhs, cfm, diag, lo, hi, lam, mu;
+} row_t;
+
+typedef struct {
+  const b2e_model* m;
+  const b2e_params* P;
+  const fk_t* fk;
+  const aba_t* w;
+  int nd;
+  real cinv_m, cinv_I;
+} rowctx_t;
+
+static void finish_row(const rowctx_t* cx, row_t* r, const real* vstar, real desired) {
+  int nd = cx->nd;
+  minv_mul(cx->m, cx->fk, cx->w, r->J, r->W);
+  for (int k = 0; k < 3; k++) {
+    r->W[nd + k] = r->J[nd + k] * cx->cinv_m;
+    r->W[nd + 3 + k] = r->J[nd + 3 + k] * cx->cinv_I;
+  }
+  real d = 0, jv = 0;
+  for (int k = 0; k < nd + 6; k++) { d += r->J[k] * r->W[k]; jv += r->J[k] * vstar[k]; }
+  r->diag = d + r->cfm;
+  r->rhs = desired - jv;
+  r->lam = 0;
+}
+
+/* contact direction row: relative velocity of A w.r.t. B along dir */
+static void contact_J(const rowctx_t* cx, const contact_t* c, const real* cpos, const real* dir, real* J) {
+  int nd = cx->nd;
+  for (int k = 0; k < nd + 6; k++) J[k] = 0;
+  if (c->type == CT_CUBE_STATIC) {
+    real rel[3] = {c->pA[0] - cpos[0], c->pA[1] - cpos[1], c->pA[2] - cpos[2]}, t[3];
+    cross3(rel, dir, t);
+    for (int k = 0; k < 3; k++) { J[nd + k] = dir[k]; J[nd + 3 + k] = t[k]; }
+  } else {
+    real Jl[ND][3], Ja[ND][3];
+    point_jacobian(cx->m, cx->fk, c->link, c->pA, Jl, Ja);
+    for (int d = 0; d < nd; d++) J[d] = dot3(Jl[d], dir);
+    if (c->type == CT_SPHERE_CUBE) {
+      real rel[3] = {c->pB[0] - cpos[0], c->pB[1] - cpos[1], c->pB[2] - cpos[2]}, t[3];
+      cross3(rel, dir, t);
+      for (int k = 0; k < 3; k++) { J[nd + k] = -dir[k]; J[nd + 3 + k] = -t[k]; }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ observation, reward */
+static void ee_state(const b2e_model* m, const fk_t* fk, const real* qd, real* pos, real* quat, real* vlin) {
+  int ee = m->ee_link;
+  real c[3] = {m->com[ee][0], m->com[ee][1], m->com[ee][2]}, o[3];
+  m3_vec(fk->R[ee], c, o);
+  for (int k = 0; k < 3; k++) pos[k] = fk->p[ee][k] + o[k];
+  mat_to_quat(fk->R[ee], quat);
+  real Jl[ND][3], Ja[ND][3];
+  point_jacobian(m, fk, ee, pos, Jl, Ja);
+  for (int k = 0; k < 3; k++) {
+    real s = 0;
+    for (int d = 0; d < m->n_dof; d++) s += Jl[d][k] * qd[d];
+    vlin[k] = s;
+  }
+}
+
+/* panda_push_gym_env.py:150-187 (Push, 33 entries) / panda_reach_gym_env.py:140-171 (Reach, 30) */
+static int extended_observation(const b2e_model* m, const b2e_params* P, const fk_t* fk, const real* q, const real* qd,
+                                const real* cpos, const real* cquat, const real* target, real* obs) {
+  real pos[3], quat[4], vl[3], eu[3];
+  ee_state(m, fk, qd, pos, quat, vl);
+  quat_to_euler(quat, eu);
+  int n = 0;
+  for (int k = 0; k < 3; k++) obs[n++] = pos[k];
+  for (int k = 0; k < 3; k++) obs[n++] = eu[k];
+  for (int k = 0; k < 3; k++) obs[n++] = (vl[k] - P->vel_mean[k]) / P->vel_std[k]; /* panda_env.py:171-181 */
+  for (int d = 0; d < m->n_dof; d++) obs[n++] = q[d];
+  real ceu[3];
+  quat_to_euler(cquat, ceu);
+  for (int k = 0; k < 3; k++) obs[n++] = cpos[k];
+  for (int k = 0; k < 3; k++) obs[n++] = ceu[k];
+  /* object pose in the hand frame; both orientations round-trip through Euler (:168-174) */
+  real hq[4], oq[4], hqi[4], rel[3], relq[4], releu[3], d[3];
+  euler_to_quat(eu, hq);
+  euler_to_quat(ceu, oq);
+  hqi[0] = -hq[0]; hqi[1] = -hq[1]; hqi[2] = -hq[2]; hqi[3] = hq[3];
+  for (int k = 0; k < 3; k++) d[k] = cpos[k] - pos[k];
+  quat_rot(hqi, d, rel);
+  quat_mul(hqi, oq, relq);
+  quat_to_euler(relq, releu);
+  for (int k = 0; k < 3; k++) obs[n++] = rel[k];
+  for (int k = 0; k < 3; k++) obs[n++] = releu[k];
+  if (P->task == B2E_TASK_PUSH)
+    for (int k = 0; k < 3; k++) obs[n++] = target[k];
+  return n;
+}
+
+static real dist3(const real* a, const real* b) {
+  real d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+  return RSQRT(dot3(d, d));
+}
+
+/* ------------------------------------------------------------------ one physics step of one env */
+typedef struct {
+  real q[ND], qd[ND], cpos[3], cquat[4], cv[3], cw[3], mtarget[ND];
+  int cache_key[B2E_CACHE_SLOTS];
+  real cache_lam[B2E_CACHE_SLOTS][3];
+  int flags, iters, n_contacts, n_rows;
+  real contact_out[MAXC][8];
+} env_t;
+
+static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int kp_ctrl_active) {
+  int nd = m->n_dof, nv = nd + 6;
+  real dt = P->dt;
+  fk_t fk;
+  aba_t w;
+  forward_kinematics(m, e->q, &fk);
+
+  /* --- unconstrained velocities: v* = v + dt * a(q, v) --- */
+  real tau[ND], qdd[ND], grav[3] = {P->gravity[0], P->gravity[1], P->gravity[2]};
+  for (int d = 0; d < nd; d++) tau[d] = -m->joint_damping[d] * e->qd[d];
+  aba(m, &fk, e->qd, tau, grav, &w, qdd);
+  real vstar[NV];
+  for (int d = 0; d < nd; d++) vstar[d] = e->qd[d] + dt * qdd[d];
+  real vn = RSQRT(dot3(e->cv, e->cv)), wn = RSQRT(dot3(e->cw, e->cw));
+  for (int k = 0; k < 3; k++) {
+    vstar[nd + k] = e->cv[k] + dt * (grav[k] - e->cv[k] * (P->damp_lin_k1 + P->damp_lin_k2 * vn));
+    vstar[nd + 3 + k] = e->cw[k] + dt * (-e->cw[k] * (P->damp_ang_k1 + P->damp_ang_k2 * wn));
+  }
+
+  /* --- collision detection on the pre-step poses --- */
+  contact_t con[MAXC];
+  int overflow = 0;
+  int nc = collide(m, P, &fk, e->cpos, e->cquat, con, &overflow);
+  if (overflow) e->flags |= B2E_ST_CONTACT_OVERFLOW;
+
+  /* --- rows: motors, limits, contact normals, contact frictions --- */
+  row_t rows[MAXROWS];
+  int nr = 0;
+  rowctx_t cx = {m, P, &fk, &w, nd, 1 / P->cube_mass, 1 / P->cube_inertia};
+  for (int d = 0; d < nd; d++) { /* btMultiBodyJointMotor: desired = kp*(target-q)/dt (kd=1, erp=1) */
+    row_t* r = &rows[nr++];
+    memset(r, 0, sizeof(*r));
+    r->type = ROW_MOTOR; r->island = ISL_ARM;
+    r->J[d] = 1;
+    real kp = (kp_ctrl_active && d < P->n_ctrl) ? P->kp_ctrl : P->kp_hold;
+    real desired = kp * (e->mtarget[d] - e->q[d]) / dt;
+    if (m->max_vel[d] > 0) {
+      if (desired > m->max_vel[d]) desired = m->max_vel[d];
+      if (desired < -m->max_vel[d]) desired = -m->max_vel[d];
+    }
+    r->cfm = 0;
+    r->hi = m->max_force[d] * dt;
+    r->lo = -r->hi;
+    finish_row(&cx, r, vstar, desired);
+  }
+  int nlim = 0;
+  for (int d = 0; d < nd; d++) { /* btMultiBodyJointLimitConstraint rows, only near a limit */
+    for (int side = 0; side < 2; side++) {
+      real dist = side == 0 ? e->q[d] - m->lower[d] : m->upper[d] - e->q[d];
+      if (!(dist < m->limit_margin[d])) continue;
+      if (nlim >= B2E_MAX_LIMROWS) { e->flags |= B2E_ST_LIMIT_OVERFLOW; continue; }
+      nlim++;
+      row_t* r = &rows[nr++];
+      memset(r, 0, sizeof(*r));
+      r->type = ROW_LIMIT; r->island = ISL_ARM;
+      r->J[d] = side == 0 ? 1 : -1;
+      real pen = dist + P->slop;
+      real desired = pen > 0 ? -pen / dt : -pen * P->erp / dt;
+      r->lo = 0; r->hi = (real)1e30; r->cfm = 0;
+      finish_row(&cx, r, vstar, desired);
+    }
+  }
+  int coupled = 0;
+  int normal_row[MAXC];
+  for (int c = 0; c < nc; c++) {
+    row_t* r = &rows[nr];
+    memset(r, 0, sizeof(*r));
+    r->type = ROW_NORMAL;
+    r->island = con[c].type == CT_CUBE_STATIC ? ISL_CUBE : ISL_ARM;
+    if (con[c].type == CT_SPHERE_CUBE) coupled = 1;
+    contact_J(&cx, &con[c], e->cpos, con[c].n, r->J);
+    real pen = con[c].dist + P->slop;
+    real desired = pen > 0 ? -pen / dt : -pen * con[c].erp / dt;
+    r->lo = 0; r->hi = (real)1e30; r->cfm = con[c].cfm;
+    finish_row(&cx, r, vstar, desired);
+    normal_row[c] = nr++;
+  }
+  for (int c = 0; c < nc; c++) {
+    real t1[3], t2[3];
+    plane_space(con[c].n, t1, t2);
+    for (int f = 0; f < 2; f++) {
+      row_t* r = &rows[nr++];
+      memset(r, 0, sizeof(*r));
+      r->type = ROW_FRICTION;
+      r->island = rows[normal_row[c]].island;
+      r->nrow = normal_row[c];
+      r->mu = con[c].mu;
+      contact_J(&cx, &con[c], e->cpos, f == 0 ? t1 : t2, r->J);
+      r->cfm = 0;
+      finish_row(&cx, r, vstar, 0);
+    }
+  }
+
+  /* --- warm start from the cache (contact rows only) --- */
+  real dv[NV];
+  for (int k = 0; k < nv; k++) dv[k] = 0;
+  for (int c = 0; c < nc; c++) {
+    for (int s = 0; s < B2E_CACHE_SLOTS; s++) {
+      if (e->cache_key[s] != con[c].key) continue;
+      int ri[3] = {normal_row[c], nd + nlim + nc + 2 * c, nd + nlim + nc + 2 * c + 1};
+      for (int j = 0; j < 3; j++) {
+        real l = e->cache_lam[s][j] * P->warmstart;
+        rows[ri[j]].lam = l;
+        for (int k = 0; k < nv; k++) dv[k] += rows[ri[j]].W[k] * l;
+      }
+      break;
+    }
+  }
+
+  /* --- projected Gauss-Seidel (Bullet btMultiBodyConstraintSolver::solveSingleIteration order:
+   *     non-contact rows, contact normals, then frictions bounded by mu * normal impulse);
+   *     islands that do not share a body converge independently --- */
+  int done_isl[2] = {0, 0};
+  int it = 0;
+  int has_cube_rows = 0;
+  for (int i = 0; i < nr; i++) if (rows[i].island == ISL_CUBE) has_cube_rows = 1;
+  if (!has_cube_rows) done_isl[ISL_CUBE] = 1;
+  for (it = 0; it < P->solver_iters; it++) {
+    real res[2] = {0, 0};
+    for (int i = 0; i < nr; i++) {
+      row_t* r = &rows[i];
+      int isl = coupled ? 0 : r->island;
+      if (done_isl[isl]) continue;
+      if (r->type == ROW_FRICTION) {
+        real lim = r->mu * rows[r->nrow].lam;
+        r->lo = -lim; r->hi = lim;
+      }
+      real jdv = 0;
+      for (int k = 0; k < nv; k++) jdv += r->J[k] * dv[k];
+      real dl = (r->rhs - jdv - r->cfm * r->lam) / r->diag;
+      real nl = r->lam + dl;
+      if (nl < r->lo) nl = r->lo;
+      if (nl > r->hi) nl = r->hi;
+      dl = nl - r->lam;
+      r->lam = nl;
+      for (int k = 0; k < nv; k++) dv[k] += r->W[k] * dl;
+      real rv = dl * r->diag;
+      if (rv * rv > res[isl]) res[isl] = rv * rv;
+    }
+    if (coupled) {
+      if (res[0] <= P->residual_tol) { it++; break; }
+    } else {
+      if (!done_isl[0] && res[0] <= P->residual_tol) done_isl[0] = 1;
+      if (!done_isl[1] && res[1] <= P->residual_tol) done_isl[1] = 1;
+      if (done_isl[0] && done_isl[1]) { it++; break; }
+    }
+  }
+  e->iters = it;
+  e->n_contacts = nc;
+  e->n_rows = nr;
+
+  /* --- integrate (semi-implicit Euler) --- */
+  for (int d = 0; d < nd; d++) {
+    e->qd[d] = vstar[d] + dv[d];
+    e->q[d] += dt * e->qd[d];
+  }
+  for (int k = 0; k < 3; k++) {
+    e->cv[k] = vstar[nd + k] + dv[nd + k];
+    e->cw[k] = vstar[nd + 3 + k] + dv[nd + 3 + k];
+    e->cpos[k] += dt * e->cv[k];
+  }
+  {
+    real wl = RSQRT(dot3(e->cw, e->cw)), ang = wl * dt, f;
+    if (ang < (real)1e-3) f = (real)0.5 * dt - dt * dt * dt * (real)(1.0 / 48.0) * wl * wl;
+    else f = RSIN((real)0.5 * ang) / wl;
+    real dq[4] = {e->cw[0] * f, e->cw[1] * f, e->cw[2] * f, RCOS((real)0.5 * ang)}, nq[4];
+    quat_mul(dq, e->cquat, nq);
+    real nn = 1 / RSQRT(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+    for (int k = 0; k < 4; k++) e->cquat[k] = nq[k] * nn;
+  }
+
+  /* --- write back the contact cache + diagnostics --- */
+  for (int s = 0; s < B2E_CACHE_SLOTS; s++) { e->cache_key[s] = -1; e->cache_lam[s][0] = e->cache_lam[s][1] = e->cache_lam[s][2] = 0; }
+  memset(e->contact_out, 0, sizeof(e->contact_out));
+  for (int c = 0; c < nc; c++) {
+    int ri[3] = {normal_row[c], nd + nlim + nc + 2 * c, nd + nlim + nc + 2 * c + 1};
+    e->cache_key[c] = con[c].key;
+    for (int j = 0; j < 3; j++) e->cache_lam[c][j] = rows[ri[j]].lam;
+    e->contact_out[c][0] = (real)con[c].key;
+    e->contact_out[c][1] = con[c].dist;
+    for (int j = 0; j < 3; j++) { e->contact_out[c][2 + j] = con[c].n[j]; e->contact_out[c][5 + j] = rows[ri[j]].lam; }
+  }
+  int bad = 0;
+  for (int d = 0; d < nd; d++) if (!isfinite(e->q[d]) || !isfinite(e->qd[d])) bad = 1;
+  for (int k = 0; k < 3; k++) if (!isfinite(e->cpos[k]) || !isfinite(e->cv[k]) || !isfinite(e->cw[k])) bad = 1;
+  if (bad) e->flags |= B2E_ST_NAN;
+}
+
+/* ------------------------------------------------------------------ batched entry points */
+static void load_env(const b2e_model* m, const b2o_state* S, int b, env_t* e) {
+  int nd = m->n_dof;
+  for (int d = 0; d < nd; d++) {
+    e->q[d] = S->q[b * nd + d];
+    e->qd[d] = S->qd[b * nd + d];
+    e->mtarget[d] = S->mtarget[b * nd + d];
+  }
+  for (int k = 0; k < 3; k++) {
+    e->cpos[k] = S->obj_pose[b * 7 + k];
+    e->cv[k] = S->obj_vel[b * 6 + k];
+    e->cw[k] = S->obj_vel[b * 6 + 3 + k];
+  }
+  for (int k = 0; k < 4; k++) e->cquat[k] = S->obj_pose[b * 7 + 3 + k];
+  for (int s = 0; s < B2E_CACHE_SLOTS; s++) {
+    e->cache_key[s] = S->cache_key[b * B2E_CACHE_SLOTS + s];
+    for (int j = 0; j < 3; j++) e->cache_lam[s][j] = S->cache_lam[(b * B2E_CACHE_SLOTS + s) * 3 + j];
+  }
+  e->flags = S->status[b * 4];
+  e->iters = 0; e->n_contacts = 0; e->n_rows = 0;
+}
+static void store_env(const b2e_model* m, b2o_state* S, int b, const env_t* e) {
+  int nd = m->n_dof;
+  for (int d = 0; d < nd; d++) {
+    S->q[b * nd + d] = (float)e->q[d];
+    S->qd[b * nd + d] = (float)e->qd[d];
+    S->mtarget[b * nd + d] = (float)e->mtarget[d];
+  }
+  for (int k = 0; k < 3; k++) {
+    S->obj_pose[b * 7 + k] = (float)e->cpos[k];
+    S->obj_vel[b * 6 + k] = (float)e->cv[k];
+    S->obj_vel[b * 6 + 3 + k] = (float)e->cw[k];
+  }
+  for (int k = 0; k < 4; k++) S->obj_pose[b * 7 + 3 + k] = (float)e->cquat[k];
+  for (int s = 0; s < B2E_CACHE_SLOTS; s++) {
+    S->cache_key[b * B2E_CACHE_SLOTS + s] = e->cache_key[s];
+    for (int j = 0; j < 3; j++) S->cache_lam[(b * B2E_CACHE_SLOTS + s) * 3 + j] = (float)e->cache_lam[s][j];
+  }
+  S->status[b * 4 + 0] = e->flags;
+  S->status[b * 4 + 1] = e->iters;
+  S->status[b * 4 + 2] = e->n_contacts;
+  S->status[b * 4 + 3] = e->n_rows;
+  for (int c = 0; c < MAXC; c++)
+    for (int j = 0; j < 8; j++) S->contacts[(b * MAXC + c) * 8 + j] = (float)e->contact_out[c][j];
+}
+
+static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int b, const float* action, float* obs,
+                     float* reward, float* done, int nsub, int mode) {
+  env_t e;
+  load_env(m, S, b, &e);
+  int counter = S->counters[b * 2], terminated = S->counters[b * 2 + 1];
+  real target[3] = {S->target[b * 3], S->target[b * 3 + 1], S->target[b * 3 + 2]};
+  real act[ND];
+  if (mode == B2E_MODE_ACTION)
+    for (int k = 0; k < P->n_act; k++) act[k] = action[b * P->n_act + k];
+  for (int sub = 0; sub < nsub; sub++) {
+    if (mode == B2E_MODE_ACTION && !P->use_ik) {
+      /* panda_push_gym_env.py:225-230: action *= 0.05 (compounding in place across repeats, quirk E.4),
+       * new = q[:n_ctrl] + action; panda_env.py:303: clamp to [ll, ul] */
+      for (int k = 0; k < P->n_ctrl; k++) {
+        act[k] *= P->act_scale;
+        real t = e.q[k] + act[k];
+        if (t < m->lower[k]) t = m->lower[k];
+        if (t > m->upper[k]) t = m->upper[k];
+        e.mtarget[k] = t;
+      }
+    }
+    physics_step(m, P, &e, mode == B2E_MODE_ACTION);
+    if (mode == B2E_MODE_ACTION) {
+      /* _termination() inside apply_action (:239-242): counter only advances when not terminated */
+      fk_t fk;
+      forward_kinematics(m, e.q, &fk);
+      real d;
+      if (P->task == B2E_TASK_PUSH) d = dist3(e.cpos, target);
+      else { real pos[3], qt[4], vl[3]; ee_state(m, &fk, e.qd, pos, qt, vl); d = dist3(pos, e.cpos); }
+      int term = 0;
+      if (d <= P->dist_min) { terminated = 1; term = 1; }
+      else if (terminated || counter > P->max_steps) term = 1;
+      if (term) break;
+      counter++;
+    }
+  }
+  store_env(m, S, b, &e);
+  S->counters[b * 2] = counter;
+  if (mode == B2E_MODE_ACTION || obs) {
+    fk_t fk;
+    forward_kinematics(m, e.q, &fk);
+    real raw[B2E_MAX_OBS];
+    int n = extended_observation(m, P, &fk, e.q, e.qd, e.cpos, e.cquat, target, raw);
+    for (int k = 0; k < n; k++) {
+      S->raw_obs[b * P->n_obs + k] = (float)raw[k];
+      if (obs) /* scale_gym_data, utils.py:91 (no clipping) */
+        obs[b * P->n_obs + k] = (float)(2 * ((raw[k] - P->obs_low[k]) / (P->obs_high[k] - P->obs_low[k])) - 1);
+    }
+    /* _termination (:301-316) then _compute_reward (:318-331) */
+    real d1 = dist3(raw, e.cpos), d2 = 0, rew;
+    int dn = 0;
+    if (P->task == B2E_TASK_PUSH) {
+      d2 = dist3(e.cpos, target);
+      if (d2 <= P->dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P->max_steps) dn = 1;
+      rew = -d1 - d2;
+      if (d2 <= P->dist_min) rew = (real)1000.0 + (100 - d2 * 80);
+    } else {
+      if (d1 <= P->dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P->max_steps) dn = 1;
+      rew = -d1;
+      if (d1 <= P->dist_min) rew = (real)1000.0 + (100 - d1 * 80);
+    }
+    if (reward) reward[b] = (float)rew;
+    if (done) done[b] = (float)dn;
+  }
+  S->counters[b * 2 + 1] = terminated;
+}
+
+#include <pthread.h>
+typedef struct {
+  const b2e_model* m; const b2e_params* P; b2o_state* S; const float* action; float* obs; float* reward; float* done;
+  int nsub, mode, b0, b1;
+} job_t;
+static void* worker(void* arg) {
+  job_t* j = (job_t*)arg;
+  for (int b = j->b0; b < j->b1; b++) step_env(j->m, j->P, j->S, b, j->action, j->obs, j->reward, j->done, j->nsub, j->mode);
+  return NULL;
+}
+
+/* One env.step() for every env; nthreads > 1 splits the batch over host threads. */
+int b2o_step(const b2e_model* m, const b2e_params* P, b2o_state* S, const float* action, float* obs, float* reward,
+             float* done, int nsub, int mode, int nthreads) {
+  if (!m || !P || !S) return B2E_EINVAL;
+  if (m->n_dof + 6 > NV) return B2E_EINVAL;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads == 1 || S->B < 2 * nthreads) {
+    job_t j = {m, P, S, action, obs, reward, done, nsub, mode, 0, S->B};
+    worker(&j);
+    return 0;
+  }
+  pthread_t th[256];
+  job_t jobs[256];
+  int per = (S->B + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    int b0 = t * per, b1 = b0 + per > S->B ? S->B : b0 + per;
+    if (b0 > b1) b0 = b1;
+    jobs[t] = (job_t){m, P, S, action, obs, reward, done, nsub, mode, b0, b1};
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  return 0;
+}
+
+/* Masked reset (panda_env.py:63-79 home state; world_env.py:81-84 object pose). */
+int b2o_reset(const b2e_model* m, const b2e_params* P, b2o_state* S, const uint8_t* mask, const float* obj_init_pose,
+              const float* target) {
+  (void)P;
+  int nd = m->n_dof;
+  for (int b = 0; b < S->B; b++) {
+    if (mask && !mask[b]) continue;
+    for (int d = 0; d < nd; d++) {
+      S->q[b * nd + d] = m->home[d];
+      S->qd[b * nd + d] = 0;
+      S->mtarget[b * nd + d] = m->home[d];
+    }
+    for (int k = 0; k < 7; k++) S->obj_pose[b * 7 + k] = obj_init_pose[b * 7 + k];
+    for (int k = 0; k < 6; k++) S->obj_vel[b * 6 + k] = 0;
+    for (int k = 0; k < 3; k++) S->target[b * 3 + k] = target[b * 3 + k];
+    S->counters[b * 2] = 0; S->counters[b * 2 + 1] = 0;
+    for (int s = 0; s < B2E_CACHE_SLOTS; s++) {
+      S->cache_key[b * B2E_CACHE_SLOTS + s] = -1;
+      for (int j = 0; j < 3; j++) S->cache_lam[(b * B2E_CACHE_SLOTS + s) * 3 + j] = 0;
+    }
+    for (int k = 0; k < 6; k++) S->hand_pose[b * 6 + k] = P->home_hand_pose[k];
+    for (int k = 0; k < 4; k++) S->status[b * 4 + k] = 0;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ known-answer helpers (tests only) */
+int b2o_fk(const b2e_model* m, const float* q, float* link_pos /*[n][3]*/, float* link_rot /*[n][9]*/) {
+  real qq[ND];
+  for (int d = 0; d < m->n_dof; d++) qq[d] = q[d];
+  fk_t fk;
+  forward_kinematics(m, qq, &fk);
+  for (int i = 0; i < m->n_links; i++) {
+    for (int k = 0; k < 3; k++) link_pos[3 * i + k] = (float)fk.p[i][k];
+    for (int k = 0; k < 9; k++) link_rot[9 * i + k] = (float)fk.R[i][k];
+  }
+  return 0;
+}
+int b2o_forward_dynamics(const b2e_model* m, const b2e_params* P, const float* q, const float* qd, const float* tau,
+                         float* qdd) {
+  real qq[ND], qv[ND], tt[ND], out[ND], g[3] = {P->gravity[0], P->gravity[1], P->gravity[2]};
+  for (int d = 0; d < m->n_dof; d++) { qq[d] = q[d]; qv[d] = qd[d]; tt[d] = tau[d]; }
+  fk_t fk; aba_t w;
+  forward_kinematics(m, qq, &fk);
+  aba(m, &fk, qv, tt, g, &w, out);
+  for (int d = 0; d < m->n_dof; d++) qdd[d] = (float)out[d];
+  return 0;
+}
+int b2o_minv(const b2e_model* m, const float* q, float* Minv /*[nd][nd]*/) {
+  real qq[ND], z[ND], out[ND], g[3] = {0, 0, 0};
+  int nd = m->n_dof;
+  for (int d = 0; d < nd; d++) { qq[d] = q[d]; z[d] = 0; }
+  fk_t fk; aba_t w;
+  forward_kinematics(m, qq, &fk);
+  aba(m, &fk, z, z, g, &w, out);
+  for (int c = 0; c < nd; c++) {
+    real e[ND];
+    for (int d = 0; d < nd; d++) e[d] = d == c;
+    minv_mul(m, &fk, &w, e, out);
+    for (int d = 0; d < nd; d++) Minv[d * nd + c] = (float)out[d];
+  }
+  return 0;
+}
+int b2o_ee_jacobian(const b2e_model* m, const float* q, float* J /*[6][nd] linear rows then angular rows*/,
+                    float* pos, float* quat) {
+  real qq[ND], z[ND];
+  int nd = m->n_dof;
+  for (int d = 0; d < nd; d++) { qq[d] = q[d]; z[d] = 0; }
+  fk_t fk;
+  forward_kinematics(m, qq, &fk);
+  real p[3], qt[4], vl[3];
+  ee_state(m, &fk, z, p, qt, vl);
+  real Jl[ND][3], Ja[ND][3];
+  point_jacobian(m, &fk, m->ee_link, p, Jl, Ja);
+  for (int d = 0; d < nd; d++)
+    for (int k = 0; k < 3; k++) { J[k * nd + d] = (float)Jl[d][k]; J[(3 + k) * nd + d] = (float)Ja[d][k]; }
+  for (int k = 0; k < 3; k++) pos[k] = (float)p[k];
+  for (int k = 0; k < 4; k++) quat[k] = (float)qt[k];
+  return 0;
+}
+int b2o_real_size(void) { return (int)sizeof(real); }

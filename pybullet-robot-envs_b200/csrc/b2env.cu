@@ -1,0 +1,1433 @@
+// b2env.cu — B200 (sm_100a) batched rigid-body step + reward pipeline and its C-ABI.
+//
+// One warp advances one environment through a complete env.step() of the reference
+// (pybullet_robot_envs/envs/panda_envs/panda_push_gym_env.py:244-255): action -> motor targets
+// (:225-230, panda_env.py:303-310), p.stepSimulation (:236) = articulated forward dynamics +
+// collision detection + PGS over motor/limit/contact rows + semi-implicit Euler, then the
+// observation gather (:150-187), termination (:301-316) and reward (:318-331), all fused in a
+// single launch.  See DESIGN.md for the algorithm statement shared with oracle/b2oracle.c.
+//
+// Mapping of the work onto a warp (32 lanes):
+//   * kinematics / dynamics : lane = link (<=32 links); parent->child recursions are carried
+//     by pointer-jumping over __shfl_sync (log2(depth) rounds), child->parent accumulations
+//     by a shuffle walk over the links; the joint-space inertia matrix is built CRBA-style in
+//     world coordinates and inverted in registers by Gauss-Jordan (lane = row).
+//   * collision             : lane = cube vertex / lane = collision sphere, ballot compaction.
+//   * PGS                   : lane = constraint row.  The solver runs on the Delassus form
+//     A = J M^-1 J^T (staged in shared memory), so one row update is a handful of scalar
+//     instructions + one shuffle + one LDS/FMA per lane instead of two n-wide dot/axpy.
+//     This is the same Gauss-Seidel iteration Bullet runs in delta-velocity space
+//     (identical iterates in exact arithmetic, same row order).
+// There is no dense contraction anywhere (largest matrix 9x9 / 48x48 per env): no tensor cores.
+//
+// State lives in HBM as env-major field groups ([B][width] arrays, see enum b2e_field), read
+// once and written once per step.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b2env.h"
+
+#define FULL 0xffffffffu
+#define WPB 2             // warps (= envs) per block
+#define RMAX 48           // max constraint rows per env: 9 motors + 3 limits + 3*12 contact rows
+#define WSTRIDE 16        // row stride of the W = M^-1 J^T table
+#define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
+#define NLMAX 32          // links (lanes)
+
+#define KEY_CUBE_TABLE 0
+#define KEY_CUBE_PLANE 8
+#define KEY_SPHERE_CUBE 16
+#define KEY_SPHERE_TABLE 32
+#define CT_CUBE_STATIC 0
+#define CT_SPHERE_CUBE 1
+#define CT_SPHERE_STATIC 2
+#define ROW_MOTOR 0
+#define ROW_LIMIT 1
+#define ROW_NORMAL 2
+#define ROW_FRICTION 3
+
+// ------------------------------------------------------------------------------------------
+// device-side model (preprocessed copy of b2e_model)
+struct DevModel {
+  int n_links, n_dof, ee_link, n_spheres, fk_rounds;
+  int parent[NLMAX], jtype[NLMAX], dof[NLMAX];
+  int dof_link[NLMAX];
+  unsigned link_dofmask[NLMAX];  // dofs on the path base -> link (inclusive)
+  float jpos[NLMAX][3], jrot[NLMAX][9], axis[NLMAX][3];
+  float mass[NLMAX], com[NLMAX][3], inertia[NLMAX][9];
+  float lower[NLMAX], upper[NLMAX], limit_margin[NLMAX], max_force[NLMAX], max_vel[NLMAX], joint_damping[NLMAX],
+      home[NLMAX];
+  float base_pos[3], base_rot[9];
+  int sph_link[B2E_MAX_SPHERES];
+  float sph_c[B2E_MAX_SPHERES][3], sph_r[B2E_MAX_SPHERES], sph_mu[B2E_MAX_SPHERES], sph_erp[B2E_MAX_SPHERES],
+      sph_cfm[B2E_MAX_SPHERES];
+};
+
+struct DevState {
+  int B;
+  float* q; float* qd; float* obj_pose; float* obj_vel; float* target; float* mtarget;
+  int* counters; int* cache_key; float* cache_lam; float* hand_pose; int* status; float* raw_obs; float* contacts;
+};
+
+struct b2e_sim {
+  int B, device;
+  b2e_model model;
+  b2e_params params;
+  DevModel* d_model;
+  DevState st;
+  void* fields[B2E_F_COUNT];
+  float *d_action, *d_obs, *d_reward, *d_done;     // staging for the host-buffer entry point
+  float *h_action, *h_obs, *h_reward, *h_done;     // pinned
+  int64_t launches;
+  int record_contacts;
+  cudaEvent_t ev0, ev1;
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* detail) {
+  snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+  return code;
+}
+#define CUDA_TRY(x)                                                            \
+  do {                                                                         \
+    cudaError_t e_ = (x);                                                      \
+    if (e_ != cudaSuccess) return fail(B2E_ECUDA, #x ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// small device math (all on register arrays with static indexing)
+__device__ __forceinline__ float shf(float v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ int shi(int v, int src) { return __shfl_sync(FULL, v, src); }
+
+__device__ __forceinline__ void m3mul(const float* a, const float* b, float* c) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+__device__ __forceinline__ void m3vec(const float* a, const float* v, float* o) {
+  float x = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
+  float y = a[3] * v[0] + a[4] * v[1] + a[5] * v[2];
+  float z = a[6] * v[0] + a[7] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void m3tvec(const float* a, const float* v, float* o) {
+  float x = a[0] * v[0] + a[3] * v[1] + a[6] * v[2];
+  float y = a[1] * v[0] + a[4] * v[1] + a[7] * v[2];
+  float z = a[2] * v[0] + a[5] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  float x = a[1] * b[2] - a[2] * b[1];
+  float y = a[2] * b[0] - a[0] * b[2];
+  float z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ __forceinline__ void quat_to_mat(const float* q, float* R) {
+  float x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z);     R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y);     R[7] = 2 * (y * z + w * x);     R[8] = 1 - 2 * (x * x + y * y);
+}
+__device__ __forceinline__ void mat_to_quat(const float* R, float* q) {
+  float tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    float s = sqrtf(tr + 1) * 2;
+    q[3] = s / 4; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    float s = sqrtf(1 + R[0] - R[4] - R[8]) * 2;
+    q[3] = (R[7] - R[5]) / s; q[0] = s / 4; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    float s = sqrtf(1 + R[4] - R[0] - R[8]) * 2;
+    q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = s / 4; q[2] = (R[5] + R[7]) / s;
+  } else {
+    float s = sqrtf(1 + R[8] - R[0] - R[4]) * 2;
+    q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = s / 4;
+  }
+}
+__device__ __forceinline__ void quat_mul(const float* a, const float* b, float* o) {
+  float x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  float y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  float z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  float w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+// p.getEulerFromQuaternion restated (panda_env.py:160, world_env.py:119) [EXT-recalled]
+__device__ __forceinline__ void quat_to_euler(const float* q, float* e) {
+  float x = q[0], y = q[1], z = q[2], w = q[3];
+  float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+  float sarg = -2 * (x * z - w * y);
+  if (sarg <= -0.99999f) {
+    e[0] = 0; e[1] = -1.57079632679489661923f; e[2] = 2 * atan2f(x, -y);
+  } else if (sarg >= 0.99999f) {
+    e[0] = 0; e[1] = 1.57079632679489661923f; e[2] = 2 * atan2f(-x, y);
+  } else {
+    e[0] = atan2f(2 * (y * z + w * x), sqw - sqx - sqy + sqz);
+    e[1] = asinf(sarg);
+    e[2] = atan2f(2 * (x * y + w * z), sqw + sqx - sqy - sqz);
+  }
+}
+// p.getQuaternionFromEuler restated (panda_push_gym_env.py:169,172) [EXT-recalled]
+__device__ __forceinline__ void euler_to_quat(const float* e, float* q) {
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(e[0] * 0.5f, &sr, &cr);
+  sincosf(e[1] * 0.5f, &sp, &cp);
+  sincosf(e[2] * 0.5f, &sy, &cy);
+  q[0] = sr * cp * cy - cr * sp * sy;
+  q[1] = cr * sp * cy + sr * cp * sy;
+  q[2] = cr * cp * sy - sr * sp * cy;
+  q[3] = cr * cp * cy + sr * sp * sy;
+}
+__device__ __forceinline__ void plane_space(const float* n, float* p, float* q) {
+  if (fabsf(n[2]) > 0.7071067811865475244f) {
+    float a = n[1] * n[1] + n[2] * n[2];
+    float k = 1.0f / sqrtf(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    float a = n[0] * n[0] + n[1] * n[1];
+    float k = 1.0f / sqrtf(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-warp shared memory
+struct Contact {   // 16 words
+  int key, type, link, pad;
+  float pA[3], pB[3], n[3];
+  float dist, mu, erp;
+};
+struct WarpSmem {
+  float A[RMAX * RMAX];        // Delassus matrix, A[i*RMAX + r]
+  float W[RMAX * WSTRIDE];     // W[r][k] = (M^-1 J_r^T)_k, k<9 arm dofs, 9..14 cube (lin, ang)
+  float T[NLMAX][12];          // link world transforms: R (9) + p (3)
+  float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
+  float Minv[NDMAX][NDMAX + 1];
+  float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
+  float lam[RMAX];
+  Contact con[B2E_MAX_CONTACTS];
+  float con_cfm[B2E_MAX_CONTACTS];
+  int lim_d[4];                // limit rows: dof | side << 8
+  float lim_dist[4];
+  int ckey[B2E_CACHE_SLOTS];
+  float clam[B2E_CACHE_SLOTS][3];
+  float obs[B2E_MAX_OBS];
+};
+
+// ------------------------------------------------------------------------------------------
+// forward kinematics: lane = link.  Composition along the tree by pointer jumping.
+__device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, int lane, float qi, float* R, float* p) {
+  const int nl = M->n_links;
+  const bool act = lane < nl;
+  const int li = act ? lane : 0;
+  float jr[9], ax[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) jr[k] = __ldg(&M->jrot[li][k]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ax[k] = __ldg(&M->axis[li][k]); p[k] = __ldg(&M->jpos[li][k]); }
+  const int jt = __ldg(&M->jtype[li]);
+  if (jt == B2E_JOINT_REVOLUTE) {
+    float s, c;
+    sincosf(qi, &s, &c);
+    float t = 1 - c, x = ax[0], y = ax[1], z = ax[2];
+    float Rq[9] = {t * x * x + c,     t * x * y - s * z, t * x * z + s * y,
+                   t * x * y + s * z, t * y * y + c,     t * y * z - s * x,
+                   t * x * z - s * y, t * y * z + s * x, t * z * z + c};
+    m3mul(jr, Rq, R);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = jr[k];
+    if (jt == B2E_JOINT_PRISMATIC) {
+      float t[3] = {ax[0] * qi, ax[1] * qi, ax[2] * qi}, o[3];
+      m3vec(jr, t, o);
+      p[0] += o[0]; p[1] += o[1]; p[2] += o[2];
+    }
+  }
+  int anc = act ? __ldg(&M->parent[li]) : -1;
+  const int rounds = M->fk_rounds;
+  for (int rd = 0; rd < rounds; rd++) {
+    const int src = anc < 0 ? 0 : anc;
+    float Ra[9], pa[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ra[k] = shf(R[k], src);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pa[k] = shf(p[k], src);
+    const int anca = shi(anc, src);
+    if (anc >= 0) {
+      float Rn[9], o[3];
+      m3mul(Ra, R, Rn);
+      m3vec(Ra, p, o);
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = Rn[k];
+      p[0] = pa[0] + o[0]; p[1] = pa[1] + o[1]; p[2] = pa[2] + o[2];
+      anc = anca;
+    }
+  }
+  {  // base pose
+    float Rb[9], Rn[9], o[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rb[k] = M->base_rot[k];
+    m3mul(Rb, R, Rn);
+    m3vec(Rb, p, o);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rn[k];
+    p[0] = M->base_pos[0] + o[0]; p[1] = M->base_pos[1] + o[1]; p[2] = M->base_pos[2] + o[2];
+  }
+}
+
+// inclusive sum over the path base..link of a 6-vector held per link lane (pointer jumping)
+__device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, int lane, float* x) {
+  int anc = lane < M->n_links ? __ldg(&M->parent[lane]) : -1;
+  const int rounds = M->fk_rounds;
+  for (int rd = 0; rd < rounds; rd++) {
+    const int src = anc < 0 ? 0 : anc;
+    float xa[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) xa[k] = shf(x[k], src);
+    const int anca = shi(anc, src);
+    if (anc >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) x[k] += xa[k];
+      anc = anca;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PGS sweep helpers.  NS = number of 32-row sets in use (rows r = lane + 32*s).
+template <int NS>
+struct RowRegs {
+  float lam[NS], w[NS], rhs[NS], cfm[NS], invd[NS], diag[NS], lo[NS], hi[NS], mu[NS], lastdl[NS];
+  int type[NS], isl[NS], nidx[NS];
+};
+
+template <int NS, int SI>
+__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* __restrict__ A, int i, int lane) {
+  const int li = i & 31;
+  float d = (r.rhs[SI] - r.w[SI] - r.cfm[SI] * r.lam[SI]) * r.invd[SI];
+  float nl = fminf(fmaxf(r.lam[SI] + d, r.lo[SI]), r.hi[SI]);
+  float dl = nl - r.lam[SI];
+  const float dli = shf(dl, li);
+  if (lane == li) { r.lam[SI] = nl; r.lastdl[SI] = dl; }
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
+    r.w[s] = fmaf(A[i * RMAX + col], dli, r.w[s]);
+  }
+}
+
+// process rows [i0, i1) in order, skipping rows whose island has converged
+template <int NS>
+__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ A, int i0, int i1, int lane,
+                                      const unsigned* islbits, bool coupled, const bool* done_isl) {
+  int e0 = i1 < 32 ? i1 : 32;
+  for (int i = i0; i < e0; i++) {
+    int isl = coupled ? 0 : ((islbits[0] >> i) & 1);
+    if (done_isl[isl]) continue;
+    row_step<NS, 0>(r, A, i, lane);
+  }
+  if (NS > 1) {
+    int b0 = i0 > 32 ? i0 : 32;
+    for (int i = b0; i < i1; i++) {
+      int isl = coupled ? 0 : ((islbits[NS - 1] >> (i - 32)) & 1);
+      if (done_isl[isl]) continue;
+      row_step<NS, NS - 1>(r, A, i, lane);
+    }
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict__ A, int R, int fric_start, int lane,
+                                         bool coupled, bool has_cube_rows, int max_iters, float tol) {
+  unsigned islbits[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) islbits[s] = __ballot_sync(FULL, r.isl[s] == 1);
+  bool done_isl[2] = {false, !has_cube_rows};
+  int it = 0;
+  for (it = 0; it < max_iters; it++) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) r.lastdl[s] = 0.f;
+    sweep<NS>(r, A, 0, fric_start, lane, islbits, coupled, done_isl);
+    // friction bounds from the current normal impulses (mu * lambda_n)
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const int ni = r.nidx[s];
+      float v0 = shf(r.lam[0], ni & 31);
+      float v1 = NS > 1 ? shf(r.lam[NS - 1], ni & 31) : 0.f;
+      if (r.type[s] == ROW_FRICTION) {
+        float lim = r.mu[s] * ((ni >> 5) ? v1 : v0);
+        r.lo[s] = -lim; r.hi[s] = lim;
+      }
+    }
+    sweep<NS>(r, A, fric_start, R, lane, islbits, coupled, done_isl);
+    float ra = 0.f, rc = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      float rv = r.lastdl[s] * r.diag[s];
+      rv = rv * rv;
+      if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
+    }
+    ra = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ra)));
+    rc = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rc)));
+    if (coupled) {
+      if (ra <= tol) { it++; break; }
+    } else {
+      if (!done_isl[0] && ra <= tol) done_isl[0] = true;
+      if (!done_isl[1] && rc <= tol) done_isl[1] = true;
+      if (done_isl[0] && done_isl[1]) { it++; break; }
+    }
+  }
+  return it;
+}
+
+// Build the row(s) owned by this lane, the W table, the Delassus matrix, warm start, solve, and
+// leave the impulses in sm.lam[].  Returns the PGS iteration count.
+template <int NS>
+__device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const b2e_params& P,
+                                               int lane, int nd, int nlim, int nc, float my_q, float my_target,
+                                               float my_kp, const float* cpos, bool kp_active) {
+  const int nnc = nd + nlim;         // non-contact rows
+  const int fric_start = nnc + nc;
+  const int R = nnc + 3 * nc;
+  const float dt = P.dt, inv_dt = 1.0f / P.dt;
+  const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
+  RowRegs<NS> rr;
+  bool coupled = false, has_cube = false;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int r = lane + 32 * s;
+    const bool valid = r < R;
+    float J[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) J[k] = 0.f;
+    float desired = 0.f, cfm = 0.f, lo = 0.f, hi = 0.f, mu = 0.f;
+    int type = ROW_MOTOR, isl = 0, nidx = 0;
+    if (valid) {
+      if (r < nd) {  // btMultiBodyJointMotor: velocity target kp*(target-q)/dt (kd = 1, erp = 1)
+        type = ROW_MOTOR;
+#pragma unroll
+        for (int k = 0; k < NDMAX; k++) J[k] = (k == r) ? 1.f : 0.f;
+        desired = my_kp * (my_target - my_q) * inv_dt;
+        const float mv = __ldg(&M->max_vel[r]);
+        if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
+        hi = __ldg(&M->max_force[r]) * dt;
+        lo = -hi;
+      } else if (r < nnc) {  // joint limit row
+        type = ROW_LIMIT;
+        const int code = sm.lim_d[r - nd];
+        const int d = code & 0xff, side = code >> 8;
+#pragma unroll
+        for (int k = 0; k < NDMAX; k++) J[k] = (k == d) ? (side ? -1.f : 1.f) : 0.f;
+        const float pen = sm.lim_dist[r - nd] + P.slop;
+        desired = pen > 0 ? -pen * inv_dt : -pen * P.erp * inv_dt;
+        lo = 0.f; hi = 1e30f;
+      } else {  // contact rows
+        int c, which;  // which: 0 normal, 1/2 friction
+        if (r < fric_start) { c = r - nnc; which = 0; }
+        else { c = (r - fric_start) >> 1; which = 1 + ((r - fric_start) & 1); }
+        const Contact& ct = sm.con[c];
+        float n[3] = {ct.n[0], ct.n[1], ct.n[2]}, dir[3];
+        if (which == 0) { dir[0] = n[0]; dir[1] = n[1]; dir[2] = n[2]; }
+        else {
+          float t1[3], t2[3];
+          plane_space(n, t1, t2);
+          if (which == 1) { dir[0] = t1[0]; dir[1] = t1[1]; dir[2] = t1[2]; }
+          else { dir[0] = t2[0]; dir[1] = t2[1]; dir[2] = t2[2]; }
+        }
+        isl = ct.type == CT_CUBE_STATIC ? 1 : 0;
+        if (ct.type == CT_CUBE_STATIC) {
+          float rel[3] = {ct.pA[0] - cpos[0], ct.pA[1] - cpos[1], ct.pA[2] - cpos[2]}, t[3];
+          cross3(rel, dir, t);
+#pragma unroll
+          for (int k = 0; k < 3; k++) { J[9 + k] = dir[k]; J[12 + k] = t[k]; }
+        } else {
+          const unsigned mask = __ldg(&M->link_dofmask[ct.link]);
+          float rel[3] = {ct.pA[0] - M->base_pos[0], ct.pA[1] - M->base_pos[1], ct.pA[2] - M->base_pos[2]}, wn[3];
+          cross3(rel, dir, wn);
+#pragma unroll
+          for (int d = 0; d < NDMAX; d++) {
+            float v = sm.S[d][0] * wn[0] + sm.S[d][1] * wn[1] + sm.S[d][2] * wn[2] + sm.S[d][3] * dir[0] +
+                      sm.S[d][4] * dir[1] + sm.S[d][5] * dir[2];
+            J[d] = ((mask >> d) & 1) ? v : 0.f;
+          }
+          if (ct.type == CT_SPHERE_CUBE) {
+            float relc[3] = {ct.pB[0] - cpos[0], ct.pB[1] - cpos[1], ct.pB[2] - cpos[2]}, t[3];
+            cross3(relc, dir, t);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { J[9 + k] = -dir[k]; J[12 + k] = -t[k]; }
+          }
+        }
+        if (which == 0) {
+          type = ROW_NORMAL;
+          const float pen = ct.dist + P.slop;
+          desired = pen > 0 ? -pen * inv_dt : -pen * ct.erp * inv_dt;
+          lo = 0.f; hi = 1e30f;
+          cfm = sm.con_cfm[c];
+        } else {
+          type = ROW_FRICTION;
+          mu = ct.mu;
+          nidx = nnc + c;
+        }
+      }
+    }
+    // W = M^-1 J^T
+    float Wv[15];
+#pragma unroll
+    for (int d = 0; d < NDMAX; d++) {
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < NDMAX; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
+      Wv[d] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Wv[9 + k] = J[9 + k] * cinv_m; Wv[12 + k] = J[12 + k] * cinv_I; }
+    float diag = 0.f, jv = 0.f;
+#pragma unroll
+    for (int k = 0; k < 15; k++) { diag = fmaf(J[k], Wv[k], diag); jv = fmaf(J[k], sm.vstar[k], jv); }
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 15; k++) sm.W[r * WSTRIDE + k] = Wv[k];
+      sm.W[r * WSTRIDE + 15] = 0.f;
+    }
+    rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
+    rr.cfm[s] = cfm; rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
+    rr.diag[s] = valid ? diag + cfm : 1.f;
+    rr.invd[s] = valid ? 1.0f / (diag + cfm) : 0.f;
+    rr.rhs[s] = valid ? desired - jv : 0.f;
+    rr.lam[s] = 0.f; rr.w[s] = 0.f; rr.lastdl[s] = 0.f;
+    __syncwarp();
+    // Delassus columns: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
+    for (int c = 0; c < R; c++) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 15; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+      if (valid) sm.A[c * RMAX + r] = acc;
+    }
+    coupled = coupled || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0 && (J[9] != 0.f || J[10] != 0.f || J[11] != 0.f));
+    has_cube = has_cube || __any_sync(FULL, valid && isl == 1);
+  }
+  __syncwarp();
+  // NOTE: with NS == 2 the loop above computed A[c][r] for set-0 rows before the set-1 W rows were
+  // written; redo the columns c >= 32 for set 0 now that every W row is in shared memory.
+  if (NS > 1) {
+    // recompute J for set 0 is expensive; instead use symmetry: A[c][r] = A[r][c] for c >= 32 > r.
+    for (int c = 32; c < R; c++) {
+      if (lane + 0 < 32 && lane < R) sm.A[c * RMAX + lane] = sm.A[lane * RMAX + c];
+    }
+    __syncwarp();
+  }
+  // warm start (contact rows): lambda0 = cached impulse * factor, w = A * lambda0
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int r = lane + 32 * s;
+    if (r >= nnc && r < R) {
+      int c, j;
+      if (r < fric_start) { c = r - nnc; j = 0; }
+      else { c = (r - fric_start) >> 1; j = 1 + ((r - fric_start) & 1); }
+      const int key = sm.con[c].key;
+      float l0 = 0.f;
+      for (int sl = 0; sl < B2E_CACHE_SLOTS; sl++)
+        if (sm.ckey[sl] == key) { l0 = sm.clam[sl][j] * P.warmstart; break; }
+      rr.lam[s] = l0;
+    }
+  }
+  for (int c = nnc; c < R; c++) {
+    float l0 = (c >> 5) ? shf(rr.lam[NS - 1], c & 31) : shf(rr.lam[0], c & 31);
+    if (l0 != 0.f) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
+        rr.w[s] = fmaf(sm.A[c * RMAX + col], l0, rr.w[s]);
+      }
+    }
+  }
+  const int iters = pgs_solve<NS>(rr, sm.A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol);
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int r = lane + 32 * s;
+    if (r < R) sm.lam[r] = rr.lam[s];
+  }
+  __syncwarp();
+  (void)kp_active;
+  return iters;
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused step kernel
+__global__ void __launch_bounds__(32 * WPB)
+step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, const float* __restrict__ action,
+            float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
+            int mode, int record_contacts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * WPB + warp;
+  if (env >= st.B) return;
+  WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  const int nd = M->n_dof, nl = M->n_links;
+  const float dt = P.dt;
+
+  // ---- load state (env-major field groups; lanes = dofs for q/qd/targets) ----
+  const bool is_dof = lane < nd;
+  float my_q = is_dof ? st.q[env * nd + lane] : 0.f;
+  float my_qd = is_dof ? st.qd[env * nd + lane] : 0.f;
+  float my_target = is_dof ? st.mtarget[env * nd + lane] : 0.f;
+  float cpos[3], cquat[4], cv[3], cw[3], target[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    cpos[k] = st.obj_pose[env * 7 + k];
+    cv[k] = st.obj_vel[env * 6 + k];
+    cw[k] = st.obj_vel[env * 6 + 3 + k];
+    target[k] = st.target[env * 3 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) cquat[k] = st.obj_pose[env * 7 + 3 + k];
+  int counter = st.counters[env * 2], terminated = st.counters[env * 2 + 1];
+  int flags = st.status[env * 4];
+  if (lane < B2E_CACHE_SLOTS) {
+    sm.ckey[lane] = st.cache_key[env * B2E_CACHE_SLOTS + lane];
+#pragma unroll
+    for (int j = 0; j < 3; j++) sm.clam[lane][j] = st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j];
+  }
+  float my_act = 0.f;
+  if (mode == B2E_MODE_ACTION && lane < P.n_act) my_act = action[env * P.n_act + lane];
+  const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
+  const float my_kp = (mode == B2E_MODE_ACTION && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
+  int iters = 0, nc = 0, R = 0;
+  bool stop = false;
+  __syncwarp();
+
+  for (int sub = 0; sub < nsub && !stop; sub++) {
+    // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
+    if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl) {
+      my_act *= P.act_scale;
+      my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
+    }
+
+    // ---- forward kinematics (lane = link) ----
+    const int li = lane < nl ? lane : 0;
+    const int my_dof = __ldg(&M->dof[li]);
+    const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
+    const float qdi_raw = shf(my_qd, my_dof < 0 ? 0 : my_dof);
+    const float qdi = (lane < nl && my_dof >= 0) ? qdi_raw : 0.f;
+    float Rm[9], pw[3];
+    fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, Rm, pw);
+    if (lane < nl) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) sm.T[lane][k] = Rm[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.T[lane][9 + k] = pw[k];
+    }
+
+    // ---- dynamics in world coordinates about O = base position ----
+    // spatial axis S = (w ; v_O), link spatial inertia (m, h = m c, I_O sym6)
+    float S[6] = {0, 0, 0, 0, 0, 0};
+    float Iw[16];  // f(6) | m | h(3) | I_O(6): the subtree-summed block
+    {
+      const int jt = __ldg(&M->jtype[li]);
+      float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])}, aw[3];
+      m3vec(Rm, ax, aw);
+      float rel[3] = {pw[0] - M->base_pos[0], pw[1] - M->base_pos[1], pw[2] - M->base_pos[2]};
+      if (lane < nl && jt == B2E_JOINT_REVOLUTE) {
+        float t[3];
+        cross3(rel, aw, t);
+        S[0] = aw[0]; S[1] = aw[1]; S[2] = aw[2]; S[3] = t[0]; S[4] = t[1]; S[5] = t[2];
+      } else if (lane < nl && jt == B2E_JOINT_PRISMATIC) {
+        S[3] = aw[0]; S[4] = aw[1]; S[5] = aw[2];
+      }
+      float cm[3] = {__ldg(&M->com[li][0]), __ldg(&M->com[li][1]), __ldg(&M->com[li][2])}, c[3];
+      m3vec(Rm, cm, c);
+      c[0] += rel[0]; c[1] += rel[1]; c[2] += rel[2];
+      const float ms = lane < nl ? __ldg(&M->mass[li]) : 0.f;
+      float Ic[9], RI[9], Icw[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Ic[k] = lane < nl ? __ldg(&M->inertia[li][k]) : 0.f;
+      m3mul(Rm, Ic, RI);
+      // Icw = RI * Rm^T
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Icw[3 * i + j] = RI[3 * i] * Rm[3 * j] + RI[3 * i + 1] * Rm[3 * j + 1] + RI[3 * i + 2] * Rm[3 * j + 2];
+      const float cc = dot3(c, c);
+      Iw[6] = ms;
+      Iw[7] = ms * c[0]; Iw[8] = ms * c[1]; Iw[9] = ms * c[2];
+      Iw[10] = Icw[0] + ms * (cc - c[0] * c[0]);  // xx
+      Iw[11] = Icw[1] - ms * c[0] * c[1];         // xy
+      Iw[12] = Icw[2] - ms * c[0] * c[2];         // xz
+      Iw[13] = Icw[4] + ms * (cc - c[1] * c[1]);  // yy
+      Iw[14] = Icw[5] - ms * c[1] * c[2];         // yz
+      Iw[15] = Icw[8] + ms * (cc - c[2] * c[2]);  // zz
+    }
+    // link velocities v = sum over path of S*qd ; bias accelerations
+    float vJ[6], v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { vJ[k] = S[k] * qdi; v[k] = vJ[k]; }
+    path_sum6(M, lane, v);
+    float ab[6];
+    {
+      float a[3], b[3], c2[3];
+      cross3(v, vJ, a);
+      cross3(v, vJ + 3, b);
+      cross3(v + 3, vJ, c2);
+      ab[0] = a[0]; ab[1] = a[1]; ab[2] = a[2];
+      ab[3] = b[0] + c2[0]; ab[4] = b[1] + c2[1]; ab[5] = b[2] + c2[2];
+    }
+    path_sum6(M, lane, ab);
+    ab[3] -= P.gravity[0]; ab[4] -= P.gravity[1]; ab[5] -= P.gravity[2];  // a_0 = -g
+    {
+      // f = I*ab + v x* (I*v)
+      const float ms = Iw[6];
+      const float* h = &Iw[7];
+      const float* I = &Iw[10];
+      float Ia_n[3], Ia_f[3], Iv_n[3], Iv_f[3], t[3];
+      // I*x: n = I_O w + h x vlin ; f = m vlin - h x w
+      cross3(h, ab + 3, t);
+      Ia_n[0] = I[0] * ab[0] + I[1] * ab[1] + I[2] * ab[2] + t[0];
+      Ia_n[1] = I[1] * ab[0] + I[3] * ab[1] + I[4] * ab[2] + t[1];
+      Ia_n[2] = I[2] * ab[0] + I[4] * ab[1] + I[5] * ab[2] + t[2];
+      cross3(h, ab, t);
+      Ia_f[0] = ms * ab[3] - t[0]; Ia_f[1] = ms * ab[4] - t[1]; Ia_f[2] = ms * ab[5] - t[2];
+      cross3(h, v + 3, t);
+      Iv_n[0] = I[0] * v[0] + I[1] * v[1] + I[2] * v[2] + t[0];
+      Iv_n[1] = I[1] * v[0] + I[3] * v[1] + I[4] * v[2] + t[1];
+      Iv_n[2] = I[2] * v[0] + I[4] * v[1] + I[5] * v[2] + t[2];
+      cross3(h, v, t);
+      Iv_f[0] = ms * v[3] - t[0]; Iv_f[1] = ms * v[4] - t[1]; Iv_f[2] = ms * v[5] - t[2];
+      float x1[3], x2[3], x3[3];
+      cross3(v, Iv_n, x1);
+      cross3(v + 3, Iv_f, x2);
+      cross3(v, Iv_f, x3);
+      Iw[0] = Ia_n[0] + x1[0] + x2[0]; Iw[1] = Ia_n[1] + x1[1] + x2[1]; Iw[2] = Ia_n[2] + x1[2] + x2[2];
+      Iw[3] = Ia_f[0] + x3[0]; Iw[4] = Ia_f[1] + x3[1]; Iw[5] = Ia_f[2] + x3[2];
+    }
+    // child -> parent accumulation of [f | composite inertia] (serial walk carried by shuffles)
+    for (int j = nl - 1; j >= 1; j--) {
+      const int pj = M->parent[j];
+      if (pj < 0) continue;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const float val = shf(Iw[k], j);
+        if (lane == pj) Iw[k] += val;
+      }
+    }
+    // move to dof lanes: lane d gets S, f^c, I^c of its link
+    const int lk = is_dof ? __ldg(&M->dof_link[lane]) : 0;
+    float Sd[6], Fc[6], Ic[10];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { Sd[k] = shf(S[k], lk); Fc[k] = shf(Iw[k], lk); }
+#pragma unroll
+    for (int k = 0; k < 10; k++) Ic[k] = shf(Iw[6 + k], lk);
+    if (is_dof) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) sm.S[lane][k] = Sd[k];
+    }
+    // F = I^c S_d ; tau_bias = S_d . f^c
+    float F[6];
+    {
+      const float ms = Ic[0];
+      const float* h = &Ic[1];
+      const float* I = &Ic[4];
+      float t[3];
+      cross3(h, Sd + 3, t);
+      F[0] = I[0] * Sd[0] + I[1] * Sd[1] + I[2] * Sd[2] + t[0];
+      F[1] = I[1] * Sd[0] + I[3] * Sd[1] + I[4] * Sd[2] + t[1];
+      F[2] = I[2] * Sd[0] + I[4] * Sd[1] + I[5] * Sd[2] + t[2];
+      cross3(h, Sd, t);
+      F[3] = ms * Sd[3] - t[0]; F[4] = ms * Sd[4] - t[1]; F[5] = ms * Sd[5] - t[2];
+    }
+    const float tau_b = Sd[0] * Fc[0] + Sd[1] * Fc[1] + Sd[2] * Fc[2] + Sd[3] * Fc[3] + Sd[4] * Fc[4] + Sd[5] * Fc[5];
+    // joint-space inertia: M[d][e] = S_e . F_d for e on the path to d; symmetrised through smem
+    const unsigned my_mask = is_dof ? __ldg(&M->link_dofmask[lk]) : 0u;
+    for (int k = lane; k < NDMAX * (NDMAX + 1); k += 32) (&sm.Minv[0][0])[k] = 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < NDMAX; e++) {
+      float Se[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) Se[k] = shf(Sd[k], e);
+      const float val = Se[0] * F[0] + Se[1] * F[1] + Se[2] * F[2] + Se[3] * F[3] + Se[4] * F[4] + Se[5] * F[5];
+      if (is_dof && e < nd && ((my_mask >> e) & 1)) {
+        sm.Minv[lane][e] = val;
+        sm.Minv[e][lane] = val;
+      }
+    }
+    __syncwarp();
+    float a[NDMAX];
+#pragma unroll
+    for (int e = 0; e < NDMAX; e++) a[e] = (is_dof && e < nd) ? sm.Minv[lane][e] : ((e == lane) ? 1.f : 0.f);
+    // in-place Gauss-Jordan inverse, lane = row
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) {
+      float rk[NDMAX];
+#pragma unroll
+      for (int j = 0; j < NDMAX; j++) rk[j] = shf(a[j], k);
+      const float pinv = 1.0f / rk[k];
+      if (lane == k) {
+#pragma unroll
+        for (int j = 0; j < NDMAX; j++) a[j] = (j == k) ? pinv : rk[j] * pinv;
+      } else {
+        const float f = a[k];
+#pragma unroll
+        for (int j = 0; j < NDMAX; j++) a[j] = (j == k) ? -f * pinv : fmaf(-f * pinv, rk[j], a[j]);
+      }
+    }
+    __syncwarp();
+    if (lane < NDMAX) {
+#pragma unroll
+      for (int e = 0; e < NDMAX; e++) sm.Minv[lane][e] = (lane < nd && e < nd) ? a[e] : 0.f;
+    }
+    // unconstrained acceleration and v*
+    const float rhs_d = is_dof ? (-tau_b - __ldg(&M->joint_damping[lane]) * my_qd) : 0.f;
+    float qdd = 0.f;
+#pragma unroll
+    for (int e = 0; e < NDMAX; e++) qdd = fmaf(a[e], shf(rhs_d, e), qdd);
+    const float vstar_d = my_qd + dt * qdd;
+    float cvs[3], cws[3];
+    {
+      const float vn = sqrtf(dot3(cv, cv)), wn = sqrtf(dot3(cw, cw));
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        cvs[k] = cv[k] + dt * (P.gravity[k] - cv[k] * (P.damp_lin_k1 + P.damp_lin_k2 * vn));
+        cws[k] = cw[k] + dt * (-cw[k] * (P.damp_ang_k1 + P.damp_ang_k2 * wn));
+      }
+    }
+    if (is_dof) sm.vstar[lane] = vstar_d;
+    if (lane >= NDMAX && lane < 16) {
+      const int k = lane - NDMAX;
+      sm.vstar[lane] = k < 3 ? cvs[k] : (k < 6 ? cws[k - 3] : 0.f);
+    }
+    if (lane < NDMAX && !is_dof) sm.vstar[lane] = 0.f;
+
+    // ---- collision detection (pre-step poses) ----
+    float Rc[9];
+    quat_to_mat(cquat, Rc);
+    const float ca = P.cube_half, margin = P.contact_margin;
+    // cube vertices vs table slab / ground plane: lane = vertex
+    bool v_hit = false;
+    float v_pos[3] = {0, 0, 0}, v_dist = 0.f, v_top = 0.f, v_mu = 0.f;
+    int v_key = 0;
+    if (lane < 8) {
+      float l[3] = {(lane & 1) ? ca : -ca, (lane & 2) ? ca : -ca, (lane & 4) ? ca : -ca};
+      m3vec(Rc, l, v_pos);
+      v_pos[0] += cpos[0]; v_pos[1] += cpos[1]; v_pos[2] += cpos[2];
+      const bool over = v_pos[0] >= P.table_min[0] && v_pos[0] <= P.table_max[0] && v_pos[1] >= P.table_min[1] &&
+                        v_pos[1] <= P.table_max[1] && v_pos[2] > P.table_min[2];
+      if (over) { v_top = P.table_max[2]; v_mu = P.cube_mu * P.table_mu; v_key = KEY_CUBE_TABLE + lane; }
+      else { v_top = 0.f; v_mu = P.cube_mu * P.plane_mu; v_key = KEY_CUBE_PLANE + lane; }
+      v_dist = v_pos[2] - v_top;
+      v_hit = v_dist < margin;
+    }
+    // spheres: lane = sphere
+    const int ns = M->n_spheres;
+    bool sc_hit = false, st_hit = false;
+    float s_c[3] = {0, 0, 0}, sc_n[3] = {0, 0, 0}, sc_pB[3] = {0, 0, 0}, sc_dist = 0.f, st_dist = 0.f, s_r = 0.f;
+    int s_link = 0;
+    __syncwarp();
+    if (lane < ns) {
+      s_link = __ldg(&M->sph_link[lane]);
+      s_r = __ldg(&M->sph_r[lane]);
+      float lc[3] = {__ldg(&M->sph_c[lane][0]), __ldg(&M->sph_c[lane][1]), __ldg(&M->sph_c[lane][2])}, o[3];
+      float Rl[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rl[k] = sm.T[s_link][k];
+      m3vec(Rl, lc, o);
+      s_c[0] = sm.T[s_link][9] + o[0]; s_c[1] = sm.T[s_link][10] + o[1]; s_c[2] = sm.T[s_link][11] + o[2];
+      // vs cube
+      float rel[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]}, l[3], cl[3];
+      m3tvec(Rc, rel, l);
+      bool inside = true;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        cl[j] = l[j] < -ca ? -ca : (l[j] > ca ? ca : l[j]);
+        if (cl[j] != l[j]) inside = false;
+      }
+      float nloc[3];
+      if (!inside) {
+        float dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+        const float d = sqrtf(dot3(dv, dv));
+        sc_dist = d - s_r;
+        sc_hit = sc_dist < margin;
+        nloc[0] = dv[0] / d; nloc[1] = dv[1] / d; nloc[2] = dv[2] / d;
+      } else {
+        int axm = 0;
+        float best = ca - fabsf(l[0]);
+#pragma unroll
+        for (int j = 1; j < 3; j++) {
+          const float pen = ca - fabsf(l[j]);
+          if (pen < best) { best = pen; axm = j; }
+        }
+        nloc[0] = nloc[1] = nloc[2] = 0.f;
+        const float sgn = ((axm == 0 ? l[0] : (axm == 1 ? l[1] : l[2])) >= 0) ? 1.f : -1.f;
+        if (axm == 0) { nloc[0] = sgn; cl[0] = sgn * ca; }
+        else if (axm == 1) { nloc[1] = sgn; cl[1] = sgn * ca; }
+        else { nloc[2] = sgn; cl[2] = sgn * ca; }
+        sc_dist = -best - s_r;
+        sc_hit = true;
+      }
+      if (sc_hit) {
+        float pwl[3];
+        m3vec(Rc, nloc, sc_n);
+        m3vec(Rc, cl, pwl);
+        sc_pB[0] = cpos[0] + pwl[0]; sc_pB[1] = cpos[1] + pwl[1]; sc_pB[2] = cpos[2] + pwl[2];
+      }
+      // vs table top
+      const bool over = s_c[0] >= P.table_min[0] && s_c[0] <= P.table_max[0] && s_c[1] >= P.table_min[1] &&
+                        s_c[1] <= P.table_max[1] && s_c[2] > P.table_min[2];
+      st_dist = s_c[2] - s_r - P.table_max[2];
+      st_hit = over && (st_dist < margin);
+    }
+    // canonical order: cube-static by vertex, sphere-cube by sphere, sphere-table by sphere
+    const unsigned bv = __ballot_sync(FULL, v_hit), bsc = __ballot_sync(FULL, sc_hit), bst = __ballot_sync(FULL, st_hit);
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
+    const int total = n_v + n_sc + n_st;
+    if (total > B2E_MAX_CONTACTS) flags |= B2E_ST_CONTACT_OVERFLOW;
+    nc = total > B2E_MAX_CONTACTS ? B2E_MAX_CONTACTS : total;
+    if (v_hit) {
+      const int slot = __popc(bv & lt);
+      if (slot < B2E_MAX_CONTACTS) {
+        Contact& c = sm.con[slot];
+        c.key = v_key; c.type = CT_CUBE_STATIC; c.link = -1;
+        c.pA[0] = v_pos[0]; c.pA[1] = v_pos[1]; c.pA[2] = v_pos[2];
+        c.pB[0] = v_pos[0]; c.pB[1] = v_pos[1]; c.pB[2] = v_top;
+        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+        c.dist = v_dist; c.mu = v_mu; c.erp = P.erp;
+        sm.con_cfm[slot] = 0.f;
+      }
+    }
+    if (sc_hit) {
+      const int slot = n_v + __popc(bsc & lt);
+      if (slot < B2E_MAX_CONTACTS) {
+        Contact& c = sm.con[slot];
+        const float serp = __ldg(&M->sph_erp[lane]);
+        c.key = KEY_SPHERE_CUBE + lane; c.type = CT_SPHERE_CUBE; c.link = s_link;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c.n[j] = sc_n[j]; c.pB[j] = sc_pB[j]; c.pA[j] = s_c[j] - sc_n[j] * s_r; }
+        c.dist = sc_dist; c.mu = P.cube_mu * __ldg(&M->sph_mu[lane]);
+        c.erp = serp >= 0 ? serp : P.erp;
+        sm.con_cfm[slot] = __ldg(&M->sph_cfm[lane]);
+      }
+    }
+    if (st_hit) {
+      const int slot = n_v + n_sc + __popc(bst & lt);
+      if (slot < B2E_MAX_CONTACTS) {
+        Contact& c = sm.con[slot];
+        const float serp = __ldg(&M->sph_erp[lane]);
+        c.key = KEY_SPHERE_TABLE + lane; c.type = CT_SPHERE_STATIC; c.link = s_link;
+        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+        c.pA[0] = s_c[0]; c.pA[1] = s_c[1]; c.pA[2] = s_c[2] - s_r;
+        c.pB[0] = s_c[0]; c.pB[1] = s_c[1]; c.pB[2] = P.table_max[2];
+        c.dist = st_dist; c.mu = P.table_mu * __ldg(&M->sph_mu[lane]);
+        c.erp = serp >= 0 ? serp : P.erp;
+        sm.con_cfm[slot] = __ldg(&M->sph_cfm[lane]);
+      }
+    }
+    // joint-limit rows near a limit (lane = dof): order (dof, lower) then (dof, upper)
+    const float dlo = my_q - my_lower, dup = my_upper - my_q;
+    const float lmar = is_dof ? __ldg(&M->limit_margin[lane]) : 0.f;
+    const bool lo_hit = is_dof && dlo < lmar, up_hit = is_dof && dup < lmar;
+    const unsigned blo = __ballot_sync(FULL, lo_hit), bup = __ballot_sync(FULL, up_hit);
+    int nlim = __popc(blo) + __popc(bup);
+    if (nlim > B2E_MAX_LIMROWS) { flags |= B2E_ST_LIMIT_OVERFLOW; nlim = B2E_MAX_LIMROWS; }
+    if (lo_hit) {
+      const int slot = __popc(blo & lt) + __popc(bup & lt);
+      if (slot < B2E_MAX_LIMROWS) { sm.lim_d[slot] = lane; sm.lim_dist[slot] = dlo; }
+    }
+    if (up_hit) {
+      const int slot = __popc(blo & lt) + __popc(bup & lt) + (lo_hit ? 1 : 0);
+      if (slot < B2E_MAX_LIMROWS) { sm.lim_d[slot] = lane | (1 << 8); sm.lim_dist[slot] = dup; }
+    }
+    __syncwarp();
+
+    // ---- rows + PGS ----
+    R = nd + nlim + 3 * nc;
+    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos, true);
+    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos, true);
+
+    // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
+    float dvk = 0.f;
+    for (int r = 0; r < R; r++) dvk = fmaf(sm.W[r * WSTRIDE + (lane & 15)], sm.lam[r], dvk);
+    // ---- integrate (semi-implicit Euler) ----
+    if (is_dof) {
+      my_qd = vstar_d + dvk;
+      my_q += dt * my_qd;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      cv[k] = cvs[k] + shf(dvk, NDMAX + k);
+      cw[k] = cws[k] + shf(dvk, NDMAX + 3 + k);
+      cpos[k] += dt * cv[k];
+    }
+    {
+      const float wl = sqrtf(dot3(cw, cw)), ang = wl * dt;
+      float f, cs;
+      if (ang < 1e-3f) { f = 0.5f * dt - dt * dt * dt * (1.0f / 48.0f) * wl * wl; cs = cosf(0.5f * ang); }
+      else { float sn; sincosf(0.5f * ang, &sn, &cs); f = sn / wl; }
+      float dq[4] = {cw[0] * f, cw[1] * f, cw[2] * f, cs}, nq[4];
+      quat_mul(dq, cquat, nq);
+      const float nn = 1.0f / sqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) cquat[k] = nq[k] * nn;
+    }
+    // ---- contact cache for the next step's warm start ----
+    {
+      const int nnc = nd + nlim;
+      int key = -1;
+      float l3[3] = {0.f, 0.f, 0.f};
+      if (lane < nc) {
+        key = sm.con[lane].key;
+        l3[0] = sm.lam[nnc + lane];
+        l3[1] = sm.lam[nnc + nc + 2 * lane];
+        l3[2] = sm.lam[nnc + nc + 2 * lane + 1];
+      }
+      if (record_contacts && lane < B2E_MAX_CONTACTS) {
+        float* o = st.contacts + ((size_t)env * B2E_MAX_CONTACTS + lane) * 8;
+        if (lane < nc) {
+          o[0] = (float)key; o[1] = sm.con[lane].dist;
+          o[2] = sm.con[lane].n[0]; o[3] = sm.con[lane].n[1]; o[4] = sm.con[lane].n[2];
+          o[5] = l3[0]; o[6] = l3[1]; o[7] = l3[2];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; k++) o[k] = 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane < B2E_CACHE_SLOTS) {
+        sm.ckey[lane] = key;
+        sm.clam[lane][0] = l3[0]; sm.clam[lane][1] = l3[1]; sm.clam[lane][2] = l3[2];
+      }
+      __syncwarp();
+    }
+    {
+      bool bad = is_dof && !(isfinite(my_q) && isfinite(my_qd));
+      bad = bad || !(isfinite(cpos[0]) && isfinite(cpos[1]) && isfinite(cpos[2]) && isfinite(cv[0]) && isfinite(cv[1]) &&
+                     isfinite(cv[2]) && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]));
+      if (__any_sync(FULL, bad)) flags |= B2E_ST_NAN;
+    }
+
+    // ---- termination inside apply_action (panda_push_gym_env.py:239-242) ----
+    if (mode == B2E_MODE_ACTION) {
+      float d;
+      if (P.task == B2E_TASK_PUSH) {
+        float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+        d = sqrtf(dot3(dd, dd));
+      } else {
+        // EE position needs the post-step kinematics
+        const float qi2 = shf(my_q, my_dof < 0 ? 0 : my_dof);
+        float R2[9], p2[3];
+        fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi2 : 0.f, R2, p2);
+        const int ee = M->ee_link;
+        float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
+        m3vec(R2, cm, o);
+        float e3[3] = {shf(p2[0] + o[0], ee), shf(p2[1] + o[1], ee), shf(p2[2] + o[2], ee)};
+        float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
+        d = sqrtf(dot3(dd, dd));
+      }
+      bool term = false;
+      if (d <= P.dist_min) { terminated = 1; term = true; }
+      else if (terminated || counter > P.max_steps) term = true;
+      if (term) stop = true; else counter++;
+    }
+  }
+
+  // ---- store state ----
+  if (is_dof) {
+    st.q[env * nd + lane] = my_q;
+    st.qd[env * nd + lane] = my_qd;
+    st.mtarget[env * nd + lane] = my_target;
+  }
+  if (lane == 0) {
+    st.obj_pose[env * 7 + 0] = cpos[0]; st.obj_pose[env * 7 + 1] = cpos[1]; st.obj_pose[env * 7 + 2] = cpos[2];
+    st.obj_pose[env * 7 + 3] = cquat[0]; st.obj_pose[env * 7 + 4] = cquat[1];
+    st.obj_pose[env * 7 + 5] = cquat[2]; st.obj_pose[env * 7 + 6] = cquat[3];
+    st.obj_vel[env * 6 + 0] = cv[0]; st.obj_vel[env * 6 + 1] = cv[1]; st.obj_vel[env * 6 + 2] = cv[2];
+    st.obj_vel[env * 6 + 3] = cw[0]; st.obj_vel[env * 6 + 4] = cw[1]; st.obj_vel[env * 6 + 5] = cw[2];
+  }
+  if (lane < B2E_CACHE_SLOTS) {
+    st.cache_key[env * B2E_CACHE_SLOTS + lane] = sm.ckey[lane];
+#pragma unroll
+    for (int j = 0; j < 3; j++) st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j] = sm.clam[lane][j];
+  }
+
+  // ---- observation / termination / reward (panda_push_gym_env.py:249-253) ----
+  if (mode == B2E_MODE_ACTION || obs_out) {
+    const int li = lane < nl ? lane : 0;
+    const int my_dof = __ldg(&M->dof[li]);
+    const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
+    float R2[9], p2[3];
+    fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, R2, p2);
+    const int ee = M->ee_link;
+    // EE COM pose
+    float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
+    m3vec(R2, cm, o);
+    float epos[3], Re[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) epos[k] = shf(p2[k] + o[k], ee);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Re[k] = shf(R2[k], ee);
+    // EE linear velocity: sum over the dofs on the path of (axis x (p_ee - o_j)) qd_j  /  axis qd_j
+    float vl[3] = {0, 0, 0};
+    {
+      const unsigned eemask = M->link_dofmask[ee];
+      const int jt = __ldg(&M->jtype[li]);
+      float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])}, aw[3];
+      m3vec(R2, ax, aw);
+      const float qdl = shf(my_qd, my_dof < 0 ? 0 : my_dof);
+      if (lane < nl && my_dof >= 0 && ((eemask >> my_dof) & 1)) {
+        if (jt == B2E_JOINT_REVOLUTE) {
+          float rel[3] = {epos[0] - p2[0], epos[1] - p2[1], epos[2] - p2[2]}, t[3];
+          cross3(aw, rel, t);
+          vl[0] = t[0] * qdl; vl[1] = t[1] * qdl; vl[2] = t[2] * qdl;
+        } else {
+          vl[0] = aw[0] * qdl; vl[1] = aw[1] * qdl; vl[2] = aw[2] * qdl;
+        }
+      }
+      // fixed-order sum over links 0..nl-1 so the result does not depend on lane scheduling
+      float acc[3] = {0, 0, 0};
+      for (int j = 0; j < nl; j++) {
+        acc[0] += shf(vl[0], j); acc[1] += shf(vl[1], j); acc[2] += shf(vl[2], j);
+      }
+      vl[0] = acc[0]; vl[1] = acc[1]; vl[2] = acc[2];
+    }
+    float equat[4], eeu[3], ceu[3];
+    mat_to_quat(Re, equat);
+    quat_to_euler(equat, eeu);
+    quat_to_euler(cquat, ceu);
+    float hq[4], oq[4], hqi[4], relq[4], releu[3], relp[3];
+    euler_to_quat(eeu, hq);
+    euler_to_quat(ceu, oq);
+    hqi[0] = -hq[0]; hqi[1] = -hq[1]; hqi[2] = -hq[2]; hqi[3] = hq[3];
+    {
+      float dd[3] = {cpos[0] - epos[0], cpos[1] - epos[1], cpos[2] - epos[2]}, Rh[9];
+      quat_to_mat(hqi, Rh);
+      m3vec(Rh, dd, relp);
+    }
+    quat_mul(hqi, oq, relq);
+    quat_to_euler(relq, releu);
+    if (lane == 0) {
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = epos[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = eeu[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = (vl[k] - P.vel_mean[k]) / P.vel_std[k];
+      n += nd;
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = cpos[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = ceu[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = relp[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.obs[n++] = releu[k];
+      if (P.task == B2E_TASK_PUSH) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) sm.obs[n++] = target[k];
+      }
+    }
+    if (is_dof) sm.obs[9 + lane] = my_q;
+    __syncwarp();
+    for (int k = lane; k < P.n_obs; k += 32) {
+      const float raw = sm.obs[k];
+      st.raw_obs[(size_t)env * P.n_obs + k] = raw;
+      if (obs_out) obs_out[(size_t)env * P.n_obs + k] = 2.0f * ((raw - P.obs_low[k]) / (P.obs_high[k] - P.obs_low[k])) - 1.0f;
+    }
+    float dd1[3] = {epos[0] - cpos[0], epos[1] - cpos[1], epos[2] - cpos[2]};
+    const float d1 = sqrtf(dot3(dd1, dd1));
+    float rew;
+    int dn = 0;
+    if (P.task == B2E_TASK_PUSH) {
+      float dd2[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+      const float d2 = sqrtf(dot3(dd2, dd2));
+      if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1 - d2;
+      if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
+    } else {
+      if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1;
+      if (d1 <= P.dist_min) rew = 1000.0f + (100.0f - d1 * 80.0f);
+    }
+    if (lane == 0) {
+      if (reward_out) reward_out[env] = rew;
+      if (done_out) done_out[env] = (float)dn;
+    }
+  }
+  if (lane == 0) {
+    st.counters[env * 2] = counter;
+    st.counters[env * 2 + 1] = terminated;
+    st.status[env * 4 + 0] = flags;
+    st.status[env * 4 + 1] = iters;
+    st.status[env * 4 + 2] = nc;
+    st.status[env * 4 + 3] = R;
+  }
+}
+
+// masked reset: home joint state, object pose, target, counters, empty cache
+__global__ void reset_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st,
+                             const uint8_t* __restrict__ mask, const float* __restrict__ obj_init_pose,
+                             const float* __restrict__ target) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= st.B) return;
+  if (mask && !mask[env]) return;
+  const int nd = M->n_dof;
+  for (int d = 0; d < nd; d++) {
+    st.q[env * nd + d] = M->home[d];
+    st.qd[env * nd + d] = 0.f;
+    st.mtarget[env * nd + d] = M->home[d];
+  }
+  for (int k = 0; k < 7; k++) st.obj_pose[env * 7 + k] = obj_init_pose[env * 7 + k];
+  for (int k = 0; k < 6; k++) st.obj_vel[env * 6 + k] = 0.f;
+  for (int k = 0; k < 3; k++) st.target[env * 3 + k] = target[env * 3 + k];
+  st.counters[env * 2] = 0; st.counters[env * 2 + 1] = 0;
+  for (int s = 0; s < B2E_CACHE_SLOTS; s++) {
+    st.cache_key[env * B2E_CACHE_SLOTS + s] = -1;
+    for (int j = 0; j < 3; j++) st.cache_lam[(env * B2E_CACHE_SLOTS + s) * 3 + j] = 0.f;
+  }
+  for (int k = 0; k < 6; k++) st.hand_pose[env * 6 + k] = P.home_hand_pose[k];
+  for (int k = 0; k < 4; k++) st.status[env * 4 + k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: C-ABI
+static int field_width(const b2e_sim* s, int f) {
+  const int nd = s->model.n_dof;
+  switch (f) {
+    case B2E_F_Q: case B2E_F_QD: case B2E_F_MTARGET: return nd;
+    case B2E_F_OBJ_POSE: return 7;
+    case B2E_F_OBJ_VEL: return 6;
+    case B2E_F_TARGET: return 3;
+    case B2E_F_COUNTERS: return 2;
+    case B2E_F_CACHE_KEY: return B2E_CACHE_SLOTS;
+    case B2E_F_CACHE_LAM: return B2E_CACHE_SLOTS * 3;
+    case B2E_F_HAND_POSE: return 6;
+    case B2E_F_STATUS: return 4;
+    case B2E_F_RAW_OBS: return s->params.n_obs;
+    case B2E_F_CONTACTS: return B2E_MAX_CONTACTS * 8;
+    default: return -1;
+  }
+}
+
+static int build_dev_model(const b2e_model* m, DevModel* d) {
+  memset(d, 0, sizeof(*d));
+  if (m->n_links > NLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 32 links%s", "");
+  if (m->n_dof > NDMAX) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 9 dofs%s", "");
+  if (m->n_spheres > B2E_MAX_SPHERES || m->n_spheres < 0) return fail(B2E_EINVAL, "bad n_spheres%s", "");
+  d->n_links = m->n_links; d->n_dof = m->n_dof; d->ee_link = m->ee_link; d->n_spheres = m->n_spheres;
+  int maxdepth = 1;
+  for (int i = 0; i < m->n_links; i++) {
+    if (m->parent[i] >= i) return fail(B2E_EINVAL, "links must be ordered parent-first%s", "");
+    d->parent[i] = m->parent[i]; d->jtype[i] = m->jtype[i]; d->dof[i] = m->dof[i];
+    if (m->dof[i] >= 0) d->dof_link[m->dof[i]] = i;
+    for (int k = 0; k < 3; k++) { d->jpos[i][k] = m->jpos[i][k]; d->axis[i][k] = m->axis[i][k]; d->com[i][k] = m->com[i][k]; }
+    for (int k = 0; k < 9; k++) { d->jrot[i][k] = m->jrot[i][k]; d->inertia[i][k] = m->inertia[i][k]; }
+    d->mass[i] = m->mass[i];
+    unsigned mask = 0;
+    int depth = 0;
+    for (int j = i; j >= 0; j = m->parent[j]) {
+      if (m->dof[j] >= 0) mask |= 1u << m->dof[j];
+      depth++;
+    }
+    d->link_dofmask[i] = mask;
+    if (depth > maxdepth) maxdepth = depth;
+  }
+  int rounds = 0;
+  while ((1 << rounds) < maxdepth) rounds++;
+  d->fk_rounds = rounds;
+  for (int k = 0; k < m->n_dof; k++) {
+    d->lower[k] = m->lower[k]; d->upper[k] = m->upper[k]; d->limit_margin[k] = m->limit_margin[k];
+    d->max_force[k] = m->max_force[k]; d->max_vel[k] = m->max_vel[k]; d->joint_damping[k] = m->joint_damping[k];
+    d->home[k] = m->home[k];
+  }
+  for (int k = 0; k < 3; k++) d->base_pos[k] = m->base_pos[k];
+  for (int k = 0; k < 9; k++) d->base_rot[k] = m->base_rot[k];
+  for (int s = 0; s < m->n_spheres; s++) {
+    d->sph_link[s] = m->sph_link[s];
+    for (int k = 0; k < 3; k++) d->sph_c[s][k] = m->sph_c[s][k];
+    d->sph_r[s] = m->sph_r[s]; d->sph_mu[s] = m->sph_mu[s]; d->sph_erp[s] = m->sph_erp[s]; d->sph_cfm[s] = m->sph_cfm[s];
+  }
+  return 0;
+}
+
+extern "C" {
+
+const char* b2e_last_error(void) { return g_err; }
+const char* b2e_version(void) { return "b2env 0.1 (sm_100a, warp-per-env)"; }
+
+int b2e_field_elem_size(int field) {
+  (void)field;
+  return 4;
+}
+int b2e_field_width(const b2e_sim* sim, int field) { return sim ? field_width(sim, field) : -1; }
+int b2e_num_envs(const b2e_sim* sim) { return sim ? sim->B : -1; }
+int64_t b2e_launch_count(const b2e_sim* sim) { return sim ? sim->launches : -1; }
+
+int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, int device, b2e_sim** out) {
+  if (!model || !params || !out || num_envs < 1) return fail(B2E_EINVAL, "b2e_create: bad argument%s", "");
+  if (params->n_obs > B2E_MAX_OBS || params->n_obs < 1) return fail(B2E_EINVAL, "b2e_create: bad n_obs%s", "");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B2E_ECUDA, "b2e_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(B2E_EINVAL, "b2e_create: bad device index%s", "");
+  CUDA_TRY(cudaSetDevice(device));
+  DevModel hm;
+  int rc = build_dev_model(model, &hm);
+  if (rc) return rc;
+  b2e_sim* s = new b2e_sim();
+  memset(s, 0, sizeof(*s));
+  s->B = num_envs; s->device = device; s->model = *model; s->params = *params;
+  CUDA_TRY(cudaMalloc(&s->d_model, sizeof(DevModel)));
+  CUDA_TRY(cudaMemcpy(s->d_model, &hm, sizeof(DevModel), cudaMemcpyHostToDevice));
+  for (int f = 0; f < B2E_F_COUNT; f++) {
+    size_t bytes = (size_t)num_envs * field_width(s, f) * 4;
+    CUDA_TRY(cudaMalloc(&s->fields[f], bytes));
+    CUDA_TRY(cudaMemset(s->fields[f], 0, bytes));
+  }
+  CUDA_TRY(cudaMemset(s->fields[B2E_F_CACHE_KEY], 0xff, (size_t)num_envs * B2E_CACHE_SLOTS * 4));
+  s->st.B = num_envs;
+  s->st.q = (float*)s->fields[B2E_F_Q]; s->st.qd = (float*)s->fields[B2E_F_QD];
+  s->st.obj_pose = (float*)s->fields[B2E_F_OBJ_POSE]; s->st.obj_vel = (float*)s->fields[B2E_F_OBJ_VEL];
+  s->st.target = (float*)s->fields[B2E_F_TARGET]; s->st.mtarget = (float*)s->fields[B2E_F_MTARGET];
+  s->st.counters = (int*)s->fields[B2E_F_COUNTERS]; s->st.cache_key = (int*)s->fields[B2E_F_CACHE_KEY];
+  s->st.cache_lam = (float*)s->fields[B2E_F_CACHE_LAM]; s->st.hand_pose = (float*)s->fields[B2E_F_HAND_POSE];
+  s->st.status = (int*)s->fields[B2E_F_STATUS]; s->st.raw_obs = (float*)s->fields[B2E_F_RAW_OBS];
+  s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
+  const size_t na = (size_t)num_envs * (params->n_act > 0 ? params->n_act : 1) * 4, no = (size_t)num_envs * params->n_obs * 4;
+  CUDA_TRY(cudaMalloc(&s->d_action, na)); CUDA_TRY(cudaMalloc(&s->d_obs, no));
+  CUDA_TRY(cudaMalloc(&s->d_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMalloc(&s->d_done, (size_t)num_envs * 4));
+  CUDA_TRY(cudaMallocHost(&s->h_action, na)); CUDA_TRY(cudaMallocHost(&s->h_obs, no));
+  CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
+  CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
+  *out = s;
+  return 0;
+}
+
+void b2e_destroy(b2e_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (int f = 0; f < B2E_F_COUNT; f++) cudaFree(s->fields[f]);
+  cudaFree(s->d_model); cudaFree(s->d_action); cudaFree(s->d_obs); cudaFree(s->d_reward); cudaFree(s->d_done);
+  cudaFreeHost(s->h_action); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_reward); cudaFreeHost(s->h_done);
+  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+int b2e_set_params(b2e_sim* s, const b2e_params* p) {
+  if (!s || !p) return fail(B2E_EINVAL, "b2e_set_params: null%s", "");
+  if (p->n_obs != s->params.n_obs || p->n_act != s->params.n_act)
+    return fail(B2E_EINVAL, "b2e_set_params: n_obs / n_act cannot change after create%s", "");
+  s->params = *p;
+  return 0;
+}
+
+int b2e_set_option(b2e_sim* s, int option, int value) {
+  if (!s) return fail(B2E_EINVAL, "b2e_set_option: null%s", "");
+  if (option == 0) { s->record_contacts = value; return 0; }
+  return fail(B2E_EINVAL, "b2e_set_option: unknown option%s", "");
+}
+
+int b2e_reset(b2e_sim* s, const uint8_t* env_mask, const float* obj_init_pose, const float* target, void* stream) {
+  if (!s || !obj_init_pose || !target) return fail(B2E_EINVAL, "b2e_reset: null argument%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int tpb = 128;
+  reset_kernel<<<(s->B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(s->d_model, s->params, s->st, env_mask,
+                                                                         obj_init_pose, target);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
+             void* stream) {
+  if (!s) return fail(B2E_EINVAL, "b2e_step: null sim%s", "");
+  if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step: action is required in ACTION mode%s", "");
+  if (n_substeps < 1) return fail(B2E_EINVAL, "b2e_step: n_substeps < 1%s", "");
+  if (s->params.use_ik && mode == B2E_MODE_ACTION) return fail(B2E_EUNSUPPORTED, "b2e_step: IK control mode not built yet%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int blocks = (s->B + WPB - 1) / WPB;
+  step_kernel<<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+      s->d_model, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b2e_step_host(b2e_sim* s, const float* action_host, float* obs_host, float* reward_host, float* done_host,
+                  int n_substeps, int mode) {
+  if (!s) return fail(B2E_EINVAL, "b2e_step_host: null sim%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const size_t na = (size_t)s->B * s->params.n_act * 4, no = (size_t)s->B * s->params.n_obs * 4, nb = (size_t)s->B * 4;
+  if (mode == B2E_MODE_ACTION) {
+    if (!action_host) return fail(B2E_EINVAL, "b2e_step_host: action required%s", "");
+    memcpy(s->h_action, action_host, na);
+    CUDA_TRY(cudaMemcpyAsync(s->d_action, s->h_action, na, cudaMemcpyHostToDevice, 0));
+  }
+  int rc = b2e_step(s, s->d_action, obs_host ? s->d_obs : nullptr, reward_host ? s->d_reward : nullptr,
+                    done_host ? s->d_done : nullptr, n_substeps, mode, 0);
+  if (rc) return rc;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(s->h_obs, s->d_obs, no, cudaMemcpyDeviceToHost, 0));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(s->h_reward, s->d_reward, nb, cudaMemcpyDeviceToHost, 0));
+  if (done_host) CUDA_TRY(cudaMemcpyAsync(s->h_done, s->d_done, nb, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  if (obs_host) memcpy(obs_host, s->h_obs, no);
+  if (reward_host) memcpy(reward_host, s->h_reward, nb);
+  if (done_host) memcpy(done_host, s->h_done, nb);
+  return 0;
+}
+
+int b2e_get(b2e_sim* s, int field, void* dst_dev, void* stream) {
+  if (!s || !dst_dev || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_get: bad argument%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpyAsync(dst_dev, s->fields[field], (size_t)s->B * field_width(s, field) * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return 0;
+}
+int b2e_set(b2e_sim* s, int field, const void* src_dev, void* stream) {
+  if (!s || !src_dev || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_set: bad argument%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpyAsync(s->fields[field], src_dev, (size_t)s->B * field_width(s, field) * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return 0;
+}
+int b2e_get_host(b2e_sim* s, int field, void* dst_host) {
+  if (!s || !dst_host || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_get_host: bad argument%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(dst_host, s->fields[field], (size_t)s->B * field_width(s, field) * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b2e_set_host(b2e_sim* s, int field, const void* src_host) {
+  if (!s || !src_host || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_set_host: bad argument%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(s->fields[field], src_host, (size_t)s->B * field_width(s, field) * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2e_timer_start(b2e_sim* s, void* stream) {
+  if (!s) return fail(B2E_EINVAL, "b2e_timer_start: null%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaEventRecord(s->ev0, (cudaStream_t)stream));
+  return 0;
+}
+int b2e_timer_stop(b2e_sim* s, void* stream, float* ms_out) {
+  if (!s || !ms_out) return fail(B2E_EINVAL, "b2e_timer_stop: null%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaEventRecord(s->ev1, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventSynchronize(s->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms_out, s->ev0, s->ev1));
+  return 0;
+}
+
+}  // extern "C"

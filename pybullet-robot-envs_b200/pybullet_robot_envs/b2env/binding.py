@@ -1,0 +1,179 @@
+"""ctypes binding of libb2env.so (include/b2env.h) — the only door to the CUDA path.
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the
+constructor raises, so a silent non-GPU path cannot exist.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .model import B2EModel, B2EParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libb2env.so"))
+
+F_Q, F_QD, F_OBJ_POSE, F_OBJ_VEL, F_TARGET, F_MTARGET, F_COUNTERS, F_CACHE_KEY, F_CACHE_LAM, \
+    F_HAND_POSE, F_STATUS, F_RAW_OBS, F_CONTACTS = range(13)
+FIELD_NAMES = {
+    "q": F_Q, "qd": F_QD, "obj_pose": F_OBJ_POSE, "obj_vel": F_OBJ_VEL, "target": F_TARGET,
+    "mtarget": F_MTARGET, "counters": F_COUNTERS, "cache_key": F_CACHE_KEY, "cache_lam": F_CACHE_LAM,
+    "hand_pose": F_HAND_POSE, "status": F_STATUS, "raw_obs": F_RAW_OBS, "contacts": F_CONTACTS,
+}
+INT_FIELDS = {F_COUNTERS, F_CACHE_KEY, F_STATUS}
+MODE_ACTION, MODE_HOLD = 0, 1
+OPT_RECORD_CONTACTS = 0
+
+EXPORTS = [
+    "b2e_create", "b2e_destroy", "b2e_set_params", "b2e_set_option", "b2e_reset", "b2e_step",
+    "b2e_step_host", "b2e_get", "b2e_set", "b2e_get_host", "b2e_set_host", "b2e_field_width",
+    "b2e_field_elem_size", "b2e_num_envs", "b2e_launch_count", "b2e_timer_start", "b2e_timer_stop",
+    "b2e_last_error", "b2e_version",
+]
+
+_lib = None
+
+
+class B2EError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libb2env.so and declare prototypes.  Raises if the extension is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise B2EError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    vp, ci = C.c_void_p, C.c_int
+    lib.b2e_create.argtypes = [C.POINTER(B2EModel), C.POINTER(B2EParams), ci, ci, C.POINTER(vp)]
+    lib.b2e_destroy.argtypes = [vp]
+    lib.b2e_destroy.restype = None
+    lib.b2e_set_params.argtypes = [vp, C.POINTER(B2EParams)]
+    lib.b2e_set_option.argtypes = [vp, ci, ci]
+    lib.b2e_reset.argtypes = [vp, vp, vp, vp, vp]
+    lib.b2e_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp]
+    lib.b2e_step_host.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+    lib.b2e_get.argtypes = [vp, ci, vp, vp]
+    lib.b2e_set.argtypes = [vp, ci, vp, vp]
+    lib.b2e_get_host.argtypes = [vp, ci, vp]
+    lib.b2e_set_host.argtypes = [vp, ci, vp]
+    lib.b2e_field_width.argtypes = [vp, ci]
+    lib.b2e_field_elem_size.argtypes = [ci]
+    lib.b2e_num_envs.argtypes = [vp]
+    lib.b2e_launch_count.argtypes = [vp]
+    lib.b2e_launch_count.restype = C.c_int64
+    lib.b2e_timer_start.argtypes = [vp, vp]
+    lib.b2e_timer_stop.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    lib.b2e_last_error.restype = C.c_char_p
+    lib.b2e_version.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """Device/host pointer of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    return C.c_void_p(x.data_ptr())  # torch tensor
+
+
+class B2Sim:
+    """Thin object wrapper over the C-ABI: one simulation of ``num_envs`` envs on one GPU."""
+
+    def __init__(self, model: B2EModel, params: B2EParams, num_envs: int, device: int = 0):
+        self.lib = load_library()
+        self.model, self.params, self.B, self.device = model, params, int(num_envs), int(device)
+        h = C.c_void_p()
+        self._check(self.lib.b2e_create(C.byref(model), C.byref(params), self.B, self.device, C.byref(h)))
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2EError("libb2env error %d: %s" % (rc, self.lib.b2e_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2e_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        self._check(self.lib.b2e_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def set_option(self, option, value):
+        self._check(self.lib.b2e_set_option(self.h, option, int(value)))
+
+    # device-pointer entry points (torch tensors on the sim's device, or raw ints)
+    def reset(self, obj_init_pose, target, env_mask=None, stream=0):
+        self._check(self.lib.b2e_reset(self.h, _ptr(env_mask), _ptr(obj_init_pose), _ptr(target), C.c_void_p(stream)))
+
+    def step(self, action, obs=None, reward=None, done=None, n_substeps=1, mode=MODE_ACTION, stream=0):
+        self._check(self.lib.b2e_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done), n_substeps, mode,
+                                      C.c_void_p(stream)))
+
+    # host-buffer entry points (numpy)
+    def step_host(self, action=None, n_substeps=1, mode=MODE_ACTION, want_obs=True):
+        no = self.params.n_obs
+        act = None
+        if action is not None:
+            act = np.ascontiguousarray(action, dtype=np.float32)
+            if act.shape != (self.B, self.params.n_act):
+                raise AssertionError(("number of motor commands differs from number of motor to control", act.shape))
+        if not want_obs:
+            self._check(self.lib.b2e_step_host(self.h, _ptr(act), None, None, None, n_substeps, mode))
+            return None
+        obs = np.empty((self.B, no), np.float32)
+        rew = np.empty(self.B, np.float32)
+        done = np.empty(self.B, np.float32)
+        self._check(self.lib.b2e_step_host(self.h, _ptr(act), _ptr(obs), _ptr(rew), _ptr(done), n_substeps, mode))
+        return obs, rew, done
+
+    def get(self, name):
+        f = FIELD_NAMES[name]
+        w = self.lib.b2e_field_width(self.h, f)
+        out = np.empty((self.B, w), np.int32 if f in INT_FIELDS else np.float32)
+        self._check(self.lib.b2e_get_host(self.h, f, _ptr(out)))
+        return out
+
+    def set(self, name, value):
+        f = FIELD_NAMES[name]
+        w = self.lib.b2e_field_width(self.h, f)
+        arr = np.ascontiguousarray(value, np.int32 if f in INT_FIELDS else np.float32).reshape(self.B, w)
+        self._check(self.lib.b2e_set_host(self.h, f, _ptr(arr)))
+
+    def reset_host(self, obj_init_pose, target, env_mask=None):
+        """Reset from host arrays (copies through temporary device buffers owned by torch)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        o = torch.as_tensor(np.ascontiguousarray(obj_init_pose, np.float32)).to(dev)
+        t = torch.as_tensor(np.ascontiguousarray(target, np.float32)).to(dev)
+        m = None if env_mask is None else torch.as_tensor(np.ascontiguousarray(env_mask, np.uint8)).to(dev)
+        torch.cuda.synchronize(dev)
+        self.reset(o, t, m)
+        torch.cuda.synchronize(dev)
+
+    def launch_count(self):
+        return int(self.lib.b2e_launch_count(self.h))
+
+    def timer_start(self, stream=0):
+        self._check(self.lib.b2e_timer_start(self.h, C.c_void_p(stream)))
+
+    def timer_stop(self, stream=0):
+        ms = C.c_float()
+        self._check(self.lib.b2e_timer_stop(self.h, C.c_void_p(stream), C.byref(ms)))
+        return ms.value

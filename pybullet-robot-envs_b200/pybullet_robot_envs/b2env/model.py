@@ -1,0 +1,355 @@
+"""Model descriptor: URDF -> flat arrays (the host half of what ``p.loadURDF`` does).
+
+The reference loads ``robot_data/franka_panda/panda_model.urdf`` through
+``p.loadURDF(..., useFixedBase=True, flags=URDF_USE_INERTIA_FROM_FILE | ...)``
+(reference panda_env.py:53-56) and then addresses joints by PyBullet joint index
+(= URDF joint order, panda_env.py:60-79).  This module parses the same file into
+the ``b2e_model`` struct of include/b2env.h.  Because ``/root/reference`` does not
+travel to the GPU box, ``tools/gen_model.py`` runs this parser once and commits the
+result as ``robot_data/franka_panda/panda_model.json``; ``load_panda()`` reads that.
+
+Collision geometry: the reference's collision meshes are git-LFS stubs,
+so links carry sphere proxies defined in ``proxies.py`` (documented deviation).
+"""
+import ctypes as C
+import json
+import math
+import os
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+MAX_LINKS = 40
+MAX_DOF = 32
+MAX_SPHERES = 16
+MAX_OBS = 40
+MAX_CONTACTS = 12
+CACHE_SLOTS = 16
+
+JOINT_REVOLUTE = 0
+JOINT_PRISMATIC = 1
+JOINT_FIXED = 4
+
+TASK_REACH = 0
+TASK_PUSH = 1
+
+_f = C.c_float
+_i = C.c_int32
+
+
+class B2EModel(C.Structure):
+    """ctypes mirror of ``struct b2e_model`` (include/b2env.h)."""
+    _fields_ = [
+        ("n_links", _i), ("n_dof", _i), ("ee_link", _i), ("n_spheres", _i),
+        ("parent", _i * MAX_LINKS), ("jtype", _i * MAX_LINKS), ("dof", _i * MAX_LINKS),
+        ("jpos", (_f * 3) * MAX_LINKS), ("jrot", (_f * 9) * MAX_LINKS),
+        ("axis", (_f * 3) * MAX_LINKS),
+        ("mass", _f * MAX_LINKS), ("com", (_f * 3) * MAX_LINKS),
+        ("inertia", (_f * 9) * MAX_LINKS),
+        ("lower", _f * MAX_DOF), ("upper", _f * MAX_DOF), ("limit_margin", _f * MAX_DOF),
+        ("max_force", _f * MAX_DOF), ("max_vel", _f * MAX_DOF),
+        ("joint_damping", _f * MAX_DOF), ("home", _f * MAX_DOF),
+        ("base_pos", _f * 3), ("base_rot", _f * 9),
+        ("sph_link", _i * MAX_SPHERES), ("sph_c", (_f * 3) * MAX_SPHERES),
+        ("sph_r", _f * MAX_SPHERES), ("sph_mu", _f * MAX_SPHERES),
+        ("sph_erp", _f * MAX_SPHERES), ("sph_cfm", _f * MAX_SPHERES),
+    ]
+
+
+class B2EParams(C.Structure):
+    """ctypes mirror of ``struct b2e_params`` (include/b2env.h)."""
+    _fields_ = [
+        ("dt", _f), ("gravity", _f * 3), ("solver_iters", _i), ("residual_tol", _f),
+        ("erp", _f), ("slop", _f), ("warmstart", _f), ("contact_margin", _f),
+        ("table_min", _f * 3), ("table_max", _f * 3), ("table_mu", _f), ("plane_mu", _f),
+        ("cube_half", _f), ("cube_mass", _f), ("cube_inertia", _f), ("cube_mu", _f),
+        ("damp_lin_k1", _f), ("damp_lin_k2", _f), ("damp_ang_k1", _f), ("damp_ang_k2", _f),
+        ("task", _i), ("n_act", _i), ("n_ctrl", _i), ("use_ik", _i), ("ik_orientation", _i),
+        ("ik_iters", _i), ("ik_residual", _f), ("ik_damping", _f),
+        ("act_scale", _f), ("act_scale_pos", _f), ("act_scale_rot", _f),
+        ("kp_ctrl", _f), ("kp_hold", _f), ("dist_min", _f), ("max_steps", _i), ("n_obs", _i),
+        ("obs_low", _f * MAX_OBS), ("obs_high", _f * MAX_OBS),
+        ("vel_mean", _f * 3), ("vel_std", _f * 3),
+        ("ws_lim", (_f * 2) * 3), ("eu_lim", (_f * 2) * 3), ("home_hand_pose", _f * 6),
+    ]
+
+
+def rpy_to_matrix(r, p, y):
+    """URDF fixed-axis roll-pitch-yaw -> rotation matrix R = Rz(y) Ry(p) Rx(r)."""
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    return np.array([
+        [cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+        [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+        [-sp, cp * sr, cp * cr]], dtype=np.float64)
+
+
+def _vec(s, n=3):
+    v = [float(x) for x in s.split()]
+    assert len(v) == n
+    return v
+
+
+def parse_urdf(path):
+    """Parse a URDF into a plain dict (JSON-serialisable), joints in PyBullet index order.
+
+    PyBullet numbers joints by a depth-first walk from the root link that visits a link's
+    child joints in file order; for the Panda file this equals file order.
+    """
+    root = ET.parse(path).getroot()
+    links = {}
+    for ln in root.findall("link"):
+        name = ln.get("name")
+        inert = ln.find("inertial")
+        mass, com, rpy, I = 0.0, [0, 0, 0], [0, 0, 0], np.zeros((3, 3))
+        if inert is not None:
+            o = inert.find("origin")
+            if o is not None:
+                com = _vec(o.get("xyz", "0 0 0"))
+                rpy = _vec(o.get("rpy", "0 0 0"))
+            mass = float(inert.find("mass").get("value"))
+            it = inert.find("inertia")
+            ixx, ixy, ixz = float(it.get("ixx")), float(it.get("ixy")), float(it.get("ixz"))
+            iyy, iyz, izz = float(it.get("iyy")), float(it.get("iyz")), float(it.get("izz"))
+            I = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]])
+            Ri = rpy_to_matrix(*rpy)
+            I = Ri @ I @ Ri.T  # express about COM in link-frame axes
+        contact = {}
+        ct = ln.find("contact")
+        if ct is not None:
+            for tag in ("lateral_friction", "stiffness", "damping", "rolling_friction", "spinning_friction"):
+                e = ct.find(tag)
+                if e is not None:
+                    contact[tag] = float(e.get("value"))
+        links[name] = dict(name=name, mass=mass, com=com, inertia=I.tolist(), contact=contact)
+
+    joints = []
+    for jn in root.findall("joint"):
+        o = jn.find("origin")
+        xyz = _vec(o.get("xyz", "0 0 0")) if o is not None else [0, 0, 0]
+        rpy = _vec(o.get("rpy", "0 0 0")) if o is not None else [0, 0, 0]
+        ax = jn.find("axis")
+        axis = _vec(ax.get("xyz")) if ax is not None else [1, 0, 0]
+        lim = jn.find("limit")
+        joints.append(dict(
+            name=jn.get("name"), type=jn.get("type"),
+            parent=jn.find("parent").get("link"), child=jn.find("child").get("link"),
+            xyz=xyz, rpy=rpy, axis=axis,
+            lower=float(lim.get("lower", 0)) if lim is not None else 0.0,
+            upper=float(lim.get("upper", 0)) if lim is not None else 0.0,
+            effort=float(lim.get("effort", 0)) if lim is not None else 0.0,
+            velocity=float(lim.get("velocity", 0)) if lim is not None else 0.0))
+
+    children = {j["child"] for j in joints}
+    roots = [n for n in links if n not in children]
+    assert len(roots) == 1, roots
+    base = roots[0]
+
+    order = []
+
+    def walk(link_name):
+        for j in joints:
+            if j["parent"] == link_name:
+                order.append(j)
+                walk(j["child"])
+    walk(base)
+    assert len(order) == len(joints)
+
+    link_index = {base: -1}
+    for idx, j in enumerate(order):
+        link_index[j["child"]] = idx
+    out_j = []
+    for idx, j in enumerate(order):
+        out_j.append(dict(j, index=idx, parent_index=link_index[j["parent"]]))
+    return dict(name=root.get("name"), base=links[base], joints=out_j,
+                links=[links[j["child"]] for j in order])
+
+
+def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres):
+    """Flatten the parsed URDF dict into a ``B2EModel``."""
+    m = B2EModel()
+    n = len(d["joints"])
+    assert n <= MAX_LINKS
+    m.n_links = n
+    m.ee_link = ee_link
+    ndof = 0
+    for i, (j, l) in enumerate(zip(d["joints"], d["links"])):
+        m.parent[i] = j["parent_index"]
+        t = {"revolute": JOINT_REVOLUTE, "continuous": JOINT_REVOLUTE,
+             "prismatic": JOINT_PRISMATIC, "fixed": JOINT_FIXED}[j["type"]]
+        m.jtype[i] = t
+        R = rpy_to_matrix(*j["rpy"])
+        for k in range(3):
+            m.jpos[i][k] = j["xyz"][k]
+            m.com[i][k] = l["com"][k]
+        for k in range(9):
+            m.jrot[i][k] = R.flat[k]
+            m.inertia[i][k] = np.asarray(l["inertia"]).flat[k]
+        m.mass[i] = l["mass"]
+        if t != JOINT_FIXED:
+            a = np.asarray(j["axis"], dtype=np.float64)
+            a = a / np.linalg.norm(a)
+            for k in range(3):
+                m.axis[i][k] = a[k]
+            m.dof[i] = ndof
+            m.lower[ndof] = j["lower"]
+            m.upper[ndof] = j["upper"]
+            # limit rows are only instantiated inside this distance of a limit; a joint would
+            # have to move faster than margin/dt (24 rad/s, 2.4 m/s) for the omission to matter.
+            m.limit_margin[ndof] = 0.1 if t == JOINT_REVOLUTE else 0.01
+            m.max_force[ndof] = 1.0e5   # pybullet setJointMotorControl2 default force [EXT-recalled]
+            m.max_vel[ndof] = -1.0
+            m.joint_damping[ndof] = 0.0  # the Panda URDF has no <dynamics>
+            m.home[ndof] = home[j["name"]]
+            ndof += 1
+        else:
+            m.dof[i] = -1
+    m.n_dof = ndof
+    for k in range(3):
+        m.base_pos[k] = base_position[k]
+    for k in range(9):
+        m.base_rot[k] = float(np.eye(3).flat[k])
+    assert len(spheres) <= MAX_SPHERES
+    m.n_spheres = len(spheres)
+    names = [l["name"] for l in d["links"]]
+    for s, sp in enumerate(spheres):
+        li = names.index(sp["link"])
+        m.sph_link[s] = li
+        for k in range(3):
+            m.sph_c[s][k] = sp["c"][k]
+        m.sph_r[s] = sp["r"]
+        ct = d["links"][li]["contact"]
+        m.sph_mu[s] = ct.get("lateral_friction", 0.5)  # Bullet default link friction 0.5 [EXT-recalled]
+        m.sph_erp[s] = -1.0
+        m.sph_cfm[s] = 0.0
+    return m
+
+
+PANDA_HOME = {  # reference panda_env.py:19-23
+    'panda_joint1': 0.0, 'panda_joint2': -0.54, 'panda_joint3': 0.0,
+    'panda_joint4': -2.6, 'panda_joint5': -0.30, 'panda_joint6': 2.0,
+    'panda_joint7': 1.0, 'panda_finger_joint1': 0.02, 'panda_finger_joint2': 0.02,
+}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PANDA_JSON = os.path.join(_HERE, "..", "robot_data", "franka_panda", "panda_model.json")
+
+
+def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
+    """Build the Panda ``B2EModel``.  ``urdf_path`` (e.g. the reference's own
+    ``robot_data/franka_panda/panda_model.urdf``) overrides the committed JSON."""
+    from .proxies import PANDA_SPHERES
+    if urdf_path is not None:
+        d = parse_urdf(urdf_path)
+    else:
+        with open(PANDA_JSON) as f:
+            d = json.load(f)
+    m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES)
+    # soft finger contacts: <stiffness>/<damping> (URDF:256-263) -> per-contact erp/cfm the way
+    # Bullet derives them: denom = dt*k + d, erp = dt*k/denom, cfm = 1/(denom*dt) [EXT-recalled]
+    names = [l["name"] for l in d["links"]]
+    for s in range(m.n_spheres):
+        ct = d["links"][m.sph_link[s]]["contact"]
+        if "stiffness" in ct:
+            k = ct["stiffness"]
+            dmp = ct.get("damping", 0.0) + 0.1  # + default contact damping of the other body
+            denom = dt * k + dmp
+            m.sph_erp[s] = dt * k / denom
+            m.sph_cfm[s] = 1.0 / (denom * dt)
+    del names
+    return m, d
+
+
+def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orientation=0,
+                   max_steps=1000, dist_min=None, ws_lim=None, eu_lim=None):
+    """World/solver/task constants.  Sources: reference panda_push_gym_env.py:39,52,122-126,
+    panda_env.py:76,174-175,308; world assets from pybullet_data [EXT-recalled, SURVEY App. B.3]."""
+    p = B2EParams()
+    p.dt = 1.0 / 240.0
+    p.gravity[0], p.gravity[1], p.gravity[2] = 0.0, 0.0, -9.8
+    p.solver_iters = 150
+    p.residual_tol = 1e-7   # pybullet default solverResidualThreshold [EXT-recalled]
+    p.erp = 0.2             # pybullet default contact erp [EXT-recalled]
+    p.slop = 1e-5
+    p.warmstart = 0.85      # btContactSolverInfo default [EXT-recalled]
+    p.contact_margin = 0.01
+    # table/table.urdf at (0.85,0,0): top slab 1.5 x 1.0 x 0.05 centred z=0.6 (top 0.625 = world_env.py:68-69)
+    p.table_min[0], p.table_min[1], p.table_min[2] = 0.85 - 0.75, -0.5, 0.575
+    p.table_max[0], p.table_max[1], p.table_max[2] = 0.85 + 0.75, 0.5, 0.625
+    p.table_mu = 1.0
+    p.plane_mu = 1.0
+    p.cube_half = 0.025
+    p.cube_mass = 0.1
+    p.cube_inertia = 0.1 * (0.05 ** 2) / 6.0
+    p.cube_mu = 1.0
+    p.damp_lin_k1, p.damp_lin_k2 = 0.1, 0.04   # btMultiBody base damping [EXT-recalled]
+    p.damp_ang_k1, p.damp_ang_k2 = 0.2, 0.04
+    p.task = task
+    p.n_act = n_act
+    p.n_ctrl = n_ctrl
+    p.use_ik = use_ik
+    p.ik_orientation = ik_orientation
+    p.ik_iters = 100
+    p.ik_residual = 1e-3
+    p.ik_damping = 0.1
+    p.act_scale = 0.05
+    p.act_scale_pos = 0.005
+    p.act_scale_rot = 0.01
+    p.kp_ctrl = 0.5
+    p.kp_hold = 0.2
+    if dist_min is None:
+        dist_min = 0.1 if task == TASK_PUSH else 0.03
+    p.dist_min = dist_min
+    p.max_steps = max_steps
+    n_obs = len(obs_low)
+    assert n_obs <= MAX_OBS and len(obs_high) == n_obs
+    p.n_obs = n_obs
+    lo32 = np.asarray(obs_low, dtype=np.float32)
+    hi32 = np.asarray(obs_high, dtype=np.float32)
+    for k in range(n_obs):
+        p.obs_low[k] = float(lo32[k])
+        p.obs_high[k] = float(hi32[k])
+    for k, (mu, sd) in enumerate(zip((0.0, 0.01, 0.0), (0.04, 0.07, 0.03))):
+        p.vel_mean[k] = mu
+        p.vel_std[k] = sd
+    if ws_lim is None:
+        ws_lim = [[0.3, 0.65], [-0.3, 0.3], [0.65, 1.5]]  # panda_env.py:37
+    if eu_lim is None:
+        eu_lim = [[-math.pi, math.pi]] * 3
+    for k in range(3):
+        p.ws_lim[k][0], p.ws_lim[k][1] = ws_lim[k]
+        p.eu_lim[k][0], p.eu_lim[k][1] = eu_lim[k]
+    for k, v in enumerate((0.2, 0.0, 0.8, math.pi, 0.0, 0.0)):  # panda_env.py:85-88
+        p.home_hand_pose[k] = v
+    return p
+
+
+def panda_obs_limits(task, robot_ws, world_ws, lower, upper, eu_lim=None):
+    """Per-entry (low, high) of the extended observation: robot obs (panda_env.py:141-193),
+    world obs (world_env.py:109-126), relative pose and target (panda_push_gym_env.py:178-185)."""
+    pi = math.pi
+    if eu_lim is None:
+        eu_lim = [[-pi, pi]] * 3
+    lim = [list(x) for x in robot_ws] + [list(x) for x in eu_lim] + [[-1, 1]] * 3
+    lim += [[lower[i], upper[i]] for i in range(len(lower))]
+    lim += [list(x) for x in world_ws] + [[-pi, pi]] * 3
+    lim += [[-0.5, 0.5]] * 3 + [[0, 2 * pi]] * 3
+    if task == TASK_PUSH:
+        lim += [list(x) for x in world_ws]
+    low = [x[0] for x in lim]
+    high = [x[1] for x in lim]
+    return low, high
+
+
+def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7):
+    """Model + params of the registered pandaPush-v0 / pandaReach-v0 configuration
+    (reference pybullet_robot_envs/__init__.py:47-68), joint control mode."""
+    m, _ = load_panda()
+    h_table = 0.625
+    robot_ws = [[0.3, 0.65], [-0.3, 0.3], [0.65, 1.5]]
+    world_ws = [[0.3, 0.65], [-0.3, 0.3], [h_table, h_table + 0.3]]     # world_env.py:72
+    robot_ws[2][0] = h_table - 0.2 if task == TASK_PUSH else h_table     # push :74 / reach :69
+    lower = [m.lower[i] for i in range(m.n_dof)]
+    upper = [m.upper[i] for i in range(m.n_dof)]
+    low, high = panda_obs_limits(task, robot_ws, world_ws, lower, upper)
+    p = default_params(task, low, high, n_act=n_ctrl, n_ctrl=n_ctrl, max_steps=max_steps, ws_lim=robot_ws)
+    return m, p

@@ -1,0 +1,136 @@
+"""GPU-vs-oracle parity of the fused step kernel, through the C-ABI (libb2env.so).
+
+Tolerances (fp32 on both sides, different but mathematically equivalent formulations:
+oracle = ABA + delta-velocity PGS, GPU = CRBA/Gauss-Jordan + Delassus-form PGS):
+  * single step from identical state: joint/object state 2e-4 abs (solver exits on a velocity
+    residual of sqrt(1e-7) ~ 3e-4 m/s, i.e. ~1.3e-6 m per step), contact keys exact;
+  * trajectories: stated per test.
+"""
+import numpy as np
+import pytest
+
+from common import TASK_PUSH, TASK_REACH, copy_state_to_gpu, panda_task_setup, sample_object_poses, targets_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(task, B, oracle_lib, seed=0, nthreads=8):
+    from pybullet_robot_envs.b2env.binding import B2Sim, OPT_RECORD_CONTACTS
+    m, p = panda_task_setup(task)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=nthreads)
+    sim = B2Sim(m, p, B, 0)
+    sim.set_option(OPT_RECORD_CONTACTS, 1)
+    pose = sample_object_poses(B, seed)
+    tg = targets_for(pose, z=0.65)
+    orc.reset(pose, tg)
+    sim.reset_host(pose, tg)
+    return m, p, orc, sim
+
+
+def test_reset_state_matches(oracle_lib):
+    m, p, orc, sim = _mk(TASK_PUSH, 64, oracle_lib)
+    for f in ("q", "qd", "obj_pose", "obj_vel", "target", "mtarget", "counters", "cache_key", "cache_lam"):
+        np.testing.assert_array_equal(sim.get(f), orc.state[f], err_msg=f)
+
+
+def test_single_step_from_identical_state(oracle_lib):
+    """Every step restarts the GPU from the oracle's state: isolates per-step error."""
+    B = 256
+    m, p, orc, sim = _mk(TASK_PUSH, B, oracle_lib)
+    rng = np.random.RandomState(1)
+    worst = {}
+    for i in range(160):
+        copy_state_to_gpu(orc, sim)
+        if i < 60:
+            orc.step(None, 1, 1, want_obs=False)
+            sim.step_host(None, 1, 1, want_obs=False)
+        else:
+            a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+            o_obs, o_rew, o_done = orc.step(a, 1, 0)
+            g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+            np.testing.assert_allclose(g_obs, o_obs, atol=2e-2, rtol=0, err_msg="obs step %d" % i)
+            np.testing.assert_allclose(g_rew, o_rew, atol=1e-3, rtol=1e-5, err_msg="reward step %d" % i)
+            np.testing.assert_array_equal(g_done, o_done)
+        for f, tol in (("q", 2e-5), ("qd", 5e-3), ("obj_pose", 2e-5), ("obj_vel", 5e-3), ("mtarget", 1e-6)):
+            err = np.abs(sim.get(f) - orc.state[f]).max()
+            worst[f] = max(worst.get(f, 0), err)
+            assert err <= tol, (f, i, err)
+        # contact feature keys and counts are integers: exact
+        g_st, o_st = sim.get("status"), orc.state["status"]
+        np.testing.assert_array_equal(g_st[:, 2:], o_st[:, 2:], err_msg="n_contacts/n_rows step %d" % i)
+        np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="keys step %d" % i)
+        np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
+    print("worst single-step abs errors:", worst)
+
+
+def test_settle_trajectory(oracle_lib):
+    """reset + 101 settle steps run free on both sides (panda_push_gym_env.py:132-148 analogue)."""
+    B = 128
+    m, p, orc, sim = _mk(TASK_PUSH, B, oracle_lib)
+    for _ in range(101):
+        orc.step(None, 1, 1, want_obs=False)
+    sim.step_host(None, 101, 1, want_obs=False)  # 101 sub-steps fused in one launch
+    np.testing.assert_allclose(sim.get("q"), orc.state["q"], atol=1e-5)
+    np.testing.assert_allclose(sim.get("obj_pose"), orc.state["obj_pose"], atol=2e-4)
+    # the cube rests on the table: centre at table top + half extent - slop-level penetration
+    assert np.all(np.abs(sim.get("obj_pose")[:, 2] - 0.65) < 1e-3)
+    assert np.all(np.abs(sim.get("obj_vel")) < 5e-3)
+    np.testing.assert_array_equal(np.sort(sim.get("cache_key"), axis=1), np.sort(orc.state["cache_key"], axis=1))
+
+
+@pytest.mark.parametrize("task", [TASK_PUSH, TASK_REACH])
+def test_free_running_rollout(oracle_lib, task):
+    """240 random-action steps, both sides free running.  Arm states are motor-dominated and stay
+    within 1e-3 rad; observations within 5e-2 (scaled units) for envs without robot contact."""
+    B = 128
+    m, p, orc, sim = _mk(task, B, oracle_lib, seed=3)
+    for _ in range(101):
+        orc.step(None, 1, 1, want_obs=False)
+    sim.step_host(None, 101, 1, want_obs=False)
+    rng = np.random.RandomState(7)
+    touched = np.zeros(B, bool)
+    for i in range(240):
+        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)
+        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+        touched |= orc.state["status"][:, 2] > 4
+        touched |= sim.get("status")[:, 2] > 4
+    ok = ~touched
+    assert ok.sum() > B // 2
+    assert np.abs(sim.get("q") - orc.state["q"])[ok].max() < 1e-3
+    assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"])[ok].max() < 1e-3
+    assert np.abs(g_obs - o_obs)[ok][:, [0, 1, 2, 3, 4, 5] + list(range(9, 24))].max() < 5e-2
+    assert np.abs(g_rew - o_rew)[ok].max() < 1e-2
+    assert (sim.get("status")[:, 0] & 1).sum() == 0  # no NaN flag
+
+
+def test_full_batch_properties():
+    """BASELINE batch (16384): size-independent properties — no NaN flags, unit quaternions,
+    joint limits respected, resting cubes stay on the table, determinism of a repeated run."""
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    B = 16384
+    m, p = panda_task_setup(TASK_PUSH)
+    pose = sample_object_poses(B, 11)
+    tg = targets_for(pose, z=0.65)
+    outs = []
+    for rep in range(2):
+        sim = B2Sim(m, p, B, 0)
+        sim.reset_host(pose, tg)
+        sim.step_host(None, 101, 1, want_obs=False)
+        rng = np.random.RandomState(5)
+        for i in range(20):
+            a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+            obs, rew, done = sim.step_host(a, 1, 0)
+        st = sim.get("status")
+        assert (st[:, 0] & 1).sum() == 0
+        q = sim.get("q")
+        lo = np.array([m.lower[i] for i in range(9)]) - 1e-3
+        hi = np.array([m.upper[i] for i in range(9)]) + 1e-3
+        assert np.all(q >= lo) and np.all(q <= hi)
+        qt = sim.get("obj_pose")[:, 3:]
+        np.testing.assert_allclose(np.linalg.norm(qt, axis=1), 1.0, atol=1e-5)
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+        outs.append((q.copy(), obs.copy(), rew.copy()))
+        sim.close()
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)  # bitwise deterministic
