@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of random-policy pandaPush rollouts (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port, host cores)
+
+One "step" = one env.step() of the whole batch (16384 envs per GPU): action -> motor targets ->
+physics (dt = 1/240, <=150 PGS iterations) -> observation, reward, done, fused in one launch.
+`value`  : device-timed (CUDA events around each launch, L2 flushed between launches, flush excluded).
+`e2e`    : same metric through the public Gym-style API with HOST numpy buffers (H2D of the
+           actions and D2H of obs/reward/done inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pybullet-robot-envs_b200"))
+
+B_ALG_PUSH = 968  # algorithmic bytes per pandaPush env-step
+METRIC = "env-steps/sec PandaPush-v0 batch=16384"
+WORKLOAD = "pandaPush-v0 joint mode, random policy U(-1,1)^7, post-reset state, done ignored"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_cpu_arm(B, seed0, nthreads):
+    """The CPU restatement (oracle port) set up on the same workload: reset + settle, like env.reset()."""
+    from oracle import b2oracle
+    from pybullet_robot_envs.b2env.model import TASK_PUSH, panda_task_setup
+    from pybullet_robot_envs.gym_compat import seeding
+    m, p = panda_task_setup(TASK_PUSH)
+    orc = b2oracle.Oracle(m, p, B, nthreads=nthreads)
+    pose = np.zeros((B, 7), np.float32)
+    for i in range(B):
+        rng, _ = seeding.np_random(seed0 + i)
+        pose[i, 0] = np.clip(0.45 + rng.uniform(-0.05, 0.05), 0.35, 0.55)
+        pose[i, 1] = np.clip(rng.uniform(-0.05, 0.05), -0.25, 0.25)
+        pose[i, 2] = 0.695
+        yaw = rng.uniform(-np.pi / 4, np.pi / 4)
+        pose[i, 5], pose[i, 6] = np.sin(yaw / 2), np.cos(yaw / 2)
+    tg = pose[:, :3].copy()
+    orc.reset(pose, tg)
+    orc.step(None, 101, 1, want_obs=False)
+    tg = orc.state["obj_pose"][:, :3].copy()
+    tg[:, 0] = np.clip(tg[:, 0] + 0.05, 0.37, 0.58)
+    tg[:, 1] = np.clip(tg[:, 1] + 0.05, -0.3, 0.3)
+    orc.state["target"][:] = tg
+    return orc
+
+
+def time_cpu(orc, steps, warmup, seed=1234):
+    rng = np.random.RandomState(seed)
+    B = orc.B
+    for _ in range(warmup):
+        orc.step(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+    acts = [rng.uniform(-1, 1, (B, 7)).astype(np.float32) for _ in range(steps)]
+    t0 = time.perf_counter()
+    for a in acts:
+        orc.step(a, 1, 0)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  PyBullet is not installable
+    here, so this is the oracle port on all host cores, a bounded sample per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.cpu_batch
+    orc = make_cpu_arm(B, 0, cores)
+    rate, dt = time_cpu(orc, args.steps, max(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d envs x %d steps per step-call on %d host threads" % (B, 1, cores),
+                   "note": "CPU restatement (oracle port), not PyBullet: pybullet is absent from this image; "
+                           "as-shipped reference is additionally capped at 240 steps/s/process by time.sleep"},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d steps" % (B, args.steps)},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="environments per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pybullet_robot_envs.envs import pandaPushGymEnv
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    env = pandaPushGymEnv(num_envs=B, device=local, renders=False, obj_pose_rnd_std=0.05, tg_pose_rnd_std=0,
+                          max_steps=1000)
+    env.seed(rank * B)   # env i of rank r is the reference env seeded r*B + i
+    env.reset()
+    sim = env._sim
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.rand((W + K, B, 7), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)  # > 126 MB L2
+    returns = torch.zeros(B, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        obs, rew, done, _ = env.step(actions[i])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    l0 = sim.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                                  # evict the 16 MB state from L2 (not timed)
+        ev_s[i].record()
+        obs, rew, done, _ = env.step(actions[W + i])   # ONE launch of step_kernel
+        ev_e[i].record()
+        returns += rew
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sim.launch_count() - l0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    status = sim.get("status")
+    mean_iters = float(status[:, 1].mean())
+    nan_flags = int((status[:, 0] & 1).sum())
+
+    # ---- end-to-end through the public API with host buffers ----
+    Ke = min(args.e2e_steps, K)
+    host_actions = (np.random.RandomState(99 + rank).uniform(-1, 1, (Ke, B, 7))).astype(np.float32)
+    for i in range(3):
+        env.step(host_actions[i % Ke])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        o, r, d, _ = env.step(host_actions[i])        # H2D actions, launch, D2H obs/reward/done
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_rate = B * world * Ke / float(te.item())
+
+    # ---- episode returns gathered over NCCL (the only collective of the path) ----
+    if world > 1:
+        allret = [torch.empty_like(returns) for _ in range(world)]
+        dist.all_gather(allret, returns)
+        mean_return = float(torch.stack(allret).mean().item())
+    else:
+        mean_return = float(returns.mean().item())
+
+    if rank == 0:
+        peak, which = peaks()
+        value = B * world * K / (dev_ms_max * 1e-3)
+        per_gpu_rate = B * K / (dev_ms_max * 1e-3)
+        achieved = per_gpu_rate * B_ALG_PUSH / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "dt": 1.0 / 240, "solver_iters_max": 150, "residual_tol": 1e-7,
+                       "mean_pgs_iters_last_step": mean_iters, "nan_flags": nan_flags,
+                       "l2": "256 MiB flush between timed launches (excluded from timing)",
+                       "wall_ms_per_step_incl_flush": 1e3 * t_wall / K, "mean_episode_return": mean_return},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "alg_bytes_per_env_step": B_ALG_PUSH,
+                         "kernel": "step_kernel", "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step"},
+            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 7 * 4,
+                    "d2h_bytes_per_step": B * (33 + 2) * 4, "steps": Ke},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            orc = make_cpu_arm(args.cpu_batch, 0, cores)
+            probe, _ = time_cpu(orc, 5, 2)
+            n = int(max(10, min(400, 15.0 * probe / args.cpu_batch)))
+            rate, dt = time_cpu(orc, n, 0)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": "%d envs x %d steps (%.1f s) of the same workload" % (args.cpu_batch, n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

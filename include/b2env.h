@@ -159,7 +159,9 @@ enum b2e_field {
 
 /* step modes */
 #define B2E_MODE_ACTION 0 /* targets from the action (apply_action)             */
-#define B2E_MODE_HOLD 1   /* keep motor targets (settle steps of reset)         */
+#define B2E_MODE_HOLD 1   /* keep motor targets, hold gains (settle steps of reset) */
+#define B2E_MODE_TARGETS 2 /* keep motor targets already written to B2E_F_MTARGET by
+                              robot.apply_action, control gains; no task bookkeeping */
 
 typedef struct b2e_sim b2e_sim;
 
@@ -189,7 +191,9 @@ int b2e_reset(b2e_sim* sim, const uint8_t* env_mask, const float* obj_init_pose 
  * PGS, integrate) -> observation, reward, done
  * (panda_push_gym_env.py:244-255).  action [B][n_act], obs [B][n_obs] (scaled
  * with scale_gym_data, utils.py:78-91), reward [B], done [B] (float 0/1).
- * obs/reward/done may be NULL (settle steps).  All device pointers.             */
+ * obs/reward/done may be NULL (settle steps).  All device pointers.
+ * n_substeps == 0 with mode HOLD only evaluates observation / reward / done on
+ * the current state (get_extended_observation, _termination, _compute_reward). */
 int b2e_step(b2e_sim* sim, const float* action, float* obs, float* reward, float* done,
              int n_substeps, int mode, void* stream);
 

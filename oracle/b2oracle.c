@@ -957,7 +957,7 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
         e.mtarget[k] = t;
       }
     }
-    physics_step(m, P, &e, mode == B2E_MODE_ACTION);
+    physics_step(m, P, &e, mode != B2E_MODE_HOLD);
     if (mode == B2E_MODE_ACTION) {
       /* _termination() inside apply_action (:239-242): counter only advances when not terminated */
       fk_t fk;
@@ -1069,7 +1069,7 @@ int b2o_reset(const b2e_model* m, const b2e_params* P, b2o_state* S, const uint8
 
 /* ------------------------------------------------------------------ known-answer helpers (tests only) */
 int b2o_fk(const b2e_model* m, const float* q, float* link_pos /*[n][3]*/, float* link_rot /*[n][9]*/) {
-  real qq[ND];
+  real qq[ND] = {0};
   for (int d = 0; d < m->n_dof; d++) qq[d] = q[d];
   fk_t fk;
   forward_kinematics(m, qq, &fk);
@@ -1081,7 +1081,7 @@ int b2o_fk(const b2e_model* m, const float* q, float* link_pos /*[n][3]*/, float
 }
 int b2o_forward_dynamics(const b2e_model* m, const b2e_params* P, const float* q, const float* qd, const float* tau,
                          float* qdd) {
-  real qq[ND], qv[ND], tt[ND], out[ND], g[3] = {P->gravity[0], P->gravity[1], P->gravity[2]};
+  real qq[ND] = {0}, qv[ND] = {0}, tt[ND] = {0}, out[ND], g[3] = {P->gravity[0], P->gravity[1], P->gravity[2]};
   for (int d = 0; d < m->n_dof; d++) { qq[d] = q[d]; qv[d] = qd[d]; tt[d] = tau[d]; }
   fk_t fk; aba_t w;
   forward_kinematics(m, qq, &fk);
@@ -1090,7 +1090,7 @@ int b2o_forward_dynamics(const b2e_model* m, const b2e_params* P, const float* q
   return 0;
 }
 int b2o_minv(const b2e_model* m, const float* q, float* Minv /*[nd][nd]*/) {
-  real qq[ND], z[ND], out[ND], g[3] = {0, 0, 0};
+  real qq[ND] = {0}, z[ND] = {0}, out[ND], g[3] = {0, 0, 0};
   int nd = m->n_dof;
   for (int d = 0; d < nd; d++) { qq[d] = q[d]; z[d] = 0; }
   fk_t fk; aba_t w;
@@ -1106,7 +1106,7 @@ int b2o_minv(const b2e_model* m, const float* q, float* Minv /*[nd][nd]*/) {
 }
 int b2o_ee_jacobian(const b2e_model* m, const float* q, float* J /*[6][nd] linear rows then angular rows*/,
                     float* pos, float* quat) {
-  real qq[ND], z[ND];
+  real qq[ND] = {0}, z[ND] = {0};
   int nd = m->n_dof;
   for (int d = 0; d < nd; d++) { qq[d] = q[d]; z[d] = 0; }
   fk_t fk;

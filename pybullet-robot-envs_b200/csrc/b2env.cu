@@ -599,7 +599,7 @@ step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, con
   float my_act = 0.f;
   if (mode == B2E_MODE_ACTION && lane < P.n_act) my_act = action[env * P.n_act + lane];
   const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
-  const float my_kp = (mode == B2E_MODE_ACTION && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
+  const float my_kp = (mode != B2E_MODE_HOLD && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
   __syncwarp();
@@ -1352,7 +1352,7 @@ int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* 
              void* stream) {
   if (!s) return fail(B2E_EINVAL, "b2e_step: null sim%s", "");
   if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step: action is required in ACTION mode%s", "");
-  if (n_substeps < 1) return fail(B2E_EINVAL, "b2e_step: n_substeps < 1%s", "");
+  if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step: n_substeps < 0%s", "");
   if (s->params.use_ik && mode == B2E_MODE_ACTION) return fail(B2E_EUNSUPPORTED, "b2e_step: IK control mode not built yet%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (s->B + WPB - 1) / WPB;

@@ -1,0 +1,72 @@
+"""The object that stands where the reference passes ``physicsClientId``.
+
+In the reference, ``p.connect(p.DIRECT)`` (panda_push_gym_env.py:62) returns an int naming an
+in-process Bullet server that every robot/world/task object then addresses.  Here the same
+role is played by a ``B2Client``: it owns one batched CUDA simulation (``B2Sim``) of
+``num_envs`` environments on one GPU and hands it to the robot, world and task objects.
+"""
+import numpy as np
+
+from . import binding
+from .model import TASK_REACH, panda_task_setup
+
+
+class B2Client:
+    def __init__(self, num_envs=1, device=0):
+        self.num_envs = int(num_envs)
+        self.device = int(device)
+        self.sim = None
+        self.model = None
+        self.params = None
+        self._obs_cache_valid = False
+        self._last = None
+
+    def configure(self, model, params):
+        """(Re)create the simulation for a model + task constants."""
+        if self.sim is not None:
+            self.sim.close()
+        self.model, self.params = model, params
+        self.sim = binding.B2Sim(model, params, self.num_envs, self.device)
+        self._obs_cache_valid = False
+        return self.sim
+
+    def ensure(self):
+        if self.sim is None:
+            m, p = panda_task_setup(TASK_REACH)
+            self.configure(m, p)
+        return self.sim
+
+    # ---- p.stepSimulation ---------------------------------------------------------------
+    def step_simulation(self, n=1, mode=binding.MODE_HOLD):
+        self.ensure().step_host(None, n, mode, want_obs=False)
+        self._obs_cache_valid = False
+
+    # ---- observation / reward / done of the current state (no physics) --------------------
+    def observe(self):
+        """Returns (scaled_obs, reward, done, raw_obs) for the current state."""
+        if not self._obs_cache_valid:
+            sim = self.ensure()
+            obs, rew, done = sim.step_host(None, 0, binding.MODE_HOLD, want_obs=True)
+            self._last = (obs, rew, done, sim.get("raw_obs"))
+            self._obs_cache_valid = True
+        return self._last
+
+    def invalidate(self):
+        self._obs_cache_valid = False
+
+    def get(self, name):
+        return self.ensure().get(name)
+
+    def set(self, name, value):
+        self.ensure().set(name, value)
+        self._obs_cache_valid = False
+
+    def close(self):
+        if self.sim is not None:
+            self.sim.close()
+            self.sim = None
+
+
+def squeeze1(x, num_envs):
+    """Single-env compatibility: drop the batch axis so shapes equal the reference's."""
+    return x[0] if num_envs == 1 else x
