@@ -37,6 +37,7 @@
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
+#define TLMAX 16          // links whose transforms are staged in shared memory
 
 #define KEY_CUBE_TABLE 0
 #define KEY_CUBE_PLANE 8
@@ -208,7 +209,7 @@ struct Contact {   // 16 words
 struct WarpSmem {
   float A[RMAX * RMAX];        // Delassus matrix, A[i*RMAX + r]
   float W[RMAX * WSTRIDE];     // W[r][k] = (M^-1 J_r^T)_k, k<9 arm dofs, 9..14 cube (lin, ang)
-  float T[NLMAX][12];          // link world transforms: R (9) + p (3)
+  float T[TLMAX][12];          // link world transforms: R (9) + p (3)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
   float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
@@ -303,43 +304,43 @@ __device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, int la
 
 // ------------------------------------------------------------------------------------------
 // PGS sweep helpers.  NS = number of 32-row sets in use (rows r = lane + 32*s).
+// Per-row registers: u = rhs - (A lambda)_r is the running velocity error, base = lambda*(1 - cfm*invd),
+// so the candidate impulse is fma(u, invd, base) and the dependent chain per row update is
+// FFMA -> FMNMX -> FMNMX -> FADD -> SHFL -> FFMA.
 template <int NS>
 struct RowRegs {
-  float lam[NS], w[NS], rhs[NS], cfm[NS], invd[NS], diag[NS], lo[NS], hi[NS], mu[NS], lastdl[NS];
+  float lam[NS], u[NS], base[NS], g[NS], invd[NS], diag[NS], lo[NS], hi[NS], mu[NS], lastdl[NS];
   int type[NS], isl[NS], nidx[NS];
 };
 
 template <int NS, int SI>
-__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* __restrict__ A, int i, int lane) {
+__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* __restrict__ Acol, int i, int lane) {
   const int li = i & 31;
-  float d = (r.rhs[SI] - r.w[SI] - r.cfm[SI] * r.lam[SI]) * r.invd[SI];
-  float nl = fminf(fmaxf(r.lam[SI] + d, r.lo[SI]), r.hi[SI]);
-  float dl = nl - r.lam[SI];
+  float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
+  nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
+  const float dl = nl - r.lam[SI];
   const float dli = shf(dl, li);
-  if (lane == li) { r.lam[SI] = nl; r.lastdl[SI] = dl; }
-#pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
-    r.w[s] = fmaf(A[i * RMAX + col], dli, r.w[s]);
+  if (lane == li) { r.lam[SI] = nl; r.base[SI] = nl * r.g[SI]; r.lastdl[SI] = dl; }
+  r.u[0] = fmaf(-Acol[i * RMAX], dli, r.u[0]);
+  if (NS > 1) {
+    const int off1 = (lane + 32 < RMAX) ? 32 : RMAX - 1 - lane;  // clamp: rows >= RMAX do not exist
+    r.u[NS - 1] = fmaf(-Acol[i * RMAX + off1], dli, r.u[NS - 1]);
   }
 }
 
-// process rows [i0, i1) in order, skipping rows whose island has converged
+// visit the rows whose bits are set, in ascending order
 template <int NS>
-__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ A, int i0, int i1, int lane,
-                                      const unsigned* islbits, bool coupled, const bool* done_isl) {
-  int e0 = i1 < 32 ? i1 : 32;
-  for (int i = i0; i < e0; i++) {
-    int isl = coupled ? 0 : ((islbits[0] >> i) & 1);
-    if (done_isl[isl]) continue;
-    row_step<NS, 0>(r, A, i, lane);
+__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ Acol, unsigned m0, unsigned m1, int lane) {
+  while (m0) {
+    const int i = __ffs(m0) - 1;
+    m0 &= m0 - 1;
+    row_step<NS, 0>(r, Acol, i, lane);
   }
   if (NS > 1) {
-    int b0 = i0 > 32 ? i0 : 32;
-    for (int i = b0; i < i1; i++) {
-      int isl = coupled ? 0 : ((islbits[NS - 1] >> (i - 32)) & 1);
-      if (done_isl[isl]) continue;
-      row_step<NS, NS - 1>(r, A, i, lane);
+    while (m1) {
+      const int i = __ffs(m1) - 1;
+      m1 &= m1 - 1;
+      row_step<NS, NS - 1>(r, Acol, i + 32, lane);
     }
   }
 }
@@ -347,27 +348,41 @@ __device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ 
 template <int NS>
 __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict__ A, int R, int fric_start, int lane,
                                          bool coupled, bool has_cube_rows, int max_iters, float tol) {
-  unsigned islbits[NS];
+  // row masks per set: island (0 arm, 1 cube) x phase (non-friction, friction)
+  unsigned arm_nf[2] = {0, 0}, arm_f[2] = {0, 0}, cube_nf[2] = {0, 0}, cube_f[2] = {0, 0};
 #pragma unroll
-  for (int s = 0; s < NS; s++) islbits[s] = __ballot_sync(FULL, r.isl[s] == 1);
-  bool done_isl[2] = {false, !has_cube_rows};
+  for (int s = 0; s < NS; s++) {
+    const int row = lane + 32 * s;
+    const bool valid = row < R, fr = row >= fric_start;
+    const bool cube = !coupled && r.isl[s] == 1;
+    arm_nf[s] = __ballot_sync(FULL, valid && !cube && !fr);
+    arm_f[s] = __ballot_sync(FULL, valid && !cube && fr);
+    cube_nf[s] = __ballot_sync(FULL, valid && cube && !fr);
+    cube_f[s] = __ballot_sync(FULL, valid && cube && fr);
+  }
+  const float* Acol = A + lane;
+  bool done0 = false, done1 = !has_cube_rows || coupled;
   int it = 0;
   for (it = 0; it < max_iters; it++) {
 #pragma unroll
     for (int s = 0; s < NS; s++) r.lastdl[s] = 0.f;
-    sweep<NS>(r, A, 0, fric_start, lane, islbits, coupled, done_isl);
-    // friction bounds from the current normal impulses (mu * lambda_n)
+    const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
+    sweep<NS>(r, Acol, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0), lane);
+    const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0);
+    if (f0 | f1) {
+      // friction bounds from the current normal impulses (mu * lambda_n)
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
-      const int ni = r.nidx[s];
-      float v0 = shf(r.lam[0], ni & 31);
-      float v1 = NS > 1 ? shf(r.lam[NS - 1], ni & 31) : 0.f;
-      if (r.type[s] == ROW_FRICTION) {
-        float lim = r.mu[s] * ((ni >> 5) ? v1 : v0);
-        r.lo[s] = -lim; r.hi[s] = lim;
+      for (int s = 0; s < NS; s++) {
+        const int ni = r.nidx[s];
+        float v0 = shf(r.lam[0], ni & 31);
+        float v1 = NS > 1 ? shf(r.lam[NS - 1], ni & 31) : 0.f;
+        if (r.type[s] == ROW_FRICTION) {
+          float lim = r.mu[s] * ((ni >> 5) ? v1 : v0);
+          r.lo[s] = -lim; r.hi[s] = lim;
+        }
       }
+      sweep<NS>(r, Acol, f0, f1, lane);
     }
-    sweep<NS>(r, A, fric_start, R, lane, islbits, coupled, done_isl);
     float ra = 0.f, rc = 0.f;
 #pragma unroll
     for (int s = 0; s < NS; s++) {
@@ -376,14 +391,10 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
       if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
     }
     ra = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ra)));
-    rc = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rc)));
-    if (coupled) {
-      if (ra <= tol) { it++; break; }
-    } else {
-      if (!done_isl[0] && ra <= tol) done_isl[0] = true;
-      if (!done_isl[1] && rc <= tol) done_isl[1] = true;
-      if (done_isl[0] && done_isl[1]) { it++; break; }
-    }
+    if (!done1) rc = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rc)));
+    if (!done0 && ra <= tol) done0 = true;
+    if (!done1 && rc <= tol) done1 = true;
+    if (done0 && done1) { it++; break; }
   }
   return it;
 }
@@ -391,9 +402,10 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
 // Build the row(s) owned by this lane, the W table, the Delassus matrix, warm start, solve, and
 // leave the impulses in sm.lam[].  Returns the PGS iteration count.
 template <int NS>
-__device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const b2e_params& P,
-                                               int lane, int nd, int nlim, int nc, float my_q, float my_target,
-                                               float my_kp, const float* cpos, bool kp_active) {
+__device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const b2e_params& P,
+                                            int lane, int nd, int nlim, int nc, float my_q, float my_target,
+                                            float my_kp, float cpx, float cpy, float cpz) {
+  const float cpos[3] = {cpx, cpy, cpz};
   const int nnc = nd + nlim;         // non-contact rows
   const int fric_start = nnc + nc;
   const int R = nnc + 3 * nc;
@@ -498,11 +510,12 @@ __device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __r
       sm.W[r * WSTRIDE + 15] = 0.f;
     }
     rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
-    rr.cfm[s] = cfm; rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
+    rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
     rr.diag[s] = valid ? diag + cfm : 1.f;
     rr.invd[s] = valid ? 1.0f / (diag + cfm) : 0.f;
-    rr.rhs[s] = valid ? desired - jv : 0.f;
-    rr.lam[s] = 0.f; rr.w[s] = 0.f; rr.lastdl[s] = 0.f;
+    rr.g[s] = 1.0f - cfm * rr.invd[s];
+    rr.u[s] = valid ? desired - jv : 0.f;
+    rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.lastdl[s] = 0.f;
     __syncwarp();
     // Delassus columns: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
     for (int c = 0; c < R; c++) {
@@ -537,6 +550,7 @@ __device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __r
       for (int sl = 0; sl < B2E_CACHE_SLOTS; sl++)
         if (sm.ckey[sl] == key) { l0 = sm.clam[sl][j] * P.warmstart; break; }
       rr.lam[s] = l0;
+      rr.base[s] = l0 * rr.g[s];
     }
   }
   for (int c = nnc; c < R; c++) {
@@ -545,7 +559,7 @@ __device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __r
 #pragma unroll
       for (int s = 0; s < NS; s++) {
         const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
-        rr.w[s] = fmaf(sm.A[c * RMAX + col], l0, rr.w[s]);
+        rr.u[s] = fmaf(-sm.A[c * RMAX + col], l0, rr.u[s]);
       }
     }
   }
@@ -556,14 +570,13 @@ __device__ __forceinline__ int build_and_solve(WarpSmem& sm, const DevModel* __r
     if (r < R) sm.lam[r] = rr.lam[s];
   }
   __syncwarp();
-  (void)kp_active;
   return iters;
 }
 
 // ------------------------------------------------------------------------------------------
 // the fused step kernel
-__global__ void __launch_bounds__(32 * WPB)
-step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, const float* __restrict__ action,
+__global__ void __launch_bounds__(32 * WPB, 7)
+step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
             int mode, int record_contacts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -604,21 +617,44 @@ step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, con
   bool stop = false;
   __syncwarp();
 
-  for (int sub = 0; sub < nsub && !stop; sub++) {
+  const int li = lane < nl ? lane : 0;
+  const int my_dof = __ldg(&M->dof[li]);
+  const bool link_has_dof = lane < nl && my_dof >= 0;
+  float Rm[9], pw[3];
+  for (int sub = 0;; sub++) {
+    // ---- forward kinematics (lane = link) of the current q: start-of-step kinematics of this
+    //      sub-step, and at the same time the post-step kinematics of the previous one ----
+    {
+      const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
+      fk_lanes(M, lane, link_has_dof ? qi : 0.f, Rm, pw);
+    }
+    // ---- termination inside apply_action (panda_push_gym_env.py:239-242), for the previous sub-step ----
+    if (sub > 0 && mode == B2E_MODE_ACTION) {
+      float d;
+      if (P.task == B2E_TASK_PUSH) {
+        float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+        d = sqrtf(dot3(dd, dd));
+      } else {
+        const int ee = M->ee_link;
+        float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
+        m3vec(Rm, cm, o);
+        float e3[3] = {shf(pw[0] + o[0], ee), shf(pw[1] + o[1], ee), shf(pw[2] + o[2], ee)};
+        float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
+        d = sqrtf(dot3(dd, dd));
+      }
+      if (d <= P.dist_min) { terminated = 1; stop = true; }
+      else if (terminated || counter > P.max_steps) stop = true;
+      else counter++;
+    }
+    if (sub >= nsub || stop) break;
+
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
     if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl) {
       my_act *= P.act_scale;
       my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
     }
-
-    // ---- forward kinematics (lane = link) ----
-    const int li = lane < nl ? lane : 0;
-    const int my_dof = __ldg(&M->dof[li]);
-    const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
     const float qdi_raw = shf(my_qd, my_dof < 0 ? 0 : my_dof);
-    const float qdi = (lane < nl && my_dof >= 0) ? qdi_raw : 0.f;
-    float Rm[9], pw[3];
-    fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, Rm, pw);
+    const float qdi = link_has_dof ? qdi_raw : 0.f;
     if (lane < nl) {
 #pragma unroll
       for (int k = 0; k < 9; k++) sm.T[lane][k] = Rm[k];
@@ -948,8 +984,8 @@ step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, con
 
     // ---- rows + PGS ----
     R = nd + nlim + 3 * nc;
-    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos, true);
-    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos, true);
+    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2]);
+    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2]);
 
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
@@ -1012,29 +1048,6 @@ step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, con
       if (__any_sync(FULL, bad)) flags |= B2E_ST_NAN;
     }
 
-    // ---- termination inside apply_action (panda_push_gym_env.py:239-242) ----
-    if (mode == B2E_MODE_ACTION) {
-      float d;
-      if (P.task == B2E_TASK_PUSH) {
-        float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
-        d = sqrtf(dot3(dd, dd));
-      } else {
-        // EE position needs the post-step kinematics
-        const float qi2 = shf(my_q, my_dof < 0 ? 0 : my_dof);
-        float R2[9], p2[3];
-        fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi2 : 0.f, R2, p2);
-        const int ee = M->ee_link;
-        float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
-        m3vec(R2, cm, o);
-        float e3[3] = {shf(p2[0] + o[0], ee), shf(p2[1] + o[1], ee), shf(p2[2] + o[2], ee)};
-        float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
-        d = sqrtf(dot3(dd, dd));
-      }
-      bool term = false;
-      if (d <= P.dist_min) { terminated = 1; term = true; }
-      else if (terminated || counter > P.max_steps) term = true;
-      if (term) stop = true; else counter++;
-    }
   }
 
   // ---- store state ----
@@ -1058,11 +1071,8 @@ step_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st, con
 
   // ---- observation / termination / reward (panda_push_gym_env.py:249-253) ----
   if (mode == B2E_MODE_ACTION || obs_out) {
-    const int li = lane < nl ? lane : 0;
-    const int my_dof = __ldg(&M->dof[li]);
-    const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
-    float R2[9], p2[3];
-    fk_lanes(M, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, R2, p2);
+    const float* R2 = Rm;   // kinematics of the final q (computed at the top of the last loop pass)
+    const float* p2 = pw;
     const int ee = M->ee_link;
     // EE COM pose
     float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
@@ -1219,7 +1229,7 @@ static int field_width(const b2e_sim* s, int f) {
 
 static int build_dev_model(const b2e_model* m, DevModel* d) {
   memset(d, 0, sizeof(*d));
-  if (m->n_links > NLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 32 links%s", "");
+  if (m->n_links > TLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 16 links%s", "");
   if (m->n_dof > NDMAX) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 9 dofs%s", "");
   if (m->n_spheres > B2E_MAX_SPHERES || m->n_spheres < 0) return fail(B2E_EINVAL, "bad n_spheres%s", "");
   d->n_links = m->n_links; d->n_dof = m->n_dof; d->ee_link = m->ee_link; d->n_spheres = m->n_spheres;
