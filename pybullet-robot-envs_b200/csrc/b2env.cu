@@ -160,7 +160,7 @@ __device__ __forceinline__ void quat_mul(const float* a, const float* b, float* 
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
 // p.getEulerFromQuaternion restated (panda_env.py:160, world_env.py:119) [EXT-recalled]
-__device__ __forceinline__ void quat_to_euler(const float* q, float* e) {
+__device__ __noinline__ void quat_to_euler(const float* q, float* e) {
   float x = q[0], y = q[1], z = q[2], w = q[3];
   float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
   float sarg = -2 * (x * z - w * y);
@@ -320,7 +320,7 @@ __device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* __restrict
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
   const float dl = nl - r.lam[SI];
   const float dli = shf(dl, li);
-  if (lane == li) { r.lam[SI] = nl; r.base[SI] = nl * r.g[SI]; r.lastdl[SI] = dl; }
+  if (lane == li) r.lam[SI] = nl;   // base/lastdl are refreshed once per iteration (each row moves once per sweep)
   r.u[0] = fmaf(-Acol[i * RMAX], dli, r.u[0]);
   if (NS > 1) {
     const int off1 = (lane + 32 < RMAX) ? 32 : RMAX - 1 - lane;  // clamp: rows >= RMAX do not exist
@@ -347,7 +347,8 @@ __device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ 
 
 template <int NS>
 __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict__ A, int R, int fric_start, int lane,
-                                         bool coupled, bool has_cube_rows, int max_iters, float tol) {
+                                         bool coupled, bool has_cube_rows, int max_iters, float tol,
+                                         bool arm_done_init) {
   // row masks per set: island (0 arm, 1 cube) x phase (non-friction, friction)
   unsigned arm_nf[2] = {0, 0}, arm_f[2] = {0, 0}, cube_nf[2] = {0, 0}, cube_f[2] = {0, 0};
 #pragma unroll
@@ -361,11 +362,12 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
     cube_f[s] = __ballot_sync(FULL, valid && cube && fr);
   }
   const float* Acol = A + lane;
-  bool done0 = false, done1 = !has_cube_rows || coupled;
+  bool done0 = arm_done_init, done1 = !has_cube_rows || coupled;
+  if (done0 && done1) return 0;
   int it = 0;
   for (it = 0; it < max_iters; it++) {
 #pragma unroll
-    for (int s = 0; s < NS; s++) r.lastdl[s] = 0.f;
+    for (int s = 0; s < NS; s++) { r.lastdl[s] = r.lam[s]; r.base[s] = r.lam[s] * r.g[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
     sweep<NS>(r, Acol, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0), lane);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0);
@@ -386,7 +388,7 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
     float ra = 0.f, rc = 0.f;
 #pragma unroll
     for (int s = 0; s < NS; s++) {
-      float rv = r.lastdl[s] * r.diag[s];
+      float rv = (r.lam[s] - r.lastdl[s]) * r.diag[s];   // impulse change of this sweep
       rv = rv * rv;
       if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
     }
@@ -396,6 +398,66 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
     if (!done1 && rc <= tol) done1 = true;
     if (done0 && done1) { it++; break; }
   }
+  return it;
+}
+
+
+// Arm island made only of the n_dof position-motor rows (no limit row, no arm contact): bounds are
+// +-max_force*dt and in practice never active, so one Gauss-Seidel sweep over those rows IS the affine
+// map lambda' = G lambda + c with G = -(D+L)^-1 U, c = (D+L)^-1 b (A = L + D + U the motor block of
+// the Delassus matrix).  Same iterates in exact arithmetic, same per-sweep residual test; the nine
+// serial, shuffle-dependent row updates of a sweep become one 9-wide mat-vec.  If a bound would
+// activate the caller falls back to the serial sweep.  Returns the sweep count, or -1 on fallback.
+__device__ __forceinline__ int arm_affine_solve(const float* __restrict__ A, int lane, int nd, float b, float invd,
+                                                float diag, float lo, float hi, int max_iters, float tol,
+                                                float& lam_out) {
+  const bool row = lane < nd;
+  float Ar[NDMAX];
+#pragma unroll
+  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? A[k * RMAX + lane] : ((k == lane) ? 1.f : 0.f);
+  const float idg = row ? invd : 1.f;
+  // T = (D+L)^-1 by forward substitution, lane = row
+  float T[NDMAX];
+#pragma unroll
+  for (int k = 0; k < NDMAX; k++) T[k] = (k == lane) ? 1.f : 0.f;
+#pragma unroll
+  for (int j = 0; j < NDMAX; j++) {
+#pragma unroll
+    for (int k = 0; k <= j; k++) {
+      const float tj = shf(T[k] * idg, j);       // final row j of T
+      if (lane == j) T[k] = tj;
+      else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
+    }
+  }
+  // G = -T U, c = T b
+  float G[NDMAX];
+#pragma unroll
+  for (int k = 0; k < NDMAX; k++) G[k] = 0.f;
+  float c = 0.f;
+  const float bb = row ? b : 0.f;
+#pragma unroll
+  for (int j = 0; j < NDMAX; j++) {
+    c = fmaf(T[j], shf(bb, j), c);
+#pragma unroll
+    for (int k = j + 1; k < NDMAX; k++) G[k] = fmaf(-T[j], shf(Ar[k], j), G[k]);
+  }
+  float lam = 0.f;
+  int it;
+  for (it = 0; it < max_iters; it++) {
+    float a0 = c, a1 = 0.f;
+#pragma unroll
+    for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], shf(lam, k), a0);
+#pragma unroll
+    for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], shf(lam, k), a1);
+    const float nl = a0 + a1;
+    if (__any_sync(FULL, row && !(nl >= lo && nl <= hi))) return -1;
+    float rv = row ? (nl - lam) * diag : 0.f;
+    rv = rv * rv;
+    lam = nl;
+    rv = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rv)));
+    if (rv <= tol) { it++; break; }
+  }
+  lam_out = lam;
   return it;
 }
 
@@ -412,7 +474,7 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
   RowRegs<NS> rr;
-  bool coupled = false, has_cube = false;
+  bool coupled = false, has_cube = false, arm_contact = false;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
     const int r = lane + 32 * s;
@@ -490,14 +552,23 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
         }
       }
     }
-    // W = M^-1 J^T
+    // W = M^-1 J^T.  Motor rows take a column of M^-1 directly; the generic 9x9 product is only
+    // needed when some row of this set has another arm part (limit row or robot contact).
     float Wv[15];
+    const bool arm_general = valid && (type == ROW_LIMIT || (type != ROW_MOTOR && isl == 0));
+    if (__any_sync(FULL, arm_general)) {
 #pragma unroll
-    for (int d = 0; d < NDMAX; d++) {
-      float acc = 0.f;
+      for (int d = 0; d < NDMAX; d++) {
+        float acc = 0.f;
 #pragma unroll
-      for (int e = 0; e < NDMAX; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
-      Wv[d] = acc;
+        for (int e = 0; e < NDMAX; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
+        Wv[d] = acc;
+      }
+    } else {
+      const int col = (valid && type == ROW_MOTOR) ? r : 0;
+      const float sc = (valid && type == ROW_MOTOR) ? 1.f : 0.f;
+#pragma unroll
+      for (int d = 0; d < NDMAX; d++) Wv[d] = sc * sm.Minv[d][col];
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { Wv[9 + k] = J[9 + k] * cinv_m; Wv[12 + k] = J[12 + k] * cinv_I; }
@@ -518,14 +589,26 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
     rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.lastdl[s] = 0.f;
     __syncwarp();
     // Delassus columns: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
-    for (int c = 0; c < R; c++) {
-      float acc = 0.f;
+    // motor column c: J_c = e_c, so A[c][r] = J_c . W_r = W_r[c] (no dot product)
 #pragma unroll
-      for (int k = 0; k < 15; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+    for (int c = 0; c < NDMAX; c++)
+      if (valid && c < nd) sm.A[c * RMAX + r] = Wv[c];
+    for (int c = nd; c < R; c++) {
+      float acc = 0.f;
+      const bool cube_only = (c >= nnc) && sm.con[c < fric_start ? c - nnc : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
+      if (!cube_only) {
+#pragma unroll
+        for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+      }
+      if (c >= nnc) {
+#pragma unroll
+        for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+      }
       if (valid) sm.A[c * RMAX + r] = acc;
     }
     coupled = coupled || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0 && (J[9] != 0.f || J[10] != 0.f || J[11] != 0.f));
     has_cube = has_cube || __any_sync(FULL, valid && isl == 1);
+    arm_contact = arm_contact || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0);
   }
   __syncwarp();
   // NOTE: with NS == 2 the loop above computed A[c][r] for set-0 rows before the set-1 W rows were
@@ -563,7 +646,16 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
       }
     }
   }
-  const int iters = pgs_solve<NS>(rr, sm.A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol);
+  int iters_arm = -1;
+  if (!coupled && !arm_contact && nlim == 0) {
+    float lam_arm = 0.f;
+    iters_arm = arm_affine_solve(sm.A, lane, nd, rr.u[0], rr.invd[0], rr.diag[0], rr.lo[0], rr.hi[0], P.solver_iters,
+                                 P.residual_tol, lam_arm);
+    if (iters_arm >= 0 && lane < nd) rr.lam[0] = lam_arm;
+  }
+  int iters = pgs_solve<NS>(rr, sm.A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol,
+                            iters_arm >= 0);
+  if (iters_arm > iters) iters = iters_arm;
 #pragma unroll
   for (int s = 0; s < NS; s++) {
     const int r = lane + 32 * s;
