@@ -32,9 +32,23 @@
 #include "../../include/b2env.h"
 
 #define FULL 0xffffffffu
-#define WPB 2             // warps (= envs) per block
+#ifndef PHASE_SYNC
+#define PHASE_SYNC 1       // block barriers between stages keep the warps of a block on the same code
+#endif
+#if PHASE_SYNC
+#define PHASE_BARRIER() __syncthreads()
+#else
+#define PHASE_BARRIER() __syncwarp()
+#endif
+#ifndef WPB
+#define WPB 8             // warps (= envs) per block
+#endif
+#ifndef MINB
+#define MINB 3            // resident blocks per SM the register allocation targets (24 warps, 80 regs)
+#endif
 #define RMAX 48           // max constraint rows per env: 9 motors + 3 limits + 3*12 contact rows
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
+#define SCRATCH_PER_ENV (RMAX * RMAX + RMAX * WSTRIDE)
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
 #define TLMAX 16          // links whose transforms are staged in shared memory
@@ -72,6 +86,7 @@ struct DevState {
   int B;
   float* q; float* qd; float* obj_pose; float* obj_vel; float* target; float* mtarget;
   int* counters; int* cache_key; float* cache_lam; float* hand_pose; int* status; float* raw_obs; float* contacts;
+  float* scratch;  // [B][RMAX*RMAX + RMAX*WSTRIDE]: Delassus matrix + W for envs with more than 32 rows
 };
 
 struct b2e_sim {
@@ -207,8 +222,8 @@ struct Contact {   // 16 words
   float dist, mu, erp;
 };
 struct WarpSmem {
-  float A[RMAX * RMAX];        // Delassus matrix, A[i*RMAX + r]
-  float W[RMAX * WSTRIDE];     // W[r][k] = (M^-1 J_r^T)_k, k<9 arm dofs, 9..14 cube (lin, ang)
+  float A[32 * 32];            // Delassus matrix A[i*32 + r] when R <= 32 (else: global scratch, stride RMAX)
+  float W[32 * WSTRIDE];       // W[r][k] = (M^-1 J_r^T)_k, k<9 arm dofs, 9..14 cube (lin, ang)
   float T[TLMAX][12];          // link world transforms: R (9) + p (3)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
@@ -314,23 +329,24 @@ struct RowRegs {
 };
 
 template <int NS, int SI>
-__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* __restrict__ Acol, int i, int lane) {
+__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* Acol, int i, int lane) {
   const int li = i & 31;
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
   const float dl = nl - r.lam[SI];
   const float dli = shf(dl, li);
   if (lane == li) r.lam[SI] = nl;   // base/lastdl are refreshed once per iteration (each row moves once per sweep)
-  r.u[0] = fmaf(-Acol[i * RMAX], dli, r.u[0]);
+  constexpr int AS = (NS == 1) ? 32 : RMAX;
+  r.u[0] = fmaf(-Acol[i * AS], dli, r.u[0]);
   if (NS > 1) {
     const int off1 = (lane + 32 < RMAX) ? 32 : RMAX - 1 - lane;  // clamp: rows >= RMAX do not exist
-    r.u[NS - 1] = fmaf(-Acol[i * RMAX + off1], dli, r.u[NS - 1]);
+    r.u[NS - 1] = fmaf(-Acol[i * AS + off1], dli, r.u[NS - 1]);
   }
 }
 
 // visit the rows whose bits are set, in ascending order
 template <int NS>
-__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ Acol, unsigned m0, unsigned m1, int lane) {
+__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* Acol, unsigned m0, unsigned m1, int lane) {
   while (m0) {
     const int i = __ffs(m0) - 1;
     m0 &= m0 - 1;
@@ -346,7 +362,7 @@ __device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* __restrict__ 
 }
 
 template <int NS>
-__device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict__ A, int R, int fric_start, int lane,
+__device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* A, int R, int fric_start, int lane,
                                          bool coupled, bool has_cube_rows, int max_iters, float tol,
                                          bool arm_done_init) {
   // row masks per set: island (0 arm, 1 cube) x phase (non-friction, friction)
@@ -408,13 +424,13 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* __restrict
 // the Delassus matrix).  Same iterates in exact arithmetic, same per-sweep residual test; the nine
 // serial, shuffle-dependent row updates of a sweep become one 9-wide mat-vec.  If a bound would
 // activate the caller falls back to the serial sweep.  Returns the sweep count, or -1 on fallback.
-__device__ __forceinline__ int arm_affine_solve(const float* __restrict__ A, int lane, int nd, float b, float invd,
+__device__ __forceinline__ int arm_affine_solve(const float* A, int AS, int lane, int nd, float b, float invd,
                                                 float diag, float lo, float hi, int max_iters, float tol,
                                                 float& lam_out) {
   const bool row = lane < nd;
   float Ar[NDMAX];
 #pragma unroll
-  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? A[k * RMAX + lane] : ((k == lane) ? 1.f : 0.f);
+  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? A[k * AS + lane] : ((k == lane) ? 1.f : 0.f);
   const float idg = row ? invd : 1.f;
   // T = (D+L)^-1 by forward substitution, lane = row
   float T[NDMAX];
@@ -466,8 +482,11 @@ __device__ __forceinline__ int arm_affine_solve(const float* __restrict__ A, int
 template <int NS>
 __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const b2e_params& P,
                                             int lane, int nd, int nlim, int nc, float my_q, float my_target,
-                                            float my_kp, float cpx, float cpy, float cpz) {
+                                            float my_kp, float cpx, float cpy, float cpz, float* scratch) {
   const float cpos[3] = {cpx, cpy, cpz};
+  constexpr int AS = (NS == 1) ? 32 : RMAX;
+  float* A = (NS == 1) ? sm.A : scratch;
+  float* W = (NS == 1) ? sm.W : scratch + RMAX * RMAX;
   const int nnc = nd + nlim;         // non-contact rows
   const int fric_start = nnc + nc;
   const int R = nnc + 3 * nc;
@@ -577,8 +596,8 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
     for (int k = 0; k < 15; k++) { diag = fmaf(J[k], Wv[k], diag); jv = fmaf(J[k], sm.vstar[k], jv); }
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 15; k++) sm.W[r * WSTRIDE + k] = Wv[k];
-      sm.W[r * WSTRIDE + 15] = 0.f;
+      for (int k = 0; k < 15; k++) W[r * WSTRIDE + k] = Wv[k];
+      W[r * WSTRIDE + 15] = 0.f;
     }
     rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
     rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
@@ -592,19 +611,19 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
     // motor column c: J_c = e_c, so A[c][r] = J_c . W_r = W_r[c] (no dot product)
 #pragma unroll
     for (int c = 0; c < NDMAX; c++)
-      if (valid && c < nd) sm.A[c * RMAX + r] = Wv[c];
+      if (valid && c < nd) A[c * AS + r] = Wv[c];
     for (int c = nd; c < R; c++) {
       float acc = 0.f;
       const bool cube_only = (c >= nnc) && sm.con[c < fric_start ? c - nnc : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
       if (!cube_only) {
 #pragma unroll
-        for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+        for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
       }
       if (c >= nnc) {
 #pragma unroll
-        for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], sm.W[c * WSTRIDE + k], acc);
+        for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
       }
-      if (valid) sm.A[c * RMAX + r] = acc;
+      if (valid) A[c * AS + r] = acc;
     }
     coupled = coupled || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0 && (J[9] != 0.f || J[10] != 0.f || J[11] != 0.f));
     has_cube = has_cube || __any_sync(FULL, valid && isl == 1);
@@ -616,7 +635,7 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
   if (NS > 1) {
     // recompute J for set 0 is expensive; instead use symmetry: A[c][r] = A[r][c] for c >= 32 > r.
     for (int c = 32; c < R; c++) {
-      if (lane + 0 < 32 && lane < R) sm.A[c * RMAX + lane] = sm.A[lane * RMAX + c];
+      if (lane + 0 < 32 && lane < R) A[c * AS + lane] = A[lane * AS + c];
     }
     __syncwarp();
   }
@@ -642,18 +661,18 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
 #pragma unroll
       for (int s = 0; s < NS; s++) {
         const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
-        rr.u[s] = fmaf(-sm.A[c * RMAX + col], l0, rr.u[s]);
+        rr.u[s] = fmaf(-A[c * AS + col], l0, rr.u[s]);
       }
     }
   }
   int iters_arm = -1;
   if (!coupled && !arm_contact && nlim == 0) {
     float lam_arm = 0.f;
-    iters_arm = arm_affine_solve(sm.A, lane, nd, rr.u[0], rr.invd[0], rr.diag[0], rr.lo[0], rr.hi[0], P.solver_iters,
+    iters_arm = arm_affine_solve(A, AS, lane, nd, rr.u[0], rr.invd[0], rr.diag[0], rr.lo[0], rr.hi[0], P.solver_iters,
                                  P.residual_tol, lam_arm);
     if (iters_arm >= 0 && lane < nd) rr.lam[0] = lam_arm;
   }
-  int iters = pgs_solve<NS>(rr, sm.A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol,
+  int iters = pgs_solve<NS>(rr, A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol,
                             iters_arm >= 0);
   if (iters_arm > iters) iters = iters_arm;
 #pragma unroll
@@ -667,14 +686,15 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
 
 // ------------------------------------------------------------------------------------------
 // the fused step kernel
-__global__ void __launch_bounds__(32 * WPB, 7)
+__global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
             int mode, int record_contacts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * WPB + warp;
-  if (env >= st.B) return;
+  const int env_raw = blockIdx.x * WPB + warp;
+  const bool live_env = env_raw < st.B;      // padding warps of the last block shadow the last env, stores masked
+  const int env = live_env ? env_raw : st.B - 1;
   WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
   const int nd = M->n_dof, nl = M->n_links;
   const float dt = P.dt;
@@ -721,7 +741,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       fk_lanes(M, lane, link_has_dof ? qi : 0.f, Rm, pw);
     }
     // ---- termination inside apply_action (panda_push_gym_env.py:239-242), for the previous sub-step ----
-    if (sub > 0 && mode == B2E_MODE_ACTION) {
+    if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
       float d;
       if (P.task == B2E_TASK_PUSH) {
         float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
@@ -738,10 +758,12 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       else if (terminated || counter > P.max_steps) stop = true;
       else counter++;
     }
-    if (sub >= nsub || stop) break;
+    if (sub >= nsub) break;
+    const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
+    PHASE_BARRIER();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
-    if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl) {
+    if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl && !ghost) {
       my_act *= P.act_scale;
       my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
     }
@@ -933,6 +955,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     }
     if (lane < NDMAX && !is_dof) sm.vstar[lane] = 0.f;
 
+    PHASE_BARRIER();
     // ---- collision detection (pre-step poses) ----
     float Rc[9];
     quat_to_mat(cquat, Rc);
@@ -1074,26 +1097,35 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     }
     __syncwarp();
 
+    PHASE_BARRIER();
     // ---- rows + PGS ----
     R = nd + nlim + 3 * nc;
-    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2]);
-    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2]);
+    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], nullptr);
+    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2],
+                                    st.scratch + (size_t)env * SCRATCH_PER_ENV);
 
+    PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
-    for (int r = 0; r < R; r++) dvk = fmaf(sm.W[r * WSTRIDE + (lane & 15)], sm.lam[r], dvk);
+    {
+      const float* Wp = (R <= 32) ? sm.W : st.scratch + (size_t)env * SCRATCH_PER_ENV + RMAX * RMAX;
+      for (int r = 0; r < R; r++) dvk = fmaf(Wp[r * WSTRIDE + (lane & 15)], sm.lam[r], dvk);
+    }
     // ---- integrate (semi-implicit Euler) ----
-    if (is_dof) {
+    if (is_dof && !ghost) {
       my_qd = vstar_d + dvk;
       my_q += dt * my_qd;
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      cv[k] = cvs[k] + shf(dvk, NDMAX + k);
-      cw[k] = cws[k] + shf(dvk, NDMAX + 3 + k);
-      cpos[k] += dt * cv[k];
+      const float dvl = shf(dvk, NDMAX + k), dva = shf(dvk, NDMAX + 3 + k);
+      if (!ghost) {
+        cv[k] = cvs[k] + dvl;
+        cw[k] = cws[k] + dva;
+        cpos[k] += dt * cv[k];
+      }
     }
-    {
+    if (!ghost) {
       const float wl = sqrtf(dot3(cw, cw)), ang = wl * dt;
       float f, cs;
       if (ang < 1e-3f) { f = 0.5f * dt - dt * dt * dt * (1.0f / 48.0f) * wl * wl; cs = cosf(0.5f * ang); }
@@ -1115,7 +1147,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
         l3[1] = sm.lam[nnc + nc + 2 * lane];
         l3[2] = sm.lam[nnc + nc + 2 * lane + 1];
       }
-      if (record_contacts && lane < B2E_MAX_CONTACTS) {
+      if (record_contacts && lane < B2E_MAX_CONTACTS && live_env && !ghost) {
         float* o = st.contacts + ((size_t)env * B2E_MAX_CONTACTS + lane) * 8;
         if (lane < nc) {
           o[0] = (float)key; o[1] = sm.con[lane].dist;
@@ -1127,7 +1159,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
         }
       }
       __syncwarp();
-      if (lane < B2E_CACHE_SLOTS) {
+      if (lane < B2E_CACHE_SLOTS && !ghost) {
         sm.ckey[lane] = key;
         sm.clam[lane][0] = l3[0]; sm.clam[lane][1] = l3[1]; sm.clam[lane][2] = l3[2];
       }
@@ -1142,6 +1174,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
 
   }
 
+  if (!live_env) return;   // no block barrier below this point
   // ---- store state ----
   if (is_dof) {
     st.q[env * nd + lane] = my_q;
@@ -1404,6 +1437,7 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   s->st.cache_lam = (float*)s->fields[B2E_F_CACHE_LAM]; s->st.hand_pose = (float*)s->fields[B2E_F_HAND_POSE];
   s->st.status = (int*)s->fields[B2E_F_STATUS]; s->st.raw_obs = (float*)s->fields[B2E_F_RAW_OBS];
   s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
+  CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
   const size_t na = (size_t)num_envs * (params->n_act > 0 ? params->n_act : 1) * 4, no = (size_t)num_envs * params->n_obs * 4;
   CUDA_TRY(cudaMalloc(&s->d_action, na)); CUDA_TRY(cudaMalloc(&s->d_obs, no));
   CUDA_TRY(cudaMalloc(&s->d_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMalloc(&s->d_done, (size_t)num_envs * 4));
@@ -1419,6 +1453,7 @@ void b2e_destroy(b2e_sim* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (int f = 0; f < B2E_F_COUNT; f++) cudaFree(s->fields[f]);
+  cudaFree(s->st.scratch);
   cudaFree(s->d_model); cudaFree(s->d_action); cudaFree(s->d_obs); cudaFree(s->d_reward); cudaFree(s->d_done);
   cudaFreeHost(s->h_action); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_reward); cudaFreeHost(s->h_done);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);

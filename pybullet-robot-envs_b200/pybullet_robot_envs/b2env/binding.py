@@ -11,7 +11,7 @@ import numpy as np
 from .model import B2EModel, B2EParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libb2env.so"))
+LIB_PATH = os.environ.get("B2ENV_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libb2env.so"))
 
 F_Q, F_QD, F_OBJ_POSE, F_OBJ_VEL, F_TARGET, F_MTARGET, F_COUNTERS, F_CACHE_KEY, F_CACHE_LAM, \
     F_HAND_POSE, F_STATUS, F_RAW_OBS, F_CONTACTS = range(13)
