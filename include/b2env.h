@@ -27,6 +27,7 @@
 #ifndef B2ENV_H
 #define B2ENV_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -132,6 +133,8 @@ typedef struct b2e_params {
   float ws_lim[3][2];      /* robot workspace (IK clamps)                        */
   float eu_lim[3][2];
   float home_hand_pose[6]; /* panda_env.py:85-88                                 */
+  int32_t goal_env;        /* GoalEnv semantics (panda_push_gym_goal_env.py:89-122): sparse reward
+                              -(d > dist_min), done = counter > max_steps or success, no latch */
 } b2e_params;
 
 /* state fields for b2e_get / b2e_set (all env-major, [B][width])               */
@@ -160,6 +163,8 @@ enum b2e_field {
 /* step modes */
 #define B2E_MODE_ACTION 0 /* targets from the action (apply_action)             */
 #define B2E_MODE_HOLD 1   /* keep motor targets, hold gains (settle steps of reset) */
+#define B2E_MODE_IK_POSE 3 /* Cartesian mode: IK of the stored hand pose -> motor targets, no action
+                              increment, no task bookkeeping (robot.reset, panda_env.py:83-91) */
 #define B2E_MODE_TARGETS 2 /* keep motor targets already written to B2E_F_MTARGET by
                               robot.apply_action, control gains; no task bookkeeping */
 
@@ -201,6 +206,13 @@ int b2e_step(b2e_sim* sim, const float* action, float* obs, float* reward, float
  * end-to-end benchmark: copies action H2D, steps, copies results D2H, syncs.    */
 int b2e_step_host(b2e_sim* sim, const float* action_host, float* obs_host, float* reward_host,
                   float* done_host, int n_substeps, int mode);
+
+/* Same, for PAGE-LOCKED host buffers (from b2e_host_alloc): the async copies go straight
+ * to / from the caller's memory, no staging copy.                               */
+int b2e_step_pinned(b2e_sim* sim, const float* action_pinned, float* obs_pinned, float* reward_pinned,
+                    float* done_pinned, int n_substeps, int mode);
+int b2e_host_alloc(void** out, size_t bytes);
+int b2e_host_free(void* p);
 
 /* Copy a state field to / from a DEVICE buffer of the field's full size.        */
 int b2e_get(b2e_sim* sim, int field, void* dst_dev, void* stream);

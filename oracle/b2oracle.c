@@ -693,9 +693,86 @@ static real dist3(const real* a, const real* b) {
   return RSQRT(dot3(d, d));
 }
 
+
+/* ------------------------------------------------------------------ damped-least-squares IK
+ * p.calculateInverseKinematics(robot, ee, pos, orn, maxNumIterations=100, residualThreshold=1e-3)
+ * (panda_env.py:269-272) restated [EXT-recalled: IKTrajectoryHelper, IK2_VEL_DLS_WITH_ORIENTATION]:
+ * start from the current joint positions; while |p_t - p| > residual and it < max: FK, 6 x n Jacobian of
+ * the EE link frame, e = [p_t - p ; rotation vector of q_t * q^-1], dq = J^T (J J^T + lambda I)^-1 e,
+ * largest joint step clamped to 45 deg, q += dq.  Returns positions of every movable joint.        */
+static void quat_conj_mul(const real* a, const real* b, real* o) { /* o = a * conj(b) */
+  real c[4] = {-b[0], -b[1], -b[2], b[3]};
+  quat_mul(a, c, o);
+}
+static int solve6(real U[6][7]) { /* Gaussian elimination with partial pivoting on [U | e] */
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++) if (RFABS(U[r][k]) > RFABS(U[piv][k])) piv = r;
+    if (piv != k) for (int c = 0; c < 7; c++) { real t = U[k][c]; U[k][c] = U[piv][c]; U[piv][c] = t; }
+    real inv = 1 / U[k][k];
+    for (int r = k + 1; r < 6; r++) {
+      real f = U[r][k] * inv;
+      for (int c = k; c < 7; c++) U[r][c] -= f * U[k][c];
+    }
+  }
+  for (int k = 5; k >= 0; k--) {
+    real s = U[k][6];
+    for (int c = k + 1; c < 6; c++) s -= U[k][c] * U[c][6];
+    U[k][6] = s / U[k][k];
+  }
+  return 0;
+}
+static int ik_dls(const b2e_model* m, const b2e_params* P, const real* q0, const real* tpos, const real* tquat, real* qout) {
+  int nd = m->n_dof, ee = m->ee_link, it;
+  real q[ND];
+  for (int d = 0; d < nd; d++) q[d] = q0[d];
+  for (it = 0; it < P->ik_iters; it++) {
+    fk_t fk;
+    forward_kinematics(m, q, &fk);
+    real dp[3] = {tpos[0] - fk.p[ee][0], tpos[1] - fk.p[ee][1], tpos[2] - fk.p[ee][2]};
+    if (RSQRT(dot3(dp, dp)) <= P->ik_residual) break;
+    real cq[4], eq[4], er[3];
+    mat_to_quat(fk.R[ee], cq);
+    quat_conj_mul(tquat, cq, eq);
+    if (eq[3] < 0) { eq[0] = -eq[0]; eq[1] = -eq[1]; eq[2] = -eq[2]; eq[3] = -eq[3]; }
+    real vn = RSQRT(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2]);
+    if (vn > (real)1e-9) {
+      real ang = 2 * RATAN2(vn, eq[3]);
+      for (int k = 0; k < 3; k++) er[k] = eq[k] / vn * ang;
+    } else er[0] = er[1] = er[2] = 0;
+    real Jl[ND][3], Ja[ND][3];
+    point_jacobian(m, &fk, ee, fk.p[ee], Jl, Ja);
+    real e[6] = {dp[0], dp[1], dp[2], er[0], er[1], er[2]};
+    real U[6][7];
+    for (int r = 0; r < 6; r++) {
+      for (int c = 0; c < 6; c++) {
+        real sacc = 0;
+        for (int d = 0; d < nd; d++) {
+          real jr = r < 3 ? Jl[d][r] : Ja[d][r - 3], jc = c < 3 ? Jl[d][c] : Ja[d][c - 3];
+          sacc += jr * jc;
+        }
+        U[r][c] = sacc + (r == c ? P->ik_damping : 0);
+      }
+      U[r][6] = e[r];
+    }
+    solve6(U);
+    real dq[ND], mx = 0;
+    for (int d = 0; d < nd; d++) {
+      real sacc = 0;
+      for (int r = 0; r < 6; r++) sacc += (r < 3 ? Jl[d][r] : Ja[d][r - 3]) * U[r][6];
+      dq[d] = sacc;
+      if (RFABS(sacc) > mx) mx = RFABS(sacc);
+    }
+    real scale = mx > (real)0.78539816339 ? (real)0.78539816339 / mx : 1;
+    for (int d = 0; d < nd; d++) q[d] += dq[d] * scale;
+  }
+  for (int d = 0; d < nd; d++) qout[d] = q[d];
+  return it;
+}
+
 /* ------------------------------------------------------------------ one physics step of one env */
 typedef struct {
-  real q[ND], qd[ND], cpos[3], cquat[4], cv[3], cw[3], mtarget[ND];
+  real q[ND], qd[ND], cpos[3], cquat[4], cv[3], cw[3], mtarget[ND], hand_pose[6];
   int cache_key[B2E_CACHE_SLOTS];
   real cache_lam[B2E_CACHE_SLOTS][3];
   int flags, iters, n_contacts, n_rows;
@@ -908,6 +985,7 @@ static void load_env(const b2e_model* m, const b2o_state* S, int b, env_t* e) {
     e->cache_key[s] = S->cache_key[b * B2E_CACHE_SLOTS + s];
     for (int j = 0; j < 3; j++) e->cache_lam[s][j] = S->cache_lam[(b * B2E_CACHE_SLOTS + s) * 3 + j];
   }
+  for (int k = 0; k < 6; k++) e->hand_pose[k] = S->hand_pose[b * 6 + k];
   e->flags = S->status[b * 4];
   e->iters = 0; e->n_contacts = 0; e->n_rows = 0;
 }
@@ -928,6 +1006,7 @@ static void store_env(const b2e_model* m, b2o_state* S, int b, const env_t* e) {
     S->cache_key[b * B2E_CACHE_SLOTS + s] = e->cache_key[s];
     for (int j = 0; j < 3; j++) S->cache_lam[(b * B2E_CACHE_SLOTS + s) * 3 + j] = (float)e->cache_lam[s][j];
   }
+  for (int k = 0; k < 6; k++) S->hand_pose[b * 6 + k] = (float)e->hand_pose[k];
   S->status[b * 4 + 0] = e->flags;
   S->status[b * 4 + 1] = e->iters;
   S->status[b * 4 + 2] = e->n_contacts;
@@ -957,7 +1036,42 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
         e.mtarget[k] = t;
       }
     }
-    physics_step(m, P, &e, mode != B2E_MODE_HOLD);
+    if ((mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE) && P->use_ik) {
+      /* task level (panda_push_gym_env.py:197-222): hand_pose += scaled action, clamp to rotation limits
+       * and workspace; robot level (panda_env.py:229-282): z re-clamp, orientation = home euler when it is
+       * not controlled, IK, position targets for every movable joint with gain 0.2 */
+      if (mode == B2E_MODE_ACTION) {
+        if (!P->ik_orientation) {
+          for (int k = 0; k < 3; k++) { act[k] *= P->act_scale_pos; e.hand_pose[k] += act[k]; }
+        } else {
+          for (int k = 0; k < 3; k++) { act[k] *= P->act_scale_pos; e.hand_pose[k] += act[k]; }
+          for (int k = 3; k < 6; k++) {
+            act[k] *= P->act_scale_rot;
+            real v = e.hand_pose[k] + act[k];
+            if (v < P->eu_lim[k - 3][0]) v = P->eu_lim[k - 3][0];
+            if (v > P->eu_lim[k - 3][1]) v = P->eu_lim[k - 3][1];
+            e.hand_pose[k] = v;
+          }
+        }
+        for (int k = 0; k < 3; k++) {
+          if (e.hand_pose[k] < P->ws_lim[k][0]) e.hand_pose[k] = P->ws_lim[k][0];
+          if (e.hand_pose[k] > P->ws_lim[k][1]) e.hand_pose[k] = P->ws_lim[k][1];
+        }
+      }
+      real tp[3] = {e.hand_pose[0], e.hand_pose[1], e.hand_pose[2]}, eu[3], tq[4];
+      if (tp[2] < P->ws_lim[2][0]) tp[2] = P->ws_lim[2][0];
+      if (tp[2] > P->ws_lim[2][1]) tp[2] = P->ws_lim[2][1];
+      for (int k = 0; k < 3; k++) {
+        eu[k] = P->ik_orientation ? e.hand_pose[3 + k] : P->home_hand_pose[3 + k];
+        if (eu[k] < (real)-M_PI) eu[k] = (real)-M_PI;
+        if (eu[k] > (real)M_PI) eu[k] = (real)M_PI;
+      }
+      euler_to_quat(eu, tq);
+      real qik[ND];
+      ik_dls(m, P, e.q, tp, tq, qik);
+      for (int d = 0; d < m->n_dof; d++) e.mtarget[d] = qik[d];
+    }
+    physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik);
     if (mode == B2E_MODE_ACTION) {
       /* _termination() inside apply_action (:239-242): counter only advances when not terminated */
       fk_t fk;
@@ -966,7 +1080,8 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
       if (P->task == B2E_TASK_PUSH) d = dist3(e.cpos, target);
       else { real pos[3], qt[4], vl[3]; ee_state(m, &fk, e.qd, pos, qt, vl); d = dist3(pos, e.cpos); }
       int term = 0;
-      if (d <= P->dist_min) { terminated = 1; term = 1; }
+      if (P->goal_env) { if (counter > P->max_steps) term = 1; }   /* panda_push_gym_goal_env.py:106-110 */
+      else if (d <= P->dist_min) { terminated = 1; term = 1; }
       else if (terminated || counter > P->max_steps) term = 1;
       if (term) break;
       counter++;
@@ -989,10 +1104,15 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
     int dn = 0;
     if (P->task == B2E_TASK_PUSH) {
       d2 = dist3(e.cpos, target);
-      if (d2 <= P->dist_min) { terminated = 1; dn = 1; }
-      else if (terminated || counter > P->max_steps) dn = 1;
-      rew = -d1 - d2;
-      if (d2 <= P->dist_min) rew = (real)1000.0 + (100 - d2 * 80);
+      if (P->goal_env) { /* done = _termination() or is_success; reward = -(d > dist_min) (:96-122) */
+        dn = (counter > P->max_steps) || (d2 <= P->dist_min);
+        rew = d2 > P->dist_min ? -1 : 0;
+      } else {
+        if (d2 <= P->dist_min) { terminated = 1; dn = 1; }
+        else if (terminated || counter > P->max_steps) dn = 1;
+        rew = -d1 - d2;
+        if (d2 <= P->dist_min) rew = (real)1000.0 + (100 - d2 * 80);
+      }
     } else {
       if (d1 <= P->dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P->max_steps) dn = 1;
@@ -1120,5 +1240,14 @@ int b2o_ee_jacobian(const b2e_model* m, const float* q, float* J /*[6][nd] linea
   for (int k = 0; k < 3; k++) pos[k] = (float)p[k];
   for (int k = 0; k < 4; k++) quat[k] = (float)qt[k];
   return 0;
+}
+int b2o_ik(const b2e_model* m, const b2e_params* P, const float* q0, const float* tpos, const float* tquat, float* qout) {
+  real q[ND] = {0}, tp[3], tq[4], o[ND];
+  for (int d = 0; d < m->n_dof; d++) q[d] = q0[d];
+  for (int k = 0; k < 3; k++) tp[k] = tpos[k];
+  for (int k = 0; k < 4; k++) tq[k] = tquat[k];
+  int it = ik_dls(m, P, q, tp, tq, o);
+  for (int d = 0; d < m->n_dof; d++) qout[d] = (float)o[d];
+  return it;
 }
 int b2o_real_size(void) { return (int)sizeof(real); }

@@ -46,12 +46,12 @@
 #ifndef MINB
 #define MINB 3            // resident blocks per SM the register allocation targets (24 warps, 80 regs)
 #endif
+#define TLMAX 16          // links handled by the warp kernel (transforms staged in shared memory)
 #define RMAX 48           // max constraint rows per env: 9 motors + 3 limits + 3*12 contact rows
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
 #define SCRATCH_PER_ENV (RMAX * RMAX + RMAX * WSTRIDE)
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
-#define TLMAX 16          // links whose transforms are staged in shared memory
 
 #define KEY_CUBE_TABLE 0
 #define KEY_CUBE_PLANE 8
@@ -72,6 +72,7 @@ struct DevModel {
   int parent[NLMAX], jtype[NLMAX], dof[NLMAX];
   int dof_link[NLMAX];
   unsigned link_dofmask[NLMAX];  // dofs on the path base -> link (inclusive)
+  unsigned acc_sched[2][NLMAX];  // child->parent accumulation schedule: 5-bit source lane per round (31 = none)
   float jpos[NLMAX][3], jrot[NLMAX][9], axis[NLMAX][3];
   float mass[NLMAX], com[NLMAX][3], inertia[NLMAX][9];
   float lower[NLMAX], upper[NLMAX], limit_margin[NLMAX], max_force[NLMAX], max_vel[NLMAX], joint_damping[NLMAX],
@@ -80,6 +81,14 @@ struct DevModel {
   int sph_link[B2E_MAX_SPHERES];
   float sph_c[B2E_MAX_SPHERES][3], sph_r[B2E_MAX_SPHERES], sph_mu[B2E_MAX_SPHERES], sph_erp[B2E_MAX_SPHERES],
       sph_cfm[B2E_MAX_SPHERES];
+};
+
+// warp-uniform part of the model: passed by value (constant bank), no loads on the critical path
+struct DevModelU {
+  int n_links, n_dof, ee_link, n_spheres, fk_rounds, acc_rounds;
+  unsigned ee_dofmask;
+  float base_pos[3], base_rot[9], ee_com[3];
+  int parent[TLMAX];
 };
 
 struct DevState {
@@ -94,6 +103,7 @@ struct b2e_sim {
   b2e_model model;
   b2e_params params;
   DevModel* d_model;
+  DevModelU umodel;
   DevState st;
   void* fields[B2E_F_COUNT];
   float *d_action, *d_obs, *d_reward, *d_done;     // staging for the host-buffer entry point
@@ -174,20 +184,26 @@ __device__ __forceinline__ void quat_mul(const float* a, const float* b, float* 
   float w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
-// p.getEulerFromQuaternion restated (panda_env.py:160, world_env.py:119) [EXT-recalled]
-__device__ __noinline__ void quat_to_euler(const float* q, float* e) {
-  float x = q[0], y = q[1], z = q[2], w = q[3];
+// p.getEulerFromQuaternion restated (panda_env.py:160, world_env.py:119) [EXT-recalled].  Not inlined:
+// three call sites with large libm bodies; arguments and result travel in registers.
+__device__ __noinline__ float3 quat_to_euler3(float x, float y, float z, float w) {
   float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
   float sarg = -2 * (x * z - w * y);
+  float3 e;
   if (sarg <= -0.99999f) {
-    e[0] = 0; e[1] = -1.57079632679489661923f; e[2] = 2 * atan2f(x, -y);
+    e.x = 0; e.y = -1.57079632679489661923f; e.z = 2 * atan2f(x, -y);
   } else if (sarg >= 0.99999f) {
-    e[0] = 0; e[1] = 1.57079632679489661923f; e[2] = 2 * atan2f(-x, y);
+    e.x = 0; e.y = 1.57079632679489661923f; e.z = 2 * atan2f(-x, y);
   } else {
-    e[0] = atan2f(2 * (y * z + w * x), sqw - sqx - sqy + sqz);
-    e[1] = asinf(sarg);
-    e[2] = atan2f(2 * (x * y + w * z), sqw + sqx - sqy - sqz);
+    e.x = atan2f(2 * (y * z + w * x), sqw - sqx - sqy + sqz);
+    e.y = asinf(sarg);
+    e.z = atan2f(2 * (x * y + w * z), sqw + sqx - sqy - sqz);
   }
+  return e;
+}
+__device__ __forceinline__ void quat_to_euler(const float* q, float* e) {
+  const float3 r = quat_to_euler3(q[0], q[1], q[2], q[3]);
+  e[0] = r.x; e[1] = r.y; e[2] = r.z;
 }
 // p.getQuaternionFromEuler restated (panda_push_gym_env.py:169,172) [EXT-recalled]
 __device__ __forceinline__ void euler_to_quat(const float* e, float* q) {
@@ -240,8 +256,8 @@ struct WarpSmem {
 
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
-__device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, int lane, float qi, float* R, float* p) {
-  const int nl = M->n_links;
+__device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const DevModelU& U, int lane, float qi, float* R, float* p) {
+  const int nl = U.n_links;
   const bool act = lane < nl;
   const int li = act ? lane : 0;
   float jr[9], ax[3];
@@ -268,7 +284,7 @@ __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, int lan
     }
   }
   int anc = act ? __ldg(&M->parent[li]) : -1;
-  const int rounds = M->fk_rounds;
+  const int rounds = U.fk_rounds;
   for (int rd = 0; rd < rounds; rd++) {
     const int src = anc < 0 ? 0 : anc;
     float Ra[9], pa[3];
@@ -290,19 +306,19 @@ __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, int lan
   {  // base pose
     float Rb[9], Rn[9], o[3];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Rb[k] = M->base_rot[k];
+    for (int k = 0; k < 9; k++) Rb[k] = U.base_rot[k];
     m3mul(Rb, R, Rn);
     m3vec(Rb, p, o);
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = Rn[k];
-    p[0] = M->base_pos[0] + o[0]; p[1] = M->base_pos[1] + o[1]; p[2] = M->base_pos[2] + o[2];
+    p[0] = U.base_pos[0] + o[0]; p[1] = U.base_pos[1] + o[1]; p[2] = U.base_pos[2] + o[2];
   }
 }
 
 // inclusive sum over the path base..link of a 6-vector held per link lane (pointer jumping)
-__device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, int lane, float* x) {
-  int anc = lane < M->n_links ? __ldg(&M->parent[lane]) : -1;
-  const int rounds = M->fk_rounds;
+__device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, const DevModelU& U, int lane, float* x) {
+  int anc = lane < U.n_links ? __ldg(&M->parent[lane]) : -1;
+  const int rounds = U.fk_rounds;
   for (int rd = 0; rd < rounds; rd++) {
     const int src = anc < 0 ? 0 : anc;
     float xa[6];
@@ -315,6 +331,107 @@ __device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, int la
       anc = anca;
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Damped-least-squares IK (p.calculateInverseKinematics, panda_env.py:269-272): same statement as
+// oracle/b2oracle.c ik_dls.  lane = link for FK + Jacobian columns, lane = row (<6) for the 6x6
+// system (J J^T + lambda I) x = e solved by Gauss-Jordan over shuffles, lane = dof for dq = J^T x.
+// `scr` is 6*16 floats of warp-private shared memory.  Returns the joint target of this dof lane.
+__device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ M, const DevModelU& U, int max_iters,
+                                       float residual, float damping, int lane, float my_q, float tpx, float tpy,
+                                       float tpz, float tqx, float tqy, float tqz, float tqw) {
+  const int nl = U.n_links, nd = U.n_dof, ee = U.ee_link;
+  const int li = lane < nl ? lane : 0;
+  const int my_dof = __ldg(&M->dof[li]);
+  const bool has_dof = lane < nl && my_dof >= 0 && ((U.ee_dofmask >> (my_dof < 0 ? 0 : my_dof)) & 1);
+  const int jt = __ldg(&M->jtype[li]);
+  const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
+  float qv = my_q;
+  for (int it = 0; it < max_iters; it++) {
+    float R[9], p[3];
+    const float qi = shf(qv, my_dof < 0 ? 0 : my_dof);
+    fk_lanes(M, U, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, R, p);
+    float pe[3], Re[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pe[k] = shf(p[k], ee);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Re[k] = shf(R[k], ee);
+    const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
+    if (sqrtf(dot3(dp, dp)) <= residual) break;
+    float cq[4], eq[4], er[3];
+    mat_to_quat(Re, cq);
+    {
+      const float tq[4] = {tqx, tqy, tqz, tqw}, cc[4] = {-cq[0], -cq[1], -cq[2], cq[3]};
+      quat_mul(tq, cc, eq);
+    }
+    if (eq[3] < 0) { eq[0] = -eq[0]; eq[1] = -eq[1]; eq[2] = -eq[2]; eq[3] = -eq[3]; }
+    const float vn = sqrtf(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2]);
+    if (vn > 1e-9f) {
+      const float ang = 2.f * atan2f(vn, eq[3]);
+      er[0] = eq[0] / vn * ang; er[1] = eq[1] / vn * ang; er[2] = eq[2] / vn * ang;
+    } else { er[0] = er[1] = er[2] = 0.f; }
+    // Jacobian column of this link's joint
+    float c[6] = {0, 0, 0, 0, 0, 0};
+    if (has_dof) {
+      float aw[3];
+      m3vec(R, ax, aw);
+      if (jt == B2E_JOINT_REVOLUTE) {
+        const float rel[3] = {pe[0] - p[0], pe[1] - p[1], pe[2] - p[2]};
+        cross3(aw, rel, c);
+        c[3] = aw[0]; c[4] = aw[1]; c[5] = aw[2];
+      } else {
+        c[0] = aw[0]; c[1] = aw[1]; c[2] = aw[2];
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < 6 * 16; k += 32) scr[k] = 0.f;
+    __syncwarp();
+    if (lane < nl && my_dof >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) scr[k * 16 + my_dof] = c[k];
+    }
+    __syncwarp();
+    // lane r < 6: row r of J J^T + lambda I, augmented with e_r
+    const int r = lane < 6 ? lane : 0;
+    float Ur[7];
+#pragma unroll
+    for (int cc2 = 0; cc2 < 6; cc2++) {
+      float acc = (cc2 == r) ? damping : 0.f;
+      for (int d = 0; d < nd; d++) acc = fmaf(scr[r * 16 + d], scr[cc2 * 16 + d], acc);
+      Ur[cc2] = acc;
+    }
+    Ur[6] = r < 3 ? (r == 0 ? dp[0] : (r == 1 ? dp[1] : dp[2])) : (r == 3 ? er[0] : (r == 4 ? er[1] : er[2]));
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      float rk[7];
+#pragma unroll
+      for (int j = 0; j < 7; j++) rk[j] = shf(Ur[j], k);
+      const float pinv = 1.0f / rk[k];
+      if (lane == k) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) Ur[j] = rk[j] * pinv;
+      } else {
+        const float f = Ur[k] * pinv;
+#pragma unroll
+        for (int j = 0; j < 7; j++) Ur[j] = fmaf(-f, rk[j], Ur[j]);
+      }
+    }
+    // dq_d = sum_r J[r][d] x_r  (lane = dof)
+    float dq = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) {
+      const float xr = shf(Ur[6], rr);
+      dq = fmaf(scr[rr * 16 + (lane & 15)], xr, dq);
+    }
+    if (lane >= nd) dq = 0.f;
+    const float mx = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fabsf(dq))));
+    const float scale = mx > 0.78539816339f ? 0.78539816339f / mx : 1.f;
+    qv = fmaf(dq, scale, qv);
+  }
+  __syncwarp();
+  return qv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,8 +596,16 @@ __device__ __forceinline__ int arm_affine_solve(const float* A, int AS, int lane
 
 // Build the row(s) owned by this lane, the W table, the Delassus matrix, warm start, solve, and
 // leave the impulses in sm.lam[].  Returns the PGS iteration count.
+#ifndef SOLVE_INLINE
+#define SOLVE_INLINE 0
+#endif
+#if SOLVE_INLINE
+#define SOLVE_ATTR __forceinline__
+#else
+#define SOLVE_ATTR __noinline__
+#endif
 template <int NS>
-__device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const b2e_params& P,
+__device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const DevModelU& U, const b2e_params& P,
                                             int lane, int nd, int nlim, int nc, float my_q, float my_target,
                                             float my_kp, float cpx, float cpy, float cpz, float* scratch) {
   const float cpos[3] = {cpx, cpy, cpz};
@@ -543,7 +668,7 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
           for (int k = 0; k < 3; k++) { J[9 + k] = dir[k]; J[12 + k] = t[k]; }
         } else {
           const unsigned mask = __ldg(&M->link_dofmask[ct.link]);
-          float rel[3] = {ct.pA[0] - M->base_pos[0], ct.pA[1] - M->base_pos[1], ct.pA[2] - M->base_pos[2]}, wn[3];
+          float rel[3] = {ct.pA[0] - U.base_pos[0], ct.pA[1] - U.base_pos[1], ct.pA[2] - U.base_pos[2]}, wn[3];
           cross3(rel, dir, wn);
 #pragma unroll
           for (int d = 0; d < NDMAX; d++) {
@@ -687,7 +812,7 @@ __device__ __noinline__ int build_and_solve(WarpSmem& sm, const DevModel* __rest
 // ------------------------------------------------------------------------------------------
 // the fused step kernel
 __global__ void __launch_bounds__(32 * WPB, MINB)
-step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
+step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
             int mode, int record_contacts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -696,7 +821,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
   const bool live_env = env_raw < st.B;      // padding warps of the last block shadow the last env, stores masked
   const int env = live_env ? env_raw : st.B - 1;
   WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
-  const int nd = M->n_dof, nl = M->n_links;
+  const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
 
   // ---- load state (env-major field groups; lanes = dofs for q/qd/targets) ----
@@ -723,8 +848,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
   }
   float my_act = 0.f;
   if (mode == B2E_MODE_ACTION && lane < P.n_act) my_act = action[env * P.n_act + lane];
+  float my_hp = (P.use_ik && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;   // commanded hand pose (lane = component)
   const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
-  const float my_kp = (mode != B2E_MODE_HOLD && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
+  const float my_kp = (mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P.use_ik && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
   __syncwarp();
@@ -738,7 +864,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     //      sub-step, and at the same time the post-step kinematics of the previous one ----
     {
       const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
-      fk_lanes(M, lane, link_has_dof ? qi : 0.f, Rm, pw);
+      fk_lanes(M, U, lane, link_has_dof ? qi : 0.f, Rm, pw);
     }
     // ---- termination inside apply_action (panda_push_gym_env.py:239-242), for the previous sub-step ----
     if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
@@ -747,14 +873,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
         float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
         d = sqrtf(dot3(dd, dd));
       } else {
-        const int ee = M->ee_link;
-        float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
+        const int ee = U.ee_link;
+        float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]}, o[3];
         m3vec(Rm, cm, o);
         float e3[3] = {shf(pw[0] + o[0], ee), shf(pw[1] + o[1], ee), shf(pw[2] + o[2], ee)};
         float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
         d = sqrtf(dot3(dd, dd));
       }
-      if (d <= P.dist_min) { terminated = 1; stop = true; }
+      if (P.goal_env) { if (counter > P.max_steps) stop = true; else counter++; }
+      else if (d <= P.dist_min) { terminated = 1; stop = true; }
       else if (terminated || counter > P.max_steps) stop = true;
       else counter++;
     }
@@ -766,6 +893,31 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl && !ghost) {
       my_act *= P.act_scale;
       my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
+    }
+    // ---- Cartesian control (panda_push_gym_env.py:197-222, panda_env.py:229-282): hand pose += scaled
+    //      action, clamps, IK -> position targets of every movable joint ----
+    if (P.use_ik && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE)) {
+      if (mode == B2E_MODE_ACTION && !ghost && lane < 6) {
+        if (lane < 3) {
+          my_act *= P.act_scale_pos;
+          my_hp = fminf(fmaxf(my_hp + my_act, P.ws_lim[lane][0]), P.ws_lim[lane][1]);
+        } else if (P.ik_orientation) {
+          my_act *= P.act_scale_rot;
+          my_hp = fminf(fmaxf(my_hp + my_act, P.eu_lim[lane - 3][0]), P.eu_lim[lane - 3][1]);
+        }
+      }
+      float tp[3], eu[3], tq[4];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        tp[k] = shf(my_hp, k);
+        const float e = P.ik_orientation ? shf(my_hp, 3 + k) : P.home_hand_pose[3 + k];
+        eu[k] = fminf(fmaxf(e, -3.14159265358979323846f), 3.14159265358979323846f);
+      }
+      tp[2] = fminf(fmaxf(tp[2], P.ws_lim[2][0]), P.ws_lim[2][1]);
+      euler_to_quat(eu, tq);
+      const float t = ik_solve(sm.W, M, U, P.ik_iters, P.ik_residual, P.ik_damping, lane, my_q, tp[0], tp[1], tp[2],
+                               tq[0], tq[1], tq[2], tq[3]);
+      if (is_dof && !ghost) my_target = t;
     }
     const float qdi_raw = shf(my_qd, my_dof < 0 ? 0 : my_dof);
     const float qdi = link_has_dof ? qdi_raw : 0.f;
@@ -784,7 +936,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       const int jt = __ldg(&M->jtype[li]);
       float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])}, aw[3];
       m3vec(Rm, ax, aw);
-      float rel[3] = {pw[0] - M->base_pos[0], pw[1] - M->base_pos[1], pw[2] - M->base_pos[2]};
+      float rel[3] = {pw[0] - U.base_pos[0], pw[1] - U.base_pos[1], pw[2] - U.base_pos[2]};
       if (lane < nl && jt == B2E_JOINT_REVOLUTE) {
         float t[3];
         cross3(rel, aw, t);
@@ -819,7 +971,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     float vJ[6], v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { vJ[k] = S[k] * qdi; v[k] = vJ[k]; }
-    path_sum6(M, lane, v);
+    path_sum6(M, U, lane, v);
     float ab[6];
     {
       float a[3], b[3], c2[3];
@@ -829,7 +981,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       ab[0] = a[0]; ab[1] = a[1]; ab[2] = a[2];
       ab[3] = b[0] + c2[0]; ab[4] = b[1] + c2[1]; ab[5] = b[2] + c2[2];
     }
-    path_sum6(M, lane, ab);
+    path_sum6(M, U, lane, ab);
     ab[3] -= P.gravity[0]; ab[4] -= P.gravity[1]; ab[5] -= P.gravity[2];  // a_0 = -g
     {
       // f = I*ab + v x* (I*v)
@@ -857,14 +1009,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       Iw[0] = Ia_n[0] + x1[0] + x2[0]; Iw[1] = Ia_n[1] + x1[1] + x2[1]; Iw[2] = Ia_n[2] + x1[2] + x2[2];
       Iw[3] = Ia_f[0] + x3[0]; Iw[4] = Ia_f[1] + x3[1]; Iw[5] = Ia_f[2] + x3[2];
     }
-    // child -> parent accumulation of [f | composite inertia] (serial walk carried by shuffles)
-    for (int j = nl - 1; j >= 1; j--) {
-      const int pj = M->parent[j];
-      if (pj < 0) continue;
+    // child -> parent accumulation of [f | composite inertia]: host-built schedule (heavy-path suffix
+    // scans + folds of light subtrees); every round each lane pulls one source lane (31 = a zero lane)
+    {
+      const unsigned sch0 = __ldg(&M->acc_sched[0][lane]), sch1 = __ldg(&M->acc_sched[1][lane]);
+      const int rounds = U.acc_rounds;
+      for (int rd = 0; rd < rounds; rd++) {
+        const int src = rd < 6 ? ((sch0 >> (5 * rd)) & 31) : ((sch1 >> (5 * (rd - 6))) & 31);
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const float val = shf(Iw[k], j);
-        if (lane == pj) Iw[k] += val;
+        for (int k = 0; k < 16; k++) Iw[k] += shf(Iw[k], src);
       }
     }
     // move to dof lanes: lane d gets S, f^c, I^c of its link
@@ -976,7 +1129,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
       v_hit = v_dist < margin;
     }
     // spheres: lane = sphere
-    const int ns = M->n_spheres;
+    const int ns = U.n_spheres;
     bool sc_hit = false, st_hit = false;
     float s_c[3] = {0, 0, 0}, sc_n[3] = {0, 0, 0}, sc_pB[3] = {0, 0, 0}, sc_dist = 0.f, st_dist = 0.f, s_r = 0.f;
     int s_link = 0;
@@ -1100,8 +1253,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     PHASE_BARRIER();
     // ---- rows + PGS ----
     R = nd + nlim + 3 * nc;
-    if (R <= 32) iters = build_and_solve<1>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], nullptr);
-    else iters = build_and_solve<2>(sm, M, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2],
+    if (R <= 32) iters = build_and_solve<1>(sm, M, U, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], nullptr);
+    else iters = build_and_solve<2>(sm, M, U, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2],
                                     st.scratch + (size_t)env * SCRATCH_PER_ENV);
 
     PHASE_BARRIER();
@@ -1188,6 +1341,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     st.obj_vel[env * 6 + 0] = cv[0]; st.obj_vel[env * 6 + 1] = cv[1]; st.obj_vel[env * 6 + 2] = cv[2];
     st.obj_vel[env * 6 + 3] = cw[0]; st.obj_vel[env * 6 + 4] = cw[1]; st.obj_vel[env * 6 + 5] = cw[2];
   }
+  if (P.use_ik && lane < 6) st.hand_pose[env * 6 + lane] = my_hp;
   if (lane < B2E_CACHE_SLOTS) {
     st.cache_key[env * B2E_CACHE_SLOTS + lane] = sm.ckey[lane];
 #pragma unroll
@@ -1198,9 +1352,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
   if (mode == B2E_MODE_ACTION || obs_out) {
     const float* R2 = Rm;   // kinematics of the final q (computed at the top of the last loop pass)
     const float* p2 = pw;
-    const int ee = M->ee_link;
+    const int ee = U.ee_link;
     // EE COM pose
-    float cm[3] = {M->com[ee][0], M->com[ee][1], M->com[ee][2]}, o[3];
+    float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]}, o[3];
     m3vec(R2, cm, o);
     float epos[3], Re[9];
 #pragma unroll
@@ -1210,7 +1364,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     // EE linear velocity: sum over the dofs on the path of (axis x (p_ee - o_j)) qd_j  /  axis qd_j
     float vl[3] = {0, 0, 0};
     {
-      const unsigned eemask = M->link_dofmask[ee];
+      const unsigned eemask = U.ee_dofmask;
       const int jt = __ldg(&M->jtype[li]);
       float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])}, aw[3];
       m3vec(R2, ax, aw);
@@ -1282,10 +1436,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ b2e_params P
     if (P.task == B2E_TASK_PUSH) {
       float dd2[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
       const float d2 = sqrtf(dot3(dd2, dd2));
-      if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
-      else if (terminated || counter > P.max_steps) dn = 1;
-      rew = -d1 - d2;
-      if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
+      if (P.goal_env) {
+        dn = (counter > P.max_steps) || (d2 <= P.dist_min);
+        rew = d2 > P.dist_min ? -1.0f : 0.0f;
+      } else {
+        if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
+        else if (terminated || counter > P.max_steps) dn = 1;
+        rew = -d1 - d2;
+        if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
+      }
     } else {
       if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P.max_steps) dn = 1;
@@ -1352,8 +1511,9 @@ static int field_width(const b2e_sim* s, int f) {
   }
 }
 
-static int build_dev_model(const b2e_model* m, DevModel* d) {
+static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   memset(d, 0, sizeof(*d));
+  memset(u, 0, sizeof(*u));
   if (m->n_links > TLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 16 links%s", "");
   if (m->n_dof > NDMAX) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 9 dofs%s", "");
   if (m->n_spheres > B2E_MAX_SPHERES || m->n_spheres < 0) return fail(B2E_EINVAL, "bad n_spheres%s", "");
@@ -1378,6 +1538,52 @@ static int build_dev_model(const b2e_model* m, DevModel* d) {
   int rounds = 0;
   while ((1 << rounds) < maxdepth) rounds++;
   d->fk_rounds = rounds;
+  // child->parent accumulation schedule (heavy-path decomposition)
+  {
+    const int n = m->n_links;
+    int size[TLMAX], heavy[TLMAX], depth[TLMAX], head[TLMAX];
+    for (int i = 0; i < n; i++) { size[i] = 1; heavy[i] = -1; }
+    for (int i = n - 1; i >= 0; i--) if (m->parent[i] >= 0) size[m->parent[i]] += size[i];
+    for (int i = 0; i < n; i++) {
+      depth[i] = m->parent[i] < 0 ? 0 : depth[m->parent[i]] + 1;
+      int p = m->parent[i];
+      if (p >= 0 && (heavy[p] < 0 || size[i] > size[heavy[p]])) heavy[p] = i;
+    }
+    for (int i = 0; i < n; i++) head[i] = (m->parent[i] >= 0 && heavy[m->parent[i]] == i) ? head[m->parent[i]] : i;
+    int src[12][NLMAX];
+    for (int r = 0; r < 12; r++) for (int l = 0; l < NLMAX; l++) src[r][l] = 31;
+    int rounds = 0;
+    // path heads, deepest first
+    int heads[TLMAX], nh = 0;
+    for (int i = 0; i < n; i++) if (head[i] == i) heads[nh++] = i;
+    for (int a = 0; a < nh; a++) for (int b = a + 1; b < nh; b++) if (depth[heads[b]] > depth[heads[a]]) { int t = heads[a]; heads[a] = heads[b]; heads[b] = t; }
+    for (int a = 0; a < nh; a++) {
+      int path[TLMAX], len = 0;
+      for (int v = heads[a]; v >= 0; v = heavy[v]) path[len++] = v;
+      for (int step = 1; step < len; step <<= 1) {
+        if (rounds >= 12) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 12 accumulation rounds%s", "");
+        for (int i = 0; i + step < len; i++) src[rounds][path[i]] = path[i + step];
+        rounds++;
+      }
+      if (m->parent[heads[a]] >= 0) {
+        if (rounds >= 12) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 12 accumulation rounds%s", "");
+        src[rounds][m->parent[heads[a]]] = heads[a];
+        rounds++;
+      }
+    }
+    u->acc_rounds = rounds;
+    for (int l = 0; l < NLMAX; l++) {
+      unsigned w0 = 0, w1 = 0;
+      for (int r = 0; r < 6; r++) { w0 |= (unsigned)src[r][l] << (5 * r); w1 |= (unsigned)src[6 + r][l] << (5 * r); }
+      d->acc_sched[0][l] = w0; d->acc_sched[1][l] = w1;
+    }
+  }
+  u->n_links = m->n_links; u->n_dof = m->n_dof; u->ee_link = m->ee_link; u->n_spheres = m->n_spheres;
+  u->fk_rounds = d->fk_rounds; u->ee_dofmask = d->link_dofmask[m->ee_link];
+  for (int k = 0; k < 3; k++) { u->base_pos[k] = m->base_pos[k]; u->ee_com[k] = m->com[m->ee_link][k]; }
+  for (int k = 0; k < 9; k++) u->base_rot[k] = m->base_rot[k];
+  for (int i = 0; i < TLMAX; i++) u->parent[i] = i < m->n_links ? m->parent[i] : -1;
+  if (m->n_links >= 31) return fail(B2E_EUNSUPPORTED, "lane 31 must stay free%s", "");
   for (int k = 0; k < m->n_dof; k++) {
     d->lower[k] = m->lower[k]; d->upper[k] = m->upper[k]; d->limit_margin[k] = m->limit_margin[k];
     d->max_force[k] = m->max_force[k]; d->max_vel[k] = m->max_vel[k]; d->joint_damping[k] = m->joint_damping[k];
@@ -1416,11 +1622,12 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   if (device < 0 || device >= ndev) return fail(B2E_EINVAL, "b2e_create: bad device index%s", "");
   CUDA_TRY(cudaSetDevice(device));
   DevModel hm;
-  int rc = build_dev_model(model, &hm);
+  DevModelU hu;
+  int rc = build_dev_model(model, &hm, &hu);
   if (rc) return rc;
   b2e_sim* s = new b2e_sim();
   memset(s, 0, sizeof(*s));
-  s->B = num_envs; s->device = device; s->model = *model; s->params = *params;
+  s->B = num_envs; s->device = device; s->model = *model; s->params = *params; s->umodel = hu;
   CUDA_TRY(cudaMalloc(&s->d_model, sizeof(DevModel)));
   CUDA_TRY(cudaMemcpy(s->d_model, &hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   for (int f = 0; f < B2E_F_COUNT; f++) {
@@ -1490,11 +1697,10 @@ int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* 
   if (!s) return fail(B2E_EINVAL, "b2e_step: null sim%s", "");
   if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step: action is required in ACTION mode%s", "");
   if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step: n_substeps < 0%s", "");
-  if (s->params.use_ik && mode == B2E_MODE_ACTION) return fail(B2E_EUNSUPPORTED, "b2e_step: IK control mode not built yet%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (s->B + WPB - 1) / WPB;
   step_kernel<<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
-      s->d_model, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
+      s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1520,6 +1726,36 @@ int b2e_step_host(b2e_sim* s, const float* action_host, float* obs_host, float* 
   if (obs_host) memcpy(obs_host, s->h_obs, no);
   if (reward_host) memcpy(reward_host, s->h_reward, nb);
   if (done_host) memcpy(done_host, s->h_done, nb);
+  return 0;
+}
+
+/* Host buffers that are page-locked (b2e_host_alloc): async copies go straight to/from them. */
+int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, float* reward_pinned, float* done_pinned,
+                    int n_substeps, int mode) {
+  if (!s) return fail(B2E_EINVAL, "b2e_step_pinned: null sim%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const size_t na = (size_t)s->B * s->params.n_act * 4, no = (size_t)s->B * s->params.n_obs * 4, nb = (size_t)s->B * 4;
+  if (mode == B2E_MODE_ACTION) {
+    if (!action_pinned) return fail(B2E_EINVAL, "b2e_step_pinned: action required%s", "");
+    CUDA_TRY(cudaMemcpyAsync(s->d_action, action_pinned, na, cudaMemcpyHostToDevice, 0));
+  }
+  int rc = b2e_step(s, s->d_action, obs_pinned ? s->d_obs : nullptr, reward_pinned ? s->d_reward : nullptr,
+                    done_pinned ? s->d_done : nullptr, n_substeps, mode, 0);
+  if (rc) return rc;
+  if (obs_pinned) CUDA_TRY(cudaMemcpyAsync(obs_pinned, s->d_obs, no, cudaMemcpyDeviceToHost, 0));
+  if (reward_pinned) CUDA_TRY(cudaMemcpyAsync(reward_pinned, s->d_reward, nb, cudaMemcpyDeviceToHost, 0));
+  if (done_pinned) CUDA_TRY(cudaMemcpyAsync(done_pinned, s->d_done, nb, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int b2e_host_alloc(void** out, size_t bytes) {
+  if (!out) return fail(B2E_EINVAL, "b2e_host_alloc: null%s", "");
+  CUDA_TRY(cudaMallocHost(out, bytes));
+  return 0;
+}
+int b2e_host_free(void* p) {
+  CUDA_TRY(cudaFreeHost(p));
   return 0;
 }
 

@@ -20,7 +20,10 @@ for _name in ('pandaReach-v0', 'PandaReach-v0'):
 for _name in ('pandaPush-v0', 'PandaPush-v0'):
     register(id=_name, entry_point='pybullet_robot_envs.envs:pandaPushGymEnv', max_episode_steps=1000,
              kwargs=dict(_PUSH_KW))
+for _name in ('pandaPushGoal-v0', 'PandaPushGoal-v0'):   # reference __init__.py:70-80
+    register(id=_name, entry_point='pybullet_robot_envs.envs:pandaPushGymGoalEnv', max_episode_steps=1000,
+             kwargs=dict(_PUSH_KW))
 
 
 def getList():
-    return ['pandaReach-v0', 'pandaPush-v0', 'PandaReach-v0', 'PandaPush-v0']
+    return ['pandaReach-v0', 'pandaPush-v0', 'pandaPushGoal-v0', 'PandaReach-v0', 'PandaPush-v0', 'PandaPushGoal-v0']

@@ -21,12 +21,12 @@ FIELD_NAMES = {
     "hand_pose": F_HAND_POSE, "status": F_STATUS, "raw_obs": F_RAW_OBS, "contacts": F_CONTACTS,
 }
 INT_FIELDS = {F_COUNTERS, F_CACHE_KEY, F_STATUS}
-MODE_ACTION, MODE_HOLD = 0, 1
+MODE_ACTION, MODE_HOLD, MODE_TARGETS, MODE_IK_POSE = 0, 1, 2, 3
 OPT_RECORD_CONTACTS = 0
 
 EXPORTS = [
     "b2e_create", "b2e_destroy", "b2e_set_params", "b2e_set_option", "b2e_reset", "b2e_step",
-    "b2e_step_host", "b2e_get", "b2e_set", "b2e_get_host", "b2e_set_host", "b2e_field_width",
+    "b2e_step_host", "b2e_step_pinned", "b2e_host_alloc", "b2e_host_free", "b2e_get", "b2e_set", "b2e_get_host", "b2e_set_host", "b2e_field_width",
     "b2e_field_elem_size", "b2e_num_envs", "b2e_launch_count", "b2e_timer_start", "b2e_timer_stop",
     "b2e_last_error", "b2e_version",
 ]
@@ -57,6 +57,9 @@ def load_library(path=None):
     lib.b2e_reset.argtypes = [vp, vp, vp, vp, vp]
     lib.b2e_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp]
     lib.b2e_step_host.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+    lib.b2e_step_pinned.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+    lib.b2e_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.b2e_host_free.argtypes = [vp]
     lib.b2e_get.argtypes = [vp, ci, vp, vp]
     lib.b2e_set.argtypes = [vp, ci, vp, vp]
     lib.b2e_get_host.argtypes = [vp, ci, vp]
@@ -95,6 +98,8 @@ class B2Sim:
         h = C.c_void_p()
         self._check(self.lib.b2e_create(C.byref(model), C.byref(params), self.B, self.device, C.byref(h)))
         self.h = h
+        self._pin = None
+        self._pinned_ptrs = []
 
     def _check(self, rc):
         if rc != 0:
@@ -102,6 +107,10 @@ class B2Sim:
 
     def close(self):
         if getattr(self, "h", None):
+            self._pin = None
+            for p in getattr(self, "_pinned_ptrs", []):
+                self.lib.b2e_host_free(p)
+            self._pinned_ptrs = []
             self.lib.b2e_destroy(self.h)
             self.h = None
 
@@ -125,6 +134,38 @@ class B2Sim:
     def step(self, action, obs=None, reward=None, done=None, n_substeps=1, mode=MODE_ACTION, stream=0):
         self._check(self.lib.b2e_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done), n_substeps, mode,
                                       C.c_void_p(stream)))
+
+    # page-locked numpy buffers owned by the library
+    def _pinned(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self.lib.b2e_host_alloc(C.byref(p), n))
+        self._pinned_ptrs.append(p)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def _ensure_pin(self):
+        if self._pin is None:
+            self._pin = (self._pinned((self.B, self.params.n_act)), self._pinned((self.B, self.params.n_obs)),
+                         self._pinned((self.B,)), self._pinned((self.B,)))
+        return self._pin
+
+    def step_pinned(self, action, n_substeps=1, mode=MODE_ACTION):
+        """Fast host path: `action` is copied into a page-locked staging array (or IS the array returned by
+        `pinned_action()`), results land in page-locked arrays that are returned as views — valid until the
+        next call."""
+        pa, po, pr, pd = self._ensure_pin()
+        if action is not pa:
+            act = np.asarray(action, dtype=np.float32)
+            if act.shape != pa.shape:
+                raise AssertionError(("number of motor commands differs from number of motor to control", act.shape))
+            np.copyto(pa, act)
+        self._check(self.lib.b2e_step_pinned(self.h, _ptr(pa), _ptr(po), _ptr(pr), _ptr(pd), n_substeps, mode))
+        return po, pr, pd
+
+    def pinned_action(self):
+        """Page-locked [B, n_act] array a policy can write into directly (skips one host copy)."""
+        return self._ensure_pin()[0]
 
     # host-buffer entry points (numpy)
     def step_host(self, action=None, n_substeps=1, mode=MODE_ACTION, want_obs=True):

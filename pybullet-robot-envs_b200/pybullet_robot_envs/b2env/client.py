@@ -20,6 +20,7 @@ class B2Client:
         self.params = None
         self._obs_cache_valid = False
         self._last = None
+        self.pending_mode = None   # set by robot.apply_action: how the next stepSimulation must treat the motors
 
     def configure(self, model, params):
         """(Re)create the simulation for a model + task constants."""
@@ -37,7 +38,10 @@ class B2Client:
         return self.sim
 
     # ---- p.stepSimulation ---------------------------------------------------------------
-    def step_simulation(self, n=1, mode=binding.MODE_HOLD):
+    def step_simulation(self, n=1, mode=None):
+        if mode is None:
+            mode = self.pending_mode if self.pending_mode is not None else binding.MODE_HOLD
+        self.pending_mode = None
         self.ensure().step_host(None, n, mode, want_obs=False)
         self._obs_cache_valid = False
 

@@ -71,6 +71,7 @@ class B2EParams(C.Structure):
         ("obs_low", _f * MAX_OBS), ("obs_high", _f * MAX_OBS),
         ("vel_mean", _f * 3), ("vel_std", _f * 3),
         ("ws_lim", (_f * 2) * 3), ("eu_lim", (_f * 2) * 3), ("home_hand_pose", _f * 6),
+        ("goal_env", _i),
     ]
 
 
@@ -260,7 +261,7 @@ def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
 
 
 def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orientation=0,
-                   max_steps=1000, dist_min=None, ws_lim=None, eu_lim=None):
+                   max_steps=1000, dist_min=None, ws_lim=None, eu_lim=None, goal_env=0):
     """World/solver/task constants.  Sources: reference panda_push_gym_env.py:39,52,122-126,
     panda_env.py:76,174-175,308; world assets from pybullet_data [EXT-recalled, SURVEY App. B.3]."""
     p = B2EParams()
@@ -287,6 +288,7 @@ def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orie
     p.n_act = n_act
     p.n_ctrl = n_ctrl
     p.use_ik = use_ik
+    p.goal_env = goal_env
     p.ik_orientation = ik_orientation
     p.ik_iters = 100
     p.ik_residual = 1e-3
@@ -340,9 +342,10 @@ def panda_obs_limits(task, robot_ws, world_ws, lower, upper, eu_lim=None):
     return low, high
 
 
-def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7):
+def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7, use_ik=0, ik_orientation=1, goal_env=0):
     """Model + params of the registered pandaPush-v0 / pandaReach-v0 configuration
-    (reference pybullet_robot_envs/__init__.py:47-68), joint control mode."""
+    (reference pybullet_robot_envs/__init__.py:47-68); ``use_ik=1`` gives the Cartesian control mode
+    (action = hand-pose increment, 6 wide with orientation control, 3 without)."""
     m, _ = load_panda()
     h_table = 0.625
     robot_ws = [[0.3, 0.65], [-0.3, 0.3], [0.65, 1.5]]
@@ -351,5 +354,7 @@ def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7):
     lower = [m.lower[i] for i in range(m.n_dof)]
     upper = [m.upper[i] for i in range(m.n_dof)]
     low, high = panda_obs_limits(task, robot_ws, world_ws, lower, upper)
-    p = default_params(task, low, high, n_act=n_ctrl, n_ctrl=n_ctrl, max_steps=max_steps, ws_lim=robot_ws)
+    n_act = n_ctrl if not use_ik else (6 if ik_orientation else 3)
+    p = default_params(task, low, high, n_act=n_act, n_ctrl=n_ctrl, use_ik=use_ik, ik_orientation=ik_orientation,
+                       max_steps=max_steps, ws_lim=robot_ws, goal_env=goal_env)
     return m, p

@@ -38,8 +38,6 @@ class PandaTaskBase(gym.Env):
         self._target_dist_min = target_dist_min
         self.includeVelObs = includeVelObs
         self.num_envs = int(num_envs)
-        if use_IK:
-            raise NotImplementedError("use_IK=1 (Cartesian control): SURVEY §8 row f2, not built in this round")
         # "connect": one batched simulation instead of p.connect(p.DIRECT)
         self._physics_client_id = B2Client(num_envs, device)
         self._robot = pandaEnv(self._physics_client_id, use_IK=self._use_IK, joint_action_space=numControlledJoints)
@@ -53,7 +51,9 @@ class PandaTaskBase(gym.Env):
         lim = self._observation_limits()
         params = default_params(self._task, [x[0] for x in lim], [x[1] for x in lim],
                                 n_act=self._robot.get_action_dim(), n_ctrl=numControlledJoints, use_ik=use_IK,
-                                max_steps=max_steps, dist_min=target_dist_min, ws_lim=workspace)
+                                ik_orientation=int(bool(self._robot._control_orientation)),
+                                max_steps=max_steps, dist_min=target_dist_min, ws_lim=workspace,
+                                eu_lim=self._robot.get_rotation_lim(), goal_env=int(getattr(self, '_goal_env', 0)))
         self._sim = self._physics_client_id.configure(self._robot.model, params)
         self._place_initial_world()
         self.observation_space, self.action_space = self.create_gym_spaces()
@@ -120,6 +120,9 @@ class PandaTaskBase(gym.Env):
         c.step_simulation(100, binding.MODE_HOLD)
         self._world.reset()
         c.step_simulation(100, binding.MODE_HOLD)
+        if self._use_IK:   # self._hand_pose = self._robot._home_hand_pose (reference :142-143)
+            self._hand_pose = list(self._robot._home_hand_pose)
+            c.set("hand_pose", np.tile(np.array(self._hand_pose, np.float32), (B, 1)))
         c.step_simulation(1, binding.MODE_HOLD)
 
     def _sync_target(self):
@@ -166,10 +169,14 @@ class PandaTaskBase(gym.Env):
             return self._step_device(action)
         a = np.asarray(action, np.float32)
         assert a.shape[-1:] == self.action_space.shape  # scale_gym_data's shape assert (utils.py:88)
-        obs, rew, done = self._sim.step_host(self._as_batch(a), self._action_repeat, binding.MODE_ACTION)
-        self._physics_client_id.invalidate()
         if self.num_envs == 1:
+            obs, rew, done = self._sim.step_host(self._as_batch(a), self._action_repeat, binding.MODE_ACTION)
+            self._physics_client_id.invalidate()
             return obs[0].astype(np.float64), np.array(rew[0]), np.array(done[0]), {}
+        # batched host path: page-locked staging, results are views valid until the next step()
+        obs, rew, done = self._sim.step_pinned(a if a.ndim == 2 else self._as_batch(a), self._action_repeat,
+                                               binding.MODE_ACTION)
+        self._physics_client_id.invalidate()
         return obs, rew, done, {}
 
     def _step_device(self, action):

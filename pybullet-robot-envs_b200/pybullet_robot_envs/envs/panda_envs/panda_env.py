@@ -53,10 +53,10 @@ class pandaEnv:
         c.set("mtarget", home)
         self.ll, self.ul, self.jr, self.rs = self.get_joint_ranges()
         if self._use_IK:
+            # home hand pose -> IK -> motor targets, then one physics step (reference :83-91)
             self._home_hand_pose = [0.2, 0.0, 0.8, min(m.pi, max(-m.pi, m.pi)), 0.0, 0.0]
             c.set("hand_pose", np.tile(np.array(self._home_hand_pose, np.float32), (B, 1)))
-            self.apply_action(np.tile(np.array(self._home_hand_pose, np.float32), (B, 1)))
-            c.step_simulation(1, binding.MODE_HOLD)
+            c.step_simulation(1, binding.MODE_IK_POSE)
 
     def delete_simulated_robot(self):
         pass  # bodies are fixed members of the batched simulation
@@ -140,13 +140,25 @@ class pandaEnv:
                                      '\n- 6: (dx,dy,dz,droll,dpitch,dyaw)'
                                      '\n- 7: (dx,dy,dz,qx,qy,qz,w)'
                                      '\ninstead it is: ', action.shape[1])
-            raise NotImplementedError("IK control mode: SURVEY §8 row f2, not built in this round")
+            if action.shape[1] == 7:
+                raise NotImplementedError("quaternion hand-pose commands (control_eu_or_quat=1) are not built")
+            # Cartesian command: the pose is stored; IK + motor targets happen inside the next physics
+            # launch (B2Client.step_simulation picks MODE_IK_POSE), like calculateInverseKinematics +
+            # setJointMotorControlArray(kp 0.2) at reference :269-282
+            hp = self._client.get("hand_pose")
+            hp[:, :action.shape[1]] = action
+            if action.shape[1] == 3:
+                hp[:, 3:6] = np.asarray(self._home_hand_pose[3:6], np.float32)
+            self._client.set("hand_pose", hp)
+            self._client.pending_mode = binding.MODE_IK_POSE
+            return
         assert action.shape[1] == self.joint_action_space, \
             ('number of motor commands differs from number of motor to control', action.shape[1])
         n = action.shape[1]
         mt = self._client.get("mtarget")
         mt[:, :n] = np.minimum(np.asarray(self.ul[:n], np.float32), np.maximum(np.asarray(self.ll[:n], np.float32), action))
         self._client.set("mtarget", mt)
+        self._client.pending_mode = binding.MODE_TARGETS
 
     def check_collision(self, obj_id=None):
         """True where the robot touches the object somewhere else than with the finger pads."""

@@ -75,7 +75,7 @@ def test_overridden_hook_takes_the_reference_call_sequence():
     o1, r1, d1, _ = base.step(a)
     o2, r2, d2, _ = sub.step(a)
     assert not sub._fused and base._fused
-    np.testing.assert_allclose(o2, o1, atol=1e-5)
+    np.testing.assert_allclose(o2, o1, atol=1e-5, rtol=1e-5)   # host float64 scaling vs device fp32 scaling
     np.testing.assert_allclose(r2, 2.0 * r1, rtol=1e-6)
     np.testing.assert_array_equal(d1, d2)
     base.close(); sub.close()
