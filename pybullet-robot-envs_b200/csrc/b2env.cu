@@ -811,6 +811,7 @@ __device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restri
 
 // ------------------------------------------------------------------------------------------
 // the fused step kernel
+template <bool IK>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
@@ -848,9 +849,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   }
   float my_act = 0.f;
   if (mode == B2E_MODE_ACTION && lane < P.n_act) my_act = action[env * P.n_act + lane];
-  float my_hp = (P.use_ik && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;   // commanded hand pose (lane = component)
+  float my_hp = (IK && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;   // commanded hand pose (lane = component)
   const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
-  const float my_kp = (mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P.use_ik && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
+  const float my_kp = (!IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
   __syncwarp();
@@ -890,13 +891,13 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     PHASE_BARRIER();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
-    if (mode == B2E_MODE_ACTION && !P.use_ik && lane < P.n_ctrl && !ghost) {
+    if (!IK && mode == B2E_MODE_ACTION && lane < P.n_ctrl && !ghost) {
       my_act *= P.act_scale;
       my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
     }
     // ---- Cartesian control (panda_push_gym_env.py:197-222, panda_env.py:229-282): hand pose += scaled
     //      action, clamps, IK -> position targets of every movable joint ----
-    if (P.use_ik && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE)) {
+    if (IK && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE)) {
       if (mode == B2E_MODE_ACTION && !ghost && lane < 6) {
         if (lane < 3) {
           my_act *= P.act_scale_pos;
@@ -1341,7 +1342,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     st.obj_vel[env * 6 + 0] = cv[0]; st.obj_vel[env * 6 + 1] = cv[1]; st.obj_vel[env * 6 + 2] = cv[2];
     st.obj_vel[env * 6 + 3] = cw[0]; st.obj_vel[env * 6 + 4] = cw[1]; st.obj_vel[env * 6 + 5] = cw[2];
   }
-  if (P.use_ik && lane < 6) st.hand_pose[env * 6 + lane] = my_hp;
+  if (IK && lane < 6) st.hand_pose[env * 6 + lane] = my_hp;
   if (lane < B2E_CACHE_SLOTS) {
     st.cache_key[env * B2E_CACHE_SLOTS + lane] = sm.ckey[lane];
 #pragma unroll
@@ -1651,7 +1652,8 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaMallocHost(&s->h_action, na)); CUDA_TRY(cudaMallocHost(&s->h_obs, no));
   CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
   CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
   *out = s;
   return 0;
 }
@@ -1699,8 +1701,12 @@ int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* 
   if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step: n_substeps < 0%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
   const int blocks = (s->B + WPB - 1) / WPB;
-  step_kernel<<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
-      s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
+  if (s->params.use_ik)
+    step_kernel<true><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
+  else
+    step_kernel<false><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
