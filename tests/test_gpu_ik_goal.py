@@ -60,7 +60,7 @@ def test_cartesian_env_api():
     raw, _ = env.get_extended_observation()
     # after the reset the hand sits near the home hand pose (0.2, 0, 0.8) (panda_env.py:85-88); not exactly:
     # the IK ignores joint limits and joint 4 of its solution lies beyond its lower limit
-    assert np.all(np.abs(raw[:, 0] - 0.2) < 0.12) and np.all(np.abs(raw[:, 2] - 0.8) < 0.05)
+    assert np.all(np.abs(raw[:, 0] - 0.2) < 0.12) and np.all(np.abs(raw[:, 2] - 0.8) < 0.12)
     a = np.zeros((16, 6), np.float32)
     a[:, 2] = -1.0
     for _ in range(50):
