@@ -90,6 +90,8 @@ typedef struct b2e_model {
 
 #define B2E_TASK_REACH 0
 #define B2E_TASK_PUSH 1
+#define B2E_TASK_GRASP 2 /* PandaGrasp-v0 (BASELINE.json config 5; no reference env: built from the grasp
+                            primitives panda_env.py:195-225 and helloworld_panda.py:94-148)          */
 
 /* World + solver + task constants (what the task env and WorldEnv set up).     */
 typedef struct b2e_params {
@@ -133,6 +135,9 @@ typedef struct b2e_params {
   float ws_lim[3][2];      /* robot workspace (IK clamps)                        */
   float eu_lim[3][2];
   float home_hand_pose[6]; /* panda_env.py:85-88                                 */
+  float kp_grip;           /* GRASP: finger position gain (setJointMotorControl2 default 0.1, panda_env.py:218-224) */
+  float grasp_lift;        /* GRASP: success when the object is this far above its rest height    */
+  float grasp_rest_z;      /* GRASP: object rest height (table top + half extent)                 */
   int32_t goal_env;        /* GoalEnv semantics (panda_push_gym_goal_env.py:89-122): sparse reward
                               -(d > dist_min), done = counter > max_steps or success, no latch */
 } b2e_params;
@@ -201,6 +206,15 @@ int b2e_reset(b2e_sim* sim, const uint8_t* env_mask, const float* obj_init_pose 
  * the current state (get_extended_observation, _termination, _compute_reward). */
 int b2e_step(b2e_sim* sim, const float* action, float* obs, float* reward, float* done,
              int n_substeps, int mode, void* stream);
+
+/* The same step for a SUBSET of environments (env_ids: device int32 [n_ids], distinct): per-env
+ * resets settle only the envs being reset (panda_push_gym_env.py:105-148 applied to some envs of
+ * the batch).  action/obs/reward/done are the full-batch buffers, indexed by env id.             */
+int b2e_step_subset(b2e_sim* sim, const int32_t* env_ids, int n_ids, const float* action, float* obs,
+                    float* reward, float* done, int n_substeps, int mode, void* stream);
+/* Scatter / gather rows of a state field: rows is a device buffer [n][width].                    */
+int b2e_set_rows(b2e_sim* sim, int field, const int32_t* env_ids, int n, const void* rows, void* stream);
+int b2e_get_rows(b2e_sim* sim, int field, const int32_t* env_ids, int n, void* rows, void* stream);
 
 /* Host-buffer convenience used by the single-env compatibility path and the
  * end-to-end benchmark: copies action H2D, steps, copies results D2H, syncs.    */

@@ -683,7 +683,7 @@ static int extended_observation(const b2e_model* m, const b2e_params* P, const f
   quat_to_euler(relq, releu);
   for (int k = 0; k < 3; k++) obs[n++] = rel[k];
   for (int k = 0; k < 3; k++) obs[n++] = releu[k];
-  if (P->task == B2E_TASK_PUSH)
+  if (P->task == B2E_TASK_PUSH || P->task == B2E_TASK_GRASP)
     for (int k = 0; k < 3; k++) obs[n++] = target[k];
   return n;
 }
@@ -779,7 +779,7 @@ typedef struct {
   real contact_out[MAXC][8];
 } env_t;
 
-static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int kp_ctrl_active) {
+static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int kp_ctrl_active, int grip_active) {
   int nd = m->n_dof, nv = nd + 6;
   real dt = P->dt;
   fk_t fk;
@@ -813,7 +813,7 @@ static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int 
     memset(r, 0, sizeof(*r));
     r->type = ROW_MOTOR; r->island = ISL_ARM;
     r->J[d] = 1;
-    real kp = (kp_ctrl_active && d < P->n_ctrl) ? P->kp_ctrl : P->kp_hold;
+    real kp = (kp_ctrl_active && d < P->n_ctrl) ? P->kp_ctrl : ((grip_active && d >= P->n_ctrl) ? P->kp_grip : P->kp_hold);
     real desired = kp * (e->mtarget[d] - e->q[d]) / dt;
     if (m->max_vel[d] > 0) {
       if (desired > m->max_vel[d]) desired = m->max_vel[d];
@@ -1035,6 +1035,15 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
         if (t > m->upper[k]) t = m->upper[k];
         e.mtarget[k] = t;
       }
+      if (P->task == B2E_TASK_GRASP) { /* gripper command in [-1,1] -> both finger targets in [0, 0.04] */
+        real g = action[b * P->n_act + P->n_ctrl];
+        for (int k = P->n_ctrl; k < m->n_dof; k++) {
+          real t = (real)0.02 + (real)0.02 * g;
+          if (t < m->lower[k]) t = m->lower[k];
+          if (t > m->upper[k]) t = m->upper[k];
+          e.mtarget[k] = t;
+        }
+      }
     }
     if ((mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE) && P->use_ik) {
       /* task level (panda_push_gym_env.py:197-222): hand_pose += scaled action, clamp to rotation limits
@@ -1071,13 +1080,14 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
       ik_dls(m, P, e.q, tp, tq, qik);
       for (int d = 0; d < m->n_dof; d++) e.mtarget[d] = qik[d];
     }
-    physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik);
+    physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik, mode != B2E_MODE_HOLD && P->task == B2E_TASK_GRASP);
     if (mode == B2E_MODE_ACTION) {
       /* _termination() inside apply_action (:239-242): counter only advances when not terminated */
       fk_t fk;
       forward_kinematics(m, e.q, &fk);
       real d;
       if (P->task == B2E_TASK_PUSH) d = dist3(e.cpos, target);
+      else if (P->task == B2E_TASK_GRASP) d = (e.cpos[2] - P->grasp_rest_z >= P->grasp_lift) ? 0 : 2 * P->dist_min + 1;
       else { real pos[3], qt[4], vl[3]; ee_state(m, &fk, e.qd, pos, qt, vl); d = dist3(pos, e.cpos); }
       int term = 0;
       if (P->goal_env) { if (counter > P->max_steps) term = 1; }   /* panda_push_gym_goal_env.py:106-110 */
@@ -1113,6 +1123,15 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
         rew = -d1 - d2;
         if (d2 <= P->dist_min) rew = (real)1000.0 + (100 - d2 * 80);
       }
+    } else if (P->task == B2E_TASK_GRASP) {
+      /* PandaGrasp (new task): reach the object, close the fingers, lift it grasp_lift above its rest height */
+      real lift = e.cpos[2] - P->grasp_rest_z;
+      int success = lift >= P->grasp_lift;
+      if (success) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P->max_steps) dn = 1;
+      real l = lift < 0 ? 0 : (lift > P->grasp_lift ? P->grasp_lift : lift);
+      rew = -d1 + 50 * l;
+      if (success) rew = (real)1000.0;
     } else {
       if (d1 <= P->dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P->max_steps) dn = 1;

@@ -815,12 +815,15 @@ template <bool IK>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
-            int mode, int record_contacts) {
+            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env_raw = blockIdx.x * WPB + warp;
-  const bool live_env = env_raw < st.B;      // padding warps of the last block shadow the last env, stores masked
-  const int env = live_env ? env_raw : st.B - 1;
+  // slot -> environment: the whole batch, or the subset listed in env_ids (per-env resets, row f1)
+  const int n_slots = env_ids ? n_ids : st.B;
+  const int slot = blockIdx.x * WPB + warp;
+  const bool live_env = slot < n_slots;      // padding warps of the last block shadow the last slot, stores masked
+  const int slot_c = live_env ? slot : n_slots - 1;
+  const int env = env_ids ? env_ids[slot_c] : slot_c;
   WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
   const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
@@ -851,7 +854,10 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   if (mode == B2E_MODE_ACTION && lane < P.n_act) my_act = action[env * P.n_act + lane];
   float my_hp = (IK && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;   // commanded hand pose (lane = component)
   const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
-  const float my_kp = (!IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && lane < P.n_ctrl) ? P.kp_ctrl : P.kp_hold;
+  const bool ctrl_gains = !IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE;
+  const float my_kp = (ctrl_gains && lane < P.n_ctrl) ? P.kp_ctrl
+                      : ((ctrl_gains && P.task == B2E_TASK_GRASP && lane >= P.n_ctrl) ? P.kp_grip : P.kp_hold);
+  const float grip_cmd = shf(my_act, P.n_ctrl & 31);   // GRASP: action[n_ctrl] = gripper command
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
   __syncwarp();
@@ -873,6 +879,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       if (P.task == B2E_TASK_PUSH) {
         float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
         d = sqrtf(dot3(dd, dd));
+      } else if (P.task == B2E_TASK_GRASP) {
+        d = (cpos[2] - P.grasp_rest_z >= P.grasp_lift) ? 0.f : 2.f * P.dist_min + 1.f;
       } else {
         const int ee = U.ee_link;
         float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]}, o[3];
@@ -895,6 +903,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       my_act *= P.act_scale;
       my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
     }
+    if (!IK && mode == B2E_MODE_ACTION && P.task == B2E_TASK_GRASP && is_dof && lane >= P.n_ctrl && !ghost)
+      my_target = fminf(fmaxf(0.02f + 0.02f * grip_cmd, my_lower), my_upper);
     // ---- Cartesian control (panda_push_gym_env.py:197-222, panda_env.py:229-282): hand pose += scaled
     //      action, clamps, IK -> position targets of every movable joint ----
     if (IK && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE)) {
@@ -1418,7 +1428,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       for (int k = 0; k < 3; k++) sm.obs[n++] = relp[k];
 #pragma unroll
       for (int k = 0; k < 3; k++) sm.obs[n++] = releu[k];
-      if (P.task == B2E_TASK_PUSH) {
+      if (P.task == B2E_TASK_PUSH || P.task == B2E_TASK_GRASP) {
 #pragma unroll
         for (int k = 0; k < 3; k++) sm.obs[n++] = target[k];
       }
@@ -1446,6 +1456,13 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
         rew = -d1 - d2;
         if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
       }
+    } else if (P.task == B2E_TASK_GRASP) {
+      const float lift = cpos[2] - P.grasp_rest_z;
+      const bool success = lift >= P.grasp_lift;
+      if (success) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1 + 50.0f * fminf(fmaxf(lift, 0.f), P.grasp_lift);
+      if (success) rew = 1000.0f;
     } else {
       if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P.max_steps) dn = 1;
@@ -1600,6 +1617,31 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   return 0;
 }
 
+static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
+                       const int* env_ids, int n_ids, void* stream) {
+  const int n = env_ids ? n_ids : s->B;
+  if (n <= 0) return 0;
+  const int blocks = (n + WPB - 1) / WPB;
+  if (s->params.use_ik)
+    step_kernel<true><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
+  else
+    step_kernel<false><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// scatter / gather rows of a state field
+__global__ void rows_kernel(float* field, const int* __restrict__ ids, int n, int width, float* rows, int gather) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int r = i / width, c = i - r * width;
+  if (gather) rows[i] = field[(size_t)ids[r] * width + c];
+  else field[(size_t)ids[r] * width + c] = rows[i];
+}
+
 extern "C" {
 
 const char* b2e_last_error(void) { return g_err; }
@@ -1700,13 +1742,34 @@ int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* 
   if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step: action is required in ACTION mode%s", "");
   if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step: n_substeps < 0%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
-  const int blocks = (s->B + WPB - 1) / WPB;
-  if (s->params.use_ik)
-    step_kernel<true><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
-  else
-    step_kernel<false><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts);
+  return launch_step(s, action, obs, reward, done, n_substeps, mode, nullptr, 0, stream);
+}
+
+int b2e_step_subset(b2e_sim* s, const int32_t* env_ids, int n_ids, const float* action, float* obs, float* reward,
+                    float* done, int n_substeps, int mode, void* stream) {
+  if (!s || !env_ids || n_ids < 0 || n_ids > s->B) return fail(B2E_EINVAL, "b2e_step_subset: bad argument%s", "");
+  if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step_subset: action is required in ACTION mode%s", "");
+  if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step_subset: n_substeps < 0%s", "");
+  CUDA_TRY(cudaSetDevice(s->device));
+  return launch_step(s, action, obs, reward, done, n_substeps, mode, env_ids, n_ids, stream);
+}
+
+int b2e_set_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, const void* rows, void* stream) {
+  if (!s || !env_ids || !rows || field < 0 || field >= B2E_F_COUNT || n < 0) return fail(B2E_EINVAL, "b2e_set_rows: bad argument%s", "");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int w = field_width(s, field), tot = n * w;
+  rows_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)s->fields[field], env_ids, n, w, (float*)rows, 0);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2e_get_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, void* rows, void* stream) {
+  if (!s || !env_ids || !rows || field < 0 || field >= B2E_F_COUNT || n < 0) return fail(B2E_EINVAL, "b2e_get_rows: bad argument%s", "");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int w = field_width(s, field), tot = n * w;
+  rows_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)s->fields[field], env_ids, n, w, (float*)rows, 1);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -23,7 +23,11 @@ for _name in ('pandaPush-v0', 'PandaPush-v0'):
 for _name in ('pandaPushGoal-v0', 'PandaPushGoal-v0'):   # reference __init__.py:70-80
     register(id=_name, entry_point='pybullet_robot_envs.envs:pandaPushGymGoalEnv', max_episode_steps=1000,
              kwargs=dict(_PUSH_KW))
+for _name in ('pandaGrasp-v0', 'PandaGrasp-v0'):   # BASELINE.json config 5: new task, no reference counterpart
+    register(id=_name, entry_point='pybullet_robot_envs.envs:pandaGraspGymEnv', max_episode_steps=1000,
+             kwargs={'numControlledJoints': 7, 'use_IK': 0, 'obj_pose_rnd_std': 0.05, 'max_steps': 1000, 'renders': False})
 
 
 def getList():
-    return ['pandaReach-v0', 'pandaPush-v0', 'pandaPushGoal-v0', 'PandaReach-v0', 'PandaPush-v0', 'PandaPushGoal-v0']
+    return ['pandaReach-v0', 'pandaPush-v0', 'pandaPushGoal-v0', 'PandaReach-v0', 'PandaPush-v0', 'PandaPushGoal-v0',
+            'pandaGrasp-v0', 'PandaGrasp-v0']

@@ -26,6 +26,7 @@ OPT_RECORD_CONTACTS = 0
 
 EXPORTS = [
     "b2e_create", "b2e_destroy", "b2e_set_params", "b2e_set_option", "b2e_reset", "b2e_step",
+    "b2e_step_subset", "b2e_set_rows", "b2e_get_rows",
     "b2e_step_host", "b2e_step_pinned", "b2e_host_alloc", "b2e_host_free", "b2e_get", "b2e_set", "b2e_get_host", "b2e_set_host", "b2e_field_width",
     "b2e_field_elem_size", "b2e_num_envs", "b2e_launch_count", "b2e_timer_start", "b2e_timer_stop",
     "b2e_last_error", "b2e_version",
@@ -56,6 +57,9 @@ def load_library(path=None):
     lib.b2e_set_option.argtypes = [vp, ci, ci]
     lib.b2e_reset.argtypes = [vp, vp, vp, vp, vp]
     lib.b2e_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp]
+    lib.b2e_step_subset.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, vp]
+    lib.b2e_set_rows.argtypes = [vp, ci, vp, ci, vp, vp]
+    lib.b2e_get_rows.argtypes = [vp, ci, vp, ci, vp, vp]
     lib.b2e_step_host.argtypes = [vp, vp, vp, vp, vp, ci, ci]
     lib.b2e_step_pinned.argtypes = [vp, vp, vp, vp, vp, ci, ci]
     lib.b2e_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -207,6 +211,38 @@ class B2Sim:
         torch.cuda.synchronize(dev)
         self.reset(o, t, m)
         torch.cuda.synchronize(dev)
+
+    # subset entry points (per-env resets)
+    def _ids_dev(self, ids):
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(ids, np.int32)).to(torch.device("cuda", self.device))
+
+    def step_subset(self, ids, n_substeps=1, mode=MODE_HOLD):
+        """Advance only the listed environments (no action / outputs: settle steps of a reset)."""
+        import torch
+        d = self._ids_dev(ids)
+        self._check(self.lib.b2e_step_subset(self.h, _ptr(d), int(d.numel()), None, None, None, None, n_substeps, mode,
+                                             C.c_void_p(0)))
+        torch.cuda.synchronize(d.device)
+
+    def set_rows(self, name, ids, values):
+        import torch
+        f = FIELD_NAMES[name]
+        w = self.lib.b2e_field_width(self.h, f)
+        d = self._ids_dev(ids)
+        v = torch.as_tensor(np.ascontiguousarray(values, np.int32 if f in INT_FIELDS else np.float32).reshape(-1, w)).to(d.device)
+        assert v.shape[0] == d.numel()
+        self._check(self.lib.b2e_set_rows(self.h, f, _ptr(d), int(d.numel()), _ptr(v), C.c_void_p(0)))
+        torch.cuda.synchronize(d.device)
+
+    def get_rows(self, name, ids):
+        import torch
+        f = FIELD_NAMES[name]
+        w = self.lib.b2e_field_width(self.h, f)
+        d = self._ids_dev(ids)
+        out = torch.empty((d.numel(), w), dtype=torch.int32 if f in INT_FIELDS else torch.float32, device=d.device)
+        self._check(self.lib.b2e_get_rows(self.h, f, _ptr(d), int(d.numel()), _ptr(out), C.c_void_p(0)))
+        return out.cpu().numpy()
 
     def launch_count(self):
         return int(self.lib.b2e_launch_count(self.h))

@@ -65,6 +65,14 @@ class B2Client:
         self.ensure().set(name, value)
         self._obs_cache_valid = False
 
+    def set_rows(self, name, ids, value):
+        self.ensure().set_rows(name, ids, value)
+        self._obs_cache_valid = False
+
+    def step_subset(self, ids, n=1, mode=binding.MODE_HOLD):
+        self.ensure().step_subset(ids, n, mode)
+        self._obs_cache_valid = False
+
     def close(self):
         if self.sim is not None:
             self.sim.close()

@@ -32,6 +32,7 @@ JOINT_FIXED = 4
 
 TASK_REACH = 0
 TASK_PUSH = 1
+TASK_GRASP = 2
 
 _f = C.c_float
 _i = C.c_int32
@@ -71,7 +72,7 @@ class B2EParams(C.Structure):
         ("obs_low", _f * MAX_OBS), ("obs_high", _f * MAX_OBS),
         ("vel_mean", _f * 3), ("vel_std", _f * 3),
         ("ws_lim", (_f * 2) * 3), ("eu_lim", (_f * 2) * 3), ("home_hand_pose", _f * 6),
-        ("goal_env", _i),
+        ("kp_grip", _f), ("grasp_lift", _f), ("grasp_rest_z", _f), ("goal_env", _i),
     ]
 
 
@@ -289,6 +290,9 @@ def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orie
     p.n_ctrl = n_ctrl
     p.use_ik = use_ik
     p.goal_env = goal_env
+    p.kp_grip = 0.1
+    p.grasp_lift = 0.1
+    p.grasp_rest_z = 0.65
     p.ik_orientation = ik_orientation
     p.ik_iters = 100
     p.ik_residual = 1e-3
@@ -335,7 +339,7 @@ def panda_obs_limits(task, robot_ws, world_ws, lower, upper, eu_lim=None):
     lim += [[lower[i], upper[i]] for i in range(len(lower))]
     lim += [list(x) for x in world_ws] + [[-pi, pi]] * 3
     lim += [[-0.5, 0.5]] * 3 + [[0, 2 * pi]] * 3
-    if task == TASK_PUSH:
+    if task in (TASK_PUSH, TASK_GRASP):
         lim += [list(x) for x in world_ws]
     low = [x[0] for x in lim]
     high = [x[1] for x in lim]
@@ -350,11 +354,17 @@ def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7, use_ik=0, ik_orie
     h_table = 0.625
     robot_ws = [[0.3, 0.65], [-0.3, 0.3], [0.65, 1.5]]
     world_ws = [[0.3, 0.65], [-0.3, 0.3], [h_table, h_table + 0.3]]     # world_env.py:72
-    robot_ws[2][0] = h_table - 0.2 if task == TASK_PUSH else h_table     # push :74 / reach :69
+    robot_ws[2][0] = h_table if task == TASK_REACH else h_table - 0.2   # push :74 / reach :69
     lower = [m.lower[i] for i in range(m.n_dof)]
     upper = [m.upper[i] for i in range(m.n_dof)]
     low, high = panda_obs_limits(task, robot_ws, world_ws, lower, upper)
     n_act = n_ctrl if not use_ik else (6 if ik_orientation else 3)
+    if task == TASK_GRASP:
+        assert not use_ik
+        n_act = n_ctrl + 1                         # + gripper open/close command
+        for d in (7, 8):                           # apply_action_fingers: force=10, maxVelocity=1 (panda_env.py:218-224)
+            m.max_force[d] = 10.0
+            m.max_vel[d] = 1.0
     p = default_params(task, low, high, n_act=n_act, n_ctrl=n_ctrl, use_ik=use_ik, ik_orientation=ik_orientation,
                        max_steps=max_steps, ws_lim=robot_ws, goal_env=goal_env)
     return m, p

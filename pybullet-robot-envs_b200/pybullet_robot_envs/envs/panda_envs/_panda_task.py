@@ -11,7 +11,7 @@ from pybullet_robot_envs import gym_compat as gym
 from pybullet_robot_envs.gym_compat import spaces, seeding
 from pybullet_robot_envs.b2env import binding
 from pybullet_robot_envs.b2env.client import B2Client, squeeze1
-from pybullet_robot_envs.b2env.model import TASK_PUSH, TASK_REACH, default_params
+from pybullet_robot_envs.b2env.model import TASK_GRASP, TASK_PUSH, TASK_REACH, default_params
 from pybullet_robot_envs.envs.panda_envs.panda_env import pandaEnv
 from pybullet_robot_envs.envs.world_envs.world_env import WorldEnv
 from pybullet_robot_envs.envs.utils import goal_distance, scale_gym_data
@@ -50,15 +50,21 @@ class PandaTaskBase(gym.Env):
         # constants -> simulation (observation limits are known from the lists above)
         lim = self._observation_limits()
         params = default_params(self._task, [x[0] for x in lim], [x[1] for x in lim],
-                                n_act=self._robot.get_action_dim(), n_ctrl=numControlledJoints, use_ik=use_IK,
+                                n_act=self._robot.get_action_dim() + (1 if self._task == TASK_GRASP else 0),
+                                n_ctrl=numControlledJoints, use_ik=use_IK,
                                 ik_orientation=int(bool(self._robot._control_orientation)),
                                 max_steps=max_steps, dist_min=target_dist_min, ws_lim=workspace,
                                 eu_lim=self._robot.get_rotation_lim(), goal_env=int(getattr(self, '_goal_env', 0)))
+        if self._task == TASK_GRASP:   # apply_action_fingers: force=10, maxVelocity=1 (reference panda_env.py:218-224)
+            for d in (7, 8):
+                self._robot.model.max_force[d] = 10.0
+                self._robot.model.max_vel[d] = 1.0
         self._sim = self._physics_client_id.configure(self._robot.model, params)
         self._place_initial_world()
         self.observation_space, self.action_space = self.create_gym_spaces()
         self._fused = all(getattr(type(self), h) is getattr(self._base_cls(), h) for h in self._hooks)
         self._torch_out = None
+        self.auto_reset = False   # set True for auto-resetting vectorised rollouts (host-array step path)
         self.seed()
 
     @classmethod
@@ -79,7 +85,7 @@ class PandaTaskBase(gym.Env):
     def _observation_limits(self):
         lim = self._robot.observation_limits() + self._world.observation_limits()
         lim += [[-0.5, 0.5]] * 3 + [[0, 2 * m.pi]] * 3
-        if self._task == TASK_PUSH:
+        if self._task in (TASK_PUSH, TASK_GRASP):
             lim += self._world.observation_limits()[:3]
         return lim
 
@@ -93,9 +99,14 @@ class PandaTaskBase(gym.Env):
         return observation_space, action_space
 
     # ------------------------------------------------------------------ reset
-    def reset(self):
+    def reset(self, env_ids=None):
+        """``reset()`` resets every environment like the reference (:105-115).  ``reset(env_ids)`` resets only
+        the listed environments of the batch (same 100 + 100 + 1 settle sequence, run on that subset)
+        and returns their observations [len(env_ids), O]."""
+        if env_ids is not None:
+            return self._reset_subset(np.asarray(env_ids, np.int32))
         self.reset_simulation()
-        if self._task == TASK_PUSH:
+        if self._task in (TASK_PUSH, TASK_GRASP):
             world_obs, _ = self._world.get_observation()
             self._target_pose = self.sample_tg_pose(np.asarray(world_obs).reshape(self.num_envs, 6)[:, :3])
             self._sync_target()
@@ -124,6 +135,35 @@ class PandaTaskBase(gym.Env):
             self._hand_pose = list(self._robot._home_hand_pose)
             c.set("hand_pose", np.tile(np.array(self._hand_pose, np.float32), (B, 1)))
         c.step_simulation(1, binding.MODE_HOLD)
+
+    def _reset_subset(self, ids):
+        c = self._physics_client_id
+        n = len(ids)
+        if n == 0:
+            return np.zeros((0, self.observation_space.shape[0]), np.float32)
+        c.set_rows("counters", ids, np.zeros((n, 2), np.int32))
+        c.set_rows("status", ids, np.zeros((n, 4), np.int32))
+        c.set_rows("obj_pose", ids, np.tile(np.array(_PARK_POSE, np.float32), (n, 1)))
+        c.set_rows("obj_vel", ids, np.zeros((n, 6), np.float32))
+        c.set_rows("cache_key", ids, np.full((n, 16), -1, np.int32))
+        c.set_rows("cache_lam", ids, np.zeros((n, 48), np.float32))
+        self._robot.reset(ids)
+        c.step_subset(ids, 100, binding.MODE_HOLD)
+        self._world.reset(ids)
+        c.step_subset(ids, 100, binding.MODE_HOLD)
+        if self._use_IK:
+            c.set_rows("hand_pose", ids, np.tile(np.array(self._robot._home_hand_pose, np.float32), (n, 1)))
+        c.step_subset(ids, 1, binding.MODE_HOLD)
+        if self._task in (TASK_PUSH, TASK_GRASP):
+            obj = c.sim.get_rows("obj_pose", ids)[:, :3]
+            tg = np.asarray(self.sample_tg_pose(obj), np.float32).reshape(n, 3)
+            tp = np.asarray(self._target_pose, np.float32).reshape(-1, 3)
+            if tp.shape[0] == self.num_envs:
+                tp[ids] = tg
+                self._target_pose = tp
+            c.set_rows("target", ids, tg)
+        scaled = c.observe()[0]
+        return scaled[ids]
 
     def _sync_target(self):
         tp = np.asarray(self._target_pose, np.float32).reshape(-1, 3)
@@ -169,7 +209,7 @@ class PandaTaskBase(gym.Env):
             return self._step_device(action)
         a = np.asarray(action, np.float32)
         assert a.shape[-1:] == self.action_space.shape  # scale_gym_data's shape assert (utils.py:88)
-        if self.num_envs == 1:
+        if self.num_envs == 1 and not self.auto_reset:
             obs, rew, done = self._sim.step_host(self._as_batch(a), self._action_repeat, binding.MODE_ACTION)
             self._physics_client_id.invalidate()
             return obs[0].astype(np.float64), np.array(rew[0]), np.array(done[0]), {}
@@ -177,6 +217,13 @@ class PandaTaskBase(gym.Env):
         obs, rew, done = self._sim.step_pinned(a if a.ndim == 2 else self._as_batch(a), self._action_repeat,
                                                binding.MODE_ACTION)
         self._physics_client_id.invalidate()
+        if self.auto_reset and done.any():
+            # vectorised-env convention: finished envs restart at once, their row of `obs` is the first
+            # observation of the new episode; reward / done still describe the finished episode
+            ids = np.nonzero(done)[0].astype(np.int32)
+            obs = np.array(obs)
+            rew, done = np.array(rew), np.array(done)
+            obs[ids] = self._reset_subset(ids)
         return obs, rew, done, {}
 
     def _step_device(self, action):

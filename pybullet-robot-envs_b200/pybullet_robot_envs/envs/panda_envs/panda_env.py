@@ -43,20 +43,27 @@ class pandaEnv:
             self._home_hand_pose = [0.2, 0.0, 0.8, min(m.pi, max(-m.pi, m.pi)), 0.0, 0.0]
 
     # ------------------------------------------------------------------ lifecycle
-    def reset(self):
-        """Home joint state, zero velocity, position motors targeting home (reference :51-91)."""
+    def reset(self, env_ids=None):
+        """Home joint state, zero velocity, position motors targeting home (reference :51-91).
+        ``env_ids``: only those environments (per-env reset of a batch)."""
         c = self._client
-        B, nd = c.num_envs, self.model.n_dof
-        home = np.tile(np.array([self.model.home[i] for i in range(nd)], np.float32), (B, 1))
-        c.set("q", home)
-        c.set("qd", np.zeros((B, nd), np.float32))
-        c.set("mtarget", home)
+        nd = self.model.n_dof
+        ids = None if env_ids is None else np.asarray(env_ids, np.int32)
+        n = c.num_envs if ids is None else len(ids)
+        home = np.tile(np.array([self.model.home[i] for i in range(nd)], np.float32), (n, 1))
+        put = (lambda k, v: c.set(k, v)) if ids is None else (lambda k, v: c.set_rows(k, ids, v))
+        put("q", home)
+        put("qd", np.zeros((n, nd), np.float32))
+        put("mtarget", home)
         self.ll, self.ul, self.jr, self.rs = self.get_joint_ranges()
         if self._use_IK:
             # home hand pose -> IK -> motor targets, then one physics step (reference :83-91)
             self._home_hand_pose = [0.2, 0.0, 0.8, min(m.pi, max(-m.pi, m.pi)), 0.0, 0.0]
-            c.set("hand_pose", np.tile(np.array(self._home_hand_pose, np.float32), (B, 1)))
-            c.step_simulation(1, binding.MODE_IK_POSE)
+            put("hand_pose", np.tile(np.array(self._home_hand_pose, np.float32), (n, 1)))
+            if ids is None:
+                c.step_simulation(1, binding.MODE_IK_POSE)
+            else:
+                c.step_subset(ids, 1, binding.MODE_IK_POSE)
 
     def delete_simulated_robot(self):
         pass  # bodies are fixed members of the batched simulation

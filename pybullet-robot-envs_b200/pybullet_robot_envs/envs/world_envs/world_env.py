@@ -52,24 +52,34 @@ class WorldEnv:
             self._rngs = [self.np_random] + [seeding.np_random(seed + i)[0] for i in range(1, B)]
         return [seed0]
 
-    def reset(self):
+    def reset(self, env_ids=None):
         """(Re)place the object (reference :61-84): sample a start pose per env, zero velocity,
-        forget the contact cache."""
+        forget the contact cache.  ``env_ids``: only those environments."""
         self._ws_lim[2][:] = [self._h_table, self._h_table + 0.3]
-        self.load_object(self._obj_name)
+        self.load_object(self._obj_name, env_ids)
 
-    def load_object(self, obj_name):
+    def load_object(self, obj_name, env_ids=None):
         if obj_name != 'cube_small':
             raise NotImplementedError("object '%s': only 'cube_small' has a collision model in the CUDA backend" % obj_name)
         self._obj_name = obj_name
         c = self._client
         B = c.num_envs
-        poses = np.array([self._sample_pose(i) for i in range(B)], np.float32)
-        self._obj_init_pose = poses
-        c.set("obj_pose", poses)
-        c.set("obj_vel", np.zeros((B, 6), np.float32))
-        c.set("cache_key", np.full((B, 16), -1, np.int32))
-        c.set("cache_lam", np.zeros((B, 48), np.float32))
+        if env_ids is None:
+            poses = np.array([self._sample_pose(i) for i in range(B)], np.float32)
+            self._obj_init_pose = poses
+            c.set("obj_pose", poses)
+            c.set("obj_vel", np.zeros((B, 6), np.float32))
+            c.set("cache_key", np.full((B, 16), -1, np.int32))
+            c.set("cache_lam", np.zeros((B, 48), np.float32))
+            return
+        ids = np.asarray(env_ids, np.int32)
+        poses = np.array([self._sample_pose(int(i)) for i in ids], np.float32).reshape(len(ids), 7)
+        if len(np.shape(self._obj_init_pose)) == 2:
+            self._obj_init_pose[ids] = poses
+        c.set_rows("obj_pose", ids, poses)
+        c.set_rows("obj_vel", ids, np.zeros((len(ids), 6), np.float32))
+        c.set_rows("cache_key", ids, np.full((len(ids), 16), -1, np.int32))
+        c.set_rows("cache_lam", ids, np.zeros((len(ids), 48), np.float32))
 
     def get_object_init_pose(self):
         p = np.asarray(self._obj_init_pose)

@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (seeded synthetic inputs for both backends)."""
 import numpy as np
 
-from pybullet_robot_envs.b2env.model import TASK_PUSH, TASK_REACH, panda_task_setup  # noqa: F401
+from pybullet_robot_envs.b2env.model import TASK_GRASP, TASK_PUSH, TASK_REACH, panda_task_setup  # noqa: F401
 
 
 def sample_object_poses(B, seed=0, rnd=0.05, z=0.695):

@@ -115,3 +115,42 @@ def test_device_tensor_step_path():
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     env.close()
+
+
+def test_subset_reset_and_auto_reset():
+    """reset(env_ids) re-runs the reference reset sequence for some envs of the batch only."""
+    from pybullet_robot_envs.envs import pandaPushGymEnv
+    B = 16
+    env = pandaPushGymEnv(num_envs=B, obj_pose_rnd_std=0.05, tg_pose_rnd_std=0.2)
+    env.seed(7)
+    np.random.seed(1)
+    env.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(30):
+        env.step(rng.uniform(-1, 1, (B, 7)).astype(np.float32))
+    c = env._physics_client_id
+    before = {k: c.get(k).copy() for k in ("q", "qd", "obj_pose", "obj_vel", "target", "counters", "mtarget")}
+    ids = np.array([1, 5, 6], np.int32)
+    obs = env.reset(ids)
+    assert obs.shape == (3, 33)
+    after = {k: c.get(k) for k in before}
+    keep = np.setdiff1d(np.arange(B), ids)
+    for k in before:
+        np.testing.assert_array_equal(after[k][keep], before[k][keep], err_msg=k)     # untouched envs: bit-identical
+    home = np.array([0, -0.54, 0, -2.6, -0.30, 2.0, 1.0, 0.02, 0.02], np.float32)
+    np.testing.assert_allclose(after["q"][ids], np.tile(home, (3, 1)), atol=2e-5)
+    assert np.all(after["counters"][ids] == 0)
+    assert np.all(np.abs(after["obj_pose"][ids, 2] - 0.65) < 1e-3)                   # new cube settled on the table
+    assert np.all(np.abs(after["obj_vel"][ids]) < 5e-3)
+    assert np.all(np.abs(after["obj_pose"][ids, 0] - 0.45) <= 0.0501)
+    # auto-reset: finished envs restart inside step()
+    env.auto_reset = True
+    tg = c.get("target")
+    tg[:4] = c.get("obj_pose")[:4, :3] + np.array([0.02, 0, 0], np.float32)           # envs 0-3 succeed next step
+    c.set("target", tg)
+    o, r, d, _ = env.step(np.zeros((B, 7), np.float32))
+    assert np.all(d[:4] == 1) and np.all(r[:4] > 1000)
+    cnt = c.get("counters")
+    assert np.all(cnt[:4] == 0)                                                       # fresh episodes
+    assert np.all(np.isfinite(o))
+    env.close()

@@ -109,3 +109,45 @@ def test_goal_rules_parity(oracle_lib):
         np.testing.assert_array_equal(g_rew, o_rew)
         np.testing.assert_array_equal(g_done, o_done)
         np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
+
+
+def test_grasp_task_parity_and_env(oracle_lib):
+    """PandaGrasp: finger rows carry force 10 / maxVelocity 1, so the motor-island shortcut regularly hits an
+    active bound and must fall back to the serial sweep — both must match the oracle."""
+    from common import TASK_GRASP
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    B = 128
+    m, p = panda_task_setup(TASK_GRASP)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=8)
+    sim = B2Sim(m, p, B, 0)
+    pose = sample_object_poses(B, 9)
+    tg = targets_for(pose, z=0.75)
+    orc.reset(pose, tg)
+    sim.reset_host(pose, tg)
+    orc.step(None, 101, 1, want_obs=False)
+    sim.step_host(None, 101, 1, want_obs=False)
+    rng = np.random.RandomState(2)
+    for i in range(80):
+        copy_state_to_gpu(orc, sim)
+        a = rng.uniform(-1, 1, (B, 8)).astype(np.float32)
+        if i % 20 < 10:
+            a[:, 7] = np.sign(a[:, 7])                # saturating open/close commands
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)
+        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+        assert np.abs(sim.get("q") - orc.state["q"]).max() < 2e-5, i
+        assert np.abs(sim.get("qd") - orc.state["qd"]).max() < 5e-3, i
+        np.testing.assert_allclose(sim.get("mtarget"), orc.state["mtarget"], atol=1e-6)
+        np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
+        np.testing.assert_array_equal(g_done, o_done)
+    sim.close()
+    import pybullet_robot_envs  # noqa: F401
+    from pybullet_robot_envs import gym
+    env = gym.make("PandaGrasp-v0", num_envs=32)
+    assert env.action_space.shape == (8,) and env.observation_space.shape == (33,)
+    env.seed(0)
+    obs = env.reset()
+    raw, _ = env.get_extended_observation()
+    np.testing.assert_allclose(raw[:, 32], raw[:, 20] + 0.1, atol=1e-5)     # target = object + 0.1 m lift
+    o, r, d, _ = env.step(env.action_space.sample()[None, :].repeat(32, 0))
+    assert o.shape == (32, 33) and np.all(d == 0)
+    env.close()

@@ -55,6 +55,7 @@ def test_no_gpu_fails_loudly():
 def test_registered_ids():
     import pybullet_robot_envs
     from pybullet_robot_envs.gym_compat import registry
+    assert registry.spec("PandaGrasp-v0").max_episode_steps == 1000 and registry.spec("pandaPushGoal-v0")
     for i in ("pandaReach-v0", "pandaPush-v0", "PandaReach-v0", "PandaPush-v0"):
         s = registry.spec(i)
         assert s.max_episode_steps == 1000

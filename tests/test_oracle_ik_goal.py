@@ -91,3 +91,30 @@ def test_goal_env_rules(oracle_lib):
         obs, rew, done = o.step(z, 1, 0)
     np.testing.assert_array_equal(o.state["counters"][:, 0], [6] * 4)
     np.testing.assert_array_equal(done, [1, 1, 1, 1])            # 6 > max_steps
+
+
+def test_grasp_task_rules(oracle_lib):
+    """PandaGrasp (new task): gripper command drives both finger targets with the grasp gains/force;
+    lifting the object 0.1 m above its rest height succeeds."""
+    from common import TASK_GRASP
+    B = 4
+    m, p = panda_task_setup(TASK_GRASP)
+    assert p.n_act == 8 and m.max_force[7] == 10.0 and m.max_vel[8] == 1.0
+    o = oracle_lib.Oracle(m, p, B)
+    pose = sample_object_poses(B, 3)
+    o.reset(pose, targets_for(pose, z=0.75))
+    o.step(None, 101, 1, want_obs=False)
+    a = np.zeros((B, 8), np.float32)
+    a[:, 7] = 1.0                                    # open
+    for _ in range(80):
+        obs, rew, done = o.step(a, 1, 0)
+    np.testing.assert_allclose(o.state["mtarget"][:, 7:], 0.04, atol=1e-7)
+    np.testing.assert_allclose(o.state["q"][:, 7:], 0.04, atol=2e-3)
+    assert np.all(done == 0) and np.all(rew < 0)
+    a[:, 7] = -1.0                                   # close: maxVelocity 1 m/s caps the finger speed
+    o.step(a, 1, 0)
+    assert np.all(np.abs(o.state["qd"][:, 7:]) <= 1.0 + 1e-3)
+    # teleport the object upwards: success
+    o.state["obj_pose"][:, 2] = 0.65 + 0.11
+    obs, rew, done = o.step(a, 1, 0)
+    assert np.all(done == 1) and np.all(rew == 1000)
