@@ -170,6 +170,9 @@ enum b2e_field {
 #define B2E_MODE_HOLD 1   /* keep motor targets, hold gains (settle steps of reset) */
 #define B2E_MODE_IK_POSE 3 /* Cartesian mode: IK of the stored hand pose -> motor targets, no action
                               increment, no task bookkeeping (robot.reset, panda_env.py:83-91) */
+#define B2E_MODE_OBSERVE 4 /* n_substeps = 0: observation / reward / done of the current state, nothing is
+                              written back (get_extended_observation, _compute_reward); with
+                              B2E_MODE_HOLD the success latch `terminated` is stored like _termination() */
 #define B2E_MODE_TARGETS 2 /* keep motor targets already written to B2E_F_MTARGET by
                               robot.apply_action, control gains; no task bookkeeping */
 

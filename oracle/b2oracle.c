@@ -1141,7 +1141,7 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
     if (reward) reward[b] = (float)rew;
     if (done) done[b] = (float)dn;
   }
-  S->counters[b * 2 + 1] = terminated;
+  if (mode != B2E_MODE_OBSERVE) S->counters[b * 2 + 1] = terminated;
 }
 
 #include <pthread.h>

@@ -1474,13 +1474,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       if (done_out) done_out[env] = (float)dn;
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && mode != B2E_MODE_OBSERVE) {
     st.counters[env * 2] = counter;
     st.counters[env * 2 + 1] = terminated;
     st.status[env * 4 + 0] = flags;
-    st.status[env * 4 + 1] = iters;
-    st.status[env * 4 + 2] = nc;
-    st.status[env * 4 + 3] = R;
+    if (nsub > 0) {   // solver diagnostics of the last physics step survive pure observation calls
+      st.status[env * 4 + 1] = iters;
+      st.status[env * 4 + 2] = nc;
+      st.status[env * 4 + 3] = R;
+    }
   }
 }
 

@@ -21,7 +21,7 @@ FIELD_NAMES = {
     "hand_pose": F_HAND_POSE, "status": F_STATUS, "raw_obs": F_RAW_OBS, "contacts": F_CONTACTS,
 }
 INT_FIELDS = {F_COUNTERS, F_CACHE_KEY, F_STATUS}
-MODE_ACTION, MODE_HOLD, MODE_TARGETS, MODE_IK_POSE = 0, 1, 2, 3
+MODE_ACTION, MODE_HOLD, MODE_TARGETS, MODE_IK_POSE, MODE_OBSERVE = 0, 1, 2, 3, 4
 OPT_RECORD_CONTACTS = 0
 
 EXPORTS = [

@@ -46,11 +46,13 @@ class B2Client:
         self._obs_cache_valid = False
 
     # ---- observation / reward / done of the current state (no physics) --------------------
-    def observe(self):
-        """Returns (scaled_obs, reward, done, raw_obs) for the current state."""
-        if not self._obs_cache_valid:
+    def observe(self, latch=False):
+        """Returns (scaled_obs, reward, done, raw_obs) for the current state.  ``latch=True`` also stores the
+        success latch like the reference's ``_termination()`` does (panda_push_gym_env.py:305-306)."""
+        if latch or not self._obs_cache_valid:
             sim = self.ensure()
-            obs, rew, done = sim.step_host(None, 0, binding.MODE_HOLD, want_obs=True)
+            mode = binding.MODE_HOLD if latch else binding.MODE_OBSERVE
+            obs, rew, done = sim.step_host(None, 0, mode, want_obs=True)
             self._last = (obs, rew, done, sim.get("raw_obs"))
             self._obs_cache_valid = True
         return self._last

@@ -183,7 +183,7 @@ class PandaTaskBase(gym.Env):
         self._physics_client_id.invalidate()
 
     def _termination(self):
-        done = self._physics_client_id.observe()[2]
+        done = self._physics_client_id.observe(latch=True)[2]
         self.terminated = squeeze1(self._physics_client_id.get("counters")[:, 1], self.num_envs)
         return squeeze1(done.astype(np.float32), self.num_envs)
 
