@@ -10,13 +10,12 @@ import sys
 
 src_csv, cubin = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+kfilter = sys.argv[4] if len(sys.argv) > 4 else "step_kernel"
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 in_k, line, order = False, None, []
 for ln in dis:
-    if ".text." in ln and "step_kernel" in ln:
-        in_k = True
-    elif ".text." in ln and in_k and "step_kernel" not in ln:
-        in_k = False
+    if ".text." in ln:
+        in_k = kfilter in ln
     if not in_k:
         continue
     m = re.search(r'//## File ".*?", line (\d+)(.*)', ln)
