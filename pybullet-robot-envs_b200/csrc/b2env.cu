@@ -41,13 +41,14 @@
 #define PHASE_BARRIER() __syncwarp()
 #endif
 #ifndef WPB
-#define WPB 8             // warps (= envs) per block
+#define WPB 8             // warps per block (two envs per warp)
 #endif
 #ifndef MINB
 #define MINB 3            // resident blocks per SM the register allocation targets (24 warps, 80 regs)
 #endif
-#define TLMAX 16          // links handled by the warp kernel (transforms staged in shared memory)
-#define RMAX 48           // max constraint rows per env: 9 motors + 3 limits + 3*12 contact rows
+#define TLMAX 12          // links handled by the group kernel (transforms staged in shared memory; < 15: lane 15 is the zero lane)
+#define RMAX 48           // scratch stride
+#define GMAX 48           // generic rows per env (3 limit + 36 contact rows), in sets of 16
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
 #define SCRATCH_PER_ENV (RMAX * RMAX + RMAX * WSTRIDE)
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
@@ -72,7 +73,7 @@ struct DevModel {
   int parent[NLMAX], jtype[NLMAX], dof[NLMAX];
   int dof_link[NLMAX];
   unsigned link_dofmask[NLMAX];  // dofs on the path base -> link (inclusive)
-  unsigned acc_sched[2][NLMAX];  // child->parent accumulation schedule: 5-bit source lane per round (31 = none)
+  unsigned acc_sched[2][NLMAX];  // child->parent accumulation schedule: 4-bit source lane per round (15 = none)
   float jpos[NLMAX][3], jrot[NLMAX][9], axis[NLMAX][3];
   float mass[NLMAX], com[NLMAX][3], inertia[NLMAX][9];
   float lower[NLMAX], upper[NLMAX], limit_margin[NLMAX], max_force[NLMAX], max_vel[NLMAX], joint_damping[NLMAX],
@@ -126,8 +127,6 @@ static int fail(int code, const char* fmt, const char* detail) {
 
 // ------------------------------------------------------------------------------------------
 // small device math (all on register arrays with static indexing)
-__device__ __forceinline__ float shf(float v, int src) { return __shfl_sync(FULL, v, src); }
-__device__ __forceinline__ int shi(int v, int src) { return __shfl_sync(FULL, v, src); }
 
 __device__ __forceinline__ void m3mul(const float* a, const float* b, float* c) {
 #pragma unroll
@@ -231,32 +230,54 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 }
 
 // ------------------------------------------------------------------------------------------
-// per-warp shared memory
+// Environment groups: TWO environments per warp, 16 lanes each (every stage of the pipeline needs
+// <= 16 lanes: 12 links, 9 dofs, 8 cube vertices, 14 spheres, 15 velocity components, 16 rows per set).
+// Every warp collective is issued with the member mask of the group's own 16 lanes, so the two
+// groups of a warp may diverge (different contact counts, iteration counts) without deadlock; while
+// their control flow agrees — the common case — one instruction serves both environments.
+#define GL 16
+struct Grp {
+  unsigned hm;  // member mask of this group's lanes
+  int sh;       // bit offset of the group inside the warp (0 or 16)
+  int lane;     // lane inside the group, 0..15
+};
+#define SHF(v, src) __shfl_sync(g.hm, (v), (src), GL)
+__device__ __forceinline__ unsigned gballot(const Grp& g, bool p) { return (__ballot_sync(g.hm, p) >> g.sh) & 0xffffu; }
+__device__ __forceinline__ bool gany(const Grp& g, bool p) { return __any_sync(g.hm, p) != 0; }
+__device__ __forceinline__ float gmaxf(const Grp& g, float v) {  // max of non-negative floats
+  return __uint_as_float(__reduce_max_sync(g.hm, __float_as_uint(v)));
+}
+__device__ __forceinline__ void gsync(const Grp& g) { __syncwarp(g.hm); }
+
+// per-environment shared memory (4.6 KB)
 struct Contact {   // 16 words
   int key, type, link, pad;
   float pA[3], pB[3], n[3];
   float dist, mu, erp;
 };
-struct WarpSmem {
-  float A[32 * 32];            // Delassus matrix A[i*32 + r] when R <= 32 (else: global scratch, stride RMAX)
-  float W[32 * WSTRIDE];       // W[r][k] = (M^-1 J_r^T)_k, k<9 arm dofs, 9..14 cube (lin, ang)
+struct EnvSmem {
+  float A[GL * GL];            // generic-row block of the Delassus matrix, A[c*16 + r], when <= 16 generic rows
+                               // (else: per-env global scratch, stride GMAX)
+  float W[GL * WSTRIDE];       // W[g][k] = (M^-1 J_g^T)_k of generic row g; k<9 arm dofs, 9..14 cube (lin, ang)
   float T[TLMAX][12];          // link world transforms: R (9) + p (3)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
   float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
-  float lam[RMAX];
+  float mlam[16];              // motor-row impulses (lane = dof)
+  float glam[GMAX];            // generic-row impulses
   Contact con[B2E_MAX_CONTACTS];
   float con_cfm[B2E_MAX_CONTACTS];
   int lim_d[4];                // limit rows: dof | side << 8
   float lim_dist[4];
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
-  float obs[B2E_MAX_OBS];
 };
 
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
-__device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const DevModelU& U, int lane, float qi, float* R, float* p) {
+__device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const DevModelU& U, const Grp& g, float qi,
+                                         float* R, float* p) {
+  const int lane = g.lane;
   const int nl = U.n_links;
   const bool act = lane < nl;
   const int li = act ? lane : 0;
@@ -289,10 +310,10 @@ __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const D
     const int src = anc < 0 ? 0 : anc;
     float Ra[9], pa[3];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Ra[k] = shf(R[k], src);
+    for (int k = 0; k < 9; k++) Ra[k] = SHF(R[k], src);
 #pragma unroll
-    for (int k = 0; k < 3; k++) pa[k] = shf(p[k], src);
-    const int anca = shi(anc, src);
+    for (int k = 0; k < 3; k++) pa[k] = SHF(p[k], src);
+    const int anca = SHF(anc, src);
     if (anc >= 0) {
       float Rn[9], o[3];
       m3mul(Ra, R, Rn);
@@ -316,15 +337,15 @@ __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const D
 }
 
 // inclusive sum over the path base..link of a 6-vector held per link lane (pointer jumping)
-__device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, const DevModelU& U, int lane, float* x) {
-  int anc = lane < U.n_links ? __ldg(&M->parent[lane]) : -1;
+__device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, const DevModelU& U, const Grp& g, float* x) {
+  int anc = g.lane < U.n_links ? __ldg(&M->parent[g.lane]) : -1;
   const int rounds = U.fk_rounds;
   for (int rd = 0; rd < rounds; rd++) {
     const int src = anc < 0 ? 0 : anc;
     float xa[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) xa[k] = shf(x[k], src);
-    const int anca = shi(anc, src);
+    for (int k = 0; k < 6; k++) xa[k] = SHF(x[k], src);
+    const int anca = SHF(anc, src);
     if (anc >= 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) x[k] += xa[k];
@@ -333,15 +354,16 @@ __device__ __forceinline__ void path_sum6(const DevModel* __restrict__ M, const 
   }
 }
 
-
 // ------------------------------------------------------------------------------------------
 // Damped-least-squares IK (p.calculateInverseKinematics, panda_env.py:269-272): same statement as
 // oracle/b2oracle.c ik_dls.  lane = link for FK + Jacobian columns, lane = row (<6) for the 6x6
 // system (J J^T + lambda I) x = e solved by Gauss-Jordan over shuffles, lane = dof for dq = J^T x.
-// `scr` is 6*16 floats of warp-private shared memory.  Returns the joint target of this dof lane.
+// `scr` is 6*16 floats of group-private shared memory.  Returns the joint target of this dof lane.
 __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ M, const DevModelU& U, int max_iters,
-                                       float residual, float damping, int lane, float my_q, float tpx, float tpy,
-                                       float tpz, float tqx, float tqy, float tqz, float tqw) {
+                                       float residual, float damping, unsigned hm, int sh, int lane_, float my_q,
+                                       float tpx, float tpy, float tpz, float tqx, float tqy, float tqz, float tqw) {
+  const Grp g = {hm, sh, lane_};
+  const int lane = lane_;
   const int nl = U.n_links, nd = U.n_dof, ee = U.ee_link;
   const int li = lane < nl ? lane : 0;
   const int my_dof = __ldg(&M->dof[li]);
@@ -351,13 +373,13 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
   float qv = my_q;
   for (int it = 0; it < max_iters; it++) {
     float R[9], p[3];
-    const float qi = shf(qv, my_dof < 0 ? 0 : my_dof);
-    fk_lanes(M, U, lane, (lane < nl && my_dof >= 0) ? qi : 0.f, R, p);
+    const float qi = SHF(qv, my_dof < 0 ? 0 : my_dof);
+    fk_lanes(M, U, g, (lane < nl && my_dof >= 0) ? qi : 0.f, R, p);
     float pe[3], Re[9];
 #pragma unroll
-    for (int k = 0; k < 3; k++) pe[k] = shf(p[k], ee);
+    for (int k = 0; k < 3; k++) pe[k] = SHF(p[k], ee);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Re[k] = shf(R[k], ee);
+    for (int k = 0; k < 9; k++) Re[k] = SHF(R[k], ee);
     const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
     if (sqrtf(dot3(dp, dp)) <= residual) break;
     float cq[4], eq[4], er[3];
@@ -385,14 +407,14 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
         c[0] = aw[0]; c[1] = aw[1]; c[2] = aw[2];
       }
     }
-    __syncwarp();
-    for (int k = lane; k < 6 * 16; k += 32) scr[k] = 0.f;
-    __syncwarp();
+    gsync(g);
+    for (int k = lane; k < 6 * 16; k += GL) scr[k] = 0.f;
+    gsync(g);
     if (lane < nl && my_dof >= 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) scr[k * 16 + my_dof] = c[k];
     }
-    __syncwarp();
+    gsync(g);
     // lane r < 6: row r of J J^T + lambda I, augmented with e_r
     const int r = lane < 6 ? lane : 0;
     float Ur[7];
@@ -407,7 +429,7 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
     for (int k = 0; k < 6; k++) {
       float rk[7];
 #pragma unroll
-      for (int j = 0; j < 7; j++) rk[j] = shf(Ur[j], k);
+      for (int j = 0; j < 7; j++) rk[j] = SHF(Ur[j], k);
       const float pinv = 1.0f / rk[k];
       if (lane == k) {
 #pragma unroll
@@ -422,111 +444,160 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
     float dq = 0.f;
 #pragma unroll
     for (int rr = 0; rr < 6; rr++) {
-      const float xr = shf(Ur[6], rr);
-      dq = fmaf(scr[rr * 16 + (lane & 15)], xr, dq);
+      const float xr = SHF(Ur[6], rr);
+      dq = fmaf(scr[rr * 16 + lane], xr, dq);
     }
     if (lane >= nd) dq = 0.f;
-    const float mx = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fabsf(dq))));
+    const float mx = gmaxf(g, fabsf(dq));
     const float scale = mx > 0.78539816339f ? 0.78539816339f / mx : 1.f;
     qv = fmaf(dq, scale, qv);
   }
-  __syncwarp();
+  gsync(g);
   return qv;
 }
 
 // ------------------------------------------------------------------------------------------
-// PGS sweep helpers.  NS = number of 32-row sets in use (rows r = lane + 32*s).
-// Per-row registers: u = rhs - (A lambda)_r is the running velocity error, base = lambda*(1 - cfm*invd),
-// so the candidate impulse is fma(u, invd, base) and the dependent chain per row update is
-// FFMA -> FMNMX -> FMNMX -> FADD -> SHFL -> FFMA.
-template <int NS>
+// PGS.  Rows of one env: the n_dof position-motor rows (lane = dof, MotorRegs) followed by the
+// "generic" rows (limit rows, contact normals, contact frictions) in sets of 16 (lane = row,
+// RowRegs<NSG>).  The solver runs on the Delassus form A = J M^-1 J^T; thanks to J_motor = e_d its
+// blocks are:  motor x motor = M^-1 (read from sm.Minv),  motor x generic = W_g[d] (read from the W
+// table),  generic x generic = A (shared memory when <= 16 generic rows, else global scratch).
+// Per-row state: u = rhs - (A lambda)_r is the running velocity error, base = lambda*(1 - cfm*invd),
+// so the dependent chain of one row update is FFMA -> FMNMX -> FMNMX -> FADD -> SHFL -> FFMA.
+struct MotorRegs {
+  float u, invd, diag, lo, hi, lam, prev;
+};
+template <int NSG>
 struct RowRegs {
-  float lam[NS], u[NS], base[NS], g[NS], invd[NS], diag[NS], lo[NS], hi[NS], mu[NS], lastdl[NS];
-  int type[NS], isl[NS], nidx[NS];
+  float lam[NSG], u[NSG], base[NSG], gg[NSG], invd[NSG], diag[NSG], lo[NSG], hi[NSG], mu[NSG], prev[NSG];
+  int type[NSG], isl[NSG], nidx[NSG];
 };
 
-template <int NS, int SI>
-__device__ __forceinline__ void row_step(RowRegs<NS>& r, const float* Acol, int i, int lane) {
-  const int li = i & 31;
+template <int NSG>
+__device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
+                                           const float* W, int i) {
+  float nl = fmaf(m.u, m.invd, m.lam);
+  nl = fminf(fmaxf(nl, m.lo), m.hi);
+  const float dl = nl - m.lam;
+  const float dli = SHF(dl, i);
+  if (g.lane == i) m.lam = nl;
+  const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
+  m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
+#pragma unroll
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
+}
+
+template <int NSG, int SI>
+__device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
+                                             const float* W, int gi, bool arm_sweep) {
+  constexpr int AS = (NSG == 1) ? GL : GMAX;
+  const int li = gi & (GL - 1);
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
   const float dl = nl - r.lam[SI];
-  const float dli = shf(dl, li);
-  if (lane == li) r.lam[SI] = nl;   // base/lastdl are refreshed once per iteration (each row moves once per sweep)
-  constexpr int AS = (NS == 1) ? 32 : RMAX;
-  r.u[0] = fmaf(-Acol[i * AS], dli, r.u[0]);
-  if (NS > 1) {
-    const int off1 = (lane + 32 < RMAX) ? 32 : RMAX - 1 - lane;  // clamp: rows >= RMAX do not exist
-    r.u[NS - 1] = fmaf(-Acol[i * AS + off1], dli, r.u[NS - 1]);
-  }
+  const float dli = SHF(dl, li);
+  if (g.lane == li) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
+  if (arm_sweep) m.u = fmaf(-W[gi * WSTRIDE + g.lane], dli, m.u);
+#pragma unroll
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-A[gi * AS + GL * s + g.lane], dli, r.u[s]);
 }
 
-// visit the rows whose bits are set, in ascending order
-template <int NS>
-__device__ __forceinline__ void sweep(RowRegs<NS>& r, const float* Acol, unsigned m0, unsigned m1, int lane) {
+// visit the generic rows whose bits are set, in ascending order
+template <int NSG>
+__device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
+                                              const float* W, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
+  constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
   while (m0) {
     const int i = __ffs(m0) - 1;
     m0 &= m0 - 1;
-    row_step<NS, 0>(r, Acol, i, lane);
+    generic_step<NSG, 0>(g, m, r, A, W, i, arm_sweep);
   }
-  if (NS > 1) {
+  if (NSG > 1) {
     while (m1) {
       const int i = __ffs(m1) - 1;
       m1 &= m1 - 1;
-      row_step<NS, NS - 1>(r, Acol, i + 32, lane);
+      generic_step<NSG, S1>(g, m, r, A, W, GL + i, arm_sweep);
+    }
+  }
+  if (NSG > 2) {
+    while (m2) {
+      const int i = __ffs(m2) - 1;
+      m2 &= m2 - 1;
+      generic_step<NSG, S2>(g, m, r, A, W, 2 * GL + i, arm_sweep);
     }
   }
 }
 
-template <int NS>
-__device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* A, int R, int fric_start, int lane,
-                                         bool coupled, bool has_cube_rows, int max_iters, float tol,
-                                         bool arm_done_init) {
-  // row masks per set: island (0 arm, 1 cube) x phase (non-friction, friction)
-  unsigned arm_nf[2] = {0, 0}, arm_f[2] = {0, 0}, cube_nf[2] = {0, 0}, cube_f[2] = {0, 0};
+template <int NSG>
+__device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
+                                         const float* Minv, int nd, int RG, int fric_start, bool coupled,
+                                         bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
+  // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
+  unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int row = lane + 32 * s;
-    const bool valid = row < R, fr = row >= fric_start;
+  for (int s = 0; s < NSG; s++) {
+    const int gi = GL * s + g.lane;
+    const bool valid = gi < RG, fr = gi >= fric_start;
     const bool cube = !coupled && r.isl[s] == 1;
-    arm_nf[s] = __ballot_sync(FULL, valid && !cube && !fr);
-    arm_f[s] = __ballot_sync(FULL, valid && !cube && fr);
-    cube_nf[s] = __ballot_sync(FULL, valid && cube && !fr);
-    cube_f[s] = __ballot_sync(FULL, valid && cube && fr);
+    arm_nf[s] = gballot(g, valid && !cube && !fr);
+    arm_f[s] = gballot(g, valid && !cube && fr);
+    cube_nf[s] = gballot(g, valid && cube && !fr);
+    cube_f[s] = gballot(g, valid && cube && fr);
   }
-  const float* Acol = A + lane;
-  bool done0 = arm_done_init, done1 = !has_cube_rows || coupled;
+  const unsigned motor_mask = (1u << nd) - 1u;
+  bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
   if (done0 && done1) return 0;
   int it = 0;
   for (it = 0; it < max_iters; it++) {
+    m.prev = m.lam;
 #pragma unroll
-    for (int s = 0; s < NS; s++) { r.lastdl[s] = r.lam[s]; r.base[s] = r.lam[s] * r.g[s]; }
+    for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
-    sweep<NS>(r, Acol, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0), lane);
-    const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0);
-    if (f0 | f1) {
+    if (!done0) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
+      unsigned mm = motor_mask;
+      while (mm) {
+        const int i = __ffs(mm) - 1;
+        mm &= mm - 1;
+        motor_step<NSG>(g, m, r, Minv, W, i);
+      }
+    }
+    sweep_generic<NSG>(g, m, r, A, W, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
+                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
+    const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
+                   f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
+    if (f0 | f1 | f2) {
       // friction bounds from the current normal impulses (mu * lambda_n)
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
+      for (int s = 0; s < NSG; s++) {
         const int ni = r.nidx[s];
-        float v0 = shf(r.lam[0], ni & 31);
-        float v1 = NS > 1 ? shf(r.lam[NS - 1], ni & 31) : 0.f;
+        float v = 0.f;
+#pragma unroll
+        for (int t = 0; t < NSG; t++) {
+          const float vt = SHF(r.lam[t], ni & (GL - 1));
+          if ((ni >> 4) == t) v = vt;
+        }
         if (r.type[s] == ROW_FRICTION) {
-          float lim = r.mu[s] * ((ni >> 5) ? v1 : v0);
+          const float lim = r.mu[s] * v;
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep<NS>(r, Acol, f0, f1, lane);
+      sweep_generic<NSG>(g, m, r, A, W, f0, f1, f2, !done0);
     }
     float ra = 0.f, rc = 0.f;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-      float rv = (r.lam[s] - r.lastdl[s]) * r.diag[s];   // impulse change of this sweep
-      rv = rv * rv;
-      if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
+    if (!done0 && g.lane < nd) {
+      const float rv = (m.lam - m.prev) * m.diag;
+      ra = rv * rv;
     }
-    ra = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ra)));
-    if (!done1) rc = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rc)));
+#pragma unroll
+    for (int s = 0; s < NSG; s++) {
+      float rv = (r.lam[s] - r.prev[s]) * r.diag[s];  // impulse change of this sweep
+      rv = rv * rv;
+      if (GL * s + g.lane < RG) {
+        if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
+      }
+    }
+    if (!done0) ra = gmaxf(g, ra);
+    if (!done1) rc = gmaxf(g, rc);
     if (!done0 && ra <= tol) done0 = true;
     if (!done1 && rc <= tol) done1 = true;
     if (done0 && done1) { it++; break; }
@@ -534,20 +605,20 @@ __device__ __forceinline__ int pgs_solve(RowRegs<NS>& r, const float* A, int R, 
   return it;
 }
 
-
 // Arm island made only of the n_dof position-motor rows (no limit row, no arm contact): bounds are
 // +-max_force*dt and in practice never active, so one Gauss-Seidel sweep over those rows IS the affine
-// map lambda' = G lambda + c with G = -(D+L)^-1 U, c = (D+L)^-1 b (A = L + D + U the motor block of
+// map lambda' = G lambda + c with G = -(D+L)^-1 U, c = (D+L)^-1 b (L + D + U = M^-1, the motor block of
 // the Delassus matrix).  Same iterates in exact arithmetic, same per-sweep residual test; the nine
 // serial, shuffle-dependent row updates of a sweep become one 9-wide mat-vec.  If a bound would
 // activate the caller falls back to the serial sweep.  Returns the sweep count, or -1 on fallback.
-__device__ __forceinline__ int arm_affine_solve(const float* A, int AS, int lane, int nd, float b, float invd,
-                                                float diag, float lo, float hi, int max_iters, float tol,
-                                                float& lam_out) {
+__device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv, int nd, float b, float invd, float diag,
+                                                float lo, float hi, int max_iters, float tol, float& lam_out) {
+  const int lane = g.lane;
   const bool row = lane < nd;
+  const int lc = lane < NDMAX ? lane : NDMAX;
   float Ar[NDMAX];
 #pragma unroll
-  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? A[k * AS + lane] : ((k == lane) ? 1.f : 0.f);
+  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? Minv[k * (NDMAX + 1) + lc] : ((k == lane) ? 1.f : 0.f);
   const float idg = row ? invd : 1.f;
   // T = (D+L)^-1 by forward substitution, lane = row
   float T[NDMAX];
@@ -557,7 +628,7 @@ __device__ __forceinline__ int arm_affine_solve(const float* A, int AS, int lane
   for (int j = 0; j < NDMAX; j++) {
 #pragma unroll
     for (int k = 0; k <= j; k++) {
-      const float tj = shf(T[k] * idg, j);       // final row j of T
+      const float tj = SHF(T[k] * idg, j);       // final row j of T
       if (lane == j) T[k] = tj;
       else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
     }
@@ -570,87 +641,95 @@ __device__ __forceinline__ int arm_affine_solve(const float* A, int AS, int lane
   const float bb = row ? b : 0.f;
 #pragma unroll
   for (int j = 0; j < NDMAX; j++) {
-    c = fmaf(T[j], shf(bb, j), c);
+    c = fmaf(T[j], SHF(bb, j), c);
 #pragma unroll
-    for (int k = j + 1; k < NDMAX; k++) G[k] = fmaf(-T[j], shf(Ar[k], j), G[k]);
+    for (int k = j + 1; k < NDMAX; k++) G[k] = fmaf(-T[j], SHF(Ar[k], j), G[k]);
   }
   float lam = 0.f;
   int it;
   for (it = 0; it < max_iters; it++) {
     float a0 = c, a1 = 0.f;
 #pragma unroll
-    for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], shf(lam, k), a0);
+    for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], SHF(lam, k), a0);
 #pragma unroll
-    for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], shf(lam, k), a1);
+    for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], SHF(lam, k), a1);
     const float nl = a0 + a1;
-    if (__any_sync(FULL, row && !(nl >= lo && nl <= hi))) return -1;
+    if (gany(g, row && !(nl >= lo && nl <= hi))) return -1;
     float rv = row ? (nl - lam) * diag : 0.f;
     rv = rv * rv;
     lam = nl;
-    rv = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rv)));
+    rv = gmaxf(g, rv);
     if (rv <= tol) { it++; break; }
   }
   lam_out = lam;
   return it;
 }
 
-// Build the row(s) owned by this lane, the W table, the Delassus matrix, warm start, solve, and
-// leave the impulses in sm.lam[].  Returns the PGS iteration count.
-#ifndef SOLVE_INLINE
-#define SOLVE_INLINE 0
-#endif
-#if SOLVE_INLINE
-#define SOLVE_ATTR __forceinline__
-#else
-#define SOLVE_ATTR __noinline__
-#endif
-template <int NS>
-__device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restrict__ M, const DevModelU& U, const b2e_params& P,
-                                            int lane, int nd, int nlim, int nc, float my_q, float my_target,
-                                            float my_kp, float cpx, float cpy, float cpz, float* scratch) {
+// Build the motor row of this dof lane and the generic row(s) of this lane, the W table, the generic
+// block of the Delassus matrix, warm start, solve, and leave the impulses in sm.mlam[] / sm.glam[].
+// Returns the PGS iteration count.
+template <int NSG>
+__device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U,
+                                            const b2e_params& P, unsigned hm, int sh, int lane, int nd, int nlim, int nc,
+                                            float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
+                                            float* scratch) {
+  const Grp g = {hm, sh, lane};
   const float cpos[3] = {cpx, cpy, cpz};
-  constexpr int AS = (NS == 1) ? 32 : RMAX;
-  float* A = (NS == 1) ? sm.A : scratch;
-  float* W = (NS == 1) ? sm.W : scratch + RMAX * RMAX;
-  const int nnc = nd + nlim;         // non-contact rows
-  const int fric_start = nnc + nc;
-  const int R = nnc + 3 * nc;
+  constexpr int AS = (NSG == 1) ? GL : GMAX;
+  float* A = (NSG == 1) ? sm.A : scratch;
+  float* W = (NSG == 1) ? sm.W : scratch + GMAX * GMAX;
+  const float* Minv = &sm.Minv[0][0];
+  const int fric_start = nlim + nc;   // generic index of the first friction row
+  const int RG = nlim + 3 * nc;       // generic rows
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
-  RowRegs<NS> rr;
-  bool coupled = false, has_cube = false, arm_contact = false;
+
+  // ---- motor row of dof `lane` (btMultiBodyJointMotor: velocity target kp*(target-q)/dt, kd = 1, erp = 1) ----
+  MotorRegs m;
+  {
+    const bool isd = lane < nd;
+    const int d = isd ? lane : 0;
+    float desired = my_kp * (my_target - my_q) * inv_dt;
+    const float mv = __ldg(&M->max_vel[d]);
+    if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
+    const float diag = isd ? sm.Minv[d][d] : 1.f;
+    m.diag = diag;
+    m.invd = isd ? 1.0f / diag : 0.f;
+    m.u = isd ? desired - sm.vstar[d] : 0.f;
+    m.hi = isd ? __ldg(&M->max_force[d]) * dt : 0.f;
+    m.lo = -m.hi;
+    m.lam = 0.f;
+    m.prev = 0.f;
+  }
+
+  // ---- generic rows ----
+  RowRegs<NSG> rr;
+  float Jall[NSG][15];
+  bool coupled = false, has_cube = false, arm_generic = false;
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int r = lane + 32 * s;
-    const bool valid = r < R;
-    float J[15];
+  for (int s = 0; s < NSG; s++) {
+    const int gi = GL * s + lane;
+    const bool valid = gi < RG;
+    float* J = Jall[s];
 #pragma unroll
     for (int k = 0; k < 15; k++) J[k] = 0.f;
     float desired = 0.f, cfm = 0.f, lo = 0.f, hi = 0.f, mu = 0.f;
-    int type = ROW_MOTOR, isl = 0, nidx = 0;
+    int type = ROW_LIMIT, isl = 0, nidx = 0;
+    bool sphere_cube_normal = false;
     if (valid) {
-      if (r < nd) {  // btMultiBodyJointMotor: velocity target kp*(target-q)/dt (kd = 1, erp = 1)
-        type = ROW_MOTOR;
-#pragma unroll
-        for (int k = 0; k < NDMAX; k++) J[k] = (k == r) ? 1.f : 0.f;
-        desired = my_kp * (my_target - my_q) * inv_dt;
-        const float mv = __ldg(&M->max_vel[r]);
-        if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
-        hi = __ldg(&M->max_force[r]) * dt;
-        lo = -hi;
-      } else if (r < nnc) {  // joint limit row
+      if (gi < nlim) {  // joint limit row
         type = ROW_LIMIT;
-        const int code = sm.lim_d[r - nd];
+        const int code = sm.lim_d[gi];
         const int d = code & 0xff, side = code >> 8;
 #pragma unroll
         for (int k = 0; k < NDMAX; k++) J[k] = (k == d) ? (side ? -1.f : 1.f) : 0.f;
-        const float pen = sm.lim_dist[r - nd] + P.slop;
+        const float pen = sm.lim_dist[gi] + P.slop;
         desired = pen > 0 ? -pen * inv_dt : -pen * P.erp * inv_dt;
         lo = 0.f; hi = 1e30f;
       } else {  // contact rows
         int c, which;  // which: 0 normal, 1/2 friction
-        if (r < fric_start) { c = r - nnc; which = 0; }
-        else { c = (r - fric_start) >> 1; which = 1 + ((r - fric_start) & 1); }
+        if (gi < fric_start) { c = gi - nlim; which = 0; }
+        else { c = (gi - fric_start) >> 1; which = 1 + ((gi - fric_start) & 1); }
         const Contact& ct = sm.con[c];
         float n[3] = {ct.n[0], ct.n[1], ct.n[2]}, dir[3];
         if (which == 0) { dir[0] = n[0]; dir[1] = n[1]; dir[2] = n[2]; }
@@ -681,6 +760,7 @@ __device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restri
             cross3(relc, dir, t);
 #pragma unroll
             for (int k = 0; k < 3; k++) { J[9 + k] = -dir[k]; J[12 + k] = -t[k]; }
+            sphere_cube_normal = (which == 0);
           }
         }
         if (which == 0) {
@@ -692,15 +772,15 @@ __device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restri
         } else {
           type = ROW_FRICTION;
           mu = ct.mu;
-          nidx = nnc + c;
+          nidx = nlim + c;
         }
       }
     }
-    // W = M^-1 J^T.  Motor rows take a column of M^-1 directly; the generic 9x9 product is only
-    // needed when some row of this set has another arm part (limit row or robot contact).
+    // W = M^-1 J^T.  The generic 9x9 product is only needed when some row of this set has an arm part
+    // (limit row or robot contact); rows of cube-table contacts have none.
     float Wv[15];
-    const bool arm_general = valid && (type == ROW_LIMIT || (type != ROW_MOTOR && isl == 0));
-    if (__any_sync(FULL, arm_general)) {
+    const bool arm_part = valid && isl == 0;
+    if (gany(g, arm_part)) {
 #pragma unroll
       for (int d = 0; d < NDMAX; d++) {
         float acc = 0.f;
@@ -709,10 +789,8 @@ __device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restri
         Wv[d] = acc;
       }
     } else {
-      const int col = (valid && type == ROW_MOTOR) ? r : 0;
-      const float sc = (valid && type == ROW_MOTOR) ? 1.f : 0.f;
 #pragma unroll
-      for (int d = 0; d < NDMAX; d++) Wv[d] = sc * sm.Minv[d][col];
+      for (int d = 0; d < NDMAX; d++) Wv[d] = 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { Wv[9 + k] = J[9 + k] * cinv_m; Wv[12 + k] = J[12 + k] * cinv_I; }
@@ -721,91 +799,91 @@ __device__ SOLVE_ATTR int build_and_solve(WarpSmem& sm, const DevModel* __restri
     for (int k = 0; k < 15; k++) { diag = fmaf(J[k], Wv[k], diag); jv = fmaf(J[k], sm.vstar[k], jv); }
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 15; k++) W[r * WSTRIDE + k] = Wv[k];
-      W[r * WSTRIDE + 15] = 0.f;
+      for (int k = 0; k < 15; k++) W[gi * WSTRIDE + k] = Wv[k];
+      W[gi * WSTRIDE + 15] = 0.f;
     }
     rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
     rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
-    rr.diag[s] = valid ? diag + cfm : 1.f;
+    rr.diag[s] = valid ? diag + cfm : 0.f;
     rr.invd[s] = valid ? 1.0f / (diag + cfm) : 0.f;
-    rr.g[s] = 1.0f - cfm * rr.invd[s];
+    rr.gg[s] = 1.0f - cfm * rr.invd[s];
     rr.u[s] = valid ? desired - jv : 0.f;
-    rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.lastdl[s] = 0.f;
-    __syncwarp();
-    // Delassus columns: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
-    // motor column c: J_c = e_c, so A[c][r] = J_c . W_r = W_r[c] (no dot product)
+    rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.prev[s] = 0.f;
+    coupled = coupled || gany(g, sphere_cube_normal);
+    has_cube = has_cube || gany(g, valid && isl == 1);
+    arm_generic = arm_generic || gany(g, arm_part);
+  }
+  gsync(g);
+  // generic x generic block: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
 #pragma unroll
-    for (int c = 0; c < NDMAX; c++)
-      if (valid && c < nd) A[c * AS + r] = Wv[c];
-    for (int c = nd; c < R; c++) {
+  for (int s = 0; s < NSG; s++) {
+    const int gi = GL * s + lane;
+    const bool valid = gi < RG;
+    const float* J = Jall[s];
+    for (int c = 0; c < RG; c++) {
       float acc = 0.f;
-      const bool cube_only = (c >= nnc) && sm.con[c < fric_start ? c - nnc : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
+      const bool cube_only = (c >= nlim) && sm.con[c < fric_start ? c - nlim : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
       if (!cube_only) {
 #pragma unroll
         for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
       }
-      if (c >= nnc) {
+      if (c >= nlim) {
 #pragma unroll
         for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
       }
-      if (valid) A[c * AS + r] = acc;
+      if (valid) A[c * AS + gi] = acc;
     }
-    coupled = coupled || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0 && (J[9] != 0.f || J[10] != 0.f || J[11] != 0.f));
-    has_cube = has_cube || __any_sync(FULL, valid && isl == 1);
-    arm_contact = arm_contact || __any_sync(FULL, valid && type == ROW_NORMAL && isl == 0);
   }
-  __syncwarp();
-  // NOTE: with NS == 2 the loop above computed A[c][r] for set-0 rows before the set-1 W rows were
-  // written; redo the columns c >= 32 for set 0 now that every W row is in shared memory.
-  if (NS > 1) {
-    // recompute J for set 0 is expensive; instead use symmetry: A[c][r] = A[r][c] for c >= 32 > r.
-    for (int c = 32; c < R; c++) {
-      if (lane + 0 < 32 && lane < R) A[c * AS + lane] = A[lane * AS + c];
-    }
-    __syncwarp();
-  }
-  // warm start (contact rows): lambda0 = cached impulse * factor, w = A * lambda0
+  gsync(g);
+  // warm start (contact rows): lambda0 = cached impulse * factor, u -= A lambda0
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int r = lane + 32 * s;
-    if (r >= nnc && r < R) {
+  for (int s = 0; s < NSG; s++) {
+    const int gi = GL * s + lane;
+    if (gi >= nlim && gi < RG) {
       int c, j;
-      if (r < fric_start) { c = r - nnc; j = 0; }
-      else { c = (r - fric_start) >> 1; j = 1 + ((r - fric_start) & 1); }
+      if (gi < fric_start) { c = gi - nlim; j = 0; }
+      else { c = (gi - fric_start) >> 1; j = 1 + ((gi - fric_start) & 1); }
       const int key = sm.con[c].key;
       float l0 = 0.f;
       for (int sl = 0; sl < B2E_CACHE_SLOTS; sl++)
         if (sm.ckey[sl] == key) { l0 = sm.clam[sl][j] * P.warmstart; break; }
       rr.lam[s] = l0;
-      rr.base[s] = l0 * rr.g[s];
+      rr.base[s] = l0 * rr.gg[s];
     }
   }
-  for (int c = nnc; c < R; c++) {
-    float l0 = (c >> 5) ? shf(rr.lam[NS - 1], c & 31) : shf(rr.lam[0], c & 31);
+  for (int c = nlim; c < RG; c++) {
+    float l0 = 0.f;
+#pragma unroll
+    for (int t = 0; t < NSG; t++) {
+      const float vt = SHF(rr.lam[t], c & (GL - 1));
+      if ((c >> 4) == t) l0 = vt;
+    }
     if (l0 != 0.f) {
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        const int col = (lane + 32 * s < RMAX) ? lane + 32 * s : RMAX - 1;
-        rr.u[s] = fmaf(-A[c * AS + col], l0, rr.u[s]);
-      }
+      for (int s = 0; s < NSG; s++) rr.u[s] = fmaf(-A[c * AS + GL * s + lane], l0, rr.u[s]);
+      m.u = fmaf(-W[c * WSTRIDE + lane], l0, m.u);
     }
   }
   int iters_arm = -1;
-  if (!coupled && !arm_contact && nlim == 0) {
+  bool arm_sweep = true;
+  if (!coupled && !arm_generic) {
     float lam_arm = 0.f;
-    iters_arm = arm_affine_solve(A, AS, lane, nd, rr.u[0], rr.invd[0], rr.diag[0], rr.lo[0], rr.hi[0], P.solver_iters,
-                                 P.residual_tol, lam_arm);
-    if (iters_arm >= 0 && lane < nd) rr.lam[0] = lam_arm;
+    iters_arm = arm_affine_solve(g, Minv, nd, m.u, m.invd, m.diag, m.lo, m.hi, P.solver_iters, P.residual_tol, lam_arm);
+    if (iters_arm >= 0) {
+      if (lane < nd) m.lam = lam_arm;
+      arm_sweep = false;
+    }
   }
-  int iters = pgs_solve<NS>(rr, A, R, fric_start, lane, coupled, has_cube, P.solver_iters, P.residual_tol,
-                            iters_arm >= 0);
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+                            P.residual_tol);
   if (iters_arm > iters) iters = iters_arm;
+  sm.mlam[lane] = lane < nd ? m.lam : 0.f;
 #pragma unroll
-  for (int s = 0; s < NS; s++) {
-    const int r = lane + 32 * s;
-    if (r < R) sm.lam[r] = rr.lam[s];
+  for (int s = 0; s < NSG; s++) {
+    const int gi = GL * s + lane;
+    if (gi < RG) sm.glam[gi] = rr.lam[s];
   }
-  __syncwarp();
+  gsync(g);
   return iters;
 }
 
@@ -817,14 +895,16 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
             int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  const int half = wl >> 4, lane = wl & (GL - 1);          // two environments per warp, 16 lanes each
+  const Grp g = {0xffffu << (GL * half), GL * half, lane};
   // slot -> environment: the whole batch, or the subset listed in env_ids (per-env resets, row f1)
   const int n_slots = env_ids ? n_ids : st.B;
-  const int slot = blockIdx.x * WPB + warp;
+  const int slot = (blockIdx.x * WPB + warp) * 2 + half;
   const bool live_env = slot < n_slots;      // padding warps of the last block shadow the last slot, stores masked
   const int slot_c = live_env ? slot : n_slots - 1;
   const int env = env_ids ? env_ids[slot_c] : slot_c;
-  WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  EnvSmem& sm = reinterpret_cast<EnvSmem*>(smem_raw)[warp * 2 + half];
   const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
 
@@ -857,10 +937,10 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   const bool ctrl_gains = !IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE;
   const float my_kp = (ctrl_gains && lane < P.n_ctrl) ? P.kp_ctrl
                       : ((ctrl_gains && P.task == B2E_TASK_GRASP && lane >= P.n_ctrl) ? P.kp_grip : P.kp_hold);
-  const float grip_cmd = shf(my_act, P.n_ctrl & 31);   // GRASP: action[n_ctrl] = gripper command
+  const float grip_cmd = SHF(my_act, P.n_ctrl & (GL - 1));   // GRASP: action[n_ctrl] = gripper command
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
-  __syncwarp();
+  gsync(g);
 
   const int li = lane < nl ? lane : 0;
   const int my_dof = __ldg(&M->dof[li]);
@@ -870,8 +950,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     // ---- forward kinematics (lane = link) of the current q: start-of-step kinematics of this
     //      sub-step, and at the same time the post-step kinematics of the previous one ----
     {
-      const float qi = shf(my_q, my_dof < 0 ? 0 : my_dof);
-      fk_lanes(M, U, lane, link_has_dof ? qi : 0.f, Rm, pw);
+      const float qi = SHF(my_q, my_dof < 0 ? 0 : my_dof);
+      fk_lanes(M, U, g, link_has_dof ? qi : 0.f, Rm, pw);
     }
     // ---- termination inside apply_action (panda_push_gym_env.py:239-242), for the previous sub-step ----
     if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
@@ -885,7 +965,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
         const int ee = U.ee_link;
         float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]}, o[3];
         m3vec(Rm, cm, o);
-        float e3[3] = {shf(pw[0] + o[0], ee), shf(pw[1] + o[1], ee), shf(pw[2] + o[2], ee)};
+        float e3[3] = {SHF(pw[0] + o[0], ee), SHF(pw[1] + o[1], ee), SHF(pw[2] + o[2], ee)};
         float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
         d = sqrtf(dot3(dd, dd));
       }
@@ -920,17 +1000,17 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       float tp[3], eu[3], tq[4];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        tp[k] = shf(my_hp, k);
-        const float e = P.ik_orientation ? shf(my_hp, 3 + k) : P.home_hand_pose[3 + k];
+        tp[k] = SHF(my_hp, k);
+        const float e = P.ik_orientation ? SHF(my_hp, 3 + k) : P.home_hand_pose[3 + k];
         eu[k] = fminf(fmaxf(e, -3.14159265358979323846f), 3.14159265358979323846f);
       }
       tp[2] = fminf(fmaxf(tp[2], P.ws_lim[2][0]), P.ws_lim[2][1]);
       euler_to_quat(eu, tq);
-      const float t = ik_solve(sm.W, M, U, P.ik_iters, P.ik_residual, P.ik_damping, lane, my_q, tp[0], tp[1], tp[2],
+      const float t = ik_solve(sm.W, M, U, P.ik_iters, P.ik_residual, P.ik_damping, g.hm, g.sh, lane, my_q, tp[0], tp[1], tp[2],
                                tq[0], tq[1], tq[2], tq[3]);
       if (is_dof && !ghost) my_target = t;
     }
-    const float qdi_raw = shf(my_qd, my_dof < 0 ? 0 : my_dof);
+    const float qdi_raw = SHF(my_qd, my_dof < 0 ? 0 : my_dof);
     const float qdi = link_has_dof ? qdi_raw : 0.f;
     if (lane < nl) {
 #pragma unroll
@@ -982,7 +1062,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     float vJ[6], v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { vJ[k] = S[k] * qdi; v[k] = vJ[k]; }
-    path_sum6(M, U, lane, v);
+    path_sum6(M, U, g, v);
     float ab[6];
     {
       float a[3], b[3], c2[3];
@@ -992,7 +1072,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       ab[0] = a[0]; ab[1] = a[1]; ab[2] = a[2];
       ab[3] = b[0] + c2[0]; ab[4] = b[1] + c2[1]; ab[5] = b[2] + c2[2];
     }
-    path_sum6(M, U, lane, ab);
+    path_sum6(M, U, g, ab);
     ab[3] -= P.gravity[0]; ab[4] -= P.gravity[1]; ab[5] -= P.gravity[2];  // a_0 = -g
     {
       // f = I*ab + v x* (I*v)
@@ -1021,23 +1101,23 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       Iw[3] = Ia_f[0] + x3[0]; Iw[4] = Ia_f[1] + x3[1]; Iw[5] = Ia_f[2] + x3[2];
     }
     // child -> parent accumulation of [f | composite inertia]: host-built schedule (heavy-path suffix
-    // scans + folds of light subtrees); every round each lane pulls one source lane (31 = a zero lane)
+    // scans + folds of light subtrees); every round each lane pulls one source lane (15 = a zero lane)
     {
       const unsigned sch0 = __ldg(&M->acc_sched[0][lane]), sch1 = __ldg(&M->acc_sched[1][lane]);
       const int rounds = U.acc_rounds;
       for (int rd = 0; rd < rounds; rd++) {
-        const int src = rd < 6 ? ((sch0 >> (5 * rd)) & 31) : ((sch1 >> (5 * (rd - 6))) & 31);
+        const int src = rd < 8 ? ((sch0 >> (4 * rd)) & 15) : ((sch1 >> (4 * (rd - 8))) & 15);
 #pragma unroll
-        for (int k = 0; k < 16; k++) Iw[k] += shf(Iw[k], src);
+        for (int k = 0; k < 16; k++) Iw[k] += SHF(Iw[k], src);
       }
     }
     // move to dof lanes: lane d gets S, f^c, I^c of its link
     const int lk = is_dof ? __ldg(&M->dof_link[lane]) : 0;
     float Sd[6], Fc[6], Ic[10];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { Sd[k] = shf(S[k], lk); Fc[k] = shf(Iw[k], lk); }
+    for (int k = 0; k < 6; k++) { Sd[k] = SHF(S[k], lk); Fc[k] = SHF(Iw[k], lk); }
 #pragma unroll
-    for (int k = 0; k < 10; k++) Ic[k] = shf(Iw[6 + k], lk);
+    for (int k = 0; k < 10; k++) Ic[k] = SHF(Iw[6 + k], lk);
     if (is_dof) {
 #pragma unroll
       for (int k = 0; k < 6; k++) sm.S[lane][k] = Sd[k];
@@ -1059,20 +1139,20 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const float tau_b = Sd[0] * Fc[0] + Sd[1] * Fc[1] + Sd[2] * Fc[2] + Sd[3] * Fc[3] + Sd[4] * Fc[4] + Sd[5] * Fc[5];
     // joint-space inertia: M[d][e] = S_e . F_d for e on the path to d; symmetrised through smem
     const unsigned my_mask = is_dof ? __ldg(&M->link_dofmask[lk]) : 0u;
-    for (int k = lane; k < NDMAX * (NDMAX + 1); k += 32) (&sm.Minv[0][0])[k] = 0.f;
-    __syncwarp();
+    for (int k = lane; k < NDMAX * (NDMAX + 1); k += GL) (&sm.Minv[0][0])[k] = 0.f;
+    gsync(g);
 #pragma unroll
     for (int e = 0; e < NDMAX; e++) {
       float Se[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) Se[k] = shf(Sd[k], e);
+      for (int k = 0; k < 6; k++) Se[k] = SHF(Sd[k], e);
       const float val = Se[0] * F[0] + Se[1] * F[1] + Se[2] * F[2] + Se[3] * F[3] + Se[4] * F[4] + Se[5] * F[5];
       if (is_dof && e < nd && ((my_mask >> e) & 1)) {
         sm.Minv[lane][e] = val;
         sm.Minv[e][lane] = val;
       }
     }
-    __syncwarp();
+    gsync(g);
     float a[NDMAX];
 #pragma unroll
     for (int e = 0; e < NDMAX; e++) a[e] = (is_dof && e < nd) ? sm.Minv[lane][e] : ((e == lane) ? 1.f : 0.f);
@@ -1081,7 +1161,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     for (int k = 0; k < NDMAX; k++) {
       float rk[NDMAX];
 #pragma unroll
-      for (int j = 0; j < NDMAX; j++) rk[j] = shf(a[j], k);
+      for (int j = 0; j < NDMAX; j++) rk[j] = SHF(a[j], k);
       const float pinv = 1.0f / rk[k];
       if (lane == k) {
 #pragma unroll
@@ -1092,7 +1172,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
         for (int j = 0; j < NDMAX; j++) a[j] = (j == k) ? -f * pinv : fmaf(-f * pinv, rk[j], a[j]);
       }
     }
-    __syncwarp();
+    gsync(g);
     if (lane < NDMAX) {
 #pragma unroll
       for (int e = 0; e < NDMAX; e++) sm.Minv[lane][e] = (lane < nd && e < nd) ? a[e] : 0.f;
@@ -1101,7 +1181,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const float rhs_d = is_dof ? (-tau_b - __ldg(&M->joint_damping[lane]) * my_qd) : 0.f;
     float qdd = 0.f;
 #pragma unroll
-    for (int e = 0; e < NDMAX; e++) qdd = fmaf(a[e], shf(rhs_d, e), qdd);
+    for (int e = 0; e < NDMAX; e++) qdd = fmaf(a[e], SHF(rhs_d, e), qdd);
     const float vstar_d = my_qd + dt * qdd;
     float cvs[3], cws[3];
     {
@@ -1144,7 +1224,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     bool sc_hit = false, st_hit = false;
     float s_c[3] = {0, 0, 0}, sc_n[3] = {0, 0, 0}, sc_pB[3] = {0, 0, 0}, sc_dist = 0.f, st_dist = 0.f, s_r = 0.f;
     int s_link = 0;
-    __syncwarp();
+    gsync(g);
     if (lane < ns) {
       s_link = __ldg(&M->sph_link[lane]);
       s_r = __ldg(&M->sph_r[lane]);
@@ -1199,7 +1279,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       st_hit = over && (st_dist < margin);
     }
     // canonical order: cube-static by vertex, sphere-cube by sphere, sphere-table by sphere
-    const unsigned bv = __ballot_sync(FULL, v_hit), bsc = __ballot_sync(FULL, sc_hit), bst = __ballot_sync(FULL, st_hit);
+    const unsigned bv = gballot(g, v_hit), bsc = gballot(g, sc_hit), bst = gballot(g, st_hit);
     const unsigned lt = (1u << lane) - 1u;
     const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
     const int total = n_v + n_sc + n_st;
@@ -1248,7 +1328,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const float dlo = my_q - my_lower, dup = my_upper - my_q;
     const float lmar = is_dof ? __ldg(&M->limit_margin[lane]) : 0.f;
     const bool lo_hit = is_dof && dlo < lmar, up_hit = is_dof && dup < lmar;
-    const unsigned blo = __ballot_sync(FULL, lo_hit), bup = __ballot_sync(FULL, up_hit);
+    const unsigned blo = gballot(g, lo_hit), bup = gballot(g, up_hit);
     int nlim = __popc(blo) + __popc(bup);
     if (nlim > B2E_MAX_LIMROWS) { flags |= B2E_ST_LIMIT_OVERFLOW; nlim = B2E_MAX_LIMROWS; }
     if (lo_hit) {
@@ -1259,21 +1339,31 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       const int slot = __popc(blo & lt) + __popc(bup & lt) + (lo_hit ? 1 : 0);
       if (slot < B2E_MAX_LIMROWS) { sm.lim_d[slot] = lane | (1 << 8); sm.lim_dist[slot] = dup; }
     }
-    __syncwarp();
+    gsync(g);
 
     PHASE_BARRIER();
     // ---- rows + PGS ----
     R = nd + nlim + 3 * nc;
-    if (R <= 32) iters = build_and_solve<1>(sm, M, U, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], nullptr);
-    else iters = build_and_solve<2>(sm, M, U, P, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2],
-                                    st.scratch + (size_t)env * SCRATCH_PER_ENV);
+    // generic rows (limits + contacts) come in sets of 16; both envs of the warp take the same
+    // instantiation (the larger need) so the warp does not execute two instantiations back to back
+    const int RG = nlim + 3 * nc;
+    const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));
+    float* scr = st.scratch + (size_t)env * SCRATCH_PER_ENV;
+    if (RGw <= GL) iters = build_and_solve<1>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
+    else if (RGw <= 2 * GL) iters = build_and_solve<2>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
+    else iters = build_and_solve<3>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
 
     PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
     {
-      const float* Wp = (R <= 32) ? sm.W : st.scratch + (size_t)env * SCRATCH_PER_ENV + RMAX * RMAX;
-      for (int r = 0; r < R; r++) dvk = fmaf(Wp[r * WSTRIDE + (lane & 15)], sm.lam[r], dvk);
+      const float* Wp = (RGw <= GL) ? sm.W : scr + GMAX * GMAX;
+      for (int r = 0; r < RG; r++) dvk = fmaf(Wp[r * WSTRIDE + lane], sm.glam[r], dvk);
+      // motor rows: W_d = column d of M^-1
+      if (lane < NDMAX) {
+#pragma unroll
+        for (int d = 0; d < NDMAX; d++) dvk = fmaf(sm.Minv[lane][d], sm.mlam[d], dvk);
+      }
     }
     // ---- integrate (semi-implicit Euler) ----
     if (is_dof && !ghost) {
@@ -1282,7 +1372,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const float dvl = shf(dvk, NDMAX + k), dva = shf(dvk, NDMAX + 3 + k);
+      const float dvl = SHF(dvk, NDMAX + k), dva = SHF(dvk, NDMAX + 3 + k);
       if (!ghost) {
         cv[k] = cvs[k] + dvl;
         cw[k] = cws[k] + dva;
@@ -1302,14 +1392,13 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     // ---- contact cache for the next step's warm start ----
     {
-      const int nnc = nd + nlim;
       int key = -1;
       float l3[3] = {0.f, 0.f, 0.f};
       if (lane < nc) {
         key = sm.con[lane].key;
-        l3[0] = sm.lam[nnc + lane];
-        l3[1] = sm.lam[nnc + nc + 2 * lane];
-        l3[2] = sm.lam[nnc + nc + 2 * lane + 1];
+        l3[0] = sm.glam[nlim + lane];
+        l3[1] = sm.glam[nlim + nc + 2 * lane];
+        l3[2] = sm.glam[nlim + nc + 2 * lane + 1];
       }
       if (record_contacts && lane < B2E_MAX_CONTACTS && live_env && !ghost) {
         float* o = st.contacts + ((size_t)env * B2E_MAX_CONTACTS + lane) * 8;
@@ -1322,18 +1411,18 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
           for (int k = 0; k < 8; k++) o[k] = 0.f;
         }
       }
-      __syncwarp();
+      gsync(g);
       if (lane < B2E_CACHE_SLOTS && !ghost) {
         sm.ckey[lane] = key;
         sm.clam[lane][0] = l3[0]; sm.clam[lane][1] = l3[1]; sm.clam[lane][2] = l3[2];
       }
-      __syncwarp();
+      gsync(g);
     }
     {
       bool bad = is_dof && !(isfinite(my_q) && isfinite(my_qd));
       bad = bad || !(isfinite(cpos[0]) && isfinite(cpos[1]) && isfinite(cpos[2]) && isfinite(cv[0]) && isfinite(cv[1]) &&
                      isfinite(cv[2]) && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]));
-      if (__any_sync(FULL, bad)) flags |= B2E_ST_NAN;
+      if (gany(g, bad)) flags |= B2E_ST_NAN;
     }
 
   }
@@ -1369,9 +1458,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     m3vec(R2, cm, o);
     float epos[3], Re[9];
 #pragma unroll
-    for (int k = 0; k < 3; k++) epos[k] = shf(p2[k] + o[k], ee);
+    for (int k = 0; k < 3; k++) epos[k] = SHF(p2[k] + o[k], ee);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Re[k] = shf(R2[k], ee);
+    for (int k = 0; k < 9; k++) Re[k] = SHF(R2[k], ee);
     // EE linear velocity: sum over the dofs on the path of (axis x (p_ee - o_j)) qd_j  /  axis qd_j
     float vl[3] = {0, 0, 0};
     {
@@ -1379,7 +1468,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       const int jt = __ldg(&M->jtype[li]);
       float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])}, aw[3];
       m3vec(R2, ax, aw);
-      const float qdl = shf(my_qd, my_dof < 0 ? 0 : my_dof);
+      const float qdl = SHF(my_qd, my_dof < 0 ? 0 : my_dof);
       if (lane < nl && my_dof >= 0 && ((eemask >> my_dof) & 1)) {
         if (jt == B2E_JOINT_REVOLUTE) {
           float rel[3] = {epos[0] - p2[0], epos[1] - p2[1], epos[2] - p2[2]}, t[3];
@@ -1392,7 +1481,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       // fixed-order sum over links 0..nl-1 so the result does not depend on lane scheduling
       float acc[3] = {0, 0, 0};
       for (int j = 0; j < nl; j++) {
-        acc[0] += shf(vl[0], j); acc[1] += shf(vl[1], j); acc[2] += shf(vl[2], j);
+        acc[0] += SHF(vl[0], j); acc[1] += SHF(vl[1], j); acc[2] += SHF(vl[2], j);
       }
       vl[0] = acc[0]; vl[1] = acc[1]; vl[2] = acc[2];
     }
@@ -1411,32 +1500,34 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     quat_mul(hqi, oq, relq);
     quat_to_euler(relq, releu);
+    float* obsb = sm.W;   // the W table is dead by now: staging for the observation vector
+    gsync(g);
     if (lane == 0) {
       int n = 0;
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = epos[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = epos[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = eeu[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = eeu[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = (vl[k] - P.vel_mean[k]) / P.vel_std[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = (vl[k] - P.vel_mean[k]) / P.vel_std[k];
       n += nd;
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = cpos[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = cpos[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = ceu[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = ceu[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = relp[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = relp[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) sm.obs[n++] = releu[k];
+      for (int k = 0; k < 3; k++) obsb[n++] = releu[k];
       if (P.task == B2E_TASK_PUSH || P.task == B2E_TASK_GRASP) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) sm.obs[n++] = target[k];
+        for (int k = 0; k < 3; k++) obsb[n++] = target[k];
       }
     }
-    if (is_dof) sm.obs[9 + lane] = my_q;
-    __syncwarp();
-    for (int k = lane; k < P.n_obs; k += 32) {
-      const float raw = sm.obs[k];
+    if (is_dof) obsb[9 + lane] = my_q;
+    gsync(g);
+    for (int k = lane; k < P.n_obs; k += GL) {
+      const float raw = obsb[k];
       st.raw_obs[(size_t)env * P.n_obs + k] = raw;
       if (obs_out) obs_out[(size_t)env * P.n_obs + k] = 2.0f * ((raw - P.obs_low[k]) / (P.obs_high[k] - P.obs_low[k])) - 1.0f;
     }
@@ -1534,7 +1625,7 @@ static int field_width(const b2e_sim* s, int f) {
 static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   memset(d, 0, sizeof(*d));
   memset(u, 0, sizeof(*u));
-  if (m->n_links > TLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 16 links%s", "");
+  if (m->n_links > TLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "group kernel supports <= 12 links%s", "");
   if (m->n_dof > NDMAX) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 9 dofs%s", "");
   if (m->n_spheres > B2E_MAX_SPHERES || m->n_spheres < 0) return fail(B2E_EINVAL, "bad n_spheres%s", "");
   d->n_links = m->n_links; d->n_dof = m->n_dof; d->ee_link = m->ee_link; d->n_spheres = m->n_spheres;
@@ -1570,8 +1661,8 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
       if (p >= 0 && (heavy[p] < 0 || size[i] > size[heavy[p]])) heavy[p] = i;
     }
     for (int i = 0; i < n; i++) head[i] = (m->parent[i] >= 0 && heavy[m->parent[i]] == i) ? head[m->parent[i]] : i;
-    int src[12][NLMAX];
-    for (int r = 0; r < 12; r++) for (int l = 0; l < NLMAX; l++) src[r][l] = 31;
+    int src[16][NLMAX];
+    for (int r = 0; r < 16; r++) for (int l = 0; l < NLMAX; l++) src[r][l] = 15;
     int rounds = 0;
     // path heads, deepest first
     int heads[TLMAX], nh = 0;
@@ -1581,12 +1672,12 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
       int path[TLMAX], len = 0;
       for (int v = heads[a]; v >= 0; v = heavy[v]) path[len++] = v;
       for (int step = 1; step < len; step <<= 1) {
-        if (rounds >= 12) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 12 accumulation rounds%s", "");
+        if (rounds >= 16) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 16 accumulation rounds%s", "");
         for (int i = 0; i + step < len; i++) src[rounds][path[i]] = path[i + step];
         rounds++;
       }
       if (m->parent[heads[a]] >= 0) {
-        if (rounds >= 12) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 12 accumulation rounds%s", "");
+        if (rounds >= 16) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 16 accumulation rounds%s", "");
         src[rounds][m->parent[heads[a]]] = heads[a];
         rounds++;
       }
@@ -1594,7 +1685,7 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
     u->acc_rounds = rounds;
     for (int l = 0; l < NLMAX; l++) {
       unsigned w0 = 0, w1 = 0;
-      for (int r = 0; r < 6; r++) { w0 |= (unsigned)src[r][l] << (5 * r); w1 |= (unsigned)src[6 + r][l] << (5 * r); }
+      for (int r = 0; r < 8; r++) { w0 |= (unsigned)src[r][l] << (4 * r); w1 |= (unsigned)src[8 + r][l] << (4 * r); }
       d->acc_sched[0][l] = w0; d->acc_sched[1][l] = w1;
     }
   }
@@ -1603,7 +1694,7 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   for (int k = 0; k < 3; k++) { u->base_pos[k] = m->base_pos[k]; u->ee_com[k] = m->com[m->ee_link][k]; }
   for (int k = 0; k < 9; k++) u->base_rot[k] = m->base_rot[k];
   for (int i = 0; i < TLMAX; i++) u->parent[i] = i < m->n_links ? m->parent[i] : -1;
-  if (m->n_links >= 31) return fail(B2E_EUNSUPPORTED, "lane 31 must stay free%s", "");
+
   for (int k = 0; k < m->n_dof; k++) {
     d->lower[k] = m->lower[k]; d->upper[k] = m->upper[k]; d->limit_margin[k] = m->limit_margin[k];
     d->max_force[k] = m->max_force[k]; d->max_vel[k] = m->max_vel[k]; d->joint_damping[k] = m->joint_damping[k];
@@ -1623,12 +1714,12 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
                        const int* env_ids, int n_ids, void* stream) {
   const int n = env_ids ? n_ids : s->B;
   if (n <= 0) return 0;
-  const int blocks = (n + WPB - 1) / WPB;
+  const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
   if (s->params.use_ik)
-    step_kernel<true><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+    step_kernel<true><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
   else
-    step_kernel<false><<<blocks, 32 * WPB, sizeof(WarpSmem) * WPB, (cudaStream_t)stream>>>(
+    step_kernel<false><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1696,8 +1787,8 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaMallocHost(&s->h_action, na)); CUDA_TRY(cudaMallocHost(&s->h_obs, no));
   CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
   CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WPB)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
   *out = s;
   return 0;
 }
