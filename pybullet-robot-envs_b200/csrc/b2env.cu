@@ -271,9 +271,7 @@ struct EnvSmem {
   float lim_dist[4];
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
-  float pad_[12];              // sizeof/4 = 16 (mod 32): the two groups of a warp use disjoint bank halves
 };
-static_assert((sizeof(EnvSmem) / 4) % 32 == 16, "EnvSmem must offset the second group by 16 banks");
 
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
@@ -477,12 +475,12 @@ struct RowRegs {
 
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
-                                           const float* W, int i, bool active) {
+                                           const float* W, int i) {
   float nl = fmaf(m.u, m.invd, m.lam);
   nl = fminf(fmaxf(nl, m.lo), m.hi);
-  const float dl = active ? nl - m.lam : 0.f;
+  const float dl = nl - m.lam;
   const float dli = SHF(dl, i);
-  if (g.lane == i && active) m.lam = nl;
+  if (g.lane == i) m.lam = nl;
   const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
   m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
 #pragma unroll
@@ -491,45 +489,41 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
 
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                             const float* W, int gi, bool arm_sweep, bool active) {
+                                             const float* W, int gi, bool arm_sweep) {
   constexpr int AS = (NSG == 1) ? GL : GMAX;
   const int li = gi & (GL - 1);
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-  const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits row gi in this pass
+  const float dl = nl - r.lam[SI];
   const float dli = SHF(dl, li);
-  if (g.lane == li && active) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
+  if (g.lane == li) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
   if (arm_sweep) m.u = fmaf(-W[gi * WSTRIDE + g.lane], dli, m.u);
 #pragma unroll
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-A[gi * AS + GL * s + g.lane], dli, r.u[s]);
 }
 
-// Visit the generic rows whose bits are set, in ascending order.  The loop runs over the union of the two
-// groups' masks so that its branches are warp-uniform; a group skips (dl = 0) rows only the other one has.
+// visit the generic rows whose bits are set, in ascending order
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
                                               const float* W, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  unsigned w0 = m0 | __shfl_xor_sync(FULL, m0, GL);
-  while (w0) {
-    const int i = __ffs(w0) - 1;
-    w0 &= w0 - 1;
-    generic_step<NSG, 0>(g, m, r, A, W, i, arm_sweep, (m0 >> i) & 1);
+  while (m0) {
+    const int i = __ffs(m0) - 1;
+    m0 &= m0 - 1;
+    generic_step<NSG, 0>(g, m, r, A, W, i, arm_sweep);
   }
   if (NSG > 1) {
-    unsigned w1 = m1 | __shfl_xor_sync(FULL, m1, GL);
-    while (w1) {
-      const int i = __ffs(w1) - 1;
-      w1 &= w1 - 1;
-      generic_step<NSG, S1>(g, m, r, A, W, GL + i, arm_sweep, (m1 >> i) & 1);
+    while (m1) {
+      const int i = __ffs(m1) - 1;
+      m1 &= m1 - 1;
+      generic_step<NSG, S1>(g, m, r, A, W, GL + i, arm_sweep);
     }
   }
   if (NSG > 2) {
-    unsigned w2 = m2 | __shfl_xor_sync(FULL, m2, GL);
-    while (w2) {
-      const int i = __ffs(w2) - 1;
-      w2 &= w2 - 1;
-      generic_step<NSG, S2>(g, m, r, A, W, 2 * GL + i, arm_sweep, (m2 >> i) & 1);
+    while (m2) {
+      const int i = __ffs(m2) - 1;
+      m2 &= m2 - 1;
+      generic_step<NSG, S2>(g, m, r, A, W, 2 * GL + i, arm_sweep);
     }
   }
 }
@@ -550,22 +544,28 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     cube_nf[s] = gballot(g, valid && cube && !fr);
     cube_f[s] = gballot(g, valid && cube && fr);
   }
+  const unsigned motor_mask = (1u << nd) - 1u;
   bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
-  int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
-  for (int it = 0; it < max_iters; it++) {
-    if (__all_sync(FULL, my_it >= 0)) break;
+  if (done0 && done1) return 0;
+  int it = 0;
+  for (it = 0; it < max_iters; it++) {
     m.prev = m.lam;
 #pragma unroll
     for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
-    if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
-      for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, i, !done0);
+    if (!done0) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
+      unsigned mm = motor_mask;
+      while (mm) {
+        const int i = __ffs(mm) - 1;
+        mm &= mm - 1;
+        motor_step<NSG>(g, m, r, Minv, W, i);
+      }
     }
     sweep_generic<NSG>(g, m, r, A, W, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
                        (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
-    if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
+    if (f0 | f1 | f2) {
       // friction bounds from the current normal impulses (mu * lambda_n)
 #pragma unroll
       for (int s = 0; s < NSG; s++) {
@@ -596,13 +596,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
         if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
       }
     }
-    ra = gmaxf(g, ra);
-    rc = gmaxf(g, rc);
+    if (!done0) ra = gmaxf(g, ra);
+    if (!done1) rc = gmaxf(g, rc);
     if (!done0 && ra <= tol) done0 = true;
     if (!done1 && rc <= tol) done1 = true;
-    if (my_it < 0 && done0 && done1) my_it = it + 1;
+    if (done0 && done1) { it++; break; }
   }
-  return my_it < 0 ? max_iters : my_it;
+  return it;
 }
 
 // Arm island made only of the n_dof position-motor rows (no limit row, no arm contact): bounds are
@@ -646,29 +646,23 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
     for (int k = j + 1; k < NDMAX; k++) G[k] = fmaf(-T[j], SHF(Ar[k], j), G[k]);
   }
   float lam = 0.f;
-  int my_it = -1;          // >= 0: converged after that many sweeps; -2: a bound would activate (fallback)
-  for (int it = 0; it < max_iters; it++) {
-    if (__all_sync(FULL, my_it != -1)) break;   // the loop is shared by both groups of the warp
+  int it;
+  for (it = 0; it < max_iters; it++) {
     float a0 = c, a1 = 0.f;
 #pragma unroll
     for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], SHF(lam, k), a0);
 #pragma unroll
     for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], SHF(lam, k), a1);
     const float nl = a0 + a1;
-    const bool clamp = gany(g, row && !(nl >= lo && nl <= hi));
+    if (gany(g, row && !(nl >= lo && nl <= hi))) return -1;
     float rv = row ? (nl - lam) * diag : 0.f;
-    rv = gmaxf(g, rv * rv);
-    if (my_it == -1) {
-      if (clamp) my_it = -2;
-      else {
-        lam = nl;
-        if (rv <= tol) my_it = it + 1;
-      }
-    }
+    rv = rv * rv;
+    lam = nl;
+    rv = gmaxf(g, rv);
+    if (rv <= tol) { it++; break; }
   }
-  if (my_it == -2) return -1;
   lam_out = lam;
-  return my_it < 0 ? max_iters : my_it;
+  return it;
 }
 
 // Build the motor row of this dof lane and the generic row(s) of this lane, the W table, the generic
@@ -687,7 +681,6 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   const float* Minv = &sm.Minv[0][0];
   const int fric_start = nlim + nc;   // generic index of the first friction row
   const int RG = nlim + 3 * nc;       // generic rows
-  const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));   // larger count of the two groups: shared loop bounds
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
 
@@ -827,8 +820,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     const int gi = GL * s + lane;
     const bool valid = gi < RG;
     const float* J = Jall[s];
-    for (int c = 0; c < RGw; c++) {
-      if (c >= RG) continue;   // the other group of the warp has more rows
+    for (int c = 0; c < RG; c++) {
       float acc = 0.f;
       const bool cube_only = (c >= nlim) && sm.con[c < fric_start ? c - nlim : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
       if (!cube_only) {
@@ -859,14 +851,14 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       rr.base[s] = l0 * rr.gg[s];
     }
   }
-  for (int c = 0; c < RGw; c++) {
+  for (int c = nlim; c < RG; c++) {
     float l0 = 0.f;
 #pragma unroll
     for (int t = 0; t < NSG; t++) {
       const float vt = SHF(rr.lam[t], c & (GL - 1));
       if ((c >> 4) == t) l0 = vt;
     }
-    if (l0 != 0.f && c >= nlim && c < RG) {
+    if (l0 != 0.f) {
 #pragma unroll
       for (int s = 0; s < NSG; s++) rr.u[s] = fmaf(-A[c * AS + GL * s + lane], l0, rr.u[s]);
       m.u = fmaf(-W[c * WSTRIDE + lane], l0, m.u);
@@ -874,12 +866,10 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   }
   int iters_arm = -1;
   bool arm_sweep = true;
-  const bool arm_simple = !coupled && !arm_generic;
-  if (__any_sync(FULL, arm_simple)) {   // both groups run it (shared loop); a non-simple group ignores the result
+  if (!coupled && !arm_generic) {
     float lam_arm = 0.f;
-    const int ia = arm_affine_solve(g, Minv, nd, m.u, m.invd, m.diag, m.lo, m.hi, P.solver_iters, P.residual_tol, lam_arm);
-    if (arm_simple && ia >= 0) {
-      iters_arm = ia;
+    iters_arm = arm_affine_solve(g, Minv, nd, m.u, m.invd, m.diag, m.lo, m.hi, P.solver_iters, P.residual_tol, lam_arm);
+    if (iters_arm >= 0) {
       if (lane < nd) m.lam = lam_arm;
       arm_sweep = false;
     }
@@ -1368,8 +1358,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     float dvk = 0.f;
     {
       const float* Wp = (RGw <= GL) ? sm.W : scr + GMAX * GMAX;
-      for (int r = 0; r < RGw; r++)   // shared loop bound; a group stops accumulating after its own rows
-        if (r < RG) dvk = fmaf(Wp[r * WSTRIDE + lane], sm.glam[r], dvk);
+      for (int r = 0; r < RG; r++) dvk = fmaf(Wp[r * WSTRIDE + lane], sm.glam[r], dvk);
       // motor rows: W_d = column d of M^-1
       if (lane < NDMAX) {
 #pragma unroll

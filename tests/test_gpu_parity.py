@@ -134,3 +134,75 @@ def test_full_batch_properties():
         sim.close()
     for a, b in zip(outs[0], outs[1]):
         np.testing.assert_array_equal(a, b)  # bitwise deterministic
+
+
+def _contact_rich_states(oracle_lib, m, p, B, seed):
+    """Joint states that put the hand / fingers at the cube and on the table: oracle IK towards points
+    around the resting cube, so that sphere-cube and sphere-table contacts, coupled islands, limit rows
+    and more than 16 generic rows occur."""
+    import ctypes as C
+    import math
+    o1 = oracle_lib.Oracle(m, p, 1)
+    o1.lib.b2o_ik.restype = C.c_int
+    rng = np.random.RandomState(seed)
+    home = np.array([m.home[i] for i in range(9)], np.float32)
+    tq = np.array([1.0, 0.0, 0.0, 6.123234e-17], np.float32)        # hand pointing down (euler pi,0,0)
+    qs = np.zeros((B, 9), np.float32)
+    poses = sample_object_poses(B, seed)
+    poses[:, 2] = 0.65
+    for b in range(B):
+        off = rng.uniform(-0.04, 0.04, 3).astype(np.float32)
+        off[2] = rng.uniform(0.0, 0.09)
+        tp = (poses[b, :3] + off).astype(np.float32)
+        out = np.zeros(9, np.float32)
+        o1.lib.b2o_ik(C.byref(m), C.byref(p), home.ctypes.data_as(C.c_void_p), tp.ctypes.data_as(C.c_void_p),
+                      tq.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        out[7:] = rng.uniform(0.0, 0.04, 2)
+        qs[b] = np.clip(out, [m.lower[i] for i in range(9)], [m.upper[i] for i in range(9)])
+    return qs, poses
+
+
+def test_contact_rich_single_step_parity(oracle_lib):
+    """Robot-cube and robot-table contacts: coupled islands, serial motor rows, 2-3 generic row sets.
+    GPU restarts from the oracle state every step.  Contact keys / counts / row counts must be exact;
+    states within the single-step tolerances (contacts are stiff: velocities 2e-2, positions 1e-4)."""
+    from pybullet_robot_envs.b2env.binding import B2Sim, OPT_RECORD_CONTACTS
+    B = 256
+    m, p = panda_task_setup(TASK_PUSH)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=8)
+    sim = B2Sim(m, p, B, 0)
+    sim.set_option(OPT_RECORD_CONTACTS, 1)
+    qs, poses = _contact_rich_states(oracle_lib, m, p, B, 21)
+    tg = targets_for(poses) + np.array([0.3, 0, 0], np.float32)
+    orc.reset(poses, tg)
+    orc.state["q"][:] = qs
+    orc.state["mtarget"][:] = qs
+    rng = np.random.RandomState(5)
+    seen_rows, seen_coupled, seen_limit = 0, 0, 0
+    for i in range(40):
+        copy_state_to_gpu(orc, sim)
+        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)
+        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+        g_st, o_st = sim.get("status"), orc.state["status"]
+        np.testing.assert_array_equal(g_st[:, 2:], o_st[:, 2:], err_msg="n_contacts / n_rows, step %d" % i)
+        np.testing.assert_array_equal(g_st[:, 0] & 6, o_st[:, 0] & 6, err_msg="overflow flags, step %d" % i)
+        np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="contact keys, step %d" % i)
+        assert (g_st[:, 0] & 1).sum() == 0
+        ok = np.isfinite(orc.state["q"]).all(axis=1)
+        assert ok.all()
+        dq = np.abs(sim.get("q") - orc.state["q"]).max(axis=1)
+        dv = np.abs(sim.get("qd") - orc.state["qd"]).max(axis=1)
+        dc = np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max(axis=1)
+        # iteration-limited envs (150 sweeps without meeting the residual) agree less tightly: both sides stop a
+        # non-converged Gauss-Seidel at the same sweep, rounding differences are not damped out
+        conv = o_st[:, 1] < 150
+        assert dq[conv].max() < 1e-4 and dc[conv].max() < 1e-4 and dv[conv].max() < 2e-2, (i, dq[conv].max(), dv[conv].max(), dc[conv].max())
+        assert dq.max() < 2e-3 and dc.max() < 2e-3, (i, dq.max(), dc.max())
+        seen_rows = max(seen_rows, int(o_st[:, 3].max()))
+        keys = orc.state["cache_key"]
+        seen_coupled += int(((keys >= 16) & (keys < 32)).any(axis=1).sum())
+        seen_limit += int((o_st[:, 3] - 9 - 3 * o_st[:, 2] > 0).sum())
+    assert seen_rows > 9 + 16 + 16, seen_rows        # three generic row sets were exercised
+    assert seen_coupled > 50 and seen_limit > 0, (seen_coupled, seen_limit)
+    print("contact-rich: max rows %d, coupled env-steps %d, limit-row env-steps %d" % (seen_rows, seen_coupled, seen_limit))
