@@ -225,7 +225,8 @@ def main():
 
     # ---- end-to-end through the public API with host buffers ----
     Ke = min(args.e2e_steps, K)
-    host_actions = (np.random.RandomState(99 + rank).uniform(-1, 1, (Ke, B, 7))).astype(np.float32)
+    host_actions = sim.pinned_array((Ke, B, 7))           # the policy's outputs live in page-locked host memory
+    host_actions[...] = np.random.RandomState(99 + rank).uniform(-1, 1, (Ke, B, 7)).astype(np.float32)
     for i in range(3):
         env.step(host_actions[i % Ke])
     barrier()

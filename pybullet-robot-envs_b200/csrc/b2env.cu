@@ -1,23 +1,28 @@
 // b2env.cu — B200 (sm_100a) batched rigid-body step + reward pipeline and its C-ABI.
 //
-// One warp advances one environment through a complete env.step() of the reference
+// Sixteen lanes advance one environment through a complete env.step() of the reference
 // (pybullet_robot_envs/envs/panda_envs/panda_push_gym_env.py:244-255): action -> motor targets
 // (:225-230, panda_env.py:303-310), p.stepSimulation (:236) = articulated forward dynamics +
 // collision detection + PGS over motor/limit/contact rows + semi-implicit Euler, then the
 // observation gather (:150-187), termination (:301-316) and reward (:318-331), all fused in a
 // single launch.  See DESIGN.md for the algorithm statement shared with oracle/b2oracle.c.
 //
-// Mapping of the work onto a warp (32 lanes):
-//   * kinematics / dynamics : lane = link (<=32 links); parent->child recursions are carried
-//     by pointer-jumping over __shfl_sync (log2(depth) rounds), child->parent accumulations
-//     by a shuffle walk over the links; the joint-space inertia matrix is built CRBA-style in
+// Mapping of the work onto the machine: ONE ENVIRONMENT = 16 LANES, two environments per warp.  Every
+// stage needs <= 16 lanes (12 links, 9 dofs, 8 cube vertices, 14 spheres, 15 velocity components, 16
+// rows per set); all warp collectives carry the member mask of the environment's own half-warp, so the
+// two environments of a warp may diverge and otherwise share every instruction.
+//   * kinematics / dynamics : lane = link; parent->child recursions are carried by pointer-jumping
+//     over __shfl_sync (log2(depth) rounds), child->parent accumulations by a host-built shuffle
+//     schedule (heavy-path suffix scans); the joint-space inertia matrix is built CRBA-style in
 //     world coordinates and inverted in registers by Gauss-Jordan (lane = row).
 //   * collision             : lane = cube vertex / lane = collision sphere, ballot compaction.
 //   * PGS                   : lane = constraint row.  The solver runs on the Delassus form
-//     A = J M^-1 J^T (staged in shared memory), so one row update is a handful of scalar
-//     instructions + one shuffle + one LDS/FMA per lane instead of two n-wide dot/axpy.
-//     This is the same Gauss-Seidel iteration Bullet runs in delta-velocity space
-//     (identical iterates in exact arithmetic, same row order).
+//     A = J M^-1 J^T, so one row update is a handful of scalar instructions + one shuffle + one
+//     LDS/FMA per lane instead of two n-wide dot/axpy.  Motor rows are never materialised (their
+//     Delassus block is M^-1 itself) and, when they form an island of their own, a Gauss-Seidel sweep
+//     over them is evaluated as the affine map lambda' = G lambda + c.  This is the same Gauss-Seidel
+//     iteration Bullet runs in delta-velocity space (identical iterates in exact arithmetic, same
+//     row order, same exit test).
 // There is no dense contraction anywhere (largest matrix 9x9 / 48x48 per env): no tensor cores.
 //
 // State lives in HBM as env-major field groups ([B][width] arrays, see enum b2e_field), read
@@ -112,6 +117,7 @@ struct b2e_sim {
   int64_t launches;
   int record_contacts;
   cudaEvent_t ev0, ev1;
+  cudaStream_t pstream[2];   // chunk pipeline of the page-locked host path
 };
 
 static thread_local char g_err[512] = "";
@@ -893,17 +899,17 @@ template <bool IK>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
-            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids) {
+            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
   const int half = wl >> 4, lane = wl & (GL - 1);          // two environments per warp, 16 lanes each
   const Grp g = {0xffffu << (GL * half), GL * half, lane};
   // slot -> environment: the whole batch, or the subset listed in env_ids (per-env resets, row f1)
-  const int n_slots = env_ids ? n_ids : st.B;
+  const int n_slots = n_ids;   // env_ids: listed envs; else the contiguous range [env_offset, env_offset + n_ids)
   const int slot = (blockIdx.x * WPB + warp) * 2 + half;
   const bool live_env = slot < n_slots;      // padding warps of the last block shadow the last slot, stores masked
   const int slot_c = live_env ? slot : n_slots - 1;
-  const int env = env_ids ? env_ids[slot_c] : slot_c;
+  const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
   EnvSmem& sm = reinterpret_cast<EnvSmem*>(smem_raw)[warp * 2 + half];
   const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
@@ -1711,16 +1717,18 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
 }
 
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
-                       const int* env_ids, int n_ids, void* stream) {
-  const int n = env_ids ? n_ids : s->B;
+                       const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
+  const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
   if (n <= 0) return 0;
   const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
   if (s->params.use_ik)
     step_kernel<true><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
+        env_offset);
   else
     step_kernel<false><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n_ids);
+        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
+        env_offset);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1787,6 +1795,7 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaMallocHost(&s->h_action, na)); CUDA_TRY(cudaMallocHost(&s->h_obs, no));
   CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
   CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
+  CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
   *out = s;
@@ -1801,6 +1810,7 @@ void b2e_destroy(b2e_sim* s) {
   cudaFree(s->d_model); cudaFree(s->d_action); cudaFree(s->d_obs); cudaFree(s->d_reward); cudaFree(s->d_done);
   cudaFreeHost(s->h_action); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_reward); cudaFreeHost(s->h_done);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  cudaStreamDestroy(s->pstream[0]); cudaStreamDestroy(s->pstream[1]);
   delete s;
 }
 
@@ -1835,7 +1845,7 @@ int b2e_step(b2e_sim* s, const float* action, float* obs, float* reward, float* 
   if (mode == B2E_MODE_ACTION && !action) return fail(B2E_EINVAL, "b2e_step: action is required in ACTION mode%s", "");
   if (n_substeps < 0) return fail(B2E_EINVAL, "b2e_step: n_substeps < 0%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
-  return launch_step(s, action, obs, reward, done, n_substeps, mode, nullptr, 0, stream);
+  return launch_step(s, action, obs, reward, done, n_substeps, mode, nullptr, s->B, stream, 0);
 }
 
 int b2e_step_subset(b2e_sim* s, const int32_t* env_ids, int n_ids, const float* action, float* obs, float* reward,
@@ -1895,19 +1905,29 @@ int b2e_step_host(b2e_sim* s, const float* action_host, float* obs_host, float* 
 int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, float* reward_pinned, float* done_pinned,
                     int n_substeps, int mode) {
   if (!s) return fail(B2E_EINVAL, "b2e_step_pinned: null sim%s", "");
+  if (mode == B2E_MODE_ACTION && !action_pinned) return fail(B2E_EINVAL, "b2e_step_pinned: action required%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
-  const size_t na = (size_t)s->B * s->params.n_act * 4, no = (size_t)s->B * s->params.n_obs * 4, nb = (size_t)s->B * 4;
-  if (mode == B2E_MODE_ACTION) {
-    if (!action_pinned) return fail(B2E_EINVAL, "b2e_step_pinned: action required%s", "");
-    CUDA_TRY(cudaMemcpyAsync(s->d_action, action_pinned, na, cudaMemcpyHostToDevice, 0));
+  // The batch is cut into chunks that travel on two streams: the copies of one chunk overlap the kernel of
+  // the next (inputs H2D -> fused step -> results D2H per chunk).
+  const int na = s->params.n_act, no = s->params.n_obs;
+  const int align = 2 * WPB;
+  int chunks = s->B >= 8192 ? 4 : (s->B >= 2048 ? 2 : 1);
+  const int per = ((s->B + chunks - 1) / chunks + align - 1) / align * align;
+  for (int c = 0; c * per < s->B; c++) {
+    const int lo = c * per, n = (lo + per <= s->B) ? per : s->B - lo;
+    cudaStream_t st = s->pstream[c & 1];
+    if (mode == B2E_MODE_ACTION)
+      CUDA_TRY(cudaMemcpyAsync(s->d_action + (size_t)lo * na, action_pinned + (size_t)lo * na, (size_t)n * na * 4,
+                               cudaMemcpyHostToDevice, st));
+    int rc = launch_step(s, s->d_action, obs_pinned ? s->d_obs : nullptr, reward_pinned ? s->d_reward : nullptr,
+                         done_pinned ? s->d_done : nullptr, n_substeps, mode, nullptr, n, st, lo);
+    if (rc) return rc;
+    if (obs_pinned) CUDA_TRY(cudaMemcpyAsync(obs_pinned + (size_t)lo * no, s->d_obs + (size_t)lo * no, (size_t)n * no * 4, cudaMemcpyDeviceToHost, st));
+    if (reward_pinned) CUDA_TRY(cudaMemcpyAsync(reward_pinned + lo, s->d_reward + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (done_pinned) CUDA_TRY(cudaMemcpyAsync(done_pinned + lo, s->d_done + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   }
-  int rc = b2e_step(s, s->d_action, obs_pinned ? s->d_obs : nullptr, reward_pinned ? s->d_reward : nullptr,
-                    done_pinned ? s->d_done : nullptr, n_substeps, mode, 0);
-  if (rc) return rc;
-  if (obs_pinned) CUDA_TRY(cudaMemcpyAsync(obs_pinned, s->d_obs, no, cudaMemcpyDeviceToHost, 0));
-  if (reward_pinned) CUDA_TRY(cudaMemcpyAsync(reward_pinned, s->d_reward, nb, cudaMemcpyDeviceToHost, 0));
-  if (done_pinned) CUDA_TRY(cudaMemcpyAsync(done_pinned, s->d_done, nb, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  CUDA_TRY(cudaStreamSynchronize(s->pstream[0]));
+  CUDA_TRY(cudaStreamSynchronize(s->pstream[1]));
   return 0;
 }
 

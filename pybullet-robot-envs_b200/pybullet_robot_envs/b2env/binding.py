@@ -104,6 +104,7 @@ class B2Sim:
         self.h = h
         self._pin = None
         self._pinned_ptrs = []
+        self._pinned_ranges = []
 
     def _check(self, rc):
         if rc != 0:
@@ -115,6 +116,7 @@ class B2Sim:
             for p in getattr(self, "_pinned_ptrs", []):
                 self.lib.b2e_host_free(p)
             self._pinned_ptrs = []
+            self._pinned_ranges = []
             self.lib.b2e_destroy(self.h)
             self.h = None
 
@@ -145,8 +147,18 @@ class B2Sim:
         p = C.c_void_p()
         self._check(self.lib.b2e_host_alloc(C.byref(p), n))
         self._pinned_ptrs.append(p)
+        self._pinned_ranges.append((p.value, p.value + n))
         buf = (C.c_char * n).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def pinned_array(self, shape, dtype=np.float32):
+        """Page-locked numpy array owned by this simulation (freed by close()): action batches kept in such
+        arrays are copied to the GPU straight from user memory by step_pinned."""
+        return self._pinned(shape, dtype)
+
+    def _is_pinned(self, arr):
+        a = arr.ctypes.data
+        return arr.flags["C_CONTIGUOUS"] and any(lo <= a and a + arr.nbytes <= hi for lo, hi in self._pinned_ranges)
 
     def _ensure_pin(self):
         if self._pin is None:
@@ -159,12 +171,16 @@ class B2Sim:
         `pinned_action()`), results land in page-locked arrays that are returned as views — valid until the
         next call."""
         pa, po, pr, pd = self._ensure_pin()
+        src = pa
         if action is not pa:
-            act = np.asarray(action, dtype=np.float32)
+            act = action if isinstance(action, np.ndarray) and action.dtype == np.float32 else np.asarray(action, dtype=np.float32)
             if act.shape != pa.shape:
                 raise AssertionError(("number of motor commands differs from number of motor to control", act.shape))
-            np.copyto(pa, act)
-        self._check(self.lib.b2e_step_pinned(self.h, _ptr(pa), _ptr(po), _ptr(pr), _ptr(pd), n_substeps, mode))
+            if self._is_pinned(act):
+                src = act                      # already page-locked: no staging copy
+            else:
+                np.copyto(pa, act)
+        self._check(self.lib.b2e_step_pinned(self.h, _ptr(src), _ptr(po), _ptr(pr), _ptr(pd), n_substeps, mode))
         return po, pr, pd
 
     def pinned_action(self):
