@@ -223,6 +223,16 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    # nvidia-smi needs a few hundred ms to deliver samples: keep the same load running (untimed) for ~0.7 s
+    # before the timed region so that the clock record covers the GPU under this workload
+    t_pre = time.perf_counter()
+    j = 0
+    while time.perf_counter() - t_pre < 0.7:
+        for _ in range(64):
+            sims[j % NREP].step(actions[j % (W + K)], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
+            j += 1
+        torch.cuda.synchronize(dev)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sum(s_.launch_count() for s_ in sims)
     barrier()
