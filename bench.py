@@ -4,9 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port, host cores)
 
-One "step" = one env.step() of the whole batch (16384 envs per GPU): action -> motor targets ->
+One "step" = one env.step() of a whole batch (16384 envs per GPU): action -> motor targets ->
 physics (dt = 1/240, <=150 PGS iterations) -> observation, reward, done, fused in one launch.
-`value`  : device-timed (CUDA events around each launch, L2 flushed between launches, flush excluded).
+BASELINE.md protocol: 50 warm-up + 1000 timed steps after reset, done ignored.  The cost of a step grows with
+the rollout depth (random-policy arms drift into the table / the cube; a few jammed contacts run all 150
+sweeps), so the depth matters: with the default --warmup 400 --steps 8000 and 8 replicas of the batch stepped
+round-robin (working set > L2) every replica does exactly 50 + 1000 steps.
+`value`  : device-timed, K launches between two CUDA events on the launch stream, no host sync inside.
 `e2e`    : same metric through the public Gym-style API with HOST numpy buffers (H2D of the
            actions and D2H of obs/reward/done inside the timed region).
 Prints ONE JSON line on rank 0.
@@ -114,17 +118,30 @@ def make_cpu_arm(B, seed0, nthreads):
     return orc
 
 
-def time_cpu(orc, steps, warmup, seed=1234):
+def time_cpu(orcs, steps, warmup, seed=1234):
+    """Round-robin over the replicas in `orcs` (same depth profile as the GPU arm)."""
     rng = np.random.RandomState(seed)
-    B = orc.B
-    for _ in range(warmup):
-        orc.step(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
-    acts = [rng.uniform(-1, 1, (B, 7)).astype(np.float32) for _ in range(steps)]
+    B = orcs[0].B
+    n = len(orcs)
+    for i in range(warmup):
+        orcs[i % n].step(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+    acts = [rng.uniform(-1, 1, (B, 7)).astype(np.float32) for _ in range(min(steps, 256))]
     t0 = time.perf_counter()
-    for a in acts:
-        orc.step(a, 1, 0)
+    for i in range(steps):
+        orcs[(warmup + i) % n].step(acts[i % len(acts)], 1, 0)
     dt = time.perf_counter() - t0
     return B * steps / dt, dt
+
+
+def clone_cpu_arm(orc, n):
+    from oracle import b2oracle
+    out = [orc]
+    for _ in range(n - 1):
+        o2 = b2oracle.Oracle(orc.model, orc.params, orc.B, nthreads=orc.nthreads)
+        for k, v in orc.state.items():
+            o2.state[k][...] = v
+        out.append(o2)
+    return out
 
 
 def run_reference(args, rank, world):
@@ -134,13 +151,13 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     B = args.cpu_batch
-    orc = make_cpu_arm(B, 0, cores)
-    rate, dt = time_cpu(orc, args.steps, max(args.warmup, 3))
+    orcs = clone_cpu_arm(make_cpu_arm(B, 0, cores), args.replicas)
+    rate, dt = time_cpu(orcs, args.steps, max(args.warmup, 3))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "%d envs x %d steps per step-call on %d host threads" % (B, 1, cores),
+        "config": {"workload": WORKLOAD, "sample": "%d envs per step-call on %d host threads, %d replicas round-robin (rollout depth per replica %d steps)" % (B, cores, args.replicas, (args.steps + max(args.warmup, 3)) // args.replicas),
                    "note": "CPU restatement (oracle port), not PyBullet: pybullet is absent from this image; "
                            "as-shipped reference is additionally capped at 240 steps/s/process by time.sleep"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -154,12 +171,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=8000)
+    ap.add_argument("--warmup", type=int, default=400)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="environments per GPU")
     ap.add_argument("--cpu-batch", type=int, default=2048)
-    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=8, help="independent batches stepped round-robin (working set > L2)")
     args = ap.parse_args()
@@ -188,7 +205,8 @@ def main():
     sim = env._sim
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    actions = torch.rand((W + K, B, 7), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    NACT = min(W + K, 512)   # distinct i.i.d. action batches, cycled (512 x 458 KB)
+    actions = torch.rand((NACT, B, 7), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
     returns = torch.zeros(B, device=dev)
 
     def barrier():
@@ -217,21 +235,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(max(W, NREP)):
-        sims[i % NREP].step(actions[i % (W + K)], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    # nvidia-smi needs a few hundred ms to deliver samples: keep the same load running (untimed) for ~0.7 s
-    # before the timed region so that the clock record covers the GPU under this workload
-    t_pre = time.perf_counter()
-    j = 0
-    while time.perf_counter() - t_pre < 0.7:
-        for _ in range(64):
-            sims[j % NREP].step(actions[j % (W + K)], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
-            j += 1
-        torch.cuda.synchronize(dev)
+        time.sleep(0.3)      # nvidia-smi needs a moment before the first sample; the timed region is seconds long
+    for i in range(W):
+        sims[i % NREP].step(actions[i % NACT], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sum(s_.launch_count() for s_ in sims)
@@ -239,7 +248,7 @@ def main():
     t_wall0 = time.perf_counter()
     ev0.record()
     for i in range(K):
-        sims[i % NREP].step(actions[W + i], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)   # ONE launch of step_kernel
+        sims[(W + i) % NREP].step(actions[(W + i) % NACT], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)   # ONE launch of step_kernel
         returns += rew_t
     ev1.record()
     barrier()
@@ -250,7 +259,7 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 32))]
     for i, (a_, b_) in enumerate(kev):
         a_.record()
-        sims[i % NREP].step(actions[W + i], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
+        sims[i % NREP].step(actions[i % NACT], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
         b_.record()
     barrier()
     kernel_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in kev]))
@@ -265,16 +274,22 @@ def main():
     for s_ in sims[1:]:
         s_.close()
 
-    # ---- end-to-end through the public API with host buffers ----
-    Ke = min(args.e2e_steps, K)
-    host_actions = sim.pinned_array((Ke, B, 7))           # the policy's outputs live in page-locked host memory
-    host_actions[...] = np.random.RandomState(99 + rank).uniform(-1, 1, (Ke, B, 7)).astype(np.float32)
-    for i in range(3):
-        env.step(host_actions[i % Ke])
+    # ---- end-to-end through the public API with host buffers: same protocol (fresh reset, 50 warm-up steps,
+    #      then the timed steps; every step copies the actions H2D from page-locked memory and reads obs /
+    #      reward / done back D2H) ----
+    depth = (W + K) // NREP
+    n_warm_e = min(50, depth // 2)
+    Ke = max(8, min(args.e2e_steps, depth - n_warm_e))
+    NH = min(Ke, 64)
+    host_actions = sim.pinned_array((NH, B, 7))           # the policy's outputs live in page-locked host memory
+    host_actions[...] = np.random.RandomState(99 + rank).uniform(-1, 1, (NH, B, 7)).astype(np.float32)
+    env.reset()
+    for i in range(n_warm_e):
+        env.step(host_actions[i % NH])
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
-        o, r, d, _ = env.step(host_actions[i])        # H2D actions, launch, D2H obs/reward/done
+        o, r, d, _ = env.step(host_actions[i % NH])        # H2D actions, launch, D2H obs/reward/done
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -303,24 +318,28 @@ def main():
                        "dt": 1.0 / 240, "solver_iters_max": 150, "residual_tol": 1e-7,
                        "mean_pgs_iters_last_step": mean_iters, "nan_flags": nan_flags,
                        "l2": "no flush: %d replicas of the batch stepped round-robin, working set %.0f MB > 126 MB L2" % (NREP, NREP * B * 1.2e-3),
+                       "rollout_depth_per_replica": (W + K) // NREP, "protocol": "BASELINE.md: 50 warm-up + 1000 timed steps after reset per batch, done ignored",
                        "wall_ms_per_step": 1e3 * t_wall / K, "kernel_ms_events": kernel_ms, "mean_episode_return": mean_return},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (TRAFFIC_BYTES_PER_LAUNCH_16384 if B == 16384 else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG_PUSH,
                          "kernel": "step_kernel", "kernel_ms": kernel_ms,
                          "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step; DRAM traffic per launch (ncu, profiles/): 8.5 MB read + 1.4 MB write vs 15.9 MB algorithmic"},
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 7 * 4,
-                    "d2h_bytes_per_step": B * (33 + 2) * 4, "steps": Ke},
+                    "d2h_bytes_per_step": B * (33 + 2) * 4, "steps": Ke, "warmup": n_warm_e,
+                    "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             orc = make_cpu_arm(args.cpu_batch, 0, cores)
-            probe, _ = time_cpu(orc, 5, 2)
-            n = int(max(10, min(400, 15.0 * probe / args.cpu_batch)))
-            rate, dt = time_cpu(orc, n, 0)
+            depth = (W + K) // NREP
+            n_warm = min(50, depth // 2)
+            n_timed = max(10, depth - n_warm)
+            rate, dt = time_cpu([orc], n_timed, n_warm)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d envs x %d steps (%.1f s) of the same workload" % (args.cpu_batch, n, dt)}
+                                    "sample": "%d envs x (%d warm-up + %d timed) steps from reset (%.1f s): same rollout depth as one GPU replica"
+                                              % (args.cpu_batch, n_warm, n_timed, dt)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -49,13 +49,17 @@
 #define WPB 8             // warps per block (two envs per warp)
 #endif
 #ifndef MINB
-#define MINB 3            // resident blocks per SM the register allocation targets (24 warps, 80 regs)
+#define MINB 2            // resident blocks per SM the register allocation targets (16 warps = 32 envs, 128 regs)
 #endif
 #define TLMAX 12          // links handled by the group kernel (transforms staged in shared memory; < 15: lane 15 is the zero lane)
 #define RMAX 48           // scratch stride
 #define GMAX 48           // generic rows per env (3 limit + 36 contact rows), in sets of 16
+#define BIGS 40           // row stride of a big constraint system (<= 39 generic rows) in an overflow slot
+#ifndef NSLOT
+#define NSLOT 2           // overflow slots per block for environments with more than 16 generic rows
+#endif
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
-#define SCRATCH_PER_ENV (RMAX * RMAX + RMAX * WSTRIDE)
+#define SCRATCH_PER_ENV (BIGS * BIGS + BIGS * WSTRIDE + NDMAX * BIGS)   // A | W | W^T(arm part), same layout as a slot
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
 
@@ -279,6 +283,14 @@ struct EnvSmem {
   float clam[B2E_CACHE_SLOTS][3];
 };
 
+// Storage of one big constraint system (17..39 generic rows): block-level overflow slot in shared memory,
+// or — when the block's slots are taken — the environment's global scratch (same layout).
+struct BigSlot {
+  float A[BIGS * BIGS];      // generic x generic Delassus block, A[c*BIGS + r]
+  float W[BIGS * WSTRIDE];   // W[g][k]
+  float WT[NDMAX * BIGS];    // WT[d][g] = W[g][d]: motor-row coupling read with unit stride over g
+};
+
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
 __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const DevModelU& U, const Grp& g, float qi,
@@ -481,7 +493,7 @@ struct RowRegs {
 
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
-                                           const float* W, int i) {
+                                           const float* W, const float* WT, int AS, int i) {
   float nl = fmaf(m.u, m.invd, m.lam);
   nl = fminf(fmaxf(nl, m.lo), m.hi);
   const float dl = nl - m.lam;
@@ -489,14 +501,18 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
   if (g.lane == i) m.lam = nl;
   const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
   m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
+  if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
 #pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
+    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], dli, r.u[s]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
+  }
 }
 
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                             const float* W, int gi, bool arm_sweep) {
-  constexpr int AS = (NSG == 1) ? GL : GMAX;
+                                             const float* W, int AS, int gi, bool arm_sweep) {
   const int li = gi & (GL - 1);
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
@@ -511,32 +527,32 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
 // visit the generic rows whose bits are set, in ascending order
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                              const float* W, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
+                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
   while (m0) {
     const int i = __ffs(m0) - 1;
     m0 &= m0 - 1;
-    generic_step<NSG, 0>(g, m, r, A, W, i, arm_sweep);
+    generic_step<NSG, 0>(g, m, r, A, W, AS, i, arm_sweep);
   }
   if (NSG > 1) {
     while (m1) {
       const int i = __ffs(m1) - 1;
       m1 &= m1 - 1;
-      generic_step<NSG, S1>(g, m, r, A, W, GL + i, arm_sweep);
+      generic_step<NSG, S1>(g, m, r, A, W, AS, GL + i, arm_sweep);
     }
   }
   if (NSG > 2) {
     while (m2) {
       const int i = __ffs(m2) - 1;
       m2 &= m2 - 1;
-      generic_step<NSG, S2>(g, m, r, A, W, 2 * GL + i, arm_sweep);
+      generic_step<NSG, S2>(g, m, r, A, W, AS, 2 * GL + i, arm_sweep);
     }
   }
 }
 
 template <int NSG>
 __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                         const float* Minv, int nd, int RG, int fric_start, bool coupled,
+                                         const float* WT, int AS, const float* Minv, int nd, int RG, int fric_start, bool coupled,
                                          bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
   // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
   unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
@@ -564,10 +580,10 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
       while (mm) {
         const int i = __ffs(mm) - 1;
         mm &= mm - 1;
-        motor_step<NSG>(g, m, r, Minv, W, i);
+        motor_step<NSG>(g, m, r, Minv, W, WT, AS, i);
       }
     }
-    sweep_generic<NSG>(g, m, r, A, W, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
+    sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
                        (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
@@ -587,7 +603,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep_generic<NSG>(g, m, r, A, W, f0, f1, f2, !done0);
+      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0);
     }
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
@@ -678,12 +694,16 @@ template <int NSG>
 __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U,
                                             const b2e_params& P, unsigned hm, int sh, int lane, int nd, int nlim, int nc,
                                             float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
-                                            float* scratch) {
+                                            float* big) {
   const Grp g = {hm, sh, lane};
   const float cpos[3] = {cpx, cpy, cpz};
-  constexpr int AS = (NSG == 1) ? GL : GMAX;
-  float* A = (NSG == 1) ? sm.A : scratch;
-  float* W = (NSG == 1) ? sm.W : scratch + GMAX * GMAX;
+  // up to 16 generic rows live in the environment's own shared memory; a bigger system uses `big`
+  // (an overflow slot of the block, or the env's global scratch), which also carries W^T
+  const bool use_big = (NSG > 1) && (nlim + 3 * nc > GL);
+  const int AS = use_big ? BIGS : GL;
+  float* A = use_big ? big : sm.A;
+  float* W = use_big ? big + BIGS * BIGS : sm.W;
+  float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : nullptr;
   const float* Minv = &sm.Minv[0][0];
   const int fric_start = nlim + nc;   // generic index of the first friction row
   const int RG = nlim + 3 * nc;       // generic rows
@@ -807,6 +827,10 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 #pragma unroll
       for (int k = 0; k < 15; k++) W[gi * WSTRIDE + k] = Wv[k];
       W[gi * WSTRIDE + 15] = 0.f;
+      if (WT) {
+#pragma unroll
+        for (int k = 0; k < NDMAX; k++) WT[k * AS + gi] = Wv[k];
+      }
     }
     rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
     rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
@@ -880,7 +904,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
@@ -911,6 +935,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   const int slot_c = live_env ? slot : n_slots - 1;
   const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
   EnvSmem& sm = reinterpret_cast<EnvSmem*>(smem_raw)[warp * 2 + half];
+  BigSlot* slots = reinterpret_cast<BigSlot*>(smem_raw + sizeof(EnvSmem) * 2 * WPB);
+  int* slot_owner = reinterpret_cast<int*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT);
   const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
 
@@ -982,7 +1008,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     if (sub >= nsub) break;
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
-    PHASE_BARRIER();
+    if (threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
+    __syncthreads();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
     if (!IK && mode == B2E_MODE_ACTION && lane < P.n_ctrl && !ghost) {
@@ -1354,16 +1381,26 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     // instantiation (the larger need) so the warp does not execute two instantiations back to back
     const int RG = nlim + 3 * nc;
     const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));
-    float* scr = st.scratch + (size_t)env * SCRATCH_PER_ENV;
-    if (RGw <= GL) iters = build_and_solve<1>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
-    else if (RGw <= 2 * GL) iters = build_and_solve<2>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
-    else iters = build_and_solve<3>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], scr);
+    // storage of a big system (> 16 generic rows): an overflow slot of the block if one is free, else global scratch
+    float* big = st.scratch + (size_t)env * SCRATCH_PER_ENV;
+    if (RG > GL) {
+      int got = -1;
+      if (lane == 0) {
+        for (int k = 0; k < NSLOT && got < 0; k++)
+          if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
+      }
+      got = SHF(got, 0);
+      if (got >= 0) big = reinterpret_cast<float*>(&slots[got]);
+    }
+    if (RGw <= GL) iters = build_and_solve<1>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
+    else if (RGw <= 2 * GL) iters = build_and_solve<2>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
+    else iters = build_and_solve<3>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
 
     PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
     {
-      const float* Wp = (RGw <= GL) ? sm.W : scr + GMAX * GMAX;
+      const float* Wp = (RG <= GL) ? sm.W : big + BIGS * BIGS;
       for (int r = 0; r < RG; r++) dvk = fmaf(Wp[r * WSTRIDE + lane], sm.glam[r], dvk);
       // motor rows: W_d = column d of M^-1
       if (lane < NDMAX) {
@@ -1716,17 +1753,18 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   return 0;
 }
 
+#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
   if (n <= 0) return 0;
   const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
   if (s->params.use_ik)
-    step_kernel<true><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
+    step_kernel<true><<<blocks, 32 * WPB, SMEM_BYTES, (cudaStream_t)stream>>>(
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
         env_offset);
   else
-    step_kernel<false><<<blocks, 32 * WPB, sizeof(EnvSmem) * 2 * WPB, (cudaStream_t)stream>>>(
+    step_kernel<false><<<blocks, 32 * WPB, SMEM_BYTES, (cudaStream_t)stream>>>(
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
         env_offset);
   s->launches++;
@@ -1796,8 +1834,8 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
   CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
   CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvSmem) * 2 * WPB)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   *out = s;
   return 0;
 }
