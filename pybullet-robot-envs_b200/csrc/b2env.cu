@@ -242,22 +242,25 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 // ------------------------------------------------------------------------------------------
 // Environment groups: TWO environments per warp, 16 lanes each (every stage of the pipeline needs
 // <= 16 lanes: 12 links, 9 dofs, 8 cube vertices, 14 spheres, 15 velocity components, 16 rows per set).
-// Every warp collective is issued with the member mask of the group's own 16 lanes, so the two
-// groups of a warp may diverge (different contact counts, iteration counts) without deadlock; while
-// their control flow agrees — the common case — one instruction serves both environments.
+// One instruction serves both environments.
 #define GL 16
 struct Grp {
-  unsigned hm;  // member mask of this group's lanes
+  unsigned hm;  // lanes of this group inside the warp (for masking warp-wide votes)
   int sh;       // bit offset of the group inside the warp (0 or 16)
   int lane;     // lane inside the group, 0..15
 };
-#define SHF(v, src) __shfl_sync(g.hm, (v), (src), GL)
-__device__ __forceinline__ unsigned gballot(const Grp& g, bool p) { return (__ballot_sync(g.hm, p) >> g.sh) & 0xffffu; }
-__device__ __forceinline__ bool gany(const Grp& g, bool p) { return __any_sync(g.hm, p) != 0; }
-__device__ __forceinline__ float gmaxf(const Grp& g, float v) {  // max of non-negative floats
-  return __uint_as_float(__reduce_max_sync(g.hm, __float_as_uint(v)));
+// The two groups of a warp execute every collective TOGETHER (constant full member mask, 16-wide shuffle
+// segments): control flow around collectives is kept warp-uniform — loops run for the longer of the two
+// groups, a group that is done keeps pace with frozen state — so no convergence checks are generated.
+#define SHF(v, src) __shfl_sync(FULL, (v), (src), GL)
+__device__ __forceinline__ unsigned gballot(const Grp& g, bool p) { return (__ballot_sync(FULL, p) >> g.sh) & 0xffffu; }
+__device__ __forceinline__ bool gany(const Grp& g, bool p) { return (__ballot_sync(FULL, p) & g.hm) != 0u; }
+__device__ __forceinline__ float gmaxf(const Grp& g, float v) {  // max of non-negative floats over the group
+  const unsigned b = __float_as_uint(v);
+  const unsigned lo = __reduce_max_sync(FULL, g.sh ? 0u : b), hi = __reduce_max_sync(FULL, g.sh ? b : 0u);
+  return __uint_as_float(g.sh ? hi : lo);
 }
-__device__ __forceinline__ void gsync(const Grp& g) { __syncwarp(g.hm); }
+__device__ __forceinline__ void gsync(const Grp& g) { (void)g; __syncwarp(); }
 
 // per-environment shared memory (4.6 KB)
 struct Contact {   // 16 words
@@ -389,6 +392,7 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
   const int jt = __ldg(&M->jtype[li]);
   const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
   float qv = my_q;
+  bool fin = false;   // this group reached the residual (the loop is shared by both groups of the warp)
   for (int it = 0; it < max_iters; it++) {
     float R[9], p[3];
     const float qi = SHF(qv, my_dof < 0 ? 0 : my_dof);
@@ -399,7 +403,8 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 9; k++) Re[k] = SHF(R[k], ee);
     const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
-    if (sqrtf(dot3(dp, dp)) <= residual) break;
+    if (sqrtf(dot3(dp, dp)) <= residual) fin = true;
+    if (__all_sync(FULL, fin)) break;
     float cq[4], eq[4], er[3];
     mat_to_quat(Re, cq);
     {
@@ -468,7 +473,7 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
     if (lane >= nd) dq = 0.f;
     const float mx = gmaxf(g, fabsf(dq));
     const float scale = mx > 0.78539816339f ? 0.78539816339f / mx : 1.f;
-    qv = fmaf(dq, scale, qv);
+    if (!fin) qv = fmaf(dq, scale, qv);
   }
   gsync(g);
   return qv;
@@ -493,12 +498,12 @@ struct RowRegs {
 
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
-                                           const float* W, const float* WT, int AS, int i) {
+                                           const float* W, const float* WT, int AS, int i, bool active) {
   float nl = fmaf(m.u, m.invd, m.lam);
   nl = fminf(fmaxf(nl, m.lo), m.hi);
-  const float dl = nl - m.lam;
+  const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
   const float dli = SHF(dl, i);
-  if (g.lane == i) m.lam = nl;
+  if (g.lane == i && active) m.lam = nl;
   const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
   m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
   if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
@@ -512,40 +517,45 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
 
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                             const float* W, int AS, int gi, bool arm_sweep) {
+                                             const float* W, int AS, int gi, bool arm_sweep, bool active) {
   const int li = gi & (GL - 1);
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-  const float dl = nl - r.lam[SI];
+  const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits row gi in this pass
   const float dli = SHF(dl, li);
-  if (g.lane == li) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
+  if (g.lane == li && active) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
   if (arm_sweep) m.u = fmaf(-W[gi * WSTRIDE + g.lane], dli, m.u);
 #pragma unroll
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-A[gi * AS + GL * s + g.lane], dli, r.u[s]);
 }
 
-// visit the generic rows whose bits are set, in ascending order
+// Visit the generic rows whose bits are set, in ascending order.  The loop runs over the union of the two
+// groups' masks (warp-uniform branches); a group skips (dl = 0) rows that only the other one has.
+// Reads of A / W for a row index beyond a group's own rows stay inside its own tables (stale data times 0).
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
                                               const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  while (m0) {
-    const int i = __ffs(m0) - 1;
-    m0 &= m0 - 1;
-    generic_step<NSG, 0>(g, m, r, A, W, AS, i, arm_sweep);
+  unsigned w0 = m0 | __shfl_xor_sync(FULL, m0, GL);
+  while (w0) {
+    const int i = __ffs(w0) - 1;
+    w0 &= w0 - 1;
+    generic_step<NSG, 0>(g, m, r, A, W, AS, i, arm_sweep, (m0 >> i) & 1);
   }
   if (NSG > 1) {
-    while (m1) {
-      const int i = __ffs(m1) - 1;
-      m1 &= m1 - 1;
-      generic_step<NSG, S1>(g, m, r, A, W, AS, GL + i, arm_sweep);
+    unsigned w1 = m1 | __shfl_xor_sync(FULL, m1, GL);
+    while (w1) {
+      const int i = __ffs(w1) - 1;
+      w1 &= w1 - 1;
+      generic_step<NSG, S1>(g, m, r, A, W, AS, GL + i, arm_sweep, (m1 >> i) & 1);
     }
   }
   if (NSG > 2) {
-    while (m2) {
-      const int i = __ffs(m2) - 1;
-      m2 &= m2 - 1;
-      generic_step<NSG, S2>(g, m, r, A, W, AS, 2 * GL + i, arm_sweep);
+    unsigned w2 = m2 | __shfl_xor_sync(FULL, m2, GL);
+    while (w2) {
+      const int i = __ffs(w2) - 1;
+      w2 &= w2 - 1;
+      generic_step<NSG, S2>(g, m, r, A, W, AS, 2 * GL + i, arm_sweep, (m2 >> i) & 1);
     }
   }
 }
@@ -566,28 +576,22 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     cube_nf[s] = gballot(g, valid && cube && !fr);
     cube_f[s] = gballot(g, valid && cube && fr);
   }
-  const unsigned motor_mask = (1u << nd) - 1u;
   bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
-  if (done0 && done1) return 0;
-  int it = 0;
-  for (it = 0; it < max_iters; it++) {
+  int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
+  for (int it = 0; it < max_iters; it++) {
+    if (__all_sync(FULL, my_it >= 0)) break;
     m.prev = m.lam;
 #pragma unroll
     for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
-    if (!done0) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
-      unsigned mm = motor_mask;
-      while (mm) {
-        const int i = __ffs(mm) - 1;
-        mm &= mm - 1;
-        motor_step<NSG>(g, m, r, Minv, W, WT, AS, i);
-      }
+    if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
+      for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
     }
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
                        (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
-    if (f0 | f1 | f2) {
+    if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
       // friction bounds from the current normal impulses (mu * lambda_n)
 #pragma unroll
       for (int s = 0; s < NSG; s++) {
@@ -618,13 +622,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
         if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
       }
     }
-    if (!done0) ra = gmaxf(g, ra);
-    if (!done1) rc = gmaxf(g, rc);
+    ra = gmaxf(g, ra);
+    rc = gmaxf(g, rc);
     if (!done0 && ra <= tol) done0 = true;
     if (!done1 && rc <= tol) done1 = true;
-    if (done0 && done1) { it++; break; }
+    if (my_it < 0 && done0 && done1) my_it = it + 1;
   }
-  return it;
+  return my_it < 0 ? max_iters : my_it;
 }
 
 // Arm island made only of the n_dof position-motor rows (no limit row, no arm contact): bounds are
@@ -668,23 +672,29 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
     for (int k = j + 1; k < NDMAX; k++) G[k] = fmaf(-T[j], SHF(Ar[k], j), G[k]);
   }
   float lam = 0.f;
-  int it;
-  for (it = 0; it < max_iters; it++) {
+  int my_it = -1;          // >= 0: converged after that many sweeps; -2: a bound would activate (fallback)
+  for (int it = 0; it < max_iters; it++) {
+    if (__all_sync(FULL, my_it != -1)) break;   // the loop is shared by both groups of the warp
     float a0 = c, a1 = 0.f;
 #pragma unroll
     for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], SHF(lam, k), a0);
 #pragma unroll
     for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], SHF(lam, k), a1);
     const float nl = a0 + a1;
-    if (gany(g, row && !(nl >= lo && nl <= hi))) return -1;
+    const bool clamp = gany(g, row && !(nl >= lo && nl <= hi));
     float rv = row ? (nl - lam) * diag : 0.f;
-    rv = rv * rv;
-    lam = nl;
-    rv = gmaxf(g, rv);
-    if (rv <= tol) { it++; break; }
+    rv = gmaxf(g, rv * rv);
+    if (my_it == -1) {
+      if (clamp) my_it = -2;
+      else {
+        lam = nl;
+        if (rv <= tol) my_it = it + 1;
+      }
+    }
   }
+  if (my_it == -2) return -1;
   lam_out = lam;
-  return it;
+  return my_it < 0 ? max_iters : my_it;
 }
 
 // Build the motor row of this dof lane and the generic row(s) of this lane, the W table, the generic
@@ -707,6 +717,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   const float* Minv = &sm.Minv[0][0];
   const int fric_start = nlim + nc;   // generic index of the first friction row
   const int RG = nlim + 3 * nc;       // generic rows
+  const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));   // larger count of the two groups: shared loop bounds
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
 
@@ -839,9 +850,12 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     rr.gg[s] = 1.0f - cfm * rr.invd[s];
     rr.u[s] = valid ? desired - jv : 0.f;
     rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.prev[s] = 0.f;
-    coupled = coupled || gany(g, sphere_cube_normal);
-    has_cube = has_cube || gany(g, valid && isl == 1);
-    arm_generic = arm_generic || gany(g, arm_part);
+    {  // votes are collectives: evaluate them unconditionally (no short-circuit), then combine
+      const bool v1 = gany(g, sphere_cube_normal), v2 = gany(g, valid && isl == 1), v3 = gany(g, arm_part);
+      coupled = coupled || v1;
+      has_cube = has_cube || v2;
+      arm_generic = arm_generic || v3;
+    }
   }
   gsync(g);
   // generic x generic block: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
@@ -881,14 +895,14 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       rr.base[s] = l0 * rr.gg[s];
     }
   }
-  for (int c = nlim; c < RG; c++) {
+  for (int c = 0; c < RGw; c++) {
     float l0 = 0.f;
 #pragma unroll
     for (int t = 0; t < NSG; t++) {
       const float vt = SHF(rr.lam[t], c & (GL - 1));
       if ((c >> 4) == t) l0 = vt;
     }
-    if (l0 != 0.f) {
+    if (l0 != 0.f && c >= nlim && c < RG) {
 #pragma unroll
       for (int s = 0; s < NSG; s++) rr.u[s] = fmaf(-A[c * AS + GL * s + lane], l0, rr.u[s]);
       m.u = fmaf(-W[c * WSTRIDE + lane], l0, m.u);
@@ -896,10 +910,12 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   }
   int iters_arm = -1;
   bool arm_sweep = true;
-  if (!coupled && !arm_generic) {
+  const bool arm_simple = !coupled && !arm_generic;
+  if (__any_sync(FULL, arm_simple)) {   // both groups run it (shared loop); a non-simple group ignores the result
     float lam_arm = 0.f;
-    iters_arm = arm_affine_solve(g, Minv, nd, m.u, m.invd, m.diag, m.lo, m.hi, P.solver_iters, P.residual_tol, lam_arm);
-    if (iters_arm >= 0) {
+    const int ia = arm_affine_solve(g, Minv, nd, m.u, m.invd, m.diag, m.lo, m.hi, P.solver_iters, P.residual_tol, lam_arm);
+    if (arm_simple && ia >= 0) {
+      iters_arm = ia;
       if (lane < nd) m.lam = lam_arm;
       arm_sweep = false;
     }
@@ -986,25 +1002,31 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       fk_lanes(M, U, g, link_has_dof ? qi : 0.f, Rm, pw);
     }
     // ---- termination inside apply_action (panda_push_gym_env.py:239-242), for the previous sub-step ----
-    if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
-      float d;
-      if (P.task == B2E_TASK_PUSH) {
-        float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
-        d = sqrtf(dot3(dd, dd));
-      } else if (P.task == B2E_TASK_GRASP) {
-        d = (cpos[2] - P.grasp_rest_z >= P.grasp_lift) ? 0.f : 2.f * P.dist_min + 1.f;
-      } else {
+    {
+      // EE position for the reach test: the shuffles run unconditionally (both groups together)
+      float e3[3] = {0.f, 0.f, 0.f};
+      if (P.task == B2E_TASK_REACH) {
         const int ee = U.ee_link;
         float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]}, o[3];
         m3vec(Rm, cm, o);
-        float e3[3] = {SHF(pw[0] + o[0], ee), SHF(pw[1] + o[1], ee), SHF(pw[2] + o[2], ee)};
-        float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
-        d = sqrtf(dot3(dd, dd));
+        e3[0] = SHF(pw[0] + o[0], ee); e3[1] = SHF(pw[1] + o[1], ee); e3[2] = SHF(pw[2] + o[2], ee);
       }
-      if (P.goal_env) { if (counter > P.max_steps) stop = true; else counter++; }
-      else if (d <= P.dist_min) { terminated = 1; stop = true; }
-      else if (terminated || counter > P.max_steps) stop = true;
-      else counter++;
+      if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
+        float d;
+        if (P.task == B2E_TASK_PUSH) {
+          float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+          d = sqrtf(dot3(dd, dd));
+        } else if (P.task == B2E_TASK_GRASP) {
+          d = (cpos[2] - P.grasp_rest_z >= P.grasp_lift) ? 0.f : 2.f * P.dist_min + 1.f;
+        } else {
+          float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
+          d = sqrtf(dot3(dd, dd));
+        }
+        if (P.goal_env) { if (counter > P.max_steps) stop = true; else counter++; }
+        else if (d <= P.dist_min) { terminated = 1; stop = true; }
+        else if (terminated || counter > P.max_steps) stop = true;
+        else counter++;
+      }
     }
     if (sub >= nsub) break;
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
@@ -1383,9 +1405,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));
     // storage of a big system (> 16 generic rows): an overflow slot of the block if one is free, else global scratch
     float* big = st.scratch + (size_t)env * SCRATCH_PER_ENV;
-    if (RG > GL) {
+    {
       int got = -1;
-      if (lane == 0) {
+      if (lane == 0 && RG > GL) {
         for (int k = 0; k < NSLOT && got < 0; k++)
           if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
       }
@@ -1470,22 +1492,21 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 
   }
 
-  if (!live_env) return;   // no block barrier below this point
-  // ---- store state ----
-  if (is_dof) {
+  // ---- store state (padding groups shadow the last env: they keep pace but store nothing) ----
+  if (is_dof && live_env) {
     st.q[env * nd + lane] = my_q;
     st.qd[env * nd + lane] = my_qd;
     st.mtarget[env * nd + lane] = my_target;
   }
-  if (lane == 0) {
+  if (lane == 0 && live_env) {
     st.obj_pose[env * 7 + 0] = cpos[0]; st.obj_pose[env * 7 + 1] = cpos[1]; st.obj_pose[env * 7 + 2] = cpos[2];
     st.obj_pose[env * 7 + 3] = cquat[0]; st.obj_pose[env * 7 + 4] = cquat[1];
     st.obj_pose[env * 7 + 5] = cquat[2]; st.obj_pose[env * 7 + 6] = cquat[3];
     st.obj_vel[env * 6 + 0] = cv[0]; st.obj_vel[env * 6 + 1] = cv[1]; st.obj_vel[env * 6 + 2] = cv[2];
     st.obj_vel[env * 6 + 3] = cw[0]; st.obj_vel[env * 6 + 4] = cw[1]; st.obj_vel[env * 6 + 5] = cw[2];
   }
-  if (IK && lane < 6) st.hand_pose[env * 6 + lane] = my_hp;
-  if (lane < B2E_CACHE_SLOTS) {
+  if (IK && lane < 6 && live_env) st.hand_pose[env * 6 + lane] = my_hp;
+  if (lane < B2E_CACHE_SLOTS && live_env) {
     st.cache_key[env * B2E_CACHE_SLOTS + lane] = sm.ckey[lane];
 #pragma unroll
     for (int j = 0; j < 3; j++) st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j] = sm.clam[lane][j];
@@ -1571,6 +1592,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     gsync(g);
     for (int k = lane; k < P.n_obs; k += GL) {
       const float raw = obsb[k];
+      if (!live_env) continue;
       st.raw_obs[(size_t)env * P.n_obs + k] = raw;
       if (obs_out) obs_out[(size_t)env * P.n_obs + k] = 2.0f * ((raw - P.obs_low[k]) / (P.obs_high[k] - P.obs_low[k])) - 1.0f;
     }
@@ -1603,12 +1625,12 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       rew = -d1;
       if (d1 <= P.dist_min) rew = 1000.0f + (100.0f - d1 * 80.0f);
     }
-    if (lane == 0) {
+    if (lane == 0 && live_env) {
       if (reward_out) reward_out[env] = rew;
       if (done_out) done_out[env] = (float)dn;
     }
   }
-  if (lane == 0 && mode != B2E_MODE_OBSERVE) {
+  if (lane == 0 && mode != B2E_MODE_OBSERVE && live_env) {
     st.counters[env * 2] = counter;
     st.counters[env * 2 + 1] = terminated;
     st.status[env * 4 + 0] = flags;
