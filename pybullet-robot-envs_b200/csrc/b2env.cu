@@ -503,61 +503,61 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
   nl = fminf(fmaxf(nl, m.lo), m.hi);
   const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
   const float dli = SHF(dl, i);
-  if (g.lane == i && active) m.lam = nl;
-  const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
-  m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
-  if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
+  if (active) {   // (group-uniform; an idle group must not touch its tables: stale entries may be NaN bit patterns)
+    if (g.lane == i) m.lam = nl;
+    const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
+    m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
+    if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
 #pragma unroll
-    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], dli, r.u[s]);
-  } else {
+      for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], dli, r.u[s]);
+    } else {
 #pragma unroll
-    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
+      for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
+    }
   }
 }
 
 template <int NSG, int SI>
-__device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                             const float* W, int AS, int gi, bool arm_sweep, bool active) {
-  const int li = gi & (GL - 1);
+__device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
+                                             const float* Wrow, int li, bool arm_sweep, bool active) {
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-  const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits row gi in this pass
+  const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits this row in this pass
   const float dli = SHF(dl, li);
-  if (g.lane == li && active) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
-  if (arm_sweep) m.u = fmaf(-W[gi * WSTRIDE + g.lane], dli, m.u);
+  if (active) {
+    if (g.lane == li) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
+    if (arm_sweep) m.u = fmaf(-Wrow[g.lane], dli, m.u);
 #pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-A[gi * AS + GL * s + g.lane], dli, r.u[s]);
+    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-Arow[GL * s + g.lane], dli, r.u[s]);
+  }
 }
 
-// Visit the generic rows whose bits are set, in ascending order.  The loop runs over the union of the two
-// groups' masks (warp-uniform branches); a group skips (dl = 0) rows that only the other one has.
-// Reads of A / W for a row index beyond a group's own rows stay inside its own tables (stale data times 0).
+// Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
+// over the index range spanned by BOTH groups' masks (warp-uniform trip count, no find-first-set chain; the
+// masks are contiguous ranges in practice: limits, then normals, then frictions, cube-table contacts first);
+// a group skips (dl = 0, no table access) the rows it does not visit itself.
+template <int NSG, int SI>
+__device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
+                                          int AS, unsigned mk, bool arm_sweep) {
+  const unsigned w = mk | __shfl_xor_sync(FULL, mk, GL);
+  if (w == 0u) return;
+  const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
+  const float* Arow = A + (GL * SI + lo) * AS;
+  const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
+  for (int i = lo; i < hi; i++) {
+    generic_step<NSG, SI>(g, m, r, Arow, Wrow, i, arm_sweep, (mk >> i) & 1u);
+    Arow += AS;
+    Wrow += WSTRIDE;
+  }
+}
+
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
                                               const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  unsigned w0 = m0 | __shfl_xor_sync(FULL, m0, GL);
-  while (w0) {
-    const int i = __ffs(w0) - 1;
-    w0 &= w0 - 1;
-    generic_step<NSG, 0>(g, m, r, A, W, AS, i, arm_sweep, (m0 >> i) & 1);
-  }
-  if (NSG > 1) {
-    unsigned w1 = m1 | __shfl_xor_sync(FULL, m1, GL);
-    while (w1) {
-      const int i = __ffs(w1) - 1;
-      w1 &= w1 - 1;
-      generic_step<NSG, S1>(g, m, r, A, W, AS, GL + i, arm_sweep, (m1 >> i) & 1);
-    }
-  }
-  if (NSG > 2) {
-    unsigned w2 = m2 | __shfl_xor_sync(FULL, m2, GL);
-    while (w2) {
-      const int i = __ffs(w2) - 1;
-      w2 &= w2 - 1;
-      generic_step<NSG, S2>(g, m, r, A, W, AS, 2 * GL + i, arm_sweep, (m2 >> i) & 1);
-    }
-  }
+  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep);
+  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep);
+  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep);
 }
 
 template <int NSG>
@@ -1030,7 +1030,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     if (sub >= nsub) break;
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
-    if (threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
+    if ((int)threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
     __syncthreads();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
