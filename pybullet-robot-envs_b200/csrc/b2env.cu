@@ -496,40 +496,47 @@ struct RowRegs {
   int type[NSG], isl[NSG], nidx[NSG];
 };
 
+// Row updates are branch-free: the table entries are loaded first (their latency hides under the dependent
+// FFMA -> FMNMX -> FMNMX -> FADD -> SHFL chain), and a group that does not visit the row (`active` false)
+// multiplies zero coefficients by a zero impulse change (never 0 * stale-NaN).
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
                                            const float* W, const float* WT, int AS, int i, bool active) {
+  const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
+  const float cm = Minv[i * (NDMAX + 1) + lc];
+  float cg[NSG];
+  if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
+#pragma unroll
+    for (int s = 0; s < NSG; s++) cg[s] = WT[i * AS + GL * s + g.lane];
+  } else {
+#pragma unroll
+    for (int s = 0; s < NSG; s++) cg[s] = W[(GL * s + g.lane) * WSTRIDE + i];
+  }
   float nl = fmaf(m.u, m.invd, m.lam);
   nl = fminf(fmaxf(nl, m.lo), m.hi);
   const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
   const float dli = SHF(dl, i);
-  if (active) {   // (group-uniform; an idle group must not touch its tables: stale entries may be NaN bit patterns)
-    if (g.lane == i) m.lam = nl;
-    const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
-    m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], dli, m.u);
-    if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
+  m.lam = (g.lane == i && active) ? nl : m.lam;
+  m.u = fmaf(active ? -cm : 0.f, dli, m.u);
 #pragma unroll
-      for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], dli, r.u[s]);
-    } else {
-#pragma unroll
-      for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-W[(GL * s + g.lane) * WSTRIDE + i], dli, r.u[s]);
-    }
-  }
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -cg[s] : 0.f, dli, r.u[s]);
 }
 
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
                                              const float* Wrow, int li, bool arm_sweep, bool active) {
+  float ca[NSG];
+#pragma unroll
+  for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
+  const float cw = Wrow[g.lane];
   float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
   nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
   const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits this row in this pass
   const float dli = SHF(dl, li);
-  if (active) {
-    if (g.lane == li) r.lam[SI] = nl;  // base/prev are refreshed once per sweep (each row moves once per sweep)
-    if (arm_sweep) m.u = fmaf(-Wrow[g.lane], dli, m.u);
+  r.lam[SI] = (g.lane == li && active) ? nl : r.lam[SI];  // base/prev are refreshed once per sweep
+  m.u = fmaf((active && arm_sweep) ? -cw : 0.f, dli, m.u);
 #pragma unroll
-    for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-Arow[GL * s + g.lane], dli, r.u[s]);
-  }
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -ca[s] : 0.f, dli, r.u[s]);
 }
 
 // Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
@@ -1414,10 +1421,16 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       got = SHF(got, 0);
       if (got >= 0) big = reinterpret_cast<float*>(&slots[got]);
     }
+#ifdef PROFILE_CYCLES
+    const long long t_solve0 = clock64();
+#endif
     if (RGw <= GL) iters = build_and_solve<1>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
     else if (RGw <= 2 * GL) iters = build_and_solve<2>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
     else iters = build_and_solve<3>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
 
+#ifdef PROFILE_CYCLES
+    R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (big == st.scratch + (size_t)env * SCRATCH_PER_ENV ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
+#endif
     PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
