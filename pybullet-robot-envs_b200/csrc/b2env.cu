@@ -707,17 +707,22 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
 // Build the motor row of this dof lane and the generic row(s) of this lane, the W table, the generic
 // block of the Delassus matrix, warm start, solve, and leave the impulses in sm.mlam[] / sm.glam[].
 // Returns the PGS iteration count.
-template <int NSG>
+template <int NSG, bool GB>   // GB: some group of the warp keeps its big system in GLOBAL scratch (no slot was free)
 __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U,
                                             const b2e_params& P, unsigned hm, int sh, int lane, int nd, int nlim, int nc,
                                             float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
-                                            float* big) {
+                                            int slot, float* gscratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp g = {hm, sh, lane};
   const float cpos[3] = {cpx, cpy, cpz};
   // up to 16 generic rows live in the environment's own shared memory; a bigger system uses `big`
   // (an overflow slot of the block, or the env's global scratch), which also carries W^T
   const bool use_big = (NSG > 1) && (nlim + 3 * nc > GL);
   const int AS = use_big ? BIGS : GL;
+  // the slot address is formed here from the shared-memory base so that, in the GB = false instantiations,
+  // every table access is a shared-memory access (no generic loads in the row loops)
+  float* big = reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * (slot < 0 ? 0 : slot));
+  if (GB && slot < 0) big = gscratch;
   float* A = use_big ? big : sm.A;
   float* W = use_big ? big + BIGS * BIGS : sm.W;
   float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : nullptr;
@@ -1411,25 +1416,26 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const int RG = nlim + 3 * nc;
     const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));
     // storage of a big system (> 16 generic rows): an overflow slot of the block if one is free, else global scratch
-    float* big = st.scratch + (size_t)env * SCRATCH_PER_ENV;
-    {
-      int got = -1;
-      if (lane == 0 && RG > GL) {
-        for (int k = 0; k < NSLOT && got < 0; k++)
-          if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
-      }
-      got = SHF(got, 0);
-      if (got >= 0) big = reinterpret_cast<float*>(&slots[got]);
+    float* gscratch = st.scratch + (size_t)env * SCRATCH_PER_ENV;
+    int got = -1;
+    if (lane == 0 && RG > GL) {
+      for (int k = 0; k < NSLOT && got < 0; k++)
+        if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
     }
+    got = SHF(got, 0);
+    const bool need_global = __any_sync(FULL, RG > GL && got < 0);   // rare: more big systems in the block than slots
+    const float* big = (RG > GL && got < 0) ? gscratch : reinterpret_cast<const float*>(&slots[got < 0 ? 0 : got]);
 #ifdef PROFILE_CYCLES
     const long long t_solve0 = clock64();
 #endif
-    if (RGw <= GL) iters = build_and_solve<1>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
-    else if (RGw <= 2 * GL) iters = build_and_solve<2>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
-    else iters = build_and_solve<3>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big);
+#define B2E_SOLVE(N, G) build_and_solve<N, G>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], got, gscratch)
+    if (RGw <= GL) iters = B2E_SOLVE(1, false);
+    else if (!need_global) iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, false) : B2E_SOLVE(3, false);
+    else iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, true) : B2E_SOLVE(3, true);
+#undef B2E_SOLVE
 
 #ifdef PROFILE_CYCLES
-    R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (big == st.scratch + (size_t)env * SCRATCH_PER_ENV ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
+    R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (got < 0 ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
 #endif
     PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
