@@ -31,8 +31,8 @@ sys.path.insert(0, os.path.join(ROOT, "pybullet-robot-envs_b200"))
 
 B_ALG_PUSH = 968  # algorithmic bytes per pandaPush env-step
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch at 16384 envs, from the ncu --set full
-# capture summarised in profiles/r1_ncu_step_kernel_final.csv (8.47 MB + 1.42 MB); algorithmic: 15.86 MB
-TRAFFIC_BYTES_PER_LAUNCH_16384 = 9.89e6
+# capture summarised in profiles/r1_ncu_step_kernel_final_shallow.csv (8.29 MB + 0.29 MB); algorithmic: 15.86 MB
+TRAFFIC_BYTES_PER_LAUNCH_16384 = 8.58e6
 METRIC = "env-steps/sec PandaPush-v0 batch=16384"
 WORKLOAD = "pandaPush-v0 joint mode, random policy U(-1,1)^7, post-reset state, done ignored"
 
@@ -328,7 +328,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (TRAFFIC_BYTES_PER_LAUNCH_16384 if B == 16384 else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG_PUSH,
                          "kernel": "step_kernel", "kernel_ms_avg": dev_ms_max / K, "kernel_ms_at_final_depth": kernel_ms,
-                         "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step; DRAM traffic per launch (ncu, profiles/): 8.5 MB read + 1.4 MB write vs 15.9 MB algorithmic"},
+                         "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step; the average launch is dominated by the tail of a few jammed envs (DESIGN.md §4); DRAM traffic per launch (ncu, profiles/): 8.3 MB read + 0.3 MB write vs 15.9 MB algorithmic"},
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 7 * 4,
                     "d2h_bytes_per_step": B * (33 + 2) * 4, "steps": Ke, "warmup": n_warm_e,
                     "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays"},
