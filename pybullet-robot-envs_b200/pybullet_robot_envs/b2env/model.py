@@ -368,3 +368,118 @@ def panda_task_setup(task=TASK_PUSH, max_steps=1000, n_ctrl=7, use_ik=0, ik_orie
     p = default_params(task, low, high, n_act=n_act, n_ctrl=n_ctrl, use_ik=use_ik, ik_orientation=ik_orientation,
                        max_steps=max_steps, ws_lim=robot_ws, goal_env=goal_env)
     return m, p
+
+
+# ---------------------------------------------------------------------------------------------
+# iCub (SDF).  Groundwork for the iCub envs (reference envs/icub_envs/icub_env.py): the loader and the
+# model descriptor are pinned through the generic CPU oracle on SURVEY Appendix C.5; the CUDA kernel
+# for the 38-link / 32-dof tree is not built yet.
+def _pose6(s):
+    v = [float(x) for x in s.split()]
+    assert len(v) == 6
+    return v
+
+
+def _T(xyz, rpy):
+    T = np.eye(4)
+    T[:3, :3] = rpy_to_matrix(*rpy)
+    T[:3, 3] = xyz
+    return T
+
+
+def parse_sdf(path):
+    """Parse an SDF model (the reference's robot_data/iCub/icub_model.sdf) into the same dict layout as
+    ``parse_urdf``.  SDF link poses are absolute in the model frame at the zero configuration, every joint
+    pose is zero relative to its child (joint frame = child link frame) and axes are given in the child
+    frame; PyBullet numbers joints by a depth-first walk in file order."""
+    model = ET.parse(path).getroot().find("world").find("model")
+    links, Tlink = {}, {}
+    for ln in model.findall("link"):
+        name = ln.get("name")
+        pose = _pose6(ln.find("pose").text) if ln.find("pose") is not None else [0] * 6
+        Tlink[name] = _T(pose[:3], pose[3:])
+        inert = ln.find("inertial")
+        ip = _pose6(inert.find("pose").text) if inert.find("pose") is not None else [0] * 6
+        it = inert.find("inertia")
+        g = lambda k: float(it.find(k).text)
+        I = np.array([[g("ixx"), g("ixy"), g("ixz")], [g("ixy"), g("iyy"), g("iyz")], [g("ixz"), g("iyz"), g("izz")]])
+        Ri = rpy_to_matrix(*ip[3:])
+        links[name] = dict(name=name, mass=float(inert.find("mass").text), com=ip[:3], inertia=(Ri @ I @ Ri.T).tolist(), contact={})
+    joints = []
+    for jn in model.findall("joint"):
+        ax = jn.find("axis")
+        lim = ax.find("limit") if ax is not None else None
+        dyn = ax.find("dynamics") if ax is not None else None
+        joints.append(dict(
+            name=jn.get("name"), type=jn.get("type"), parent=jn.find("parent").text, child=jn.find("child").text,
+            axis=_vec(ax.find("xyz").text) if ax is not None else [1, 0, 0],
+            lower=float(lim.find("lower").text) if lim is not None and lim.find("lower") is not None else 0.0,
+            upper=float(lim.find("upper").text) if lim is not None and lim.find("upper") is not None else 0.0,
+            effort=float(lim.find("effort").text) if lim is not None and lim.find("effort") is not None else 0.0,
+            velocity=float(lim.find("velocity").text) if lim is not None and lim.find("velocity") is not None else 0.0,
+            damping=float(dyn.find("damping").text) if dyn is not None and dyn.find("damping") is not None else 0.0))
+    children = {j["child"] for j in joints}
+    base = [n for n in links if n not in children]
+    assert len(base) == 1, base
+    base = base[0]
+    order = []
+
+    def walk(link_name):
+        for j in joints:
+            if j["parent"] == link_name:
+                order.append(j)
+                walk(j["child"])
+    walk(base)
+    assert len(order) == len(joints)
+    index = {base: -1}
+    for i, j in enumerate(order):
+        index[j["child"]] = i
+    out = []
+    for i, j in enumerate(order):
+        Trel = np.linalg.inv(Tlink[j["parent"]]) @ Tlink[j["child"]]   # joint origin in the parent link frame
+        R = Trel[:3, :3]
+        # roll-pitch-yaw of R (fixed axes, R = Rz Ry Rx), so that the dict stays URDF-like
+        pitch = -np.arcsin(np.clip(R[2, 0], -1, 1))
+        roll = np.arctan2(R[2, 1], R[2, 2])
+        yaw = np.arctan2(R[1, 0], R[0, 0])
+        out.append(dict(j, index=i, parent_index=index[j["parent"]], xyz=Trel[:3, 3].tolist(),
+                        rpy=[float(roll), float(pitch), float(yaw)], rotation=R.tolist()))
+    mp = model.find("pose")
+    return dict(name=model.get("name"), base=links[base], joints=out, links=[links[j["child"]] for j in order],
+                model_pose=_pose6(mp.text) if mp is not None else [0] * 6)
+
+
+ICUB_HOME = {  # reference icub_env.py:19-40 (all other joints 0)
+    'neck_pitch': 0.008, 'l_shoulder_pitch': -0.51, 'l_shoulder_roll': 0.7, 'l_elbow': 1.22,
+    'r_shoulder_pitch': -0.51, 'r_shoulder_roll': 0.7, 'r_elbow': 1.22,
+}
+ICUB_JSON = os.path.join(_HERE, "..", "robot_data", "iCub", "icub_model.json")
+
+
+def load_icub(sdf_path=None, pinned=False):
+    """iCub ``B2EModel`` (38 joints, 32 dofs).  The base sits at the SDF model pose; ``pinned=True`` applies the
+    reference's base pin quirk (anchor z x 1.2, icub_env.py:95-101): +0.126 m."""
+    if sdf_path is not None:
+        d = parse_sdf(sdf_path)
+    else:
+        with open(ICUB_JSON) as f:
+            d = json.load(f)
+    mp = d["model_pose"]
+    base = [mp[0], mp[1], mp[2] * (1.2 if pinned else 1.0)]
+    home = {j["name"]: ICUB_HOME.get(j["name"], 0.0) for j in d["joints"]}
+    names = [l["name"] for l in d["links"]]
+    m = descriptor_from_urdf_dict(d, base, home, ee_link=names.index("l_hand"), spheres=[])
+    Rb = rpy_to_matrix(*mp[3:])
+    for k in range(9):
+        m.base_rot[k] = float(Rb.flat[k])
+    # exact relative rotations (the rpy round trip of descriptor_from_urdf_dict is only accurate to ~1e-16)
+    for i, j in enumerate(d["joints"]):
+        R = np.asarray(j["rotation"])
+        for k in range(9):
+            m.jrot[i][k] = float(R.flat[k])
+    dnum = 0
+    for j in d["joints"]:
+        if j["type"] != "fixed":
+            m.joint_damping[dnum] = j.get("damping", 0.0)
+            dnum += 1
+    return m, d

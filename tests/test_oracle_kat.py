@@ -118,3 +118,36 @@ def test_committed_model_json_matches_reference_urdf():
         committed = json.load(f)
     assert json.loads(json.dumps(fresh["joints"])) == committed["joints"]
     assert json.loads(json.dumps(fresh["links"])) == committed["links"]
+
+
+def test_icub_model_and_tree_kinematics(oracle_lib):
+    """iCub groundwork (SDF loader + the generic tree code of the oracle), pinned on SURVEY App. B.2 / C.5:
+    39 links / 38 joints / 32 dofs, total mass 33.06 kg, joint indices in PyBullet order, hand positions."""
+    from pybullet_robot_envs.b2env.model import default_params, load_icub, TASK_REACH
+    m, d = load_icub()
+    assert m.n_links == 38 and m.n_dof == 32
+    assert abs(sum(m.mass[i] for i in range(38)) + d["base"]["mass"] - 33.06) < 5e-3
+    names = [j["name"] for j in d["joints"]]
+    assert [d["joints"][i]["type"] for i in (2, 7, 10, 15, 22, 33)] == ["fixed"] * 6          # FT sensor joints
+    assert names[16:19] == ["torso_pitch", "torso_roll", "torso_yaw"]
+    assert names[26] == "l_wrist_yaw" and names[37] == "r_wrist_yaw" and m.ee_link == 26        # icub_env.py:121-143
+    ctrl_l = [16, 17, 18, 19, 20, 21, 23, 24, 25, 26]
+    assert all(d["joints"][i]["type"] == "revolute" for i in ctrl_l)
+    p = default_params(TASK_REACH, [0] * 31, [1] * 31)
+    o = oracle_lib.Oracle(m, p, 1, double=True)
+    home = np.array([m.home[i] for i in range(32)], np.float32)
+    pos, rot = o.fk(home)
+    com = lambda i: pos[i] + rot[i] @ np.array([m.com[i][k] for k in range(3)])
+    np.testing.assert_allclose(pos[26], (0.259158, 0.192303, 0.737243), atol=2e-6)              # l_hand link origin
+    np.testing.assert_allclose(com(26), (0.319191, 0.206436, 0.767843), atol=2e-6)              # l_hand COM
+    np.testing.assert_allclose(pos[37], (0.258560, -0.224899, 0.736992), atol=2e-6)             # r_hand
+    np.testing.assert_allclose(com(37), (0.318462, -0.239160, 0.767587), atol=2e-6)
+    pos0, rot0 = o.fk(np.zeros(32, np.float32))
+    np.testing.assert_allclose(pos0[26] + rot0[26] @ np.array([m.com[26][k] for k in range(3)]),
+                               (0.028214, 0.079672, 0.435014), atol=2e-6)
+    # articulated-body algorithm on a branching tree: M^-1 symmetric positive definite, gravity torques finite
+    Minv = o.minv(home).astype(np.float64)
+    np.testing.assert_allclose(Minv, Minv.T, atol=1e-4 * np.abs(Minv).max())
+    assert np.linalg.eigvalsh(0.5 * (Minv + Minv.T)).min() > 0
+    qdd = o.forward_dynamics(home, np.zeros(32, np.float32), np.zeros(32, np.float32))
+    assert np.isfinite(qdd).all() and np.abs(qdd).max() > 1.0

@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "pybullet-robot-envs_b200"))
-from pybullet_robot_envs.b2env.model import parse_urdf, PANDA_JSON  # noqa: E402
+from pybullet_robot_envs.b2env.model import parse_urdf, parse_sdf, PANDA_JSON, ICUB_JSON  # noqa: E402
 
 SRC = "/root/reference/pybullet_robot_envs/robot_data/franka_panda/panda_model.urdf"
 
@@ -25,3 +25,9 @@ if __name__ == "__main__":
     with open(PANDA_JSON, "w") as f:
         json.dump(d, f, indent=1)
     print("wrote", os.path.normpath(PANDA_JSON), len(d["joints"]), "joints")
+    d = parse_sdf("/root/reference/pybullet_robot_envs/robot_data/iCub/icub_model.sdf")
+    d["source"] = "hsp-iit/pybullet-robot-envs robot_data/iCub/icub_model.sdf (kinematic/inertial data only)"
+    os.makedirs(os.path.dirname(ICUB_JSON), exist_ok=True)
+    with open(ICUB_JSON, "w") as f:
+        json.dump(d, f, indent=1)
+    print("wrote", os.path.normpath(ICUB_JSON), len(d["joints"]), "joints")
