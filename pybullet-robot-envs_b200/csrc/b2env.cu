@@ -539,16 +539,47 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -ca[s] : 0.f, dli, r.u[s]);
 }
 
+// Select-free variants for the case "every group either visits the whole range or is frozen".  A frozen
+// group (all its islands converged) has lo = hi = lambda on every row, so its candidate clamps back to
+// lambda (dl = 0 exactly) and it reads its coefficients from a page of zeros.
+template <int NSG, int SI>
+__device__ __forceinline__ void generic_step_fast(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
+                                                  const float* Wrow, int li) {
+  float ca[NSG];
+#pragma unroll
+  for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
+  const float cw = Wrow[g.lane];
+  float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
+  nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
+  const float dli = SHF(nl - r.lam[SI], li);
+  r.lam[SI] = (g.lane == li) ? nl : r.lam[SI];
+  m.u = fmaf(-cw, dli, m.u);
+#pragma unroll
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
+}
+
 // Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
 // over the index range spanned by BOTH groups' masks (warp-uniform trip count, no find-first-set chain; the
 // masks are contiguous ranges in practice: limits, then normals, then frictions, cube-table contacts first);
 // a group skips (dl = 0, no table access) the rows it does not visit itself.
 template <int NSG, int SI>
 __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                          int AS, unsigned mk, bool arm_sweep) {
+                                          int AS, unsigned mk, bool arm_sweep, bool frozen, const float* zeros) {
   const unsigned w = mk | __shfl_xor_sync(FULL, mk, GL);
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
+  const unsigned range = (0xffffffffu >> (32 - hi)) & ~((1u << lo) - 1u);   // bits lo .. hi-1
+  if (__all_sync(FULL, frozen || mk == range)) {
+    const float* Arow = frozen ? zeros : A + (GL * SI + lo) * AS;
+    const float* Wrow = (frozen || !arm_sweep) ? zeros : W + (GL * SI + lo) * WSTRIDE;
+    const int astep = frozen ? 0 : AS, wstep = (frozen || !arm_sweep) ? 0 : WSTRIDE;
+    for (int i = lo; i < hi; i++) {
+      generic_step_fast<NSG, SI>(g, m, r, Arow, Wrow, i);
+      Arow += astep;
+      Wrow += wstep;
+    }
+    return;
+  }
   const float* Arow = A + (GL * SI + lo) * AS;
   const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
   for (int i = lo; i < hi; i++) {
@@ -560,16 +591,17 @@ __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NS
 
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
+                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep,
+                                              bool frozen, const float* zeros) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep);
-  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep);
-  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep);
+  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep, frozen, zeros);
+  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep, frozen, zeros);
+  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep, frozen, zeros);
 }
 
 template <int NSG>
 __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                         const float* WT, int AS, const float* Minv, int nd, int RG, int fric_start, bool coupled,
+                                         const float* WT, int AS, const float* zeros, const float* Minv, int nd, int RG, int fric_start, bool coupled,
                                          bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
   // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
   unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
@@ -585,6 +617,11 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
   }
   bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
   int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
+  if (my_it >= 0) {
+    m.lo = m.lam; m.hi = m.lam;
+#pragma unroll
+    for (int s = 0; s < NSG; s++) { r.lo[s] = r.lam[s]; r.hi[s] = r.lam[s]; }
+  }
   for (int it = 0; it < max_iters; it++) {
     if (__all_sync(FULL, my_it >= 0)) break;
     m.prev = m.lam;
@@ -594,8 +631,9 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
       for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
     }
+    const bool frozen = my_it >= 0;   // this group is finished: its rows are pinned (lo = hi = lambda)
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
-                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
+                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0, frozen, zeros);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
     if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
@@ -609,12 +647,12 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
           const float vt = SHF(r.lam[t], ni & (GL - 1));
           if ((ni >> 4) == t) v = vt;
         }
-        if (r.type[s] == ROW_FRICTION) {
+        if (r.type[s] == ROW_FRICTION && !frozen) {
           const float lim = r.mu[s] * v;
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0);
+      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0, frozen, zeros);
     }
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
@@ -633,7 +671,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     rc = gmaxf(g, rc);
     if (!done0 && ra <= tol) done0 = true;
     if (!done1 && rc <= tol) done1 = true;
-    if (my_it < 0 && done0 && done1) my_it = it + 1;
+    if (my_it < 0 && done0 && done1) {
+      my_it = it + 1;
+      // freeze: from now on every candidate of this group clamps back to its impulse (exact no-op updates)
+      m.lo = m.lam; m.hi = m.lam;
+#pragma unroll
+      for (int s = 0; s < NSG; s++) { r.lo[s] = r.lam[s]; r.hi[s] = r.lam[s]; }
+    }
   }
   return my_it < 0 ? max_iters : my_it;
 }
@@ -723,6 +767,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   // every table access is a shared-memory access (no generic loads in the row loops)
   float* big = reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * (slot < 0 ? 0 : slot));
   if (GB && slot < 0) big = gscratch;
+  const float* zeros = reinterpret_cast<const float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16);
   float* A = use_big ? big : sm.A;
   float* W = use_big ? big + BIGS * BIGS : sm.W;
   float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : nullptr;
@@ -932,7 +977,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, zeros, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
@@ -1043,6 +1088,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     if (sub >= nsub) break;
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
     if ((int)threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
+    if (threadIdx.x < 64) reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)[threadIdx.x] = 0.f;
     __syncthreads();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
@@ -1794,7 +1840,7 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   return 0;
 }
 
-#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
+#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16 + 64 * 4)   // envs | slots | owners | zero page
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
