@@ -539,67 +539,16 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -ca[s] : 0.f, dli, r.u[s]);
 }
 
-// Select-free variants for the case "every group either visits the whole range or is frozen".  A frozen
-// group (all its islands converged) has lo = hi = lambda on every row, so its candidate clamps back to
-// lambda (dl = 0 exactly) and it reads its coefficients from a page of zeros.
-template <int NSG, int SI>
-__device__ __forceinline__ void generic_step_fast(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
-                                                  const float* Wrow, int li) {
-  float ca[NSG];
-#pragma unroll
-  for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
-  const float cw = Wrow[g.lane];
-  float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
-  nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-  const float dli = SHF(nl - r.lam[SI], li);
-  r.lam[SI] = (g.lane == li) ? nl : r.lam[SI];
-  m.u = fmaf(-cw, dli, m.u);
-#pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
-}
-
 // Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
 // over the index range spanned by BOTH groups' masks (warp-uniform trip count, no find-first-set chain; the
 // masks are contiguous ranges in practice: limits, then normals, then frictions, cube-table contacts first);
 // a group skips (dl = 0, no table access) the rows it does not visit itself.
 template <int NSG, int SI>
 __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                          int AS, unsigned mk, bool arm_sweep, bool frozen, const float* zeros) {
+                                          int AS, unsigned mk, bool arm_sweep) {
   const unsigned w = mk | __shfl_xor_sync(FULL, mk, GL);
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
-  const unsigned range = (0xffffffffu >> (32 - hi)) & ~((1u << lo) - 1u);   // bits lo .. hi-1
-  if (__all_sync(FULL, frozen || mk == range)) {
-    // Software-pipelined: the coefficients of row i+1 are fetched (and the bookkeeping of row i done) right after
-    // the shuffle of row i is issued, i.e. inside its latency window instead of between dependent chain links.
-    // (The prefetch of the last iteration reads one row past the range: still inside this env's tables.)
-    const float* Arow = frozen ? zeros : A + (GL * SI + lo) * AS;
-    const float* Wrow = (frozen || !arm_sweep) ? zeros : W + (GL * SI + lo) * WSTRIDE;
-    const int astep = frozen ? 0 : AS, wstep = (frozen || !arm_sweep) ? 0 : WSTRIDE;
-    float ca[NSG], cw = Wrow[g.lane];
-#pragma unroll
-    for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
-    for (int i = lo; i < hi; i++) {
-      float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
-      nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-      const float dli = SHF(nl - r.lam[SI], i);
-      Arow += astep;
-      Wrow += wstep;
-      float cn[NSG];
-#pragma unroll
-      for (int s = 0; s < NSG; s++) cn[s] = Arow[GL * s + g.lane];
-      const float cwn = Wrow[g.lane];
-      r.lam[SI] = (g.lane == i) ? nl : r.lam[SI];
-      r.u[SI] = fmaf(-ca[SI], dli, r.u[SI]);        // the next row's candidate depends on this one first
-#pragma unroll
-      for (int s = 0; s < NSG; s++) if (s != SI) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
-      m.u = fmaf(-cw, dli, m.u);
-#pragma unroll
-      for (int s = 0; s < NSG; s++) ca[s] = cn[s];
-      cw = cwn;
-    }
-    return;
-  }
   const float* Arow = A + (GL * SI + lo) * AS;
   const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
   for (int i = lo; i < hi; i++) {
@@ -611,18 +560,17 @@ __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NS
 
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep,
-                                              bool frozen, const float* zeros) {
+                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep, frozen, zeros);
-  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep, frozen, zeros);
-  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep, frozen, zeros);
+  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep);
+  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep);
+  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep);
 }
 
 template <int NSG>
 __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                         const float* WT, int AS, const float* zeros, const float* Minv, int nd, int RG, int fric_start, bool coupled,
-                                         bool has_cube_rows, bool arm_sweep, int max_iters, float tol, float* prof = nullptr) {
+                                         const float* WT, int AS, const float* Minv, int nd, int RG, int fric_start, bool coupled,
+                                         bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
   // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
   unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
 #pragma unroll
@@ -636,59 +584,18 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     cube_f[s] = gballot(g, valid && cube && fr);
   }
   bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
-#ifdef PROFILE_CYCLES
-  long long tc_motor = 0, tc_nf = 0, tc_fr = 0, tc_res = 0, tc0;
-#define TC_BEGIN() tc0 = clock64()
-#define TC_END(acc) acc += clock64() - tc0
-#else
-#define TC_BEGIN()
-#define TC_END(acc)
-#endif
   int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
-  if (my_it >= 0) {
-    m.lo = m.lam; m.hi = m.lam;
-#pragma unroll
-    for (int s = 0; s < NSG; s++) { r.lo[s] = r.lam[s]; r.hi[s] = r.lam[s]; }
-  }
   for (int it = 0; it < max_iters; it++) {
     if (__all_sync(FULL, my_it >= 0)) break;
     m.prev = m.lam;
 #pragma unroll
     for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
-    TC_BEGIN();
     if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
-      // (software-pipelined like the generic sweep: coefficients of motor row i+1 are fetched behind the shuffle of row i)
-      const bool act = !done0;
-      const int lc = g.lane < NDMAX ? g.lane : NDMAX;
-      float cm = Minv[lc], cg[NSG];
-#pragma unroll
-      for (int s = 0; s < NSG; s++) cg[s] = WT ? WT[GL * s + g.lane] : W[(GL * s + g.lane) * WSTRIDE];
-      for (int i = 0; i < nd; i++) {
-        float nl = fmaf(m.u, m.invd, m.lam);
-        nl = fminf(fmaxf(nl, m.lo), m.hi);
-        const float dli = SHF(act ? nl - m.lam : 0.f, i);
-        const int in = (i + 1 < nd) ? i + 1 : i;
-        const float cmn = Minv[in * (NDMAX + 1) + lc];
-        float cgn[NSG];
-#pragma unroll
-        for (int s = 0; s < NSG; s++) cgn[s] = WT ? WT[in * AS + GL * s + g.lane] : W[(GL * s + g.lane) * WSTRIDE + in];
-        m.lam = (g.lane == i && act) ? nl : m.lam;
-        m.u = fmaf(act ? -cm : 0.f, dli, m.u);
-#pragma unroll
-        for (int s = 0; s < NSG; s++) r.u[s] = fmaf(act ? -cg[s] : 0.f, dli, r.u[s]);
-        cm = cmn;
-#pragma unroll
-        for (int s = 0; s < NSG; s++) cg[s] = cgn[s];
-      }
+      for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
     }
-    TC_END(tc_motor);
-    TC_BEGIN();
-    const bool frozen = my_it >= 0;   // this group is finished: its rows are pinned (lo = hi = lambda)
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
-                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0, frozen, zeros);
-    TC_END(tc_nf);
-    TC_BEGIN();
+                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
     if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
@@ -702,15 +609,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
           const float vt = SHF(r.lam[t], ni & (GL - 1));
           if ((ni >> 4) == t) v = vt;
         }
-        if (r.type[s] == ROW_FRICTION && !frozen) {
+        if (r.type[s] == ROW_FRICTION) {
           const float lim = r.mu[s] * v;
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0, frozen, zeros);
+      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0);
     }
-    TC_END(tc_fr);
-    TC_BEGIN();
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
       const float rv = (m.lam - m.prev) * m.diag;
@@ -728,18 +633,8 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     rc = gmaxf(g, rc);
     if (!done0 && ra <= tol) done0 = true;
     if (!done1 && rc <= tol) done1 = true;
-    if (my_it < 0 && done0 && done1) {
-      my_it = it + 1;
-      // freeze: from now on every candidate of this group clamps back to its impulse (exact no-op updates)
-      m.lo = m.lam; m.hi = m.lam;
-#pragma unroll
-      for (int s = 0; s < NSG; s++) { r.lo[s] = r.lam[s]; r.hi[s] = r.lam[s]; }
-    }
-    TC_END(tc_res);
+    if (my_it < 0 && done0 && done1) my_it = it + 1;
   }
-#ifdef PROFILE_CYCLES
-  if (prof) { prof[0] = (float)tc_motor; prof[1] = (float)tc_nf; prof[2] = (float)tc_fr; prof[3] = (float)tc_res; }
-#endif
   return my_it < 0 ? max_iters : my_it;
 }
 
@@ -818,9 +713,6 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
                                             float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
                                             int slot, float* gscratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-#ifdef PROFILE_CYCLES
-  const long long t_build0 = clock64();
-#endif
   const Grp g = {hm, sh, lane};
   const float cpos[3] = {cpx, cpy, cpz};
   // up to 16 generic rows live in the environment's own shared memory; a bigger system uses `big`
@@ -831,7 +723,6 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   // every table access is a shared-memory access (no generic loads in the row loops)
   float* big = reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * (slot < 0 ? 0 : slot));
   if (GB && slot < 0) big = gscratch;
-  const float* zeros = reinterpret_cast<const float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16);
   float* A = use_big ? big : sm.A;
   float* W = use_big ? big + BIGS * BIGS : sm.W;
   float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : nullptr;
@@ -1041,19 +932,8 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
-#ifdef PROFILE_CYCLES
-  float prof[4] = {0, 0, 0, 0};
-  const long long t_pgs0 = clock64();
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, zeros, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
-                            P.residual_tol, prof);
-  if (lane == 0) {
-    sm.clam[13][0] = prof[0]; sm.clam[13][1] = prof[1]; sm.clam[13][2] = prof[2];
-    sm.clam[14][0] = prof[3]; sm.clam[14][1] = (float)(clock64() - t_pgs0); sm.clam[14][2] = (float)(t_pgs0 - t_build0);
-  }
-#else
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, zeros, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
-#endif
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
 #pragma unroll
@@ -1163,7 +1043,6 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     if (sub >= nsub) break;
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
     if ((int)threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
-    if (threadIdx.x < 64) reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)[threadIdx.x] = 0.f;
     __syncthreads();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
@@ -1617,11 +1496,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
         }
       }
       gsync(g);
-#ifdef PROFILE_CYCLES
-      if (lane < 13 && !ghost) {
-#else
       if (lane < B2E_CACHE_SLOTS && !ghost) {
-#endif
         sm.ckey[lane] = key;
         sm.clam[lane][0] = l3[0]; sm.clam[lane][1] = l3[1]; sm.clam[lane][2] = l3[2];
       }
@@ -1919,7 +1794,7 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   return 0;
 }
 
-#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16 + 64 * 4)   // envs | slots | owners | zero page
+#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
