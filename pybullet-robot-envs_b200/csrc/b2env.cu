@@ -52,7 +52,6 @@
 #define MINB 2            // resident blocks per SM the register allocation targets (16 warps = 32 envs, 128 regs)
 #endif
 #define TLMAX 12          // links handled by the group kernel (transforms staged in shared memory; < 15: lane 15 is the zero lane)
-#define RMAX 48           // scratch stride
 #define GMAX 48           // generic rows per env (3 limit + 36 contact rows), in sets of 16
 #define BIGS 40           // row stride of a big constraint system (<= 39 generic rows) in an overflow slot
 #ifndef NSLOT
@@ -105,7 +104,7 @@ struct DevState {
   int B;
   float* q; float* qd; float* obj_pose; float* obj_vel; float* target; float* mtarget;
   int* counters; int* cache_key; float* cache_lam; float* hand_pose; int* status; float* raw_obs; float* contacts;
-  float* scratch;  // [B][RMAX*RMAX + RMAX*WSTRIDE]: Delassus matrix + W for envs with more than 32 rows
+  float* scratch;  // [B][SCRATCH_PER_ENV]: A | W | W^T of a big system when no overflow slot of the block is free
 };
 
 struct b2e_sim {
@@ -1825,7 +1824,7 @@ __global__ void rows_kernel(float* field, const int* __restrict__ ids, int n, in
 extern "C" {
 
 const char* b2e_last_error(void) { return g_err; }
-const char* b2e_version(void) { return "b2env 0.1 (sm_100a, warp-per-env)"; }
+const char* b2e_version(void) { return "b2env 0.2 (sm_100a, two environments per warp)"; }
 
 int b2e_field_elem_size(int field) {
   (void)field;
