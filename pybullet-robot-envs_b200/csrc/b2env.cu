@@ -271,6 +271,9 @@ struct EnvSmem {
   float A[GL * GL];            // generic-row block of the Delassus matrix, A[c*16 + r], when <= 16 generic rows
                                // (else: per-env global scratch, stride GMAX)
   float W[GL * WSTRIDE];       // W[g][k] = (M^-1 J_g^T)_k of generic row g; k<9 arm dofs, 9..14 cube (lin, ang)
+  float WT[NDMAX * GL];        // WT[d][g] = W[g][d]: what a motor row reads (unit stride over g).  A 16-row system
+                               // solved in a 2/3-set instantiation (its warp mate is big) reads up to 31 floats past
+                               // the end for its non-existent rows: T follows, which nobody writes during the solve
   float T[TLMAX][12];          // link world transforms: R (9) + p (3)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
@@ -290,7 +293,8 @@ struct EnvSmem {
 struct BigSlot {
   float A[BIGS * BIGS];      // generic x generic Delassus block, A[c*BIGS + r]
   float W[BIGS * WSTRIDE];   // W[g][k]
-  float WT[NDMAX * BIGS];    // WT[d][g] = W[g][d]: motor-row coupling read with unit stride over g
+  float WT[NDMAX * BIGS + 8]; // WT[d][g] = W[g][d]: motor-row coupling read with unit stride over g (+8: lanes of the
+                             // third row set run to g = 47)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -503,14 +507,9 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
                                            const float* W, const float* WT, int AS, int i, bool active) {
   const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
   const float cm = Minv[i * (NDMAX + 1) + lc];
-  float cg[NSG];
-  if (WT) {   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
+  float cg[NSG];   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
 #pragma unroll
-    for (int s = 0; s < NSG; s++) cg[s] = WT[i * AS + GL * s + g.lane];
-  } else {
-#pragma unroll
-    for (int s = 0; s < NSG; s++) cg[s] = W[(GL * s + g.lane) * WSTRIDE + i];
-  }
+  for (int s = 0; s < NSG; s++) cg[s] = WT[i * AS + GL * s + g.lane];
   float nl = fmaf(m.u, m.invd, m.lam);
   nl = fminf(fmaxf(nl, m.lo), m.hi);
   const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
@@ -724,7 +723,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   if (GB && slot < 0) big = gscratch;
   float* A = use_big ? big : sm.A;
   float* W = use_big ? big + BIGS * BIGS : sm.W;
-  float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : nullptr;
+  float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : sm.WT;
   const float* Minv = &sm.Minv[0][0];
   const int fric_start = nlim + nc;   // generic index of the first friction row
   const int RG = nlim + 3 * nc;       // generic rows
@@ -849,10 +848,8 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 #pragma unroll
       for (int k = 0; k < 15; k++) W[gi * WSTRIDE + k] = Wv[k];
       W[gi * WSTRIDE + 15] = 0.f;
-      if (WT) {
 #pragma unroll
-        for (int k = 0; k < NDMAX; k++) WT[k * AS + gi] = Wv[k];
-      }
+      for (int k = 0; k < NDMAX; k++) WT[k * AS + gi] = Wv[k];
     }
     rr.type[s] = type; rr.isl[s] = isl; rr.nidx[s] = nidx;
     rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
