@@ -28,13 +28,22 @@
 // State lives in HBM as env-major field groups ([B][width] arrays, see enum b2e_field), read
 // once and written once per step.
 
+#ifndef B2E_EMU   // tools/emu compiles this file with g++ and cuda_emu.h force-included (CPU debugging of kernel logic)
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "../../include/b2env.h"
+
+#ifdef B2E_EMU
+__thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
+#define B2E_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+#else
+#define B2E_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
 
 #define FULL 0xffffffffu
 #ifndef PHASE_SYNC
@@ -1797,11 +1806,11 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
   if (n <= 0) return 0;
   const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
   if (s->params.use_ik)
-    step_kernel<true><<<blocks, 32 * WPB, SMEM_BYTES, (cudaStream_t)stream>>>(
+    B2E_LAUNCH(step_kernel<true>, blocks, 32 * WPB, SMEM_BYTES, stream,
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
         env_offset);
   else
-    step_kernel<false><<<blocks, 32 * WPB, SMEM_BYTES, (cudaStream_t)stream>>>(
+    B2E_LAUNCH(step_kernel<false>, blocks, 32 * WPB, SMEM_BYTES, stream,
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
         env_offset);
   s->launches++;
@@ -1907,8 +1916,8 @@ int b2e_reset(b2e_sim* s, const uint8_t* env_mask, const float* obj_init_pose, c
   if (!s || !obj_init_pose || !target) return fail(B2E_EINVAL, "b2e_reset: null argument%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
   const int tpb = 128;
-  reset_kernel<<<(s->B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(s->d_model, s->params, s->st, env_mask,
-                                                                         obj_init_pose, target);
+  B2E_LAUNCH(reset_kernel, (s->B + tpb - 1) / tpb, tpb, 0, stream, s->d_model, s->params, s->st, env_mask, obj_init_pose,
+             target);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1937,7 +1946,7 @@ int b2e_set_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, const voi
   if (n == 0) return 0;
   CUDA_TRY(cudaSetDevice(s->device));
   const int w = field_width(s, field), tot = n * w;
-  rows_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)s->fields[field], env_ids, n, w, (float*)rows, 0);
+  B2E_LAUNCH(rows_kernel, (tot + 255) / 256, 256, 0, stream, (float*)s->fields[field], env_ids, n, w, (float*)rows, 0);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1947,7 +1956,7 @@ int b2e_get_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, void* row
   if (n == 0) return 0;
   CUDA_TRY(cudaSetDevice(s->device));
   const int w = field_width(s, field), tot = n * w;
-  rows_kernel<<<(tot + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float*)s->fields[field], env_ids, n, w, (float*)rows, 1);
+  B2E_LAUNCH(rows_kernel, (tot + 255) / 256, 256, 0, stream, (float*)s->fields[field], env_ids, n, w, (float*)rows, 1);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;

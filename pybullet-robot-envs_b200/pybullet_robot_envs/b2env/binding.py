@@ -96,8 +96,10 @@ def _ptr(x):
 class B2Sim:
     """Thin object wrapper over the C-ABI: one simulation of ``num_envs`` envs on one GPU."""
 
-    def __init__(self, model: B2EModel, params: B2EParams, num_envs: int, device: int = 0):
-        self.lib = load_library()
+    def __init__(self, model: B2EModel, params: B2EParams, num_envs: int, device: int = 0, lib=None):
+        # `lib`: tests may hand in another build of the SAME source (tools/emu: the kernels compiled for the
+        # host, to debug kernel logic without a GPU).  The product never passes it.
+        self.lib = lib if lib is not None else load_library()
         self.model, self.params, self.B, self.device = model, params, int(num_envs), int(device)
         h = C.c_void_p()
         self._check(self.lib.b2e_create(C.byref(model), C.byref(params), self.B, self.device, C.byref(h)))
