@@ -140,7 +140,24 @@ typedef struct b2e_params {
   float grasp_rest_z;      /* GRASP: object rest height (table top + half extent)                 */
   int32_t goal_env;        /* GoalEnv semantics (panda_push_gym_goal_env.py:89-122): sparse reward
                               -(d > dist_min), done = counter > max_steps or success, no latch */
+  /* ---- iCub task envs (icub_envs/icub_env.py, icub_push_gym_env.py, icub_reach_gym_env.py); all zero = Panda ---- */
+  int32_t n_obs_joints;    /* joints listed in the robot observation (_joints_to_control, icub_env.py:242-247);
+                              0: every dof (panda_env.py:187-191)                                          */
+  int32_t obs_dof[16];     /* their dof indices, in joint-index order                                      */
+  int32_t ctrl_dof[16];    /* joint mode: action k drives dof ctrl_dof[k] (icub_env.py:347-361); only read
+                              when n_obs_joints > 0 (Panda: dof k)                                         */
+  uint32_t ctrl_mask;      /* bit d: dof d is controlled.  IK mode: the other joints are blocked, their target
+                              is the rest pose (icub_env.py:314-317).  Only read when n_obs_joints > 0      */
+  float ik_link_offset[3]; /* COM -> link frame of the hand: the IK target is the commanded pose composed with
+                              this translation (icub_env.py:251-257, :303-305)                             */
+  int32_t reward_kind;     /* B2E_REWARD_*                                                                 */
+  int32_t max_contacts;    /* contact points kept per env per step; <= 0: B2E_MAX_CONTACTS                 */
 } b2e_params;
+
+#define B2E_REWARD_PANDA 0       /* panda_push_gym_env.py:318-331 / panda_reach_gym_env.py:303-313 (bonus replaces) */
+#define B2E_REWARD_ICUB_REACH 1  /* icub_reach_gym_env.py:319-330: -d, bonus 1000 + (100 - 80 d) ADDED             */
+#define B2E_REWARD_ICUB_PUSH0 2  /* icub_push_gym_env.py:353-356: -d1 - d2, +1000 on success                       */
+#define B2E_REWARD_ICUB_PUSH1 3  /* icub_push_gym_env.py:358-371: shaping normalised by the distances at reset      */
 
 /* state fields for b2e_get / b2e_set (all env-major, [B][width])               */
 enum b2e_field {
@@ -157,7 +174,9 @@ enum b2e_field {
   B2E_F_STATUS = 10,  /* int32 [B][4]       flags, pgs iters, n_contacts, n_rows*/
   B2E_F_RAW_OBS = 11, /* float [B][n_obs]   unscaled observation of last step   */
   B2E_F_CONTACTS = 12,/* float [B][12][8]   last step: key, dist, n(3), lam(3)  */
-  B2E_F_COUNT = 13
+  B2E_F_SHAPING = 13, /* float [B][2]       _init_dist_hand_obj, _max_dist_obj_tg captured at reset
+                                            (icub_push_gym_env.py:126-127)       */
+  B2E_F_COUNT = 14
 };
 
 /* status flag bits */

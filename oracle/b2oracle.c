@@ -76,7 +76,14 @@ typedef struct b2o_state {
   int32_t* status;   /* [B][4] */
   float* raw_obs;    /* [B][n_obs] */
   float* contacts;   /* [B][12][8] */
+  float* shaping;    /* [B][2] */
 } b2o_state;
+
+/* Joint lists of the task (b2e_params.n_obs_joints > 0: iCub, icub_env.py:121-143; else Panda: identity). */
+static int is_ctrl_dof(const b2e_params* P, int d) {
+  return P->n_obs_joints > 0 ? (int)((P->ctrl_mask >> d) & 1u) : d < P->n_ctrl;
+}
+static int ctrl_dof_of(const b2e_params* P, int k) { return P->n_obs_joints > 0 ? P->ctrl_dof[k] : k; }
 
 /* ------------------------------------------------------------------ small math */
 static void m3_mul(const real* a, const real* b, real* c) {
@@ -468,6 +475,7 @@ typedef struct {
 static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, const real* cpos, const real* cquat,
                    contact_t* out, int* overflow) {
   int nc = 0;
+  const int maxc = (P->max_contacts > 0 && P->max_contacts < MAXC) ? P->max_contacts : MAXC;
   *overflow = 0;
   real Rc[9];
   quat_to_mat(cquat, Rc);
@@ -487,7 +495,7 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
     else { top = 0; mu = P->cube_mu * P->plane_mu; key = KEY_CUBE_PLANE + k; }
     dist = v[2] - top;
     if (dist < margin) {
-      if (nc >= MAXC) { *overflow = 1; continue; }
+      if (nc >= maxc) { *overflow = 1; continue; }
       contact_t* c = &out[nc++];
       c->key = key; c->type = CT_CUBE_STATIC; c->link = -1;
       for (int j = 0; j < 3; j++) { c->pA[j] = v[j]; c->pB[j] = v[j]; }
@@ -532,7 +540,7 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
       cl[ax] = nl[ax] * a;
       dist = -best - r;
     }
-    if (nc >= MAXC) { *overflow = 1; continue; }
+    if (nc >= maxc) { *overflow = 1; continue; }
     contact_t* c = &out[nc++];
     c->key = KEY_SPHERE_CUBE + s; c->type = CT_SPHERE_CUBE; c->link = m->sph_link[s];
     real nw[3], pw[3];
@@ -555,7 +563,7 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
       continue;
     real dist = sc[s][2] - r - P->table_max[2];
     if (!(dist < margin)) continue;
-    if (nc >= MAXC) { *overflow = 1; continue; }
+    if (nc >= maxc) { *overflow = 1; continue; }
     contact_t* c = &out[nc++];
     c->key = KEY_SPHERE_TABLE + s; c->type = CT_SPHERE_STATIC; c->link = m->sph_link[s];
     c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
@@ -667,7 +675,11 @@ static int extended_observation(const b2e_model* m, const b2e_params* P, const f
   for (int k = 0; k < 3; k++) obs[n++] = pos[k];
   for (int k = 0; k < 3; k++) obs[n++] = eu[k];
   for (int k = 0; k < 3; k++) obs[n++] = (vl[k] - P->vel_mean[k]) / P->vel_std[k]; /* panda_env.py:171-181 */
-  for (int d = 0; d < m->n_dof; d++) obs[n++] = q[d];
+  if (P->n_obs_joints > 0) { /* icub_env.py:242-247: the controlled joints only */
+    for (int k = 0; k < P->n_obs_joints; k++) obs[n++] = q[P->obs_dof[k]];
+  } else {
+    for (int d = 0; d < m->n_dof; d++) obs[n++] = q[d];
+  }
   real ceu[3];
   quat_to_euler(cquat, ceu);
   for (int k = 0; k < 3; k++) obs[n++] = cpos[k];
@@ -813,7 +825,7 @@ static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int 
     memset(r, 0, sizeof(*r));
     r->type = ROW_MOTOR; r->island = ISL_ARM;
     r->J[d] = 1;
-    real kp = (kp_ctrl_active && d < P->n_ctrl) ? P->kp_ctrl : ((grip_active && d >= P->n_ctrl) ? P->kp_grip : P->kp_hold);
+    real kp = (kp_ctrl_active && is_ctrl_dof(P, d)) ? P->kp_ctrl : ((grip_active && d >= P->n_ctrl) ? P->kp_grip : P->kp_hold);
     real desired = kp * (e->mtarget[d] - e->q[d]) / dt;
     if (m->max_vel[d] > 0) {
       if (desired > m->max_vel[d]) desired = m->max_vel[d];
@@ -1028,12 +1040,13 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
     if (mode == B2E_MODE_ACTION && !P->use_ik) {
       /* panda_push_gym_env.py:225-230: action *= 0.05 (compounding in place across repeats, quirk E.4),
        * new = q[:n_ctrl] + action; panda_env.py:303: clamp to [ll, ul] */
-      for (int k = 0; k < P->n_ctrl; k++) {
+      for (int k = 0; k < P->n_ctrl; k++) { /* iCub: icub_push_gym_env.py:256-257, icub_env.py:347-361 */
+        const int d = ctrl_dof_of(P, k);
         act[k] *= P->act_scale;
-        real t = e.q[k] + act[k];
-        if (t < m->lower[k]) t = m->lower[k];
-        if (t > m->upper[k]) t = m->upper[k];
-        e.mtarget[k] = t;
+        real t = e.q[d] + act[k];
+        if (t < m->lower[d]) t = m->lower[d];
+        if (t > m->upper[d]) t = m->upper[d];
+        e.mtarget[d] = t;
       }
       if (P->task == B2E_TASK_GRASP) { /* gripper command in [-1,1] -> both finger targets in [0, 0.04] */
         real g = action[b * P->n_act + P->n_ctrl];
@@ -1076,9 +1089,15 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
         if (eu[k] > (real)M_PI) eu[k] = (real)M_PI;
       }
       euler_to_quat(eu, tq);
+      { /* COM pose -> link-frame pose of the hand (icub_env.py:303-305; zero offset for the Panda) */
+        real off[3] = {P->ik_link_offset[0], P->ik_link_offset[1], P->ik_link_offset[2]}, o[3];
+        quat_rot(tq, off, o);
+        for (int k = 0; k < 3; k++) tp[k] += o[k];
+      }
       real qik[ND];
       ik_dls(m, P, e.q, tp, tq, qik);
-      for (int d = 0; d < m->n_dof; d++) e.mtarget[d] = qik[d];
+      for (int d = 0; d < m->n_dof; d++) /* blocked joints keep the rest pose (icub_env.py:314-317) */
+        e.mtarget[d] = (P->n_obs_joints > 0 && !is_ctrl_dof(P, d)) ? (real)m->home[d] : qik[d];
     }
     physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik, mode != B2E_MODE_HOLD && P->task == B2E_TASK_GRASP);
     if (mode == B2E_MODE_ACTION) {
@@ -1112,7 +1131,24 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
     /* _termination (:301-316) then _compute_reward (:318-331) */
     real d1 = dist3(raw, e.cpos), d2 = 0, rew;
     int dn = 0;
-    if (P->task == B2E_TASK_PUSH) {
+    if (P->reward_kind == B2E_REWARD_ICUB_REACH) { /* icub_reach_gym_env.py:301-330: the bonus is ADDED */
+      if (d1 <= P->dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P->max_steps) dn = 1;
+      rew = -d1;
+      if (d1 <= P->dist_min) rew += (real)1000.0 + (100 - d1 * 80);
+    } else if (P->reward_kind == B2E_REWARD_ICUB_PUSH0 || P->reward_kind == B2E_REWARD_ICUB_PUSH1) {
+      /* icub_push_gym_env.py:327-373 */
+      d2 = dist3(e.cpos, target);
+      if (d2 <= P->dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P->max_steps) dn = 1;
+      if (P->reward_kind == B2E_REWARD_ICUB_PUSH0) rew = -d1 - d2;
+      else {
+        real d0 = S->shaping[b * 2], dmax = S->shaping[b * 2 + 1];
+        rew = (real)0.125 * (1 - d1 / d0);
+        if (!(d1 > (real)0.1)) rew += (real)0.25 * (1 - d2 / dmax);
+      }
+      if (d2 <= P->dist_min) rew += (real)1000.0;
+    } else if (P->task == B2E_TASK_PUSH) {
       d2 = dist3(e.cpos, target);
       if (P->goal_env) { /* done = _termination() or is_success; reward = -(d > dist_min) (:96-122) */
         dn = (counter > P->max_steps) || (d2 <= P->dist_min);

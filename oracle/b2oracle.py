@@ -28,7 +28,7 @@ def build(force=False):
 class _State(C.Structure):
     _fields_ = [("B", C.c_int32)] + [(n, C.c_void_p) for n in (
         "q", "qd", "obj_pose", "obj_vel", "target", "mtarget", "counters", "cache_key", "cache_lam",
-        "hand_pose", "status", "raw_obs", "contacts")]
+        "hand_pose", "status", "raw_obs", "contacts", "shaping")]
 
 
 FIELDS = {  # name -> (width fn(n_dof, n_obs), dtype)
@@ -39,6 +39,7 @@ FIELDS = {  # name -> (width fn(n_dof, n_obs), dtype)
     "cache_lam": (lambda nd, no: CACHE_SLOTS * 3, np.float32), "hand_pose": (lambda nd, no: 6, np.float32),
     "status": (lambda nd, no: 4, np.int32), "raw_obs": (lambda nd, no: no, np.float32),
     "contacts": (lambda nd, no: MAX_CONTACTS * 8, np.float32),
+    "shaping": (lambda nd, no: 2, np.float32),
 }
 
 

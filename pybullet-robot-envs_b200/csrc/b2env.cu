@@ -91,6 +91,7 @@ struct DevModel {
   int dof_link[NLMAX];
   unsigned link_dofmask[NLMAX];  // dofs on the path base -> link (inclusive)
   unsigned acc_sched[2][NLMAX];  // child->parent accumulation schedule: 4-bit source lane per round (15 = none)
+  signed char tsched[24][NLMAX]; // tree kernel (b2env_tree.cuh): source lane per round, -1 = none
   float jpos[NLMAX][3], jrot[NLMAX][9], axis[NLMAX][3];
   float mass[NLMAX], com[NLMAX][3], inertia[NLMAX][9];
   float lower[NLMAX], upper[NLMAX], limit_margin[NLMAX], max_force[NLMAX], max_vel[NLMAX], joint_damping[NLMAX],
@@ -114,10 +115,12 @@ struct DevState {
   float* q; float* qd; float* obj_pose; float* obj_vel; float* target; float* mtarget;
   int* counters; int* cache_key; float* cache_lam; float* hand_pose; int* status; float* raw_obs; float* contacts;
   float* scratch;  // [B][SCRATCH_PER_ENV]: A | W | W^T of a big system when no overflow slot of the block is free
+  float* shaping;
 };
 
 struct b2e_sim {
   int B, device;
+  int tree;   // 0: 16-lane group kernel (<= 12 links, <= 9 dofs: the Panda), 1: warp-per-env tree kernel (<= 32 bodies: the iCub)
   b2e_model model;
   b2e_params params;
   DevModel* d_model;
@@ -1666,6 +1669,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   }
 }
 
+#include "b2env_tree.cuh"
+
 // masked reset: home joint state, object pose, target, counters, empty cache
 __global__ void reset_kernel(const DevModel* __restrict__ M, const b2e_params P, DevState st,
                              const uint8_t* __restrict__ mask, const float* __restrict__ obj_init_pose,
@@ -1689,6 +1694,7 @@ __global__ void reset_kernel(const DevModel* __restrict__ M, const b2e_params P,
   }
   for (int k = 0; k < 6; k++) st.hand_pose[env * 6 + k] = P.home_hand_pose[k];
   for (int k = 0; k < 4; k++) st.status[env * 4 + k] = 0;
+  st.shaping[env * 2] = 1.f; st.shaping[env * 2 + 1] = 1.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1707,15 +1713,26 @@ static int field_width(const b2e_sim* s, int f) {
     case B2E_F_STATUS: return 4;
     case B2E_F_RAW_OBS: return s->params.n_obs;
     case B2E_F_CONTACTS: return B2E_MAX_CONTACTS * 8;
+    case B2E_F_SHAPING: return 2;
     default: return -1;
   }
 }
 
-static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
+static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* tree_out) {
   memset(d, 0, sizeof(*d));
   memset(u, 0, sizeof(*u));
-  if (m->n_links > TLMAX || m->n_links < 1) return fail(B2E_EUNSUPPORTED, "group kernel supports <= 12 links%s", "");
-  if (m->n_dof > NDMAX) return fail(B2E_EUNSUPPORTED, "warp kernel supports <= 9 dofs%s", "");
+  if (m->n_links < 1 || m->n_dof < 1) return fail(B2E_EINVAL, "empty model%s", "");
+  // kernel choice: the 16-lane group kernel for small chains (the Panda), else the warp-per-env tree kernel,
+  // which wants one body per movable joint (model.merge_fixed_links) so that lane = body = dof
+  const bool tree = m->n_links > TLMAX || m->n_dof > NDMAX;
+  *tree_out = tree ? 1 : 0;
+  if (tree) {
+    if (m->n_links > NLMAX || m->n_dof != m->n_links)
+      return fail(B2E_EUNSUPPORTED, "tree kernel: <= 32 bodies, one per movable joint (merge fixed links on the host)%s", "");
+    for (int i = 0; i < m->n_links; i++)
+      if (m->dof[i] != i || m->jtype[i] == B2E_JOINT_FIXED)
+        return fail(B2E_EUNSUPPORTED, "tree kernel: body i must carry dof i%s", "");
+  }
   if (m->n_spheres > B2E_MAX_SPHERES || m->n_spheres < 0) return fail(B2E_EINVAL, "bad n_spheres%s", "");
   d->n_links = m->n_links; d->n_dof = m->n_dof; d->ee_link = m->ee_link; d->n_spheres = m->n_spheres;
   int maxdepth = 1;
@@ -1738,8 +1755,32 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
   int rounds = 0;
   while ((1 << rounds) < maxdepth) rounds++;
   d->fk_rounds = rounds;
-  // child->parent accumulation schedule (heavy-path decomposition)
-  {
+  if (tree) {
+    // child -> parent accumulation schedule: every round, each body pulls at most one child whose own subtree is
+    // complete (greedy, deepest bodies first)
+    const int n = m->n_links;
+    int pending[NLMAX], folded[NLMAX];
+    for (int i = 0; i < n; i++) { pending[i] = 0; folded[i] = 0; }
+    for (int i = 0; i < n; i++) if (m->parent[i] >= 0) pending[m->parent[i]]++;
+    int left = 0, rounds = 0;
+    for (int i = 0; i < n; i++) if (m->parent[i] >= 0) left++;
+    while (left > 0) {
+      if (rounds >= 24) return fail(B2E_EUNSUPPORTED, "kinematic tree needs more than 24 accumulation rounds%s", "");
+      int busy[NLMAX], pick[NLMAX], np = 0;
+      for (int l = 0; l < NLMAX; l++) { d->tsched[rounds][l] = -1; busy[l] = 0; }
+      for (int i = n - 1; i >= 0; i--) {
+        const int p = m->parent[i];
+        if (p < 0 || folded[i] || pending[i] > 0 || busy[p]) continue;
+        d->tsched[rounds][p] = (signed char)i;
+        busy[p] = 1;
+        pick[np++] = i;
+      }
+      for (int k = 0; k < np; k++) { folded[pick[k]] = 1; pending[m->parent[pick[k]]]--; left--; }
+      rounds++;
+    }
+    u->acc_rounds = rounds;
+  } else {
+    // child->parent accumulation schedule (heavy-path decomposition)
     const int n = m->n_links;
     int size[TLMAX], heavy[TLMAX], depth[TLMAX], head[TLMAX];
     for (int i = 0; i < n; i++) { size[i] = 1; heavy[i] = -1; }
@@ -1800,10 +1841,25 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u) {
 }
 
 #define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
+#define TREE_SMEM_BYTES (sizeof(TreeSmem) * TREE_WPB)
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
   if (n <= 0) return 0;
+  if (s->tree) {
+    const int tb = (n + TREE_WPB - 1) / TREE_WPB;
+    if (s->params.use_ik)
+      B2E_LAUNCH(tree_step_kernel<true>, tb, 32 * TREE_WPB, TREE_SMEM_BYTES, stream,
+          s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
+          env_offset);
+    else
+      B2E_LAUNCH(tree_step_kernel<false>, tb, 32 * TREE_WPB, TREE_SMEM_BYTES, stream,
+          s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
+          env_offset);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
   if (s->params.use_ik)
     B2E_LAUNCH(step_kernel<true>, blocks, 32 * WPB, SMEM_BYTES, stream,
@@ -1830,7 +1886,11 @@ __global__ void rows_kernel(float* field, const int* __restrict__ ids, int n, in
 extern "C" {
 
 const char* b2e_last_error(void) { return g_err; }
-const char* b2e_version(void) { return "b2env 0.2 (sm_100a, two environments per warp)"; }
+#ifdef B2E_EMU
+const char* b2e_version(void) { return "b2env 0.3 EMULATION (host build of the CUDA source: test infrastructure, not the product)"; }
+#else
+const char* b2e_version(void) { return "b2env 0.3 (sm_100a; Panda: two environments per warp, iCub: one warp per environment)"; }
+#endif
 
 int b2e_field_elem_size(int field) {
   (void)field;
@@ -1851,11 +1911,15 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaSetDevice(device));
   DevModel hm;
   DevModelU hu;
-  int rc = build_dev_model(model, &hm, &hu);
+  int tree = 0;
+  int rc = build_dev_model(model, &hm, &hu, &tree);
   if (rc) return rc;
+  if (!tree && params->n_obs_joints > 0)
+    return fail(B2E_EUNSUPPORTED, "b2e_create: joint lists (n_obs_joints > 0) need the tree kernel%s", "");
+  if (tree && params->task == B2E_TASK_GRASP) return fail(B2E_EUNSUPPORTED, "b2e_create: the grasp task needs the Panda model%s", "");
   b2e_sim* s = new b2e_sim();
   memset(s, 0, sizeof(*s));
-  s->B = num_envs; s->device = device; s->model = *model; s->params = *params; s->umodel = hu;
+  s->B = num_envs; s->device = device; s->model = *model; s->params = *params; s->umodel = hu; s->tree = tree;
   CUDA_TRY(cudaMalloc(&s->d_model, sizeof(DevModel)));
   CUDA_TRY(cudaMemcpy(s->d_model, &hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   for (int f = 0; f < B2E_F_COUNT; f++) {
@@ -1872,6 +1936,7 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   s->st.cache_lam = (float*)s->fields[B2E_F_CACHE_LAM]; s->st.hand_pose = (float*)s->fields[B2E_F_HAND_POSE];
   s->st.status = (int*)s->fields[B2E_F_STATUS]; s->st.raw_obs = (float*)s->fields[B2E_F_RAW_OBS];
   s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
+  s->st.shaping = (float*)s->fields[B2E_F_SHAPING];
   CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
   const size_t na = (size_t)num_envs * (params->n_act > 0 ? params->n_act : 1) * 4, no = (size_t)num_envs * params->n_obs * 4;
   CUDA_TRY(cudaMalloc(&s->d_action, na)); CUDA_TRY(cudaMalloc(&s->d_obs, no));
@@ -1882,6 +1947,8 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
   *out = s;
   return 0;
 }

@@ -1,0 +1,1130 @@
+// b2env_tree.cuh — the fused step kernel for kinematic TREES of up to 32 bodies (the iCub: 32 revolute joints
+// after the six welded F/T-sensor links are folded into their parents), included by b2env.cu.
+//
+// One env.step() of the reference's iCub task envs (icub_envs/icub_push_gym_env.py:271-282,
+// icub_reach_gym_env.py:248-259): hand-pose increment + clamps (:227-253) -> damped-least-squares IK
+// (icub_env.py:303-317) -> 32 position motors (:319-326) -> p.stepSimulation (:263) -> observation
+// (:166-203, icub_env.py:202-249) -> termination (:327-342) -> reward (:344-373), one launch.
+//
+// Mapping: ONE WARP = ONE ENVIRONMENT, lane = body = dof (a body is the child of its movable joint, so
+// body index == dof index; fixed joints are merged on the host).  The statement is the one of the 16-lane
+// Panda kernel: world-frame composite-rigid-body inertia matrix, Gauss-Jordan inverse held one
+// row per lane, Delassus-form projected Gauss-Seidel with lane = constraint row (32 motor rows = one row per
+// lane, then up to 32 "generic" rows: joint limits and contact normals / frictions).
+
+#define TREE_WPB 4      // warps (= environments) per block
+#define TREE_MAXC 8     // contacts kept per env (4 cube-table + 4 proxy contacts): 3 + 3*8 = 27 generic rows <= 32
+#define TREE_WS 40      // row stride of the W table (32 arm dofs + 6 cube components, padded)
+#define TREE_ROUNDS 24  // child -> parent accumulation rounds the host schedule may use
+#define SHW(v, src) __shfl_sync(FULL, (v), (src))
+
+struct TreeSmem {
+  float Minv[32][33];        // joint-space inertia, then its inverse (row stride 33: conflict-free column reads)
+  float A[32 * 32];          // generic x generic Delassus block, A[c*32 + r]
+  float W[32 * TREE_WS];     // W[g][k] = (M^-1 J_g^T)_k; k < 32 arm dofs, 32..37 cube (lin, ang)
+  float WT[32 * 32];         // WT[d][g] = W[g][d]: what motor row d reads (unit stride over g)
+  float T[32][12];           // body world transforms: R (9) + p (3)
+  float S[32][6];            // world spatial axes about O = base position: (w ; v_O)
+  float vstar[TREE_WS];      // unconstrained velocities (32 arm + 6 cube)
+  float mlam[32];            // motor-row impulses
+  float glam[32];            // generic-row impulses
+  float scr[6 * 32];         // IK: Jacobian rows; later the observation staging
+  Contact con[TREE_MAXC];
+  float con_cfm[TREE_MAXC];
+  int lim_d[4];
+  float lim_dist[4];
+  int ckey[B2E_CACHE_SLOTS];
+  float clam[B2E_CACHE_SLOTS][3];
+};
+
+__device__ __forceinline__ float wmaxf(float v) {   // max of non-negative floats over the warp
+  return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
+}
+__device__ __forceinline__ float wsumf(float v) {   // butterfly sum: every lane gets the same bits
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// forward kinematics, lane = body: local joint transform, composition along the tree by pointer jumping
+__device__ __forceinline__ void tree_fk(const DevModel* __restrict__ M, const DevModelU& U, int lane, float qi, float* R,
+                                        float* p) {
+  const int nl = U.n_links;
+  const bool act = lane < nl;
+  const int li = act ? lane : 0;
+  float jr[9], ax[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) jr[k] = __ldg(&M->jrot[li][k]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ax[k] = __ldg(&M->axis[li][k]); p[k] = __ldg(&M->jpos[li][k]); }
+  const int jt = __ldg(&M->jtype[li]);
+  if (jt == B2E_JOINT_REVOLUTE) {
+    float s, c;
+    sincosf(qi, &s, &c);
+    const float t = 1 - c, x = ax[0], y = ax[1], z = ax[2];
+    const float Rq[9] = {t * x * x + c,     t * x * y - s * z, t * x * z + s * y,
+                         t * x * y + s * z, t * y * y + c,     t * y * z - s * x,
+                         t * x * z - s * y, t * y * z + s * x, t * z * z + c};
+    m3mul(jr, Rq, R);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = jr[k];
+    if (jt == B2E_JOINT_PRISMATIC) {
+      const float t[3] = {ax[0] * qi, ax[1] * qi, ax[2] * qi};
+      float o[3];
+      m3vec(jr, t, o);
+      p[0] += o[0]; p[1] += o[1]; p[2] += o[2];
+    }
+  }
+  int anc = act ? __ldg(&M->parent[li]) : -1;
+  const int rounds = U.fk_rounds;
+  for (int rd = 0; rd < rounds; rd++) {
+    const int src = anc < 0 ? 0 : anc;
+    float Ra[9], pa[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ra[k] = SHW(R[k], src);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pa[k] = SHW(p[k], src);
+    const int anca = SHW(anc, src);
+    if (anc >= 0) {
+      float Rn[9], o[3];
+      m3mul(Ra, R, Rn);
+      m3vec(Ra, p, o);
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = Rn[k];
+      p[0] = pa[0] + o[0]; p[1] = pa[1] + o[1]; p[2] = pa[2] + o[2];
+      anc = anca;
+    }
+  }
+  {  // base pose
+    float Rb[9], Rn[9], o[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rb[k] = U.base_rot[k];
+    m3mul(Rb, R, Rn);
+    m3vec(Rb, p, o);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rn[k];
+    p[0] = U.base_pos[0] + o[0]; p[1] = U.base_pos[1] + o[1]; p[2] = U.base_pos[2] + o[2];
+  }
+}
+
+// inclusive sum over the path base..body of a 6-vector held per body lane (pointer jumping)
+__device__ __forceinline__ void tree_path_sum6(const DevModel* __restrict__ M, const DevModelU& U, int lane, float* x) {
+  int anc = lane < U.n_links ? __ldg(&M->parent[lane]) : -1;
+  const int rounds = U.fk_rounds;
+  for (int rd = 0; rd < rounds; rd++) {
+    const int src = anc < 0 ? 0 : anc;
+    float xa[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) xa[k] = SHW(x[k], src);
+    const int anca = SHW(anc, src);
+    if (anc >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) x[k] += xa[k];
+      anc = anca;
+    }
+  }
+}
+
+// Damped-least-squares IK (p.calculateInverseKinematics with jointDamping, icub_env.py:307-312): the statement
+// of oracle/b2oracle.c ik_dls.  Every joint on the base -> hand path is a controlled joint with damping 0.1 and
+// the blocked joints (damping 100) have zero Jacobian columns, so (J^T J + D)^-1 J^T e = J^T (J J^T + 0.1 I)^-1 e.
+// lane = dof for the Jacobian column and dq; lanes 0..5 hold the rows of the 6x6 system.
+__device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M, const DevModelU& U, int max_iters,
+                                      float residual, float damping, int lane, float my_q, float tpx, float tpy, float tpz,
+                                      float tqx, float tqy, float tqz, float tqw) {
+  const int nl = U.n_links, ee = U.ee_link;
+  const int li = lane < nl ? lane : 0;
+  const bool on_path = lane < nl && ((U.ee_dofmask >> lane) & 1u);
+  const int jt = __ldg(&M->jtype[li]);
+  const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
+  float qv = my_q;
+  for (int it = 0; it < max_iters; it++) {
+    float R[9], p[3];
+    tree_fk(M, U, lane, lane < nl ? qv : 0.f, R, p);
+    float pe[3], Re[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pe[k] = SHW(p[k], ee);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Re[k] = SHW(R[k], ee);
+    const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
+    if (sqrtf(dot3(dp, dp)) <= residual) break;   // warp-uniform
+    float cq[4], eq[4], er[3];
+    mat_to_quat(Re, cq);
+    {
+      const float tq[4] = {tqx, tqy, tqz, tqw}, cc[4] = {-cq[0], -cq[1], -cq[2], cq[3]};
+      quat_mul(tq, cc, eq);
+    }
+    if (eq[3] < 0) { eq[0] = -eq[0]; eq[1] = -eq[1]; eq[2] = -eq[2]; eq[3] = -eq[3]; }
+    const float vn = sqrtf(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2]);
+    if (vn > 1e-9f) {
+      const float ang = 2.f * atan2f(vn, eq[3]);
+      er[0] = eq[0] / vn * ang; er[1] = eq[1] / vn * ang; er[2] = eq[2] / vn * ang;
+    } else { er[0] = er[1] = er[2] = 0.f; }
+    float c[6] = {0, 0, 0, 0, 0, 0};   // Jacobian column of this joint
+    if (on_path) {
+      float aw[3];
+      m3vec(R, ax, aw);
+      if (jt == B2E_JOINT_REVOLUTE) {
+        const float rel[3] = {pe[0] - p[0], pe[1] - p[1], pe[2] - p[2]};
+        cross3(aw, rel, c);
+        c[3] = aw[0]; c[4] = aw[1]; c[5] = aw[2];
+      } else {
+        c[0] = aw[0]; c[1] = aw[1]; c[2] = aw[2];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; k++) scr[k * 32 + lane] = c[k];
+    __syncwarp();
+    const int r = lane < 6 ? lane : 0;   // lane r < 6: row r of J J^T + lambda I, augmented with e_r
+    float Ur[7];
+#pragma unroll
+    for (int cc2 = 0; cc2 < 6; cc2++) {
+      float acc = (cc2 == r) ? damping : 0.f;
+      for (int d = 0; d < 32; d++) acc = fmaf(scr[r * 32 + d], scr[cc2 * 32 + d], acc);
+      Ur[cc2] = acc;
+    }
+    Ur[6] = r < 3 ? (r == 0 ? dp[0] : (r == 1 ? dp[1] : dp[2])) : (r == 3 ? er[0] : (r == 4 ? er[1] : er[2]));
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      float rk[7];
+#pragma unroll
+      for (int j = 0; j < 7; j++) rk[j] = SHW(Ur[j], k);
+      const float pinv = 1.0f / rk[k];
+      if (lane == k) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) Ur[j] = rk[j] * pinv;
+      } else {
+        const float f = Ur[k] * pinv;
+#pragma unroll
+        for (int j = 0; j < 7; j++) Ur[j] = fmaf(-f, rk[j], Ur[j]);
+      }
+    }
+    float dq = 0.f;   // dq_d = sum_r J[r][d] x_r
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) dq = fmaf(c[rr], SHW(Ur[6], rr), dq);
+    const float mx = wmaxf(fabsf(dq));
+    const float scale = mx > 0.78539816339f ? 0.78539816339f / mx : 1.f;
+    qv = fmaf(dq, scale, qv);
+  }
+  __syncwarp();
+  return qv;
+}
+
+struct TreeRow {   // the generic row of this lane
+  float lam, u, base, gg, invd, diag, lo, hi, mu, prev;
+  int type, isl, nidx;
+};
+
+// Projected Gauss-Seidel on the Delassus form: rows in Bullet's order (motors, limits, contact normals, then the
+// frictions bounded by mu * normal impulse); the arm island and the cube island converge independently unless a
+// proxy-cube contact couples them.  Same iteration as oracle/b2oracle.c physics_step.  Warp-uniform control flow.
+__device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, TreeRow& r, int nd, int RG, int fric_start,
+                                        bool coupled, bool has_cube_rows, int max_iters, float tol) {
+  const bool valid = lane < RG, fr = lane >= fric_start;
+  const bool cube = !coupled && r.isl == 1;
+  const unsigned arm_nf = __ballot_sync(FULL, valid && !cube && !fr), arm_f = __ballot_sync(FULL, valid && !cube && fr);
+  const unsigned cube_nf = __ballot_sync(FULL, valid && cube && !fr), cube_f = __ballot_sync(FULL, valid && cube && fr);
+  const float* Minv = &sm.Minv[0][0];
+  bool done0 = false, done1 = !has_cube_rows || coupled;
+  int it = 0;
+  for (; it < max_iters; it++) {
+    if (done0 && done1) break;
+    m.prev = m.lam;
+    r.prev = r.lam;
+    r.base = r.lam * r.gg;
+    if (!done0) {
+      for (int i = 0; i < nd; i++) {   // motor rows: Delassus column i = [M^-1[:, i] ; W_g[i]]
+        const float cm = Minv[i * 33 + lane], cg = sm.WT[i * 32 + lane];
+        float nl = fmaf(m.u, m.invd, m.lam);
+        nl = fminf(fmaxf(nl, m.lo), m.hi);
+        const float dli = SHW(nl - m.lam, i);
+        if (lane == i) m.lam = nl;
+        m.u = fmaf(-cm, dli, m.u);
+        r.u = fmaf(-cg, dli, r.u);
+      }
+    }
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+      unsigned mk = phase == 0 ? ((done0 ? 0u : arm_nf) | (done1 ? 0u : cube_nf)) : ((done0 ? 0u : arm_f) | (done1 ? 0u : cube_f));
+      if (phase == 1 && mk != 0u) {   // friction bounds from the current normal impulses
+        const float v = SHW(r.lam, r.nidx);
+        if (r.type == ROW_FRICTION) { const float lim = r.mu * v; r.lo = -lim; r.hi = lim; }
+      }
+      while (mk) {
+        const int g = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const float ca = sm.A[g * 32 + lane], cw = sm.W[g * TREE_WS + lane];
+        float nl = fmaf(r.u, r.invd, r.base);
+        nl = fminf(fmaxf(nl, r.lo), r.hi);
+        const float dli = SHW(nl - r.lam, g);
+        if (lane == g) r.lam = nl;
+        m.u = fmaf(-cw, dli, m.u);
+        r.u = fmaf(-ca, dli, r.u);
+      }
+    }
+    float ra = 0.f, rc = 0.f;
+    if (!done0 && lane < nd) {
+      const float rv = (m.lam - m.prev) * m.diag;
+      ra = rv * rv;
+    }
+    if (valid) {
+      float rv = (r.lam - r.prev) * r.diag;
+      rv = rv * rv;
+      if (coupled || r.isl == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
+    }
+    ra = wmaxf(ra);
+    rc = wmaxf(rc);
+    if (!done0 && ra <= tol) done0 = true;
+    if (!done1 && rc <= tol) done1 = true;
+    if (done0 && done1) { it++; break; }
+  }
+  return it;
+}
+
+template <bool IK>
+__global__ void __launch_bounds__(32 * TREE_WPB, 2)
+tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P,
+                 DevState st, const float* __restrict__ action, float* __restrict__ obs_out, float* __restrict__ reward_out,
+                 float* __restrict__ done_out, int nsub, int mode, int record_contacts, const int* __restrict__ env_ids,
+                 int n_ids, int env_offset) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slots = n_ids;
+  const int slot = blockIdx.x * TREE_WPB + warp;
+  const bool live_env = slot < n_slots;   // padding warps of the last block shadow the last slot, stores masked
+  const int slot_c = live_env ? slot : n_slots - 1;
+  const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
+  TreeSmem& sm = reinterpret_cast<TreeSmem*>(smem_raw)[warp];
+  const int nd = U.n_dof, nl = U.n_links;   // nl == nd: body index == dof index
+  const float dt = P.dt;
+  const int maxc = (P.max_contacts > 0 && P.max_contacts < TREE_MAXC) ? P.max_contacts : TREE_MAXC;
+
+  // ---- load state ----
+  const bool is_dof = lane < nd;
+  const int li = is_dof ? lane : 0;
+  float my_q = is_dof ? st.q[env * nd + lane] : 0.f;
+  float my_qd = is_dof ? st.qd[env * nd + lane] : 0.f;
+  float my_target = is_dof ? st.mtarget[env * nd + lane] : 0.f;
+  float cpos[3], cquat[4], cv[3], cw[3], target[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    cpos[k] = st.obj_pose[env * 7 + k];
+    cv[k] = st.obj_vel[env * 6 + k];
+    cw[k] = st.obj_vel[env * 6 + 3 + k];
+    target[k] = st.target[env * 3 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) cquat[k] = st.obj_pose[env * 7 + 3 + k];
+  int counter = st.counters[env * 2], terminated = st.counters[env * 2 + 1];
+  int flags = st.status[env * 4];
+  if (lane < B2E_CACHE_SLOTS) {
+    sm.ckey[lane] = st.cache_key[env * B2E_CACHE_SLOTS + lane];
+#pragma unroll
+    for (int j = 0; j < 3; j++) sm.clam[lane][j] = st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j];
+  }
+  // joint lists of the task (icub_env.py:121-143): which action entry drives this dof, which observation
+  // entry shows it, whether it is a controlled joint
+  int act_idx = -1, obs_idx = -1;
+  bool is_ctrl;
+  if (P.n_obs_joints > 0) {
+    for (int k = 0; k < P.n_ctrl; k++) if (P.ctrl_dof[k] == lane) act_idx = k;
+    for (int k = 0; k < P.n_obs_joints; k++) if (P.obs_dof[k] == lane) obs_idx = k;
+    is_ctrl = is_dof && ((P.ctrl_mask >> lane) & 1u);
+  } else {
+    act_idx = lane < P.n_ctrl ? lane : -1;
+    obs_idx = is_dof ? lane : -1;
+    is_ctrl = lane < P.n_ctrl;
+  }
+  const int n_qobs = P.n_obs_joints > 0 ? P.n_obs_joints : nd;
+  float my_act = 0.f;   // joint mode: the action entry of this dof; IK mode: entry `lane` of the hand-pose increment
+  if (mode == B2E_MODE_ACTION) {
+    if (IK) { if (lane < P.n_act) my_act = action[env * P.n_act + lane]; }
+    else if (act_idx >= 0) my_act = action[env * P.n_act + act_idx];
+  }
+  float my_hp = (IK && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;
+  const float my_lower = is_dof ? __ldg(&M->lower[li]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[li]) : 0.f;
+  const float my_home = is_dof ? __ldg(&M->home[li]) : 0.f;
+  const bool ctrl_gains = !IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE;
+  const float my_kp = (ctrl_gains && is_ctrl) ? P.kp_ctrl : P.kp_hold;
+  int iters = 0, nc = 0, R = 0;
+  bool stop = false;
+  __syncwarp();
+
+  float Rm[9], pw[3];
+  for (int sub = 0;; sub++) {
+    // ---- forward kinematics of the current q (start of this sub-step = end of the previous one) ----
+    tree_fk(M, U, lane, is_dof ? my_q : 0.f, Rm, pw);
+    // ---- termination inside apply_action (icub_push_gym_env.py:266-269), for the previous sub-step ----
+    {
+      float e3[3];
+      {
+        const float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]};
+        float o[3];
+        m3vec(Rm, cm, o);
+        e3[0] = SHW(pw[0] + o[0], U.ee_link); e3[1] = SHW(pw[1] + o[1], U.ee_link); e3[2] = SHW(pw[2] + o[2], U.ee_link);
+      }
+      if (sub > 0 && mode == B2E_MODE_ACTION && !stop) {
+        float d;
+        if (P.task == B2E_TASK_PUSH) {
+          const float dd[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+          d = sqrtf(dot3(dd, dd));
+        } else {
+          const float dd[3] = {e3[0] - cpos[0], e3[1] - cpos[1], e3[2] - cpos[2]};
+          d = sqrtf(dot3(dd, dd));
+        }
+        if (P.goal_env) { if (counter > P.max_steps) stop = true; else counter++; }
+        else if (d <= P.dist_min) { terminated = 1; stop = true; }
+        else if (terminated || counter > P.max_steps) stop = true;
+        else counter++;
+      }
+    }
+    if (sub >= nsub) break;
+    const bool ghost = stop;   // terminated mid-repeat: keep pace, change nothing
+
+    // ---- action -> motor targets ----
+    if (!IK && mode == B2E_MODE_ACTION && act_idx >= 0 && !ghost) {   // icub_push_gym_env.py:256-257, icub_env.py:347-361
+      my_act *= P.act_scale;
+      my_target = fminf(fmaxf(my_q + my_act, my_lower), my_upper);
+    }
+    if (IK && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE)) {
+      // Cartesian control (icub_push_gym_env.py:227-253, icub_env.py:261-326): hand pose += scaled action,
+      // clamps, COM -> link frame, IK, blocked joints -> rest pose, position targets for all 32 joints
+      if (mode == B2E_MODE_ACTION && !ghost && lane < 6) {
+        if (lane < 3) {
+          my_act *= P.act_scale_pos;
+          my_hp = fminf(fmaxf(my_hp + my_act, P.ws_lim[lane][0]), P.ws_lim[lane][1]);
+        } else if (P.ik_orientation) {
+          my_act *= P.act_scale_rot;
+          my_hp = fminf(fmaxf(my_hp + my_act, P.eu_lim[lane - 3][0]), P.eu_lim[lane - 3][1]);
+        }
+      }
+      float tp[3], eu[3], tq[4];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        tp[k] = SHW(my_hp, k);
+        const float e = SHW(my_hp, 3 + k);
+        eu[k] = P.ik_orientation ? fminf(fmaxf(e, P.eu_lim[k][0]), P.eu_lim[k][1]) : P.home_hand_pose[3 + k];
+      }
+      tp[2] = fminf(fmaxf(tp[2], P.ws_lim[2][0]), P.ws_lim[2][1]);
+      euler_to_quat(eu, tq);
+      {
+        float Rt[9], o[3];
+        const float off[3] = {P.ik_link_offset[0], P.ik_link_offset[1], P.ik_link_offset[2]};
+        quat_to_mat(tq, Rt);
+        m3vec(Rt, off, o);
+        tp[0] += o[0]; tp[1] += o[1]; tp[2] += o[2];
+      }
+      const float t = tree_ik(sm.scr, M, U, P.ik_iters, P.ik_residual, P.ik_damping, lane, my_q, tp[0], tp[1], tp[2], tq[0],
+                              tq[1], tq[2], tq[3]);
+      if (is_dof && !ghost) my_target = (P.n_obs_joints > 0 && !is_ctrl) ? my_home : t;
+    }
+    if (is_dof) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) sm.T[lane][k] = Rm[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) sm.T[lane][9 + k] = pw[k];
+    }
+
+    // ---- dynamics in world coordinates about O = base position ----
+    float S[6] = {0, 0, 0, 0, 0, 0};
+    float Iw[16];   // f(6) | m | h(3) | I_O(6): summed over the subtree below
+    {
+      const int jt = __ldg(&M->jtype[li]);
+      const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
+      float aw[3];
+      m3vec(Rm, ax, aw);
+      const float rel[3] = {pw[0] - U.base_pos[0], pw[1] - U.base_pos[1], pw[2] - U.base_pos[2]};
+      if (is_dof && jt == B2E_JOINT_REVOLUTE) {
+        float t[3];
+        cross3(rel, aw, t);
+        S[0] = aw[0]; S[1] = aw[1]; S[2] = aw[2]; S[3] = t[0]; S[4] = t[1]; S[5] = t[2];
+      } else if (is_dof && jt == B2E_JOINT_PRISMATIC) {
+        S[3] = aw[0]; S[4] = aw[1]; S[5] = aw[2];
+      }
+      const float cm[3] = {__ldg(&M->com[li][0]), __ldg(&M->com[li][1]), __ldg(&M->com[li][2])};
+      float c[3];
+      m3vec(Rm, cm, c);
+      c[0] += rel[0]; c[1] += rel[1]; c[2] += rel[2];
+      const float ms = is_dof ? __ldg(&M->mass[li]) : 0.f;
+      float Ic[9], RI[9], Icw[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Ic[k] = is_dof ? __ldg(&M->inertia[li][k]) : 0.f;
+      m3mul(Rm, Ic, RI);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Icw[3 * i + j] = RI[3 * i] * Rm[3 * j] + RI[3 * i + 1] * Rm[3 * j + 1] + RI[3 * i + 2] * Rm[3 * j + 2];
+      const float cc = dot3(c, c);
+      Iw[6] = ms;
+      Iw[7] = ms * c[0]; Iw[8] = ms * c[1]; Iw[9] = ms * c[2];
+      Iw[10] = Icw[0] + ms * (cc - c[0] * c[0]);
+      Iw[11] = Icw[1] - ms * c[0] * c[1];
+      Iw[12] = Icw[2] - ms * c[0] * c[2];
+      Iw[13] = Icw[4] + ms * (cc - c[1] * c[1]);
+      Iw[14] = Icw[5] - ms * c[1] * c[2];
+      Iw[15] = Icw[8] + ms * (cc - c[2] * c[2]);
+    }
+    float vJ[6], v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { vJ[k] = S[k] * my_qd; v[k] = vJ[k]; }
+    tree_path_sum6(M, U, lane, v);
+    float ab[6];
+    {
+      float a[3], b[3], c2[3];
+      cross3(v, vJ, a);
+      cross3(v, vJ + 3, b);
+      cross3(v + 3, vJ, c2);
+      ab[0] = a[0]; ab[1] = a[1]; ab[2] = a[2];
+      ab[3] = b[0] + c2[0]; ab[4] = b[1] + c2[1]; ab[5] = b[2] + c2[2];
+    }
+    tree_path_sum6(M, U, lane, ab);
+    ab[3] -= P.gravity[0]; ab[4] -= P.gravity[1]; ab[5] -= P.gravity[2];   // a_0 = -g
+    {
+      const float ms = Iw[6];
+      const float* h = &Iw[7];
+      const float* I = &Iw[10];
+      float Ia_n[3], Ia_f[3], Iv_n[3], Iv_f[3], t[3];
+      cross3(h, ab + 3, t);
+      Ia_n[0] = I[0] * ab[0] + I[1] * ab[1] + I[2] * ab[2] + t[0];
+      Ia_n[1] = I[1] * ab[0] + I[3] * ab[1] + I[4] * ab[2] + t[1];
+      Ia_n[2] = I[2] * ab[0] + I[4] * ab[1] + I[5] * ab[2] + t[2];
+      cross3(h, ab, t);
+      Ia_f[0] = ms * ab[3] - t[0]; Ia_f[1] = ms * ab[4] - t[1]; Ia_f[2] = ms * ab[5] - t[2];
+      cross3(h, v + 3, t);
+      Iv_n[0] = I[0] * v[0] + I[1] * v[1] + I[2] * v[2] + t[0];
+      Iv_n[1] = I[1] * v[0] + I[3] * v[1] + I[4] * v[2] + t[1];
+      Iv_n[2] = I[2] * v[0] + I[4] * v[1] + I[5] * v[2] + t[2];
+      cross3(h, v, t);
+      Iv_f[0] = ms * v[3] - t[0]; Iv_f[1] = ms * v[4] - t[1]; Iv_f[2] = ms * v[5] - t[2];
+      float x1[3], x2[3], x3[3];
+      cross3(v, Iv_n, x1);
+      cross3(v + 3, Iv_f, x2);
+      cross3(v, Iv_f, x3);
+      Iw[0] = Ia_n[0] + x1[0] + x2[0]; Iw[1] = Ia_n[1] + x1[1] + x2[1]; Iw[2] = Ia_n[2] + x1[2] + x2[2];
+      Iw[3] = Ia_f[0] + x3[0]; Iw[4] = Ia_f[1] + x3[1]; Iw[5] = Ia_f[2] + x3[2];
+    }
+    // child -> parent accumulation of [f | composite inertia]: host-built schedule, every round each lane pulls
+    // one finished child subtree (or nothing)
+    {
+      const int rounds = U.acc_rounds;
+      for (int rd = 0; rd < rounds; rd++) {
+        const int src = __ldg(&M->tsched[rd][lane]);
+        const int s = src < 0 ? lane : src;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const float o = SHW(Iw[k], s);
+          if (src >= 0) Iw[k] += o;
+        }
+      }
+    }
+    if (is_dof) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) sm.S[lane][k] = S[k];
+    }
+    // F = I^c S ; tau_bias = S . f^c
+    float F[6];
+    {
+      const float ms = Iw[6];
+      const float* h = &Iw[7];
+      const float* I = &Iw[10];
+      float t[3];
+      cross3(h, S + 3, t);
+      F[0] = I[0] * S[0] + I[1] * S[1] + I[2] * S[2] + t[0];
+      F[1] = I[1] * S[0] + I[3] * S[1] + I[4] * S[2] + t[1];
+      F[2] = I[2] * S[0] + I[4] * S[1] + I[5] * S[2] + t[2];
+      cross3(h, S, t);
+      F[3] = ms * S[3] - t[0]; F[4] = ms * S[4] - t[1]; F[5] = ms * S[5] - t[2];
+    }
+    const float tau_b = S[0] * Iw[0] + S[1] * Iw[1] + S[2] * Iw[2] + S[3] * Iw[3] + S[4] * Iw[4] + S[5] * Iw[5];
+    // joint-space inertia: M[d][e] = S_e . F_d for every e on the path base..d; symmetric fill through smem
+    for (int k = lane; k < 32 * 33; k += 32) (&sm.Minv[0][0])[k] = 0.f;
+    __syncwarp();
+    {
+      unsigned pm = is_dof ? __ldg(&M->link_dofmask[li]) : 0u;
+      while (pm) {
+        const int e = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const float val = sm.S[e][0] * F[0] + sm.S[e][1] * F[1] + sm.S[e][2] * F[2] + sm.S[e][3] * F[3] + sm.S[e][4] * F[4] +
+                          sm.S[e][5] * F[5];
+        sm.Minv[lane][e] = val;
+        sm.Minv[e][lane] = val;
+      }
+    }
+    __syncwarp();
+    float a[32];
+#pragma unroll
+    for (int e = 0; e < 32; e++) a[e] = (is_dof && e < nd) ? sm.Minv[lane][e] : ((e == lane) ? 1.f : 0.f);
+    // in-place Gauss-Jordan inverse (M is symmetric positive definite: no pivoting), lane = row
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      float rk[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) rk[j] = SHW(a[j], k);
+      const float pinv = 1.0f / rk[k];
+      if (lane == k) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = (j == k) ? pinv : rk[j] * pinv;
+      } else {
+        const float f = a[k];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = (j == k) ? -f * pinv : fmaf(-f * pinv, rk[j], a[j]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) sm.Minv[lane][e] = (is_dof && e < nd) ? a[e] : 0.f;
+    sm.Minv[lane][32] = 0.f;
+    // unconstrained acceleration and v*
+    const float rhs_d = is_dof ? (-tau_b - __ldg(&M->joint_damping[li]) * my_qd) : 0.f;
+    float qdd = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; e++) qdd = fmaf(a[e], SHW(rhs_d, e), qdd);
+    const float vstar_d = is_dof ? my_qd + dt * qdd : 0.f;
+    float cvs[3], cws[3];
+    {
+      const float vn = sqrtf(dot3(cv, cv)), wn = sqrtf(dot3(cw, cw));
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        cvs[k] = cv[k] + dt * (P.gravity[k] - cv[k] * (P.damp_lin_k1 + P.damp_lin_k2 * vn));
+        cws[k] = cw[k] + dt * (-cw[k] * (P.damp_ang_k1 + P.damp_ang_k2 * wn));
+      }
+    }
+    sm.vstar[lane] = vstar_d;
+    if (lane < 8) sm.vstar[32 + lane] = lane < 3 ? cvs[lane] : (lane < 6 ? cws[lane - 3] : 0.f);
+    __syncwarp();
+
+    // ---- collision detection (pre-step poses): same canonical order and keys as the Panda kernel ----
+    float Rc[9];
+    quat_to_mat(cquat, Rc);
+    const float ca = P.cube_half, margin = P.contact_margin;
+    bool v_hit = false;
+    float v_pos[3] = {0, 0, 0}, v_dist = 0.f, v_top = 0.f, v_mu = 0.f;
+    int v_key = 0;
+    if (lane < 8) {
+      const float l[3] = {(lane & 1) ? ca : -ca, (lane & 2) ? ca : -ca, (lane & 4) ? ca : -ca};
+      m3vec(Rc, l, v_pos);
+      v_pos[0] += cpos[0]; v_pos[1] += cpos[1]; v_pos[2] += cpos[2];
+      const bool over = v_pos[0] >= P.table_min[0] && v_pos[0] <= P.table_max[0] && v_pos[1] >= P.table_min[1] &&
+                        v_pos[1] <= P.table_max[1] && v_pos[2] > P.table_min[2];
+      if (over) { v_top = P.table_max[2]; v_mu = P.cube_mu * P.table_mu; v_key = KEY_CUBE_TABLE + lane; }
+      else { v_top = 0.f; v_mu = P.cube_mu * P.plane_mu; v_key = KEY_CUBE_PLANE + lane; }
+      v_dist = v_pos[2] - v_top;
+      v_hit = v_dist < margin;
+    }
+    const int ns = U.n_spheres;
+    bool sc_hit = false, st_hit = false;
+    float s_c[3] = {0, 0, 0}, sc_n[3] = {0, 0, 0}, sc_pB[3] = {0, 0, 0}, sc_dist = 0.f, st_dist = 0.f, s_r = 0.f;
+    int s_link = 0;
+    if (lane < ns) {
+      s_link = __ldg(&M->sph_link[lane]);
+      s_r = __ldg(&M->sph_r[lane]);
+      const float lc[3] = {__ldg(&M->sph_c[lane][0]), __ldg(&M->sph_c[lane][1]), __ldg(&M->sph_c[lane][2])};
+      float o[3], Rl[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rl[k] = sm.T[s_link][k];
+      m3vec(Rl, lc, o);
+      s_c[0] = sm.T[s_link][9] + o[0]; s_c[1] = sm.T[s_link][10] + o[1]; s_c[2] = sm.T[s_link][11] + o[2];
+      const float rel[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]};
+      float l[3], cl[3];
+      m3tvec(Rc, rel, l);
+      bool inside = true;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        cl[j] = l[j] < -ca ? -ca : (l[j] > ca ? ca : l[j]);
+        if (cl[j] != l[j]) inside = false;
+      }
+      float nloc[3];
+      if (!inside) {
+        const float dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+        const float d = sqrtf(dot3(dv, dv));
+        sc_dist = d - s_r;
+        sc_hit = sc_dist < margin;
+        nloc[0] = dv[0] / d; nloc[1] = dv[1] / d; nloc[2] = dv[2] / d;
+      } else {
+        int axm = 0;
+        float best = ca - fabsf(l[0]);
+#pragma unroll
+        for (int j = 1; j < 3; j++) {
+          const float pen = ca - fabsf(l[j]);
+          if (pen < best) { best = pen; axm = j; }
+        }
+        nloc[0] = nloc[1] = nloc[2] = 0.f;
+        const float sgn = ((axm == 0 ? l[0] : (axm == 1 ? l[1] : l[2])) >= 0) ? 1.f : -1.f;
+        if (axm == 0) { nloc[0] = sgn; cl[0] = sgn * ca; }
+        else if (axm == 1) { nloc[1] = sgn; cl[1] = sgn * ca; }
+        else { nloc[2] = sgn; cl[2] = sgn * ca; }
+        sc_dist = -best - s_r;
+        sc_hit = true;
+      }
+      if (sc_hit) {
+        float pwl[3];
+        m3vec(Rc, nloc, sc_n);
+        m3vec(Rc, cl, pwl);
+        sc_pB[0] = cpos[0] + pwl[0]; sc_pB[1] = cpos[1] + pwl[1]; sc_pB[2] = cpos[2] + pwl[2];
+      }
+      const bool over = s_c[0] >= P.table_min[0] && s_c[0] <= P.table_max[0] && s_c[1] >= P.table_min[1] &&
+                        s_c[1] <= P.table_max[1] && s_c[2] > P.table_min[2];
+      st_dist = s_c[2] - s_r - P.table_max[2];
+      st_hit = over && (st_dist < margin);
+    }
+    const unsigned bv = __ballot_sync(FULL, v_hit), bsc = __ballot_sync(FULL, sc_hit), bst = __ballot_sync(FULL, st_hit);
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
+    const int total = n_v + n_sc + n_st;
+    if (total > maxc) flags |= B2E_ST_CONTACT_OVERFLOW;
+    nc = total > maxc ? maxc : total;
+    if (v_hit) {
+      const int cs = __popc(bv & lt);
+      if (cs < maxc) {
+        Contact& c = sm.con[cs];
+        c.key = v_key; c.type = CT_CUBE_STATIC; c.link = -1;
+        c.pA[0] = v_pos[0]; c.pA[1] = v_pos[1]; c.pA[2] = v_pos[2];
+        c.pB[0] = v_pos[0]; c.pB[1] = v_pos[1]; c.pB[2] = v_top;
+        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+        c.dist = v_dist; c.mu = v_mu; c.erp = P.erp;
+        sm.con_cfm[cs] = 0.f;
+      }
+    }
+    if (sc_hit) {
+      const int cs = n_v + __popc(bsc & lt);
+      if (cs < maxc) {
+        Contact& c = sm.con[cs];
+        const float serp = __ldg(&M->sph_erp[lane]);
+        c.key = KEY_SPHERE_CUBE + lane; c.type = CT_SPHERE_CUBE; c.link = s_link;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { c.n[j] = sc_n[j]; c.pB[j] = sc_pB[j]; c.pA[j] = s_c[j] - sc_n[j] * s_r; }
+        c.dist = sc_dist; c.mu = P.cube_mu * __ldg(&M->sph_mu[lane]);
+        c.erp = serp >= 0 ? serp : P.erp;
+        sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+      }
+    }
+    if (st_hit) {
+      const int cs = n_v + n_sc + __popc(bst & lt);
+      if (cs < maxc) {
+        Contact& c = sm.con[cs];
+        const float serp = __ldg(&M->sph_erp[lane]);
+        c.key = KEY_SPHERE_TABLE + lane; c.type = CT_SPHERE_STATIC; c.link = s_link;
+        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+        c.pA[0] = s_c[0]; c.pA[1] = s_c[1]; c.pA[2] = s_c[2] - s_r;
+        c.pB[0] = s_c[0]; c.pB[1] = s_c[1]; c.pB[2] = P.table_max[2];
+        c.dist = st_dist; c.mu = P.table_mu * __ldg(&M->sph_mu[lane]);
+        c.erp = serp >= 0 ? serp : P.erp;
+        sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+      }
+    }
+    // joint-limit rows near a limit (lane = dof): order (dof, lower) then (dof, upper)
+    const float dlo = my_q - my_lower, dup = my_upper - my_q;
+    const float lmar = is_dof ? __ldg(&M->limit_margin[li]) : 0.f;
+    const bool lo_hit = is_dof && dlo < lmar, up_hit = is_dof && dup < lmar;
+    const unsigned blo = __ballot_sync(FULL, lo_hit), bup = __ballot_sync(FULL, up_hit);
+    int nlim = __popc(blo) + __popc(bup);
+    if (nlim > B2E_MAX_LIMROWS) { flags |= B2E_ST_LIMIT_OVERFLOW; nlim = B2E_MAX_LIMROWS; }
+    if (lo_hit) {
+      const int ls = __popc(blo & lt) + __popc(bup & lt);
+      if (ls < B2E_MAX_LIMROWS) { sm.lim_d[ls] = lane; sm.lim_dist[ls] = dlo; }
+    }
+    if (up_hit) {
+      const int ls = __popc(blo & lt) + __popc(bup & lt) + (lo_hit ? 1 : 0);
+      if (ls < B2E_MAX_LIMROWS) { sm.lim_d[ls] = lane | (1 << 8); sm.lim_dist[ls] = dup; }
+    }
+    __syncwarp();
+
+    // ---- constraint rows: motor row of dof `lane`, generic row `lane` ----
+    const int fric_start = nlim + nc;
+    const int RG = nlim + 3 * nc;
+    R = nd + RG;
+    const float inv_dt = 1.0f / dt;
+    const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
+    MotorRegs m;
+    {
+      float desired = my_kp * (my_target - my_q) * inv_dt;
+      const float mv = __ldg(&M->max_vel[li]);
+      if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
+      const float diag = is_dof ? sm.Minv[lane][lane] : 1.f;
+      m.diag = diag;
+      m.invd = is_dof ? 1.0f / diag : 0.f;
+      m.u = is_dof ? desired - vstar_d : 0.f;
+      m.hi = is_dof ? __ldg(&M->max_force[li]) * dt : 0.f;
+      m.lo = -m.hi;
+      m.lam = 0.f;
+      m.prev = 0.f;
+    }
+    TreeRow rr;
+    bool coupled, has_cube, arm_part;
+    float Jc[6];   // cube part of this row's Jacobian
+    {
+      const int gi = lane;
+      const bool valid = gi < RG;
+      float J[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) J[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; k++) Jc[k] = 0.f;
+      float desired = 0.f, cfm = 0.f, lo = 0.f, hi = 0.f, mu = 0.f;
+      int type = ROW_LIMIT, isl = 0, nidx = 0;
+      bool sphere_cube_normal = false;
+      if (valid) {
+        if (gi < nlim) {
+          const int code = sm.lim_d[gi];
+          const int d = code & 0xff, side = code >> 8;
+#pragma unroll
+          for (int k = 0; k < 32; k++) J[k] = (k == d) ? (side ? -1.f : 1.f) : 0.f;
+          const float pen = sm.lim_dist[gi] + P.slop;
+          desired = pen > 0 ? -pen * inv_dt : -pen * P.erp * inv_dt;
+          lo = 0.f; hi = 1e30f;
+        } else {
+          int c, which;
+          if (gi < fric_start) { c = gi - nlim; which = 0; }
+          else { c = (gi - fric_start) >> 1; which = 1 + ((gi - fric_start) & 1); }
+          const Contact& ct = sm.con[c];
+          const float n[3] = {ct.n[0], ct.n[1], ct.n[2]};
+          float dir[3];
+          if (which == 0) { dir[0] = n[0]; dir[1] = n[1]; dir[2] = n[2]; }
+          else {
+            float t1[3], t2[3];
+            plane_space(n, t1, t2);
+            if (which == 1) { dir[0] = t1[0]; dir[1] = t1[1]; dir[2] = t1[2]; }
+            else { dir[0] = t2[0]; dir[1] = t2[1]; dir[2] = t2[2]; }
+          }
+          isl = ct.type == CT_CUBE_STATIC ? 1 : 0;
+          if (ct.type == CT_CUBE_STATIC) {
+            const float rel[3] = {ct.pA[0] - cpos[0], ct.pA[1] - cpos[1], ct.pA[2] - cpos[2]};
+            float t[3];
+            cross3(rel, dir, t);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { Jc[k] = dir[k]; Jc[3 + k] = t[k]; }
+          } else {
+            const unsigned mask = __ldg(&M->link_dofmask[ct.link]);
+            const float rel[3] = {ct.pA[0] - U.base_pos[0], ct.pA[1] - U.base_pos[1], ct.pA[2] - U.base_pos[2]};
+            float wn[3];
+            cross3(rel, dir, wn);
+#pragma unroll
+            for (int d = 0; d < 32; d++) {
+              const float vv = sm.S[d][0] * wn[0] + sm.S[d][1] * wn[1] + sm.S[d][2] * wn[2] + sm.S[d][3] * dir[0] +
+                               sm.S[d][4] * dir[1] + sm.S[d][5] * dir[2];
+              J[d] = ((mask >> d) & 1u) ? vv : 0.f;
+            }
+            if (ct.type == CT_SPHERE_CUBE) {
+              const float relc[3] = {ct.pB[0] - cpos[0], ct.pB[1] - cpos[1], ct.pB[2] - cpos[2]};
+              float t[3];
+              cross3(relc, dir, t);
+#pragma unroll
+              for (int k = 0; k < 3; k++) { Jc[k] = -dir[k]; Jc[3 + k] = -t[k]; }
+              sphere_cube_normal = (which == 0);
+            }
+          }
+          if (which == 0) {
+            type = ROW_NORMAL;
+            const float pen = ct.dist + P.slop;
+            desired = pen > 0 ? -pen * inv_dt : -pen * ct.erp * inv_dt;
+            lo = 0.f; hi = 1e30f;
+            cfm = sm.con_cfm[c];
+          } else {
+            type = ROW_FRICTION;
+            mu = ct.mu;
+            nidx = nlim + c;
+          }
+        }
+      }
+      arm_part = valid && isl == 0;
+      // W = M^-1 J^T (rows of cube-table contacts have no arm part)
+      float diag = 0.f, jv = 0.f;
+      const bool any_arm = __any_sync(FULL, arm_part);
+#pragma unroll 4
+      for (int d = 0; d < 32; d++) {
+        float acc = 0.f;
+        if (any_arm) {
+#pragma unroll
+          for (int e = 0; e < 32; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
+        }
+        sm.W[gi * TREE_WS + d] = acc;
+        sm.WT[d * 32 + gi] = valid ? acc : 0.f;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < 32; d++) {
+        diag = fmaf(J[d], sm.W[gi * TREE_WS + d], diag);
+        jv = fmaf(J[d], sm.vstar[d], jv);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const float wv = Jc[k] * (k < 3 ? cinv_m : cinv_I);
+        sm.W[gi * TREE_WS + 32 + k] = wv;
+        diag = fmaf(Jc[k], wv, diag);
+        jv = fmaf(Jc[k], sm.vstar[32 + k], jv);
+      }
+      sm.W[gi * TREE_WS + 38] = 0.f; sm.W[gi * TREE_WS + 39] = 0.f;
+      rr.type = type; rr.isl = isl; rr.nidx = nidx;
+      rr.lo = lo; rr.hi = hi; rr.mu = mu;
+      rr.diag = valid ? diag + cfm : 0.f;
+      rr.invd = valid ? 1.0f / (diag + cfm) : 0.f;
+      rr.gg = 1.0f - cfm * rr.invd;
+      rr.u = valid ? desired - jv : 0.f;
+      rr.lam = 0.f; rr.base = 0.f; rr.prev = 0.f;
+      coupled = __any_sync(FULL, sphere_cube_normal);
+      has_cube = __any_sync(FULL, valid && isl == 1);
+      __syncwarp();
+      // generic x generic block: A[c][r] = J_r . W_c
+      for (int c = 0; c < RG; c++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k++) acc = fmaf(J[k], sm.W[c * TREE_WS + k], acc);
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc = fmaf(Jc[k], sm.W[c * TREE_WS + 32 + k], acc);
+        sm.A[c * 32 + gi] = valid ? acc : 0.f;
+      }
+      __syncwarp();
+      // warm start (contact rows): lambda0 = cached impulse * factor, u -= A lambda0
+      if (gi >= nlim && gi < RG) {
+        int c, j;
+        if (gi < fric_start) { c = gi - nlim; j = 0; }
+        else { c = (gi - fric_start) >> 1; j = 1 + ((gi - fric_start) & 1); }
+        const int key = sm.con[c].key;
+        float l0 = 0.f;
+        for (int sl = 0; sl < B2E_CACHE_SLOTS; sl++)
+          if (sm.ckey[sl] == key) { l0 = sm.clam[sl][j] * P.warmstart; break; }
+        rr.lam = l0;
+        rr.base = l0 * rr.gg;
+      }
+      for (int c = nlim; c < RG; c++) {
+        const float l0 = SHW(rr.lam, c);
+        if (l0 != 0.f) {
+          rr.u = fmaf(-sm.A[c * 32 + lane], l0, rr.u);
+          m.u = fmaf(-sm.W[c * TREE_WS + lane], l0, m.u);
+        }
+      }
+    }
+    iters = tree_pgs(sm, lane, m, rr, nd, RG, fric_start, coupled, has_cube, P.solver_iters, P.residual_tol);
+    sm.mlam[lane] = is_dof ? m.lam : 0.f;
+    sm.glam[lane] = lane < RG ? rr.lam : 0.f;
+    __syncwarp();
+
+    // ---- delta velocities dv = sum_r W_r lambda_r ----
+    float dvk = 0.f, dvc = 0.f;
+    for (int g2 = 0; g2 < RG; g2++) {
+      const float lg = sm.glam[g2];
+      dvk = fmaf(sm.W[g2 * TREE_WS + lane], lg, dvk);
+      if (lane < 6) dvc = fmaf(sm.W[g2 * TREE_WS + 32 + lane], lg, dvc);
+    }
+#pragma unroll 8
+    for (int d = 0; d < 32; d++) dvk = fmaf(sm.Minv[lane][d], sm.mlam[d], dvk);
+    // ---- integrate (semi-implicit Euler) ----
+    if (is_dof && !ghost) {
+      my_qd = vstar_d + dvk;
+      my_q += dt * my_qd;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float dvl = SHW(dvc, k), dva = SHW(dvc, 3 + k);
+      if (!ghost) {
+        cv[k] = cvs[k] + dvl;
+        cw[k] = cws[k] + dva;
+        cpos[k] += dt * cv[k];
+      }
+    }
+    if (!ghost) {
+      const float wl = sqrtf(dot3(cw, cw)), ang = wl * dt;
+      float f, cs;
+      if (ang < 1e-3f) { f = 0.5f * dt - dt * dt * dt * (1.0f / 48.0f) * wl * wl; cs = cosf(0.5f * ang); }
+      else { float sn; sincosf(0.5f * ang, &sn, &cs); f = sn / wl; }
+      const float dq[4] = {cw[0] * f, cw[1] * f, cw[2] * f, cs};
+      float nq[4];
+      quat_mul(dq, cquat, nq);
+      const float nn = 1.0f / sqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) cquat[k] = nq[k] * nn;
+    }
+    // ---- contact cache for the next step's warm start ----
+    {
+      int key = -1;
+      float l3[3] = {0.f, 0.f, 0.f};
+      if (lane < nc) {
+        key = sm.con[lane].key;
+        l3[0] = sm.glam[nlim + lane];
+        l3[1] = sm.glam[nlim + nc + 2 * lane];
+        l3[2] = sm.glam[nlim + nc + 2 * lane + 1];
+      }
+      if (record_contacts && lane < B2E_MAX_CONTACTS && live_env && !ghost) {
+        float* o = st.contacts + ((size_t)env * B2E_MAX_CONTACTS + lane) * 8;
+        if (lane < nc) {
+          o[0] = (float)key; o[1] = sm.con[lane].dist;
+          o[2] = sm.con[lane].n[0]; o[3] = sm.con[lane].n[1]; o[4] = sm.con[lane].n[2];
+          o[5] = l3[0]; o[6] = l3[1]; o[7] = l3[2];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; k++) o[k] = 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane < B2E_CACHE_SLOTS && !ghost) {
+        sm.ckey[lane] = key;
+        sm.clam[lane][0] = l3[0]; sm.clam[lane][1] = l3[1]; sm.clam[lane][2] = l3[2];
+      }
+      __syncwarp();
+    }
+    {
+      bool bad = is_dof && !(isfinite(my_q) && isfinite(my_qd));
+      bad = bad || !(isfinite(cpos[0]) && isfinite(cpos[1]) && isfinite(cpos[2]) && isfinite(cv[0]) && isfinite(cv[1]) &&
+                     isfinite(cv[2]) && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]));
+      if (__any_sync(FULL, bad)) flags |= B2E_ST_NAN;
+    }
+  }
+
+  // ---- store state ----
+  if (is_dof && live_env) {
+    st.q[env * nd + lane] = my_q;
+    st.qd[env * nd + lane] = my_qd;
+    st.mtarget[env * nd + lane] = my_target;
+  }
+  if (lane == 0 && live_env) {
+    st.obj_pose[env * 7 + 0] = cpos[0]; st.obj_pose[env * 7 + 1] = cpos[1]; st.obj_pose[env * 7 + 2] = cpos[2];
+    st.obj_pose[env * 7 + 3] = cquat[0]; st.obj_pose[env * 7 + 4] = cquat[1];
+    st.obj_pose[env * 7 + 5] = cquat[2]; st.obj_pose[env * 7 + 6] = cquat[3];
+    st.obj_vel[env * 6 + 0] = cv[0]; st.obj_vel[env * 6 + 1] = cv[1]; st.obj_vel[env * 6 + 2] = cv[2];
+    st.obj_vel[env * 6 + 3] = cw[0]; st.obj_vel[env * 6 + 4] = cw[1]; st.obj_vel[env * 6 + 5] = cw[2];
+  }
+  if (IK && lane < 6 && live_env) st.hand_pose[env * 6 + lane] = my_hp;
+  if (lane < B2E_CACHE_SLOTS && live_env) {
+    st.cache_key[env * B2E_CACHE_SLOTS + lane] = sm.ckey[lane];
+#pragma unroll
+    for (int j = 0; j < 3; j++) st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j] = sm.clam[lane][j];
+  }
+
+  // ---- observation / termination / reward (icub_push_gym_env.py:276-282) ----
+  if (mode == B2E_MODE_ACTION || obs_out) {
+    const int ee = U.ee_link;
+    const float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]};
+    float o[3];
+    m3vec(Rm, cm, o);
+    float epos[3], Re[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) epos[k] = SHW(pw[k] + o[k], ee);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Re[k] = SHW(Rm[k], ee);
+    // linear velocity of the hand COM: sum over the joints on the path of (axis x (p_ee - o_j)) qd_j
+    float vl[3] = {0, 0, 0};
+    {
+      const int jt = __ldg(&M->jtype[li]);
+      const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
+      float aw[3];
+      m3vec(Rm, ax, aw);
+      if (is_dof && ((U.ee_dofmask >> lane) & 1u)) {
+        if (jt == B2E_JOINT_REVOLUTE) {
+          const float rel[3] = {epos[0] - pw[0], epos[1] - pw[1], epos[2] - pw[2]};
+          float t[3];
+          cross3(aw, rel, t);
+          vl[0] = t[0] * my_qd; vl[1] = t[1] * my_qd; vl[2] = t[2] * my_qd;
+        } else {
+          vl[0] = aw[0] * my_qd; vl[1] = aw[1] * my_qd; vl[2] = aw[2] * my_qd;
+        }
+      }
+      // fixed-order sum over the bodies (the oracle's order)
+      float acc[3] = {0, 0, 0};
+      for (int j = 0; j < nl; j++) {
+        acc[0] += SHW(vl[0], j); acc[1] += SHW(vl[1], j); acc[2] += SHW(vl[2], j);
+      }
+      vl[0] = acc[0]; vl[1] = acc[1]; vl[2] = acc[2];
+    }
+    float equat[4], eeu[3], ceu[3];
+    mat_to_quat(Re, equat);
+    quat_to_euler(equat, eeu);
+    quat_to_euler(cquat, ceu);
+    float hq[4], oq[4], hqi[4], relq[4], releu[3], relp[3];
+    euler_to_quat(eeu, hq);
+    euler_to_quat(ceu, oq);
+    hqi[0] = -hq[0]; hqi[1] = -hq[1]; hqi[2] = -hq[2]; hqi[3] = hq[3];
+    {
+      const float dd[3] = {cpos[0] - epos[0], cpos[1] - epos[1], cpos[2] - epos[2]};
+      float Rh[9];
+      quat_to_mat(hqi, Rh);
+      m3vec(Rh, dd, relp);
+    }
+    quat_mul(hqi, oq, relq);
+    quat_to_euler(relq, releu);
+    float* obsb = sm.scr;
+    __syncwarp();
+    if (lane == 0) {
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = epos[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = eeu[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = (vl[k] - P.vel_mean[k]) / P.vel_std[k];
+      n += n_qobs;
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = cpos[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = ceu[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = relp[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) obsb[n++] = releu[k];
+      if (P.task == B2E_TASK_PUSH) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) obsb[n++] = target[k];
+      }
+    }
+    if (obs_idx >= 0) obsb[9 + obs_idx] = my_q;
+    __syncwarp();
+    for (int k = lane; k < P.n_obs; k += 32) {
+      const float raw = obsb[k];
+      if (!live_env) continue;
+      st.raw_obs[(size_t)env * P.n_obs + k] = raw;
+      if (obs_out) obs_out[(size_t)env * P.n_obs + k] = 2.0f * ((raw - P.obs_low[k]) / (P.obs_high[k] - P.obs_low[k])) - 1.0f;
+    }
+    const float dd1[3] = {epos[0] - cpos[0], epos[1] - cpos[1], epos[2] - cpos[2]};
+    const float d1 = sqrtf(dot3(dd1, dd1));
+    const float dd2[3] = {cpos[0] - target[0], cpos[1] - target[1], cpos[2] - target[2]};
+    const float d2 = sqrtf(dot3(dd2, dd2));
+    float rew;
+    int dn = 0;
+    if (P.reward_kind == B2E_REWARD_ICUB_REACH) {   // icub_reach_gym_env.py:301-330: the bonus is ADDED
+      if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1;
+      if (d1 <= P.dist_min) rew += 1000.0f + (100.0f - d1 * 80.0f);
+    } else if (P.reward_kind == B2E_REWARD_ICUB_PUSH0 || P.reward_kind == B2E_REWARD_ICUB_PUSH1) {   // icub_push_gym_env.py:327-373
+      if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      if (P.reward_kind == B2E_REWARD_ICUB_PUSH0) rew = -d1 - d2;
+      else {
+        const float d0 = st.shaping[env * 2], dmax = st.shaping[env * 2 + 1];
+        rew = 0.125f * (1.0f - d1 / d0);
+        if (!(d1 > 0.1f)) rew += 0.25f * (1.0f - d2 / dmax);
+      }
+      if (d2 <= P.dist_min) rew += 1000.0f;
+    } else if (P.task == B2E_TASK_PUSH) {
+      if (P.goal_env) {
+        dn = (counter > P.max_steps) || (d2 <= P.dist_min);
+        rew = d2 > P.dist_min ? -1.0f : 0.0f;
+      } else {
+        if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
+        else if (terminated || counter > P.max_steps) dn = 1;
+        rew = -d1 - d2;
+        if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
+      }
+    } else {
+      if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1;
+      if (d1 <= P.dist_min) rew = 1000.0f + (100.0f - d1 * 80.0f);
+    }
+    if (lane == 0 && live_env) {
+      if (reward_out) reward_out[env] = rew;
+      if (done_out) done_out[env] = (float)dn;
+    }
+  }
+  if (lane == 0 && mode != B2E_MODE_OBSERVE && live_env) {
+    st.counters[env * 2] = counter;
+    st.counters[env * 2 + 1] = terminated;
+    st.status[env * 4 + 0] = flags;
+    if (nsub > 0) {
+      st.status[env * 4 + 1] = iters;
+      st.status[env * 4 + 2] = nc;
+      st.status[env * 4 + 3] = R;
+    }
+  }
+}

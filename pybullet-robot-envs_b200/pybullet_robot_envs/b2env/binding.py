@@ -14,11 +14,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2ENV_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libb2env.so"))
 
 F_Q, F_QD, F_OBJ_POSE, F_OBJ_VEL, F_TARGET, F_MTARGET, F_COUNTERS, F_CACHE_KEY, F_CACHE_LAM, \
-    F_HAND_POSE, F_STATUS, F_RAW_OBS, F_CONTACTS = range(13)
+    F_HAND_POSE, F_STATUS, F_RAW_OBS, F_CONTACTS, F_SHAPING = range(14)
 FIELD_NAMES = {
     "q": F_Q, "qd": F_QD, "obj_pose": F_OBJ_POSE, "obj_vel": F_OBJ_VEL, "target": F_TARGET,
     "mtarget": F_MTARGET, "counters": F_COUNTERS, "cache_key": F_CACHE_KEY, "cache_lam": F_CACHE_LAM,
     "hand_pose": F_HAND_POSE, "status": F_STATUS, "raw_obs": F_RAW_OBS, "contacts": F_CONTACTS,
+    "shaping": F_SHAPING,
 }
 INT_FIELDS = {F_COUNTERS, F_CACHE_KEY, F_STATUS}
 MODE_ACTION, MODE_HOLD, MODE_TARGETS, MODE_IK_POSE, MODE_OBSERVE = 0, 1, 2, 3, 4

@@ -33,6 +33,7 @@ JOINT_FIXED = 4
 TASK_REACH = 0
 TASK_PUSH = 1
 TASK_GRASP = 2
+REWARD_PANDA, REWARD_ICUB_REACH, REWARD_ICUB_PUSH0, REWARD_ICUB_PUSH1 = 0, 1, 2, 3
 
 _f = C.c_float
 _i = C.c_int32
@@ -73,6 +74,8 @@ class B2EParams(C.Structure):
         ("vel_mean", _f * 3), ("vel_std", _f * 3),
         ("ws_lim", (_f * 2) * 3), ("eu_lim", (_f * 2) * 3), ("home_hand_pose", _f * 6),
         ("kp_grip", _f), ("grasp_lift", _f), ("grasp_rest_z", _f), ("goal_env", _i),
+        ("n_obs_joints", _i), ("obs_dof", _i * 16), ("ctrl_dof", _i * 16), ("ctrl_mask", C.c_uint32),
+        ("ik_link_offset", _f * 3), ("reward_kind", _i), ("max_contacts", _i),
     ]
 
 
@@ -483,3 +486,214 @@ def load_icub(sdf_path=None, pinned=False):
             m.joint_damping[dnum] = j.get("damping", 0.0)
             dnum += 1
     return m, d
+
+
+# ---------------------------------------------------------------------------------------------
+# iCub task setup: what icub_env.py / icub_{reach,push}_gym_env.py configure, as model + params.
+ICUB_CTRL_GROUPS = {  # reference icub_env.py:42-51
+    'torso': ['torso_pitch', 'torso_roll', 'torso_yaw'],
+    'l_arm': ['l_shoulder_pitch', 'l_shoulder_roll', 'l_shoulder_yaw', 'l_elbow', 'l_wrist_pitch', 'l_wrist_prosup', 'l_wrist_yaw'],
+    'r_arm': ['r_shoulder_pitch', 'r_shoulder_roll', 'r_shoulder_yaw', 'r_elbow', 'r_wrist_pitch', 'r_wrist_prosup', 'r_wrist_yaw'],
+}
+ICUB_HAND_OFFSET = {  # com_T_link_hand, reference icub_env.py:251-257
+    'l': (-0.064768, -0.00563, -0.02266), 'r': (0.064668, -0.0056, -0.022681)}
+ICUB_HOME_HAND_POSE = {  # reference icub_env.py:66-72
+    'l': [0.3, 0.26, 0.8, 0.0, 0.0, 0.0], 'r': [0.3, -0.26, 0.8, 0.0, 0.0, math.pi]}
+ICUB_EU_LIM = {
+    'l': [[-math.pi / 2, math.pi / 2]] * 3,
+    'r': [[-math.pi / 2, math.pi / 2], [-math.pi / 2, math.pi / 2], [math.pi / 2, 3 / 2 * math.pi]]}
+
+
+def icub_spheres(d):
+    """Collision proxies of the iCub arms (the collision meshes are git-LFS stubs): two spheres
+    along each forearm (towards the wrist joint) and two on each hand (at the COM and towards the fingers).
+    Torso, head and legs carry none — they cannot reach the table top in the pinned pose."""
+    out = []
+    names = [l["name"] for l in d["links"]]
+    for side in ('l', 'r'):
+        fore, wrist = side + "_forearm", side + "_wrist_1"
+        jw = d["joints"][names.index(wrist)]          # joint forearm -> wrist_1: origin in the forearm frame
+        c = np.asarray(jw["xyz"])
+        out.append(dict(link=fore, c=(0.35 * c).tolist(), r=0.035))
+        out.append(dict(link=fore, c=(0.80 * c).tolist(), r=0.03))
+        com = np.asarray(d["links"][names.index(side + "_hand")]["com"])
+        out.append(dict(link=side + "_hand", c=com.tolist(), r=0.03))
+        out.append(dict(link=side + "_hand", c=(1.6 * com).tolist(), r=0.025))
+    return out
+
+
+def merge_fixed_links(m):
+    """Fold every fixed-joint link into the body it is welded to: the result has one body per movable joint
+    (``n_links == n_dof``, ``dof[i] == i``, bodies in dof order) — the layout of the warp-per-environment tree
+    kernel (lane = body = dof).  Same dynamics: mass, first moment and rotational inertia of the welded links
+    are summed in the host body's frame.  Returns (merged model, host body of every original link)."""
+    n = m.n_links
+    host = [-1] * n                     # body index carrying original link i (-1: the fixed base)
+    Th = [np.eye(4) for _ in range(n)]  # pose of original link i in its host body's frame
+    out = B2EModel()
+    acc = []                            # per body: [mass, first moment (3), inertia about body origin (3x3)]
+    nb = 0
+
+    def add_mass(b, T, mass, com, I):
+        R, t = T[:3, :3], T[:3, 3]
+        c = R @ np.asarray(com, np.float64) + t
+        Io = R @ np.asarray(I, np.float64).reshape(3, 3) @ R.T + mass * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
+        acc[b][0] += mass
+        acc[b][1] += mass * c
+        acc[b][2] += Io
+
+    for i in range(n):
+        p = m.parent[i]
+        Tj = np.eye(4)
+        Tj[:3, :3] = np.asarray(list(m.jrot[i]), np.float64).reshape(3, 3)
+        Tj[:3, 3] = list(m.jpos[i])
+        Tp = np.eye(4) if p < 0 else Th[p]
+        hp = -1 if p < 0 else host[p]
+        if m.jtype[i] == JOINT_FIXED:
+            host[i] = hp
+            Th[i] = Tp @ Tj
+            if hp >= 0:
+                add_mass(hp, Th[i], m.mass[i], list(m.com[i]), list(m.inertia[i]))
+            continue
+        assert m.dof[i] == nb, "dofs must be numbered in link order"
+        b = nb
+        nb += 1
+        host[i] = b
+        Th[i] = np.eye(4)
+        T = Tp @ Tj                      # joint frame in the parent BODY frame
+        out.parent[b] = hp
+        out.jtype[b] = m.jtype[i]
+        out.dof[b] = b
+        for k in range(3):
+            out.jpos[b][k] = T[k, 3]
+            out.axis[b][k] = m.axis[i][k]
+        for k in range(9):
+            out.jrot[b][k] = T[:3, :3].flat[k]
+        acc.append([0.0, np.zeros(3), np.zeros((3, 3))])
+        add_mass(b, np.eye(4), m.mass[i], list(m.com[i]), list(m.inertia[i]))
+    out.n_links = nb
+    out.n_dof = m.n_dof
+    assert nb == m.n_dof
+    for b in range(nb):
+        mass, h, Io = acc[b]
+        c = h / mass if mass > 0 else np.zeros(3)
+        Ic = Io - mass * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
+        out.mass[b] = mass
+        for k in range(3):
+            out.com[b][k] = c[k]
+        for k in range(9):
+            out.inertia[b][k] = Ic.flat[k]
+    for name in ("lower", "upper", "limit_margin", "max_force", "max_vel", "joint_damping", "home"):
+        for k in range(m.n_dof):
+            getattr(out, name)[k] = getattr(m, name)[k]
+    for k in range(3):
+        out.base_pos[k] = m.base_pos[k]
+    for k in range(9):
+        out.base_rot[k] = m.base_rot[k]
+    out.ee_link = host[m.ee_link]
+    assert m.jtype[m.ee_link] != JOINT_FIXED
+    out.n_spheres = m.n_spheres
+    for s in range(m.n_spheres):
+        li = m.sph_link[s]
+        c = Th[li] @ np.array([m.sph_c[s][0], m.sph_c[s][1], m.sph_c[s][2], 1.0])
+        out.sph_link[s] = host[li]
+        assert host[li] >= 0
+        for k in range(3):
+            out.sph_c[s][k] = c[k]
+        out.sph_r[s], out.sph_mu[s], out.sph_erp[s], out.sph_cfm[s] = m.sph_r[s], m.sph_mu[s], m.sph_erp[s], m.sph_cfm[s]
+    return out, host
+
+
+def load_icub_arm(control_arm='l', merged=True):
+    """iCub model as the reference's ``iCubEnv`` sets it up (icub_env.py:85-151): base pinned by the fixed
+    constraint whose anchor is the base position with z x 1.2 and whose frame carries the base orientation
+    (the base ends up 0.126 m higher, at yaw -3.14 instead of +3.14) — applied here as a
+    KINEMATIC pin (documented deviation: Bullet's pin is a soft 6-row constraint).  End effector = ``l_hand`` /
+    ``r_hand`` (joint index 26 / 37); sphere proxies on the forearms and hands.  ``merged=True`` folds the six
+    fixed F/T-sensor links into their parents (32 bodies = 32 dofs)."""
+    with open(ICUB_JSON) as f:
+        d = json.load(f)
+    mp = d["model_pose"]
+    base = [mp[0], mp[1], mp[2] * 1.2]
+    home = {j["name"]: ICUB_HOME.get(j["name"], 0.0) for j in d["joints"]}
+    names = [l["name"] for l in d["links"]]
+    m = descriptor_from_urdf_dict(d, base, home, ee_link=names.index(control_arm + "_hand"), spheres=icub_spheres(d))
+    Rb = rpy_to_matrix(mp[3], mp[4], -mp[5])
+    for k in range(9):
+        m.base_rot[k] = float(Rb.flat[k])
+    for i, j in enumerate(d["joints"]):
+        R = np.asarray(j["rotation"])
+        for k in range(9):
+            m.jrot[i][k] = float(R.flat[k])
+    dnum = 0
+    for j in d["joints"]:
+        if j["type"] != "fixed":
+            m.joint_damping[dnum] = j.get("damping", 0.0)
+            dnum += 1
+    info = dict(d=d, joint_names=[j["name"] for j in d["joints"]],
+                movable=[j["name"] for j in d["joints"] if j["type"] != "fixed"])
+    if merged:
+        m, host = merge_fixed_links(m)
+        info["host"] = host
+    return m, info
+
+
+def icub_ctrl_dofs(info, control_arm='l'):
+    """dof indices of ``_joints_to_control`` in joint-index order (icub_env.py:121-136): torso, then the arm."""
+    ctrl = set(ICUB_CTRL_GROUPS['torso'] + ICUB_CTRL_GROUPS[control_arm + '_arm'])
+    return [k for k, name in enumerate(info["movable"]) if name in ctrl]
+
+
+def icub_obs_limits(task, robot_ws, world_ws, eu_lim, joint_lim):
+    """icub_env.py:202-249 (19 entries) + world_env.py:109-126 + icub_push_gym_env.py:166-203."""
+    pi = math.pi
+    lim = [list(x) for x in robot_ws] + [list(x) for x in eu_lim] + [[-1, 1]] * 3 + [list(x) for x in joint_lim]
+    lim += [list(x) for x in world_ws] + [[-pi, pi]] * 3
+    lim += [[-0.5, 0.5]] * 3 + [[0, 2 * pi]] * 3
+    if task == TASK_PUSH:
+        lim += [list(x) for x in world_ws]
+    return lim
+
+
+def icub_task_setup(task=TASK_PUSH, control_arm='l', use_ik=1, control_orientation=0, max_steps=1000, reward_type=0,
+                    goal_env=0, merged=True):
+    """Model + params of the registered iCubPush-v0 / iCubReach-v0 configurations
+    (reference pybullet_robot_envs/__init__.py:7-31)."""
+    m, info = load_icub_arm(control_arm, merged=merged)
+    h_table = 0.625
+    robot_ws = [[0.1, 0.45], [-0.3, 0.3], [h_table, 1.0]]              # icub_env.py:62, task env: z low := table height
+    world_ws = [[0.1, 0.45], [-0.3, 0.3], [h_table, h_table + 0.3]]    # world_env.py:46, :72
+    eu_lim = ICUB_EU_LIM[control_arm]
+    ctrl = icub_ctrl_dofs(info, control_arm)
+    joint_lim = [[m.lower[d], m.upper[d]] for d in ctrl]
+    lim = icub_obs_limits(task, robot_ws, world_ws, eu_lim, joint_lim)
+    n_act = len(ctrl) if not use_ik else (6 if control_orientation else 3)
+    p = default_params(task, [x[0] for x in lim], [x[1] for x in lim], n_act=n_act, n_ctrl=len(ctrl), use_ik=use_ik,
+                       ik_orientation=int(bool(control_orientation)), max_steps=max_steps, dist_min=0.03,
+                       ws_lim=robot_ws, eu_lim=eu_lim, goal_env=goal_env)
+    icub_params(p, task, control_arm, ctrl, control_orientation, reward_type)
+    return m, p
+
+
+def icub_params(p, task, control_arm, ctrl, control_orientation, reward_type):
+    """The iCub-specific constants on top of ``default_params``."""
+    p.n_obs_joints = len(ctrl)
+    mask = 0
+    for k, d in enumerate(ctrl):
+        p.obs_dof[k] = d
+        p.ctrl_dof[k] = d
+        mask |= 1 << d
+    p.ctrl_mask = mask
+    for k in range(3):
+        p.ik_link_offset[k] = ICUB_HAND_OFFSET[control_arm][k]
+        p.vel_mean[k] = 0.0          # raw EE velocity in the observation (icub_env.py:234-237)
+        p.vel_std[k] = 1.0
+    for k, v in enumerate(ICUB_HOME_HAND_POSE[control_arm]):
+        p.home_hand_pose[k] = v
+    if control_orientation:          # icub_push_gym_env.py:234-235
+        p.act_scale_pos, p.act_scale_rot = 0.01, 0.02
+    else:                            # :229
+        p.act_scale_pos, p.act_scale_rot = 0.005, 0.0
+    p.reward_kind = REWARD_ICUB_REACH if task == TASK_REACH else (REWARD_ICUB_PUSH1 if reward_type == 1 else REWARD_ICUB_PUSH0)
+    p.max_contacts = 8
+    return p
