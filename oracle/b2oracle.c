@@ -1083,10 +1083,13 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
       real tp[3] = {e.hand_pose[0], e.hand_pose[1], e.hand_pose[2]}, eu[3], tq[4];
       if (tp[2] < P->ws_lim[2][0]) tp[2] = P->ws_lim[2][0];
       if (tp[2] > P->ws_lim[2][1]) tp[2] = P->ws_lim[2][1];
-      for (int k = 0; k < 3; k++) {
+      for (int k = 0; k < 3; k++) { /* robot level: clamp to the rotation limits (panda_env.py:250-256,
+                                       icub_env.py:284-289), or the home orientation when it is not controlled */
         eu[k] = P->ik_orientation ? e.hand_pose[3 + k] : P->home_hand_pose[3 + k];
-        if (eu[k] < (real)-M_PI) eu[k] = (real)-M_PI;
-        if (eu[k] > (real)M_PI) eu[k] = (real)M_PI;
+        if (P->ik_orientation) {
+          if (eu[k] < P->eu_lim[k][0]) eu[k] = P->eu_lim[k][0];
+          if (eu[k] > P->eu_lim[k][1]) eu[k] = P->eu_lim[k][1];
+        }
       }
       euler_to_quat(eu, tq);
       { /* COM pose -> link-frame pose of the hand (icub_env.py:303-305; zero offset for the Panda) */

@@ -1,5 +1,5 @@
 """Gym registration — ids and default kwargs of reference pybullet_robot_envs/__init__.py:47-80
-(Panda ids; the iCub ids need the 32-dof tree kernel).  The reference registers
+(Panda ids) and :7-44 (iCub ids).  The reference registers
 ``renders: True``; the CUDA backend has no GUI, so ids register with ``renders: False``.
 BASELINE.json spells the ids with a capital P: both spellings are registered."""
 try:  # a real gym wins if present
@@ -28,6 +28,18 @@ for _name in ('pandaGrasp-v0', 'PandaGrasp-v0'):   # BASELINE.json config 5: new
              kwargs={'numControlledJoints': 7, 'use_IK': 0, 'obj_pose_rnd_std': 0.05, 'max_steps': 1000, 'renders': False})
 
 
+# iCub ids (reference __init__.py:7-44)
+register(id='iCubReach-v0', entry_point='pybullet_robot_envs.envs:iCubReachGymEnv', max_episode_steps=1000,
+         kwargs={'use_IK': 1, 'control_arm': 'l', 'control_orientation': 0, 'obj_pose_rnd_std': 0, 'max_steps': 1000,
+                 'renders': False})
+register(id='iCubPush-v0', entry_point='pybullet_robot_envs.envs:iCubPushGymEnv', max_episode_steps=1000,
+         kwargs={'use_IK': 1, 'control_arm': 'l', 'control_orientation': 0, 'obj_pose_rnd_std': 0.05,
+                 'tg_pose_rnd_std': 0, 'max_steps': 1000, 'reward_type': 0, 'renders': False})
+register(id='iCubPushGoal-v0', entry_point='pybullet_robot_envs.envs:iCubPushGymGoalEnv', max_episode_steps=1000,
+         kwargs={'use_IK': 1, 'control_arm': 'r', 'control_orientation': 1, 'obj_pose_rnd_std': 0.05,
+                 'tg_pose_rnd_std': 0, 'max_steps': 1000, 'renders': False})
+
+
 def getList():
-    return ['pandaReach-v0', 'pandaPush-v0', 'pandaPushGoal-v0', 'PandaReach-v0', 'PandaPush-v0', 'PandaPushGoal-v0',
+    return ['iCubReach-v0', 'iCubPush-v0', 'iCubPushGoal-v0', 'pandaReach-v0', 'pandaPush-v0', 'pandaPushGoal-v0', 'PandaReach-v0', 'PandaPush-v0', 'PandaPushGoal-v0',
             'pandaGrasp-v0', 'PandaGrasp-v0']

@@ -101,6 +101,8 @@ class B2Sim:
         # `lib`: tests may hand in another build of the SAME source (tools/emu: the kernels compiled for the
         # host, to debug kernel logic without a GPU).  The product never passes it.
         self.lib = lib if lib is not None else load_library()
+        # the emulation build (tests only) keeps "device" memory on the host: its device pointers are numpy arrays
+        self._host_mem = b"EMULATION" in self.lib.b2e_version()
         self.model, self.params, self.B, self.device = model, params, int(num_envs), int(device)
         h = C.c_void_p()
         self._check(self.lib.b2e_create(C.byref(model), C.byref(params), self.B, self.device, C.byref(h)))
@@ -222,46 +224,53 @@ class B2Sim:
 
     def reset_host(self, obj_init_pose, target, env_mask=None):
         """Reset from host arrays (copies through temporary device buffers owned by torch)."""
-        import torch
-        dev = torch.device("cuda", self.device)
-        o = torch.as_tensor(np.ascontiguousarray(obj_init_pose, np.float32)).to(dev)
-        t = torch.as_tensor(np.ascontiguousarray(target, np.float32)).to(dev)
-        m = None if env_mask is None else torch.as_tensor(np.ascontiguousarray(env_mask, np.uint8)).to(dev)
-        torch.cuda.synchronize(dev)
+        o = self._to_dev(obj_init_pose, np.float32)
+        t = self._to_dev(target, np.float32)
+        m = None if env_mask is None else self._to_dev(env_mask, np.uint8)
+        self._sync()
         self.reset(o, t, m)
-        torch.cuda.synchronize(dev)
+        self._sync()
 
     # subset entry points (per-env resets)
-    def _ids_dev(self, ids):
+    def _to_dev(self, arr, dtype):
+        a = np.ascontiguousarray(arr, dtype)
+        if self._host_mem:
+            return a
         import torch
-        return torch.as_tensor(np.ascontiguousarray(ids, np.int32)).to(torch.device("cuda", self.device))
+        return torch.as_tensor(a).to(torch.device("cuda", self.device))
+
+    def _sync(self):
+        if not self._host_mem:
+            import torch
+            torch.cuda.synchronize(torch.device("cuda", self.device))
+
+    def _ids_dev(self, ids):
+        return self._to_dev(ids, np.int32)
 
     def step_subset(self, ids, n_substeps=1, mode=MODE_HOLD):
         """Advance only the listed environments (no action / outputs: settle steps of a reset)."""
-        import torch
         d = self._ids_dev(ids)
-        self._check(self.lib.b2e_step_subset(self.h, _ptr(d), int(d.numel()), None, None, None, None, n_substeps, mode,
+        self._check(self.lib.b2e_step_subset(self.h, _ptr(d), int(len(d)), None, None, None, None, n_substeps, mode,
                                              C.c_void_p(0)))
-        torch.cuda.synchronize(d.device)
+        self._sync()
 
     def set_rows(self, name, ids, values):
-        import torch
         f = FIELD_NAMES[name]
         w = self.lib.b2e_field_width(self.h, f)
         d = self._ids_dev(ids)
-        v = torch.as_tensor(np.ascontiguousarray(values, np.int32 if f in INT_FIELDS else np.float32).reshape(-1, w)).to(d.device)
-        assert v.shape[0] == d.numel()
-        self._check(self.lib.b2e_set_rows(self.h, f, _ptr(d), int(d.numel()), _ptr(v), C.c_void_p(0)))
-        torch.cuda.synchronize(d.device)
+        v = self._to_dev(np.asarray(values).reshape(-1, w), np.int32 if f in INT_FIELDS else np.float32)
+        assert v.shape[0] == len(d)
+        self._check(self.lib.b2e_set_rows(self.h, f, _ptr(d), int(len(d)), _ptr(v), C.c_void_p(0)))
+        self._sync()
 
     def get_rows(self, name, ids):
-        import torch
         f = FIELD_NAMES[name]
         w = self.lib.b2e_field_width(self.h, f)
         d = self._ids_dev(ids)
-        out = torch.empty((d.numel(), w), dtype=torch.int32 if f in INT_FIELDS else torch.float32, device=d.device)
-        self._check(self.lib.b2e_get_rows(self.h, f, _ptr(d), int(d.numel()), _ptr(out), C.c_void_p(0)))
-        return out.cpu().numpy()
+        out = self._to_dev(np.zeros((len(d), w)), np.int32 if f in INT_FIELDS else np.float32)
+        self._check(self.lib.b2e_get_rows(self.h, f, _ptr(d), int(len(d)), _ptr(out), C.c_void_p(0)))
+        self._sync()
+        return out if self._host_mem else out.cpu().numpy()
 
     def launch_count(self):
         return int(self.lib.b2e_launch_count(self.h))

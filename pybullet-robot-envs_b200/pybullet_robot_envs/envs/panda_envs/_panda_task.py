@@ -22,6 +22,7 @@ _PARK_POSE = (5.0, 5.0, 0.025, 0.0, 0.0, 0.0, 1.0)  # where the object waits whi
 class PandaTaskBase(gym.Env):
     metadata = {'render.modes': ['human', 'rgb_array'], 'video.frames_per_second': 50}
     _task = TASK_PUSH
+    _n_robot_obs = 18   # entries of the robot observation (reference panda_env.py:141-193; iCub: 19)
     _hooks = ("apply_action", "get_extended_observation", "_termination", "_compute_reward")
 
     def _setup(self, numControlledJoints, use_IK, action_repeat, obj_name, renders, max_steps, obj_pose_rnd_std,
@@ -40,6 +41,7 @@ class PandaTaskBase(gym.Env):
         self.num_envs = int(num_envs)
         # "connect": one batched simulation instead of p.connect(p.DIRECT)
         self._physics_client_id = B2Client(num_envs, device)
+        self._physics_client_id.n_robot_obs = self._n_robot_obs
         self._robot = pandaEnv(self._physics_client_id, use_IK=self._use_IK, joint_action_space=numControlledJoints)
         self._world = WorldEnv(self._physics_client_id, obj_name=obj_name, obj_pose_rnd_std=obj_pose_rnd_std,
                                workspace_lim=self._robot.get_workspace())
@@ -110,8 +112,12 @@ class PandaTaskBase(gym.Env):
             world_obs, _ = self._world.get_observation()
             self._target_pose = self.sample_tg_pose(np.asarray(world_obs).reshape(self.num_envs, 6)[:, :3])
             self._sync_target()
+            self._after_target()
         scaled = self._physics_client_id.observe()[0]
         return squeeze1(scaled.astype(np.float64), self.num_envs)
+
+    def _after_target(self, ids=None):
+        """Hook: per-episode constants that depend on the sampled target (iCub push: reward shaping distances)."""
 
     def reset_simulation(self):
         """resetSimulation + robot.reset + 100 steps + world.reset + 100 steps + 1 step
@@ -162,6 +168,7 @@ class PandaTaskBase(gym.Env):
                 tp[ids] = tg
                 self._target_pose = tp
             c.set_rows("target", ids, tg)
+            self._after_target(ids)
         scaled = c.observe()[0]
         return scaled[ids]
 

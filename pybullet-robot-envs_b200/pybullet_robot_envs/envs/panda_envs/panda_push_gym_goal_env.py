@@ -11,17 +11,13 @@ from pybullet_robot_envs.envs.world_envs.world_env import get_objects_list
 from pybullet_robot_envs.envs.panda_envs.panda_push_gym_env import pandaPushGymEnv
 
 
-class pandaPushGymGoalEnv(gym.GoalEnv, pandaPushGymEnv):
-    _goal_env = 1   # the kernel then applies the GoalEnv termination / reward rules (reference :96-122)
-
-    def __init__(self, numControlledJoints=7, use_IK=0, action_repeat=1, obj_name=get_objects_list()[1],
-                 renders=False, max_steps=1000, obj_pose_rnd_std=0, tg_pose_rnd_std=0.2, includeVelObs=True,
-                 num_envs=1, device=0):
-        pandaPushGymEnv.__init__(self, numControlledJoints, use_IK, action_repeat, obj_name, renders, max_steps,
-                                 obj_pose_rnd_std, tg_pose_rnd_std, includeVelObs, num_envs=num_envs, device=device)
+class GoalMixin:
+    """GoalEnv surface shared by ``pandaPushGymGoalEnv`` and ``iCubPushGymGoalEnv`` (reference
+    panda_push_gym_goal_env.py:37-122, icub_push_gym_goal_env.py:40-132 — the two files are the same code)."""
+    _box_cls = None   # the task class whose Box spaces become the 'observation' entry
 
     def create_gym_spaces(self):
-        box, action_space = pandaPushGymEnv.create_gym_spaces(self)
+        box, action_space = self._box_cls.create_gym_spaces(self)
         observation_space = spaces.Dict(dict(
             desired_goal=spaces.Box(-10, 10, shape=(3,), dtype='float32'),
             achieved_goal=spaces.Box(-10, 10, shape=(3,), dtype='float32'),
@@ -30,9 +26,10 @@ class pandaPushGymGoalEnv(gym.GoalEnv, pandaPushGymEnv):
 
     def _goal_dict(self, scaled, raw):
         B = self.num_envs
+        nr = self._n_robot_obs   # robot obs | object pose (6) | relative pose (6) | target (3)
         return {'observation': squeeze1(np.asarray(scaled, np.float64), B),
-                'achieved_goal': squeeze1(np.asarray(raw[:, 18:21], np.float64), B),
-                'desired_goal': squeeze1(np.asarray(raw[:, 30:33], np.float64), B)}
+                'achieved_goal': squeeze1(np.asarray(raw[:, nr:nr + 3], np.float64), B),
+                'desired_goal': squeeze1(np.asarray(raw[:, nr + 12:nr + 15], np.float64), B)}
 
     def get_goal_observation(self):
         scaled, _, _, raw = self._physics_client_id.observe()
@@ -46,6 +43,7 @@ class pandaPushGymGoalEnv(gym.GoalEnv, pandaPushGymEnv):
         world_obs, _ = self._world.get_observation()
         self._target_pose = self.sample_tg_pose(np.asarray(world_obs).reshape(self.num_envs, 6)[:, :3])
         self._sync_target()
+        self._after_target()
         scaled, _, _, raw = self._physics_client_id.observe()
         return self._goal_dict(scaled, raw)
 
@@ -73,3 +71,14 @@ class pandaPushGymGoalEnv(gym.GoalEnv, pandaPushGymEnv):
         """Vectorisable sparse reward (HER relabels whole batches through this, reference :118-122)."""
         d = goal_distance(np.asarray(achieved_goal)[..., :3], np.asarray(goal)[..., :3])
         return -(d > self._target_dist_min).astype(np.float32)
+
+
+class pandaPushGymGoalEnv(GoalMixin, gym.GoalEnv, pandaPushGymEnv):
+    _goal_env = 1   # the kernel then applies the GoalEnv termination / reward rules (reference :96-122)
+    _box_cls = pandaPushGymEnv
+
+    def __init__(self, numControlledJoints=7, use_IK=0, action_repeat=1, obj_name=get_objects_list()[1],
+                 renders=False, max_steps=1000, obj_pose_rnd_std=0, tg_pose_rnd_std=0.2, includeVelObs=True,
+                 num_envs=1, device=0):
+        pandaPushGymEnv.__init__(self, numControlledJoints, use_IK, action_repeat, obj_name, renders, max_steps,
+                                 obj_pose_rnd_std, tg_pose_rnd_std, includeVelObs, num_envs=num_envs, device=device)

@@ -19,6 +19,8 @@ def _quat_from_yaw(yaw):
 
 
 class WorldEnv:
+    _warned_proxy = False
+
     def __init__(self, physicsClientId, obj_name='duck_vhacd', obj_pose_rnd_std=0.05, workspace_lim=None,
                  control_eu_or_quat=0):
         if not isinstance(physicsClientId, B2Client):
@@ -59,8 +61,14 @@ class WorldEnv:
         self.load_object(self._obj_name, env_ids)
 
     def load_object(self, obj_name, env_ids=None):
-        if obj_name != 'cube_small':
-            raise NotImplementedError("object '%s': only 'cube_small' has a collision model in the CUDA backend" % obj_name)
+        if obj_name not in get_objects_list():
+            raise NotImplementedError("unknown object '%s'" % obj_name)
+        if obj_name != 'cube_small' and not WorldEnv._warned_proxy:
+            # the mesh objects (duck_vhacd is the reference default of iCubReachGymEnv) live in the un-vendored
+            # pybullet_data package: they are simulated with the cube_small collision model (documented deviation)
+            import warnings
+            warnings.warn("object '%s' is simulated with the 'cube_small' collision proxy (mesh assets are not available)" % obj_name)
+            WorldEnv._warned_proxy = True
         self._obj_name = obj_name
         c = self._client
         B = c.num_envs
@@ -112,7 +120,8 @@ class WorldEnv:
     def get_observation(self):
         """Object base position + Euler angles (reference :109-126) -> (obs [B,6], limits)."""
         raw = self._client.observe()[3]
-        return squeeze1(raw[:, 18:24].astype(np.float64), self._client.num_envs), self.observation_limits()
+        nr = getattr(self._client, 'n_robot_obs', 18)   # width of the robot observation that precedes it
+        return squeeze1(raw[:, nr:nr + 6].astype(np.float64), self._client.num_envs), self.observation_limits()
 
     def check_contact(self, body_id=None, obj_id=None):
         keys = self._client.get("cache_key")

@@ -1,0 +1,121 @@
+"""The CUDA kernels of csrc/b2env.cu, compiled for the HOST by tools/emu (every CUDA thread a fiber, warp
+collectives as rendezvous points) and checked against the oracle — kernel LOGIC coverage that runs without a GPU.
+The same cases run on the real device in tests/test_gpu_icub.py / test_gpu_parity.py.  The emulation library is
+test infrastructure: the product only ever loads csrc/libb2env.so."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import icub_cases
+from common import TASK_PUSH, copy_state_to_gpu, panda_task_setup, sample_object_poses, targets_for
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tools", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = os.path.join(EMU_DIR, "libb2env_emu.so")
+    srcs = [os.path.join(ROOT, "pybullet-robot-envs_b200", "csrc", f) for f in ("b2env.cu", "b2env_tree.cuh")]
+    srcs += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "b2env.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["bash", os.path.join(EMU_DIR, "build.sh")])
+    from pybullet_robot_envs.b2env import binding
+    lib = binding.load_library(so)
+    assert b"EMULATION" in lib.b2e_version()
+    return lib
+
+
+@pytest.fixture()
+def make_sim(emu_lib):
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    sims = []
+
+    def mk(m, p, B):
+        s = B2Sim(m, p, B, 0, lib=emu_lib)
+        sims.append(s)
+        return s
+    yield mk
+    for s in sims:
+        s.close()
+
+
+def test_panda_push_kernel_matches_oracle(make_sim, oracle_lib):
+    """The 16-lane Panda kernel under emulation: same numbers as on the B200 (tests/test_gpu_parity.py)."""
+    B = 18   # two blocks, the second one with padding groups
+    m, p = panda_task_setup(TASK_PUSH)
+    sim = make_sim(m, p, B)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=4)
+    pose = sample_object_poses(B)
+    orc.reset(pose, targets_for(pose))
+    orc.step(None, 120, 1, want_obs=False)
+    copy_state_to_gpu(orc, sim)
+    rng = np.random.RandomState(1)
+    for i in range(8):
+        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)
+        np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
+        np.testing.assert_array_equal(g_done, o_done)
+    assert np.abs(sim.get("q") - orc.state["q"]).max() < 1e-5
+    assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max() < 1e-5
+    np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
+
+
+def test_icub_joint_mode(make_sim, oracle_lib):
+    icub_cases.single_step_parity(make_sim, oracle_lib, B=5, use_ik=0, n_hold=2, n_act=4)
+
+
+def test_icub_ik_mode_registered_push(make_sim, oracle_lib):
+    """iCubPush-v0 as registered: left arm, Cartesian xyz actions, reward type 0."""
+    icub_cases.single_step_parity(make_sim, oracle_lib, B=3, use_ik=1, n_hold=2, n_act=4)
+
+
+def test_icub_ik_orientation_right_arm(make_sim, oracle_lib):
+    """iCubPushGoal-v0's control mode: right arm, 6-wide actions (yaw limits [pi/2, 3pi/2])."""
+    icub_cases.single_step_parity(make_sim, oracle_lib, B=2, use_ik=1, control_orientation=1, arm='r', n_hold=1, n_act=3,
+                                  reward_type=1)
+
+
+def test_icub_reach(make_sim, oracle_lib):
+    from pybullet_robot_envs.b2env.model import TASK_REACH
+    icub_cases.single_step_parity(make_sim, oracle_lib, B=2, use_ik=1, task=TASK_REACH, n_hold=1, n_act=3)
+
+
+def test_icub_hand_contacts(make_sim, oracle_lib):
+    icub_cases.hand_contact_parity(make_sim, oracle_lib, n_check=4)
+
+
+def test_icub_gym_surface(emu_lib, monkeypatch):
+    """gym.make('iCubPush-v0') through the Python mirror (robot / world / task objects), on the emulated kernels."""
+    from pybullet_robot_envs.b2env import binding
+    monkeypatch.setattr(binding, "_lib", emu_lib)
+    import pybullet_robot_envs  # noqa: F401  (registers the ids)
+    from pybullet_robot_envs import gym_compat as gym
+    env = gym.make('iCubPush-v0')
+    assert env.observation_space.shape == (34,) and env.action_space.shape == (3,)
+    u = env.unwrapped if hasattr(env, "unwrapped") else env
+    env.seed(0)
+    obs = env.reset()
+    assert obs.shape == (34,) and obs.dtype == np.float64
+    raw = u._physics_client_id.observe()[3][0]
+    # IK of the home hand pose (icub_env.py:66-72, :148-149): the hand COM sits at (0.3, 0.26, 0.8)
+    np.testing.assert_allclose(raw[:3], [0.3, 0.26, 0.8], atol=2e-3)
+    np.testing.assert_allclose(raw[19:22], [0.25 + (raw[19] - 0.25), raw[20], 0.65], atol=2e-3)   # cube at rest on the table
+    assert abs(raw[19] - 0.25) <= 0.05 + 1e-6 and abs(raw[20]) <= 0.05 + 1e-6                     # world_env.py:145-176
+    np.testing.assert_allclose(raw[31:34], [raw[19] + 0.05, raw[20] + 0.05, raw[21]], atol=1e-5)   # target (:375-398)
+    o, r, d, info = env.step(np.array([1.0, 0.0, 0.0], np.float32))
+    assert o.shape == (34,) and np.shape(r) == () and np.shape(d) == () and info == {}
+    hp = u._physics_client_id.get("hand_pose")[0]
+    np.testing.assert_allclose(hp[:3], [0.305, 0.26, 0.8], atol=1e-6)   # += 0.005 * a (:229-231)
+    d1 = np.linalg.norm(u._physics_client_id.observe()[3][0][:3] - u._physics_client_id.observe()[3][0][19:22])
+    d2 = np.linalg.norm(np.array([0.05, 0.05, 0.0]))
+    assert abs(float(r) - (-d1 - d2)) < 2e-3    # reward type 0 (:353-356), not yet within 0.03 of the target
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(4, np.float32))
+    env.close()
