@@ -35,6 +35,14 @@ B_ALG_PUSH = 968  # algorithmic bytes per pandaPush env-step
 TRAFFIC_BYTES_PER_LAUNCH_16384 = 8.58e6
 METRIC = "env-steps/sec PandaPush-v0 batch=16384"
 WORKLOAD = "pandaPush-v0 joint mode, random policy U(-1,1)^7, post-reset state, done ignored"
+# --workload icubpush: BASELINE.json config 4 (iCubPush-v0 as registered: Cartesian control through the DLS IK,
+# 32-dof tree), an extra line next to the headline; 1492 algorithmic bytes per env-step
+WORKLOADS = {
+    "pandapush": dict(metric=METRIC, workload=WORKLOAD, n_act=7, n_obs=33, b_alg=B_ALG_PUSH, kernel="step_kernel"),
+    "icubpush": dict(metric="env-steps/sec iCubPush-v0", n_act=3, n_obs=34, b_alg=1492, kernel="tree_step_kernel<IK>",
+                     workload="iCubPush-v0 as registered (left arm, Cartesian xyz actions -> DLS IK -> 32 position motors), "
+                              "random policy U(-1,1)^3, post-reset state, done ignored"),
+}
 
 
 def peaks():
@@ -93,8 +101,34 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_cpu_arm(B, seed0, nthreads):
+def make_cpu_arm_icub(B, seed0, nthreads):
+    """CPU restatement set up like iCubPushGymEnv.reset(): IK of the home hand pose, settle, cube on the table."""
+    from oracle import b2oracle
+    from pybullet_robot_envs.b2env.model import TASK_PUSH, icub_task_setup
+    m, p = icub_task_setup(TASK_PUSH, use_ik=1)
+    orc = b2oracle.Oracle(m, p, B, nthreads=nthreads)
+    rng = np.random.RandomState(seed0)
+    pose = np.zeros((B, 7), np.float32)
+    pose[:, 0] = 0.25 + rng.uniform(-0.05, 0.05, B)
+    pose[:, 1] = rng.uniform(-0.05, 0.05, B)
+    pose[:, 2] = 0.695
+    yaw = rng.uniform(-np.pi / 4, np.pi / 4, B)
+    pose[:, 5], pose[:, 6] = np.sin(yaw / 2), np.cos(yaw / 2)
+    orc.reset(pose, pose[:, :3].copy())
+    orc.state["shaping"][:] = 1
+    orc.step(None, 1, 3, want_obs=False)
+    orc.step(None, 101, 1, want_obs=False)
+    tg = orc.state["obj_pose"][:, :3].copy()
+    tg[:, 0] = np.clip(tg[:, 0] + 0.05, 0.17, 0.38)
+    tg[:, 1] = np.clip(tg[:, 1] + 0.05, -0.3, 0.3)
+    orc.state["target"][:] = tg
+    return orc
+
+
+def make_cpu_arm(B, seed0, nthreads, workload="pandapush"):
     """The CPU restatement (oracle port) set up on the same workload: reset + settle, like env.reset()."""
+    if workload == "icubpush":
+        return make_cpu_arm_icub(B, seed0, nthreads)
     from oracle import b2oracle
     from pybullet_robot_envs.b2env.model import TASK_PUSH, panda_task_setup
     from pybullet_robot_envs.gym_compat import seeding
@@ -123,11 +157,12 @@ def time_cpu(orcs, steps, warmup, seed=1234):
     rng = np.random.RandomState(seed)
     B = orcs[0].B
     n = len(orcs)
+    na = orcs[0].params.n_act
     for i in range(warmup):
-        orcs[i % n].step(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+        orcs[i % n].step(rng.uniform(-1, 1, (B, na)).astype(np.float32), 1, 0)
     t0 = time.perf_counter()
     for i in range(steps):   # i.i.d. actions drawn per step (the draw is ~2 % of a step)
-        orcs[(warmup + i) % n].step(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+        orcs[(warmup + i) % n].step(rng.uniform(-1, 1, (B, na)).astype(np.float32), 1, 0)
     dt = time.perf_counter() - t0
     return B * steps / dt, dt
 
@@ -150,13 +185,14 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     B = args.cpu_batch
-    orcs = clone_cpu_arm(make_cpu_arm(B, 0, cores), args.replicas)
+    WL = WORKLOADS[args.workload]
+    orcs = clone_cpu_arm(make_cpu_arm(B, 0, cores, args.workload), args.replicas)
     rate, dt = time_cpu(orcs, args.steps, max(args.warmup, 3))
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": WL["metric"], "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "%d envs per step-call on %d host threads, %d replicas round-robin (rollout depth per replica %d steps)" % (B, cores, args.replicas, (args.steps + max(args.warmup, 3)) // args.replicas),
+        "config": {"workload": WL["workload"], "sample": "%d envs per step-call on %d host threads, %d replicas round-robin (rollout depth per replica %d steps)" % (B, cores, args.replicas, (args.steps + max(args.warmup, 3)) // args.replicas),
                    "note": "CPU restatement (oracle port), not PyBullet: pybullet is absent from this image; "
                            "as-shipped reference is additionally capped at 240 steps/s/process by time.sleep"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -178,6 +214,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=8, help="independent batches stepped round-robin (working set > L2)")
+    ap.add_argument("--workload", default="pandapush", choices=sorted(WORKLOADS), help="pandapush = the BASELINE.json metric")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,18 +231,24 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from pybullet_robot_envs.envs import pandaPushGymEnv
+    from pybullet_robot_envs.envs import iCubPushGymEnv, pandaPushGymEnv
 
+    WL = WORKLOADS[args.workload]
+    NA, NO, B_ALG = WL["n_act"], WL["n_obs"], WL["b_alg"]
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    env = pandaPushGymEnv(num_envs=B, device=local, renders=False, obj_pose_rnd_std=0.05, tg_pose_rnd_std=0,
-                          max_steps=1000)
+    if args.workload == "icubpush":   # registered kwargs of iCubPush-v0 (reference __init__.py:19-31)
+        env = iCubPushGymEnv(num_envs=B, device=local, renders=False, use_IK=1, control_arm='l', control_orientation=0,
+                             obj_pose_rnd_std=0.05, tg_pose_rnd_std=0, max_steps=1000, reward_type=0)
+    else:
+        env = pandaPushGymEnv(num_envs=B, device=local, renders=False, obj_pose_rnd_std=0.05, tg_pose_rnd_std=0,
+                              max_steps=1000)
     env.seed(rank * B)   # env i of rank r is the reference env seeded r*B + i
     env.reset()
     sim = env._sim
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     NACT = W + K               # one i.i.d. action batch per launch (no recycling: a periodic sequence is a drift, not a random walk)
-    actions = torch.rand((NACT, B, 7), generator=gen, device=dev, dtype=torch.float32)
+    actions = torch.rand((NACT, B, NA), generator=gen, device=dev, dtype=torch.float32)
     actions.mul_(2.0).sub_(1.0)
     returns = torch.zeros(B, device=dev)
 
@@ -222,7 +265,7 @@ def main():
     sims = [sim]
     for r in range(1, NREP):
         s2 = binding.B2Sim(sim.model, sim.params, B, local)
-        for f in ("q", "qd", "obj_pose", "obj_vel", "target", "mtarget", "counters", "cache_key", "cache_lam", "hand_pose"):
+        for f in ("q", "qd", "obj_pose", "obj_vel", "target", "mtarget", "counters", "cache_key", "cache_lam", "hand_pose", "shaping"):
             s2.set(f, sim.get(f))
         sims.append(s2)
     obs_t = torch.empty((B, sim.params.n_obs), device=dev)
@@ -257,7 +300,7 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)
     # kernel-only duration for the roofline: events directly around a few launches (no accumulation kernel)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 32))]
-    extra_actions = torch.rand((len(kev), B, 7), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    extra_actions = torch.rand((len(kev), B, NA), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
     for i, (a_, b_) in enumerate(kev):
         a_.record()
         sims[i % NREP].step(extra_actions[i], obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
@@ -282,10 +325,10 @@ def main():
     n_warm_e = min(50, depth // 2)
     Ke = max(8, min(args.e2e_steps, depth - n_warm_e))
     NH = n_warm_e + Ke
-    host_actions = sim.pinned_array((NH, B, 7))           # the policy's outputs live in page-locked host memory
+    host_actions = sim.pinned_array((NH, B, NA))          # the policy's outputs live in page-locked host memory
     rs = np.random.RandomState(99 + rank)
     for i in range(NH):                                   # i.i.d. per step
-        host_actions[i] = rs.uniform(-1, 1, (B, 7)).astype(np.float32)
+        host_actions[i] = rs.uniform(-1, 1, (B, NA)).astype(np.float32)
     env.reset()
     for i in range(n_warm_e):
         env.step(host_actions[i])
@@ -314,30 +357,30 @@ def main():
         per_gpu_rate = B * K / (dev_ms_max * 1e-3)
         # dominant kernel: algorithmic bytes per launch / its AVERAGE launch duration over the timed region (the K
         # launches run back to back between the two events; the 3 us return-accumulation add is included)
-        achieved = B * B_ALG_PUSH / (dev_ms_max / K * 1e-3) / 1e9
+        achieved = B * B_ALG / (dev_ms_max / K * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": WL["metric"], "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "config": {"workload": WL["workload"], "envs_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                        "dt": 1.0 / 240, "solver_iters_max": 150, "residual_tol": 1e-7,
                        "mean_pgs_iters_last_step": mean_iters, "nan_flags": nan_flags,
                        "l2": "no flush: %d replicas of the batch stepped round-robin, working set %.0f MB > 126 MB L2" % (NREP, NREP * B * 1.2e-3),
                        "rollout_depth_per_replica": (W + K) // NREP, "protocol": "BASELINE.md: 50 warm-up + 1000 timed steps after reset per batch, done ignored",
                        "wall_ms_per_step": 1e3 * t_wall / K, "kernel_ms_at_final_depth": kernel_ms, "mean_episode_return": mean_return},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (TRAFFIC_BYTES_PER_LAUNCH_16384 if B == 16384 else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG_PUSH,
-                         "kernel": "step_kernel", "kernel_ms_avg": dev_ms_max / K, "kernel_ms_at_final_depth": kernel_ms,
+                         "traffic": (TRAFFIC_BYTES_PER_LAUNCH_16384 if (B == 16384 and args.workload == "pandapush") else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG,
+                         "kernel": WL["kernel"], "kernel_ms_avg": dev_ms_max / K, "kernel_ms_at_final_depth": kernel_ms,
                          "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step; the average launch is dominated by the tail of a few jammed envs (DESIGN.md §4); DRAM traffic per launch (ncu, profiles/): 8.3 MB read + 0.3 MB write vs 15.9 MB algorithmic"},
-            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 7 * 4,
-                    "d2h_bytes_per_step": B * (33 + 2) * 4, "steps": Ke, "warmup": n_warm_e,
+            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * NA * 4,
+                    "d2h_bytes_per_step": B * (NO + 2) * 4, "steps": Ke, "warmup": n_warm_e,
                     "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            orc = make_cpu_arm(args.cpu_batch, 0, cores)
+            orc = make_cpu_arm(args.cpu_batch, 0, cores, args.workload)
             depth = (W + K) // NREP
             n_warm = min(50, depth // 2)
             n_timed = max(10, depth - n_warm)

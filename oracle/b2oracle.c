@@ -1134,7 +1134,13 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
     /* _termination (:301-316) then _compute_reward (:318-331) */
     real d1 = dist3(raw, e.cpos), d2 = 0, rew;
     int dn = 0;
-    if (P->reward_kind == B2E_REWARD_ICUB_REACH) { /* icub_reach_gym_env.py:301-330: the bonus is ADDED */
+    if (P->task == B2E_TASK_PUSH && P->goal_env) { /* GoalEnv variants of both robots (panda_push_gym_goal_env.py:96-122,
+                                                     icub_push_gym_goal_env.py:99-132): done = _termination() or
+                                                     is_success; reward = -(d > dist_min) */
+      d2 = dist3(e.cpos, target);
+      dn = (counter > P->max_steps) || (d2 <= P->dist_min);
+      rew = d2 > P->dist_min ? -1 : 0;
+    } else if (P->reward_kind == B2E_REWARD_ICUB_REACH) { /* icub_reach_gym_env.py:301-330: the bonus is ADDED */
       if (d1 <= P->dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P->max_steps) dn = 1;
       rew = -d1;

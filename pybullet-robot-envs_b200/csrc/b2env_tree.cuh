@@ -1081,7 +1081,10 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     const float d2 = sqrtf(dot3(dd2, dd2));
     float rew;
     int dn = 0;
-    if (P.reward_kind == B2E_REWARD_ICUB_REACH) {   // icub_reach_gym_env.py:301-330: the bonus is ADDED
+    if (P.task == B2E_TASK_PUSH && P.goal_env) {   // GoalEnv variant (icub_push_gym_goal_env.py:99-132)
+      dn = (counter > P.max_steps) || (d2 <= P.dist_min);
+      rew = d2 > P.dist_min ? -1.0f : 0.0f;
+    } else if (P.reward_kind == B2E_REWARD_ICUB_REACH) {   // icub_reach_gym_env.py:301-330: the bonus is ADDED
       if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P.max_steps) dn = 1;
       rew = -d1;
@@ -1097,15 +1100,10 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       }
       if (d2 <= P.dist_min) rew += 1000.0f;
     } else if (P.task == B2E_TASK_PUSH) {
-      if (P.goal_env) {
-        dn = (counter > P.max_steps) || (d2 <= P.dist_min);
-        rew = d2 > P.dist_min ? -1.0f : 0.0f;
-      } else {
-        if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
-        else if (terminated || counter > P.max_steps) dn = 1;
-        rew = -d1 - d2;
-        if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
-      }
+      if (d2 <= P.dist_min) { terminated = 1; dn = 1; }
+      else if (terminated || counter > P.max_steps) dn = 1;
+      rew = -d1 - d2;
+      if (d2 <= P.dist_min) rew = 1000.0f + (100.0f - d2 * 80.0f);
     } else {
       if (d1 <= P.dist_min) { terminated = 1; dn = 1; }
       else if (terminated || counter > P.max_steps) dn = 1;

@@ -42,10 +42,10 @@ def check_state(orc, sim, tag, tol_q=2e-5, tol_qd=5e-3, tol_obj=2e-5, tol_vel=5e
 
 
 def single_step_parity(make_sim, oracle_lib, B, use_ik, control_orientation=0, arm='l', task=TASK_PUSH, n_hold=3, n_act=6,
-                       reward_type=0, seed=0):
+                       reward_type=0, seed=0, goal_env=0):
     """Every step restarts the kernel from the oracle's state (isolates the per-step error)."""
     m, p = icub_task_setup(task, control_arm=arm, use_ik=use_ik, control_orientation=control_orientation,
-                           reward_type=reward_type)
+                           reward_type=reward_type, goal_env=goal_env)
     sim = make_sim(m, p, B)
     orc = oracle_lib.Oracle(m, p, B, nthreads=4)
     pose = object_poses(B, seed)

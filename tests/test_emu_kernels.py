@@ -79,7 +79,7 @@ def test_icub_ik_mode_registered_push(make_sim, oracle_lib):
 def test_icub_ik_orientation_right_arm(make_sim, oracle_lib):
     """iCubPushGoal-v0's control mode: right arm, 6-wide actions (yaw limits [pi/2, 3pi/2])."""
     icub_cases.single_step_parity(make_sim, oracle_lib, B=2, use_ik=1, control_orientation=1, arm='r', n_hold=1, n_act=3,
-                                  reward_type=1)
+                                  reward_type=1, goal_env=1)
 
 
 def test_icub_reach(make_sim, oracle_lib):

@@ -35,7 +35,7 @@ def test_ik_mode_registered_push(make_sim, oracle_lib):
 
 def test_ik_orientation_right_arm(make_sim, oracle_lib):
     icub_cases.single_step_parity(make_sim, oracle_lib, B=64, use_ik=1, control_orientation=1, arm='r', n_hold=2, n_act=8,
-                                  reward_type=1)
+                                  reward_type=1, goal_env=1)
 
 
 def test_reach(make_sim, oracle_lib):
@@ -98,7 +98,7 @@ def test_gym_surface_batched():
     assert np.isfinite(o).all() and np.isfinite(r).all()
     # per-env reset of a subset (row f1) on the tree kernel
     ids = np.array([1, 5, 17], np.int32)
-    o2 = env.reset(ids)
+    o2 = u.reset(ids)
     assert o2.shape == (3, 34)
     raw = u._physics_client_id.observe()[3]
     np.testing.assert_allclose(raw[ids, :3], np.tile([0.3, 0.26, 0.8], (3, 1)), atol=3e-3)

@@ -25,3 +25,24 @@ for kw, A in ((dict(), 7), (dict(use_ik=1), 6)):
     st = sim.get("status")
     print(kw, "rows max", st[:, 3].max(), "nan", (st[:, 0] & 1).sum(), "finite", np.isfinite(o).all())
     sim.close()
+# iCub tree kernel (one warp per env): joint mode, Cartesian mode, hand pressed onto the cube (coupled islands)
+import icub_cases
+from pybullet_robot_envs.b2env.model import icub_task_setup
+for kw, A in ((dict(use_ik=0), 10), (dict(use_ik=1), 3)):
+    m, p = icub_task_setup(TASK_PUSH, **kw)
+    B = 9    # not a multiple of the 4 envs per block
+    sim = B2Sim(m, p, B, 0)
+    pose = icub_cases.object_poses(B, 0)
+    pose[:4, 0] = [0.30, 0.33, 0.36, 0.30]; pose[:4, 1] = [0.26, 0.26, 0.27, 0.20]; pose[:, 2] = 0.651
+    sim.reset_host(pose, pose[:, :3] + np.array([0.05, 0.05, 0], np.float32))
+    sim.set("shaping", np.ones((B, 2), np.float32))
+    rng = np.random.RandomState(0)
+    if kw["use_ik"]:
+        sim.step_host(None, 1, 3, want_obs=False)
+        hp = sim.get("hand_pose"); hp[:, 2] = 0.70; sim.set("hand_pose", hp)
+        sim.step_host(None, 30, 3, want_obs=False)
+    for i in range(4):
+        o, r, d = sim.step_host(rng.uniform(-1, 1, (B, A)).astype(np.float32), 1, 0)
+    st = sim.get("status")
+    print("icub", kw, "rows max", st[:, 3].max(), "contacts max", st[:, 2].max(), "nan", (st[:, 0] & 1).sum(), "finite", np.isfinite(o).all())
+    sim.close()
