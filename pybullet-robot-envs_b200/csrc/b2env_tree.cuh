@@ -217,17 +217,121 @@ struct TreeRow {   // the generic row of this lane
   int type, isl, nidx;
 };
 
+// Arm island made of the position-motor rows and (optionally) joint-limit rows, no arm contact: every row acts
+// through one generalised coordinate (J = e_d, or -+e_d for a limit of dof d), so the island's state is the
+// generalised impulse p (lane = dof) and one Gauss-Seidel sweep over the 32 motor rows IS the affine map
+// p' = G p + c, G = -(D+L)^-1 U, c = (D+L)^-1 b with L + D + U = M^-1 (the motor block of the Delassus matrix);
+// a limit row then resets the velocity of its dof: p_d += -+(rhs - -+(M^-1 p)_d) / M^-1_dd.  Same iterates as the
+// serial sweep in exact arithmetic, same per-sweep residual test — the 32 serial, shuffle-dependent row updates
+// of a sweep become one 32-wide mat-vec.  This matters for the iCub: the IK ignores joint limits
+// (icub_env.py:307-312), a target beyond a limit makes the motor row and the limit row of that joint contradict
+// each other, and the solver then runs all 150 sweeps (the wrist pitch sits on its limit in the home hand pose).
+// If a bound would activate (motor force, or a limit impulse leaving 0) the caller falls back to the serial sweep.
+// Returns the sweep count, or -1 on fallback; motor impulses in lam_m, limit impulses in lam_l[0..nlim).
+__device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd, int nlim, float b, float invd, float diag,
+                                            float lo, float hi, float rl0, float rl1, float rl2, int max_iters, float tol,
+                                            float& lam_m, float* lam_l) {
+  const bool row = lane < nd;
+  const float* Minv = &sm.Minv[0][0];
+  float G[32];
+  float c = 0.f;
+  {
+    float Ar[32], T[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      Ar[k] = (row && k < nd) ? Minv[k * 33 + lane] : ((k == lane) ? 1.f : 0.f);
+      T[k] = (k == lane) ? 1.f : 0.f;
+      G[k] = 0.f;
+    }
+    const float idg = row ? invd : 1.f;
+    // T = (D+L)^-1 by forward substitution, lane = row
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+#pragma unroll
+      for (int k = 0; k <= j; k++) {
+        const float tj = SHW(T[k] * idg, j);   // final row j of T
+        if (lane == j) T[k] = tj;
+        else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
+      }
+    }
+    // G = -T U, c = T b
+    const float bb = row ? b : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      c = fmaf(T[j], SHW(bb, j), c);
+#pragma unroll
+      for (int k = j + 1; k < 32; k++) G[k] = fmaf(-T[j], SHW(Ar[k], j), G[k]);
+    }
+  }
+  // limit rows: dof, sign of J, row of M^-1, diagonal
+  int ld[3] = {0, 0, 0};
+  float ls[3] = {0.f, 0.f, 0.f}, lrow[3] = {0.f, 0.f, 0.f}, ldiag[3] = {1.f, 1.f, 1.f};
+  const float lrhs[3] = {rl0, rl1, rl2};
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    if (l < nlim) {
+      const int code = sm.lim_d[l];
+      ld[l] = code & 0xff;
+      ls[l] = (code >> 8) ? -1.f : 1.f;
+      lrow[l] = Minv[ld[l] * 33 + lane];
+      ldiag[l] = Minv[ld[l] * 33 + ld[l]];
+    }
+  }
+  float p = 0.f, lm = 0.f, ll[3] = {0.f, 0.f, 0.f};
+  int it = 0;
+  bool clamp = false, conv = false;
+  for (; it < max_iters; it++) {
+    float a0 = c, a1 = 0.f;
+#pragma unroll
+    for (int k = 1; k < 32; k += 2) a0 = fmaf(G[k], SHW(p, k), a0);
+#pragma unroll
+    for (int k = 2; k < 32; k += 2) a1 = fmaf(G[k], SHW(p, k), a1);
+    float p1 = a0 + a1;                      // G[0] = 0: row 0 has no strictly-upper part before it
+    const float dm = row ? p1 - p : 0.f;     // impulse change of this lane's motor row
+    if (!row) p1 = 0.f;
+    const float nlm = lm + dm;
+    bool cl = row && !(nlm >= lo && nlm <= hi);
+    float rv = dm * diag;
+    rv = rv * rv;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      if (l < nlim) {
+        const float dvd = wsumf(lrow[l] * p1);            // (M^-1 p)_d
+        const float u = lrhs[l] - ls[l] * dvd;
+        const float nl = fmaf(u, 1.0f / ldiag[l], ll[l]);
+        cl = cl || !(nl >= 0.f);
+        const float dl = nl - ll[l];
+        ll[l] = nl;
+        if (lane == ld[l]) p1 = fmaf(ls[l], dl, p1);
+        const float r2 = dl * ldiag[l];
+        rv = fmaxf(rv, r2 * r2);
+      }
+    }
+    if (__any_sync(FULL, cl)) { clamp = true; break; }
+    p = p1;
+    lm = nlm;
+    rv = wmaxf(rv);
+    if (rv <= tol) { conv = true; it++; break; }
+  }
+  if (clamp) return -1;
+  (void)conv;
+  lam_m = lm;
+#pragma unroll
+  for (int l = 0; l < 3; l++) lam_l[l] = ll[l];
+  return it;
+}
+
 // Projected Gauss-Seidel on the Delassus form: rows in Bullet's order (motors, limits, contact normals, then the
 // frictions bounded by mu * normal impulse); the arm island and the cube island converge independently unless a
 // proxy-cube contact couples them.  Same iteration as oracle/b2oracle.c physics_step.  Warp-uniform control flow.
 __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, TreeRow& r, int nd, int RG, int fric_start,
-                                        bool coupled, bool has_cube_rows, int max_iters, float tol) {
+                                        bool coupled, bool has_cube_rows, bool arm_done, int max_iters, float tol) {
   const bool valid = lane < RG, fr = lane >= fric_start;
   const bool cube = !coupled && r.isl == 1;
   const unsigned arm_nf = __ballot_sync(FULL, valid && !cube && !fr), arm_f = __ballot_sync(FULL, valid && !cube && fr);
   const unsigned cube_nf = __ballot_sync(FULL, valid && cube && !fr), cube_f = __ballot_sync(FULL, valid && cube && fr);
   const float* Minv = &sm.Minv[0][0];
-  bool done0 = false, done1 = !has_cube_rows || coupled;
+  bool done0 = arm_done, done1 = !has_cube_rows || coupled;   // arm_done: the arm island was solved by tree_arm_affine
   int it = 0;
   for (; it < max_iters; it++) {
     if (done0 && done1) break;
@@ -896,7 +1000,26 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         }
       }
     }
-    iters = tree_pgs(sm, lane, m, rr, nd, RG, fric_start, coupled, has_cube, P.solver_iters, P.residual_tol);
+    bool arm_done = false;
+    int iters_arm = 0;
+    {
+      // arm island = motor rows + limit rows only (no proxy contact): affine Gauss-Seidel
+      const bool arm_contact = __any_sync(FULL, arm_part && lane >= nlim);
+      if (!coupled && !arm_contact) {
+        float lam_m = 0.f, lam_l[3];
+        const float r0 = SHW(rr.u, 0), r1 = SHW(rr.u, 1), r2 = SHW(rr.u, 2);
+        const int ia = tree_arm_affine(sm, lane, nd, nlim, m.u, m.invd, m.diag, m.lo, m.hi, r0, r1, r2, P.solver_iters,
+                                       P.residual_tol, lam_m, lam_l);
+        if (ia >= 0) {
+          arm_done = true;
+          iters_arm = ia;
+          m.lam = lam_m;
+          if (lane < nlim) rr.lam = lane == 0 ? lam_l[0] : (lane == 1 ? lam_l[1] : lam_l[2]);
+        }
+      }
+    }
+    iters = tree_pgs(sm, lane, m, rr, nd, RG, fric_start, coupled, has_cube, arm_done, P.solver_iters, P.residual_tol);
+    if (iters_arm > iters) iters = iters_arm;
     sm.mlam[lane] = is_dof ? m.lam : 0.f;
     sm.glam[lane] = lane < RG ? rr.lam : 0.f;
     __syncwarp();
