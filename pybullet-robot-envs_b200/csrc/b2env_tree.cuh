@@ -226,7 +226,8 @@ struct TreeRow {   // the generic row of this lane
 // of a sweep become one 32-wide mat-vec.  This matters for the iCub: the IK ignores joint limits
 // (icub_env.py:307-312), a target beyond a limit makes the motor row and the limit row of that joint contradict
 // each other, and the solver then runs all 150 sweeps (the wrist pitch sits on its limit in the home hand pose).
-// If a bound would activate (motor force, or a limit impulse leaving 0) the caller falls back to the serial sweep.
+// Limit rows keep their exact projection (lambda >= 0); if a MOTOR force bound would activate the caller falls back to
+// the serial sweep.
 // Returns the sweep count, or -1 on fallback; motor impulses in lam_m, limit impulses in lam_l[0..nlim).
 __device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd, int nlim, float b, float invd, float diag,
                                             float lo, float hi, float rl0, float rl1, float rl2, int max_iters, float tol,
@@ -263,9 +264,10 @@ __device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd
       for (int k = j + 1; k < 32; k++) G[k] = fmaf(-T[j], SHW(Ar[k], j), G[k]);
     }
   }
-  // limit rows: dof, sign of J, row of M^-1, diagonal
+  // limit rows: dof, sign of J, row of M^-1, diagonal, and the couplings M^-1[d_l][d_l'] between them
   int ld[3] = {0, 0, 0};
-  float ls[3] = {0.f, 0.f, 0.f}, lrow[3] = {0.f, 0.f, 0.f}, ldiag[3] = {1.f, 1.f, 1.f};
+  float ls[3] = {0.f, 0.f, 0.f}, lrow[3] = {0.f, 0.f, 0.f}, lidg[3] = {1.f, 1.f, 1.f}, ldiag[3] = {1.f, 1.f, 1.f};
+  float x10 = 0.f, x20 = 0.f, x21 = 0.f;
   const float lrhs[3] = {rl0, rl1, rl2};
 #pragma unroll
   for (int l = 0; l < 3; l++) {
@@ -275,46 +277,84 @@ __device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd
       ls[l] = (code >> 8) ? -1.f : 1.f;
       lrow[l] = Minv[ld[l] * 33 + lane];
       ldiag[l] = Minv[ld[l] * 33 + ld[l]];
+      lidg[l] = 1.0f / ldiag[l];
     }
   }
+  if (nlim > 1) x10 = Minv[ld[1] * 33 + ld[0]];
+  if (nlim > 2) { x20 = Minv[ld[2] * 33 + ld[0]]; x21 = Minv[ld[2] * 33 + ld[1]]; }
   float p = 0.f, lm = 0.f, ll[3] = {0.f, 0.f, 0.f};
   int it = 0;
-  bool clamp = false, conv = false;
+  bool clamp = false;
   for (; it < max_iters; it++) {
     float a0 = c, a1 = 0.f;
 #pragma unroll
     for (int k = 1; k < 32; k += 2) a0 = fmaf(G[k], SHW(p, k), a0);
 #pragma unroll
     for (int k = 2; k < 32; k += 2) a1 = fmaf(G[k], SHW(p, k), a1);
-    float p1 = a0 + a1;                      // G[0] = 0: row 0 has no strictly-upper part before it
+    float p1 = a0 + a1;                      // G[0] = 0: nothing of the previous iterate enters row 0 from before it
     const float dm = row ? p1 - p : 0.f;     // impulse change of this lane's motor row
     if (!row) p1 = 0.f;
     const float nlm = lm + dm;
-    bool cl = row && !(nlm >= lo && nlm <= hi);
+    const bool cl = row && !(nlm >= lo && nlm <= hi);   // a motor force bound would activate: not affine any more
     float rv = dm * diag;
     rv = rv * rv;
+    if (nlim > 0) {
+      // limit rows, one after the other, with their exact projection lambda >= 0 (a speculative row of a joint that
+      // is merely close to its limit stays at 0).  (M^-1 p)_d of the three rows: one interleaved butterfly, then
+      // the scalar corrections for the rows handled before.
+      float d0 = lrow[0] * p1, d1 = lrow[1] * p1, d2 = lrow[2] * p1;
 #pragma unroll
-    for (int l = 0; l < 3; l++) {
-      if (l < nlim) {
-        const float dvd = wsumf(lrow[l] * p1);            // (M^-1 p)_d
-        const float u = lrhs[l] - ls[l] * dvd;
-        const float nl = fmaf(u, 1.0f / ldiag[l], ll[l]);
-        cl = cl || !(nl >= 0.f);
-        const float dl = nl - ll[l];
-        ll[l] = nl;
-        if (lane == ld[l]) p1 = fmaf(ls[l], dl, p1);
-        const float r2 = dl * ldiag[l];
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(FULL, d0, o);
+        d1 += __shfl_xor_sync(FULL, d1, o);
+        d2 += __shfl_xor_sync(FULL, d2, o);
+      }
+      float dp0, dp1 = 0.f, dp2 = 0.f;   // generalised impulse changes s_l * dlambda_l
+      {
+        const float nl = fmaxf(fmaf(lrhs[0] - ls[0] * d0, lidg[0], ll[0]), 0.f);
+        const float dl = nl - ll[0];
+        ll[0] = nl;
+        dp0 = ls[0] * dl;
+        const float r2 = dl * ldiag[0];
         rv = fmaxf(rv, r2 * r2);
       }
+      if (nlim > 1) {
+        d1 = fmaf(x10, dp0, d1);
+        const float nl = fmaxf(fmaf(lrhs[1] - ls[1] * d1, lidg[1], ll[1]), 0.f);
+        const float dl = nl - ll[1];
+        ll[1] = nl;
+        dp1 = ls[1] * dl;
+        const float r2 = dl * ldiag[1];
+        rv = fmaxf(rv, r2 * r2);
+      }
+      if (nlim > 2) {
+        d2 = fmaf(x20, dp0, fmaf(x21, dp1, d2));
+        const float nl = fmaxf(fmaf(lrhs[2] - ls[2] * d2, lidg[2], ll[2]), 0.f);
+        const float dl = nl - ll[2];
+        ll[2] = nl;
+        dp2 = ls[2] * dl;
+        const float r2 = dl * ldiag[2];
+        rv = fmaxf(rv, r2 * r2);
+      }
+      if (lane == ld[0]) p1 += dp0;
+      if (nlim > 1 && lane == ld[1]) p1 += dp1;
+      if (nlim > 2 && lane == ld[2]) p1 += dp2;
     }
     if (__any_sync(FULL, cl)) { clamp = true; break; }
     p = p1;
     lm = nlm;
     rv = wmaxf(rv);
-    if (rv <= tol) { conv = true; it++; break; }
+    if (rv <= tol) { it++; break; }
   }
-  if (clamp) return -1;
-  (void)conv;
+  if (clamp) {
+#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
+    if (lane == 0) fprintf(stderr, "affine fallback at sweep %d (nlim %d)\n", it, nlim);
+#endif
+    return -1;
+  }
+#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
+  if (lane == 0) fprintf(stderr, "affine ok: %d sweeps (nlim %d)\n", it, nlim);
+#endif
   lam_m = lm;
 #pragma unroll
   for (int l = 0; l < 3; l++) lam_l[l] = ll[l];
