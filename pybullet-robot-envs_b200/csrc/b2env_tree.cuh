@@ -23,6 +23,7 @@ struct TreeSmem {
   float A[32 * 32];          // generic x generic Delassus block, A[c*32 + r]
   float W[32 * TREE_WS];     // W[g][k] = (M^-1 J_g^T)_k; k < 32 arm dofs, 32..37 cube (lin, ang)
   float WT[32 * 32];         // WT[d][g] = W[g][d]: what motor row d reads (unit stride over g)
+  float X[32 * 32];          // tree_arm_affine: rows of the motor Delassus block, rotated (16-byte aligned)
   float T[32][12];           // body world transforms: R (9) + p (3)
   float S[32][6];            // world spatial axes about O = base position: (w ; v_O)
   float vstar[TREE_WS];      // unconstrained velocities (32 arm + 6 cube)
@@ -36,6 +37,7 @@ struct TreeSmem {
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
 };
+static_assert(sizeof(TreeSmem) % 16 == 0 && offsetof(TreeSmem, X) % 16 == 0, "TreeSmem: X is read with 16-byte loads");
 
 __device__ __forceinline__ float wmaxf(float v) {   // max of non-negative floats over the warp
   return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
@@ -229,7 +231,7 @@ struct TreeRow {   // the generic row of this lane
 // Limit rows keep their exact projection (lambda >= 0); if a MOTOR force bound would activate the caller falls back to
 // the serial sweep.
 // Returns the sweep count, or -1 on fallback; motor impulses in lam_m, limit impulses in lam_l[0..nlim).
-__device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd, int nlim, float b, float invd, float diag,
+__device__ __noinline__ int tree_arm_affine(TreeSmem& sm, int lane, int nd, int nlim, float b, float invd, float diag,
                                             float lo, float hi, float rl0, float rl1, float rl2, int max_iters, float tol,
                                             float& lam_m, float* lam_l) {
   const bool row = lane < nd;
@@ -237,31 +239,41 @@ __device__ __noinline__ int tree_arm_affine(const TreeSmem& sm, int lane, int nd
   float G[32];
   float c = 0.f;
   {
-    float Ar[32], T[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-      Ar[k] = (row && k < nd) ? Minv[k * 33 + lane] : ((k == lane) ? 1.f : 0.f);
-      T[k] = (k == lane) ? 1.f : 0.f;
-      G[k] = 0.f;
+    // G = -(D+L)^-1 U and c = (D+L)^-1 b, lane = row r, in ONE ROLLED loop (no pivot-dependent register index, no
+    // shuffle-dependent chain).  Row r of T = (D+L)^-1 solves the upper-triangular system (D+L)^T y = e_r by back
+    // substitution in column form: y_j = rhs_j / A_jj, then rhs_i -= A_ji y_j for i < j, j = 31..0; every finished
+    // y_j = T[r][j] is consumed at once: G[r][k] -= y_j A_jk for k > j, c_r += y_j b_j.  Both register files rotate one
+    // place per step (z[m] = rhs[j-m]; G[m] = G_r[j+1+m] on entry, natural order after j = 0), so all indices
+    // are static; slots that rotate in from outside the triangle only ever feed slots outside the triangle.
+    // X[j][m] = A[j][(j-m) mod 32]: m = 1..j is the lower part of row j (the solve), m = j+1..31 the upper part
+    // reversed (the G update), read as lane-uniform 16-byte loads.
+    float* X = sm.X;
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+      const int cc = (j - lane) & 31;
+      X[j * 32 + lane] = (j < nd && cc < nd) ? Minv[j * 33 + cc] : 0.f;
     }
+    __syncwarp();
     const float idg = row ? invd : 1.f;
-    // T = (D+L)^-1 by forward substitution, lane = row
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-#pragma unroll
-      for (int k = 0; k <= j; k++) {
-        const float tj = SHW(T[k] * idg, j);   // final row j of T
-        if (lane == j) T[k] = tj;
-        else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
-      }
-    }
-    // G = -T U, c = T b
     const float bb = row ? b : 0.f;
+    float z[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      c = fmaf(T[j], SHW(bb, j), c);
+    for (int m = 0; m < 32; m++) { z[m] = (31 - m == lane) ? 1.f : 0.f; G[m] = 0.f; }
+#pragma unroll 1
+    for (int j = 31; j >= 0; j--) {
+      float xr[32];
 #pragma unroll
-      for (int k = j + 1; k < 32; k++) G[k] = fmaf(-T[j], SHW(Ar[k], j), G[k]);
+      for (int q4 = 0; q4 < 8; q4++) {
+        const float4 v = *reinterpret_cast<const float4*>(X + j * 32 + 4 * q4);
+        xr[4 * q4] = v.x; xr[4 * q4 + 1] = v.y; xr[4 * q4 + 2] = v.z; xr[4 * q4 + 3] = v.w;
+      }
+      const float yj = z[0] * SHW(idg, j);
+      c = fmaf(yj, SHW(bb, j), c);
+#pragma unroll
+      for (int m = 1; m < 32; m++) z[m - 1] = fmaf(-yj, xr[m], z[m]);
+#pragma unroll
+      for (int m = 31; m >= 1; m--) G[m] = fmaf(-yj, xr[32 - m], G[m - 1]);
+      G[0] = 0.f;
     }
   }
   // limit rows: dof, sign of J, row of M^-1, diagonal, and the couplings M^-1[d_l][d_l'] between them
@@ -700,21 +712,22 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     float a[32];
 #pragma unroll
     for (int e = 0; e < 32; e++) a[e] = (is_dof && e < nd) ? sm.Minv[lane][e] : ((e == lane) ? 1.f : 0.f);
-    // in-place Gauss-Jordan inverse (M is symmetric positive definite: no pivoting), lane = row
-#pragma unroll
+    // in-place Gauss-Jordan inverse (M is symmetric positive definite: no pivoting), lane = row.  The loop over the
+    // pivots is ROLLED (the kernel is instruction-fetch bound when it is not): the row registers rotate one place per
+    // step, so the pivot column is always a[0] — the FFMA that updates column j writes it to slot j-1, the finished
+    // pivot column enters at slot 31, and after 32 steps every column is back in its own slot.  Same arithmetic,
+    // same bits as the unrolled form; body = 32 SHFL + 31 FSEL + 31 FFMA.
+#pragma unroll 1
     for (int k = 0; k < 32; k++) {
       float rk[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) rk[j] = SHW(a[j], k);
-      const float pinv = 1.0f / rk[k];
-      if (lane == k) {
+      const float pinv = 1.0f / rk[0];
+      const bool piv = lane == k;
+      const float coef = piv ? pinv : -a[0] * pinv;
 #pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = (j == k) ? pinv : rk[j] * pinv;
-      } else {
-        const float f = a[k];
-#pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = (j == k) ? -f * pinv : fmaf(-f * pinv, rk[j], a[j]);
-      }
+      for (int j = 1; j < 32; j++) a[j - 1] = fmaf(coef, rk[j], piv ? 0.f : a[j]);
+      a[31] = coef;
     }
     __syncwarp();
 #pragma unroll

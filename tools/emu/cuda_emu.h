@@ -42,6 +42,7 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float3 { float x, y, z; };
+struct alignas(16) float4 { float x, y, z, w; };
 
 using std::max;
 using std::min;
