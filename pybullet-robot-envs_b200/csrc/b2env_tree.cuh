@@ -14,7 +14,7 @@
 
 #define TREE_WPB 4      // warps (= environments) per block
 #define TREE_MAXC 8     // contacts kept per env (4 cube-table + 4 proxy contacts): 3 + 3*8 = 27 generic rows <= 32
-#define TREE_WS 40      // row stride of the W table (32 arm dofs + 6 cube components, padded)
+#define TREE_WS 41      // row stride of the W table (32 arm dofs + 6 cube components; odd: rows AND columns are conflict-free)
 #define TREE_ROUNDS 24  // child -> parent accumulation rounds the host schedule may use
 #define SHW(v, src) __shfl_sync(FULL, (v), (src))
 
@@ -22,14 +22,13 @@ struct TreeSmem {
   float Minv[32][33];        // joint-space inertia, then its inverse (row stride 33: conflict-free column reads)
   float A[32 * 32];          // generic x generic Delassus block, A[c*32 + r]
   float W[32 * TREE_WS];     // W[g][k] = (M^-1 J_g^T)_k; k < 32 arm dofs, 32..37 cube (lin, ang)
-  float WT[32 * 32];         // WT[d][g] = W[g][d]: what motor row d reads (unit stride over g)
   float X[32 * 32];          // tree_arm_affine: rows of the motor Delassus block, rotated (16-byte aligned)
   float T[32][12];           // body world transforms: R (9) + p (3)
   float S[32][6];            // world spatial axes about O = base position: (w ; v_O)
-  float vstar[TREE_WS];      // unconstrained velocities (32 arm + 6 cube)
+  float vstar[44];           // unconstrained velocities (32 arm + 6 cube)
   float mlam[32];            // motor-row impulses
   float glam[32];            // generic-row impulses
-  float scr[6 * 32];         // IK: Jacobian rows; later the observation staging
+  float scr[200];            // IK: Jacobian rows (stride 33); later the observation staging
   Contact con[TREE_MAXC];
   float con_cfm[TREE_MAXC];
   int lim_d[4];
@@ -37,7 +36,8 @@ struct TreeSmem {
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
 };
-static_assert(sizeof(TreeSmem) % 16 == 0 && offsetof(TreeSmem, X) % 16 == 0, "TreeSmem: X is read with 16-byte loads");
+static_assert(sizeof(TreeSmem) % 16 == 0 && offsetof(TreeSmem, X) % 16 == 0 && offsetof(TreeSmem, mlam) % 16 == 0,
+              "TreeSmem: X and mlam are read with 16-byte loads");
 
 __device__ __forceinline__ float wmaxf(float v) {   // max of non-negative floats over the warp
   return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
@@ -177,15 +177,19 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 6; k++) scr[k * 32 + lane] = c[k];
+    for (int k = 0; k < 6; k++) scr[k * 33 + lane] = c[k];
     __syncwarp();
     const int r = lane < 6 ? lane : 0;   // lane r < 6: row r of J J^T + lambda I, augmented with e_r
     float Ur[7];
 #pragma unroll
-    for (int cc2 = 0; cc2 < 6; cc2++) {
-      float acc = (cc2 == r) ? damping : 0.f;
-      for (int d = 0; d < 32; d++) acc = fmaf(scr[r * 32 + d], scr[cc2 * 32 + d], acc);
-      Ur[cc2] = acc;
+    for (int cc2 = 0; cc2 < 6; cc2++) Ur[cc2] = (cc2 == r) ? damping : 0.f;
+    // only the joints between the base and the hand have a Jacobian column (the others are exact zeros: skipping
+    // them leaves every partial sum unchanged); row stride 33: the six row lanes read six different banks
+    for (unsigned pm = U.ee_dofmask; pm; pm &= pm - 1) {
+      const int d = __ffs(pm) - 1;
+      const float cr = scr[r * 33 + d];
+#pragma unroll
+      for (int cc2 = 0; cc2 < 6; cc2++) Ur[cc2] = fmaf(cr, scr[cc2 * 33 + d], Ur[cc2]);
     }
     Ur[6] = r < 3 ? (r == 0 ? dp[0] : (r == 1 ? dp[1] : dp[2])) : (r == 3 ? er[0] : (r == 4 ? er[1] : er[2]));
 #pragma unroll
@@ -218,6 +222,92 @@ struct TreeRow {   // the generic row of this lane
   float lam, u, base, gg, invd, diag, lo, hi, mu, prev;
   int type, isl, nidx;
 };
+
+struct AffineLim {   // the (up to 3) joint-limit rows of the arm island, lane-uniform except lrow
+  int ld[3];
+  float ls[3], lrow[3], lidg[3], ldiag[3], lrhs[3], x10, x20, x21;
+};
+
+// The sweeps of tree_arm_affine, specialised on the number of limit rows: p' = G p + c with p read back as
+// lane-uniform 16-byte loads from shared memory (1 STS + 8 LDS.128 instead of 31 shuffles), then the limit rows;
+// a motor force bound that would activate is folded into the residual reduction as +inf (one REDUX per sweep).
+template <int NL>
+__device__ __forceinline__ int tree_affine_sweeps(float* pb, int lane, bool row, const float (&G)[32], float c, float diag,
+                                                  float lo, float hi, const AffineLim& L, int max_iters, float tol,
+                                                  float& lam_m, float* lam_l) {
+  float p = 0.f, lm = 0.f, ll[3] = {0.f, 0.f, 0.f};
+  int it = 0;
+  bool clamp = false;
+  const float INF = __int_as_float(0x7f800000);
+  for (; it < max_iters; it++) {
+    __syncwarp();
+    pb[lane] = p;
+    __syncwarp();
+    float pk[32];
+#pragma unroll
+    for (int q4 = 0; q4 < 8; q4++) {
+      const float4 v = *reinterpret_cast<const float4*>(pb + 4 * q4);
+      pk[4 * q4] = v.x; pk[4 * q4 + 1] = v.y; pk[4 * q4 + 2] = v.z; pk[4 * q4 + 3] = v.w;
+    }
+    float a0 = c, a1 = 0.f;
+#pragma unroll
+    for (int k = 1; k < 32; k += 2) a0 = fmaf(G[k], pk[k], a0);
+#pragma unroll
+    for (int k = 2; k < 32; k += 2) a1 = fmaf(G[k], pk[k], a1);
+    float p1 = a0 + a1;                      // G[0] = 0: nothing of the previous iterate enters row 0 from before it
+    const float dm = row ? p1 - p : 0.f;     // impulse change of this lane's motor row
+    if (!row) p1 = 0.f;
+    const float nlm = lm + dm;
+    const bool cl = row && !(nlm >= lo && nlm <= hi);   // a motor force bound would activate: not affine any more
+    float rv = dm * diag;
+    rv = rv * rv;
+    if (NL > 0) {
+      // limit rows, one after the other, with their exact projection lambda >= 0 (a speculative row of a joint that
+      // is merely close to its limit stays at 0).  (M^-1 p)_d of the rows: one interleaved butterfly, then the
+      // scalar corrections for the rows handled before.
+      float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int l = 0; l < NL; l++) d[l] = L.lrow[l] * p1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < NL; l++) d[l] += __shfl_xor_sync(FULL, d[l], o);
+      }
+      float dp[3] = {0.f, 0.f, 0.f};   // generalised impulse changes s_l * dlambda_l
+#pragma unroll
+      for (int l = 0; l < NL; l++) {
+        if (l == 1) d[1] = fmaf(L.x10, dp[0], d[1]);
+        if (l == 2) d[2] = fmaf(L.x20, dp[0], fmaf(L.x21, dp[1], d[2]));
+        const float nl = fmaxf(fmaf(L.lrhs[l] - L.ls[l] * d[l], L.lidg[l], ll[l]), 0.f);
+        const float dl = nl - ll[l];
+        ll[l] = nl;
+        dp[l] = L.ls[l] * dl;
+        const float r2 = dl * L.ldiag[l];
+        rv = fmaxf(rv, r2 * r2);
+      }
+#pragma unroll
+      for (int l = 0; l < NL; l++) if (lane == L.ld[l]) p1 += dp[l];
+    }
+    rv = wmaxf(cl ? INF : rv);
+    if (rv == INF) { clamp = true; break; }
+    p = p1;
+    lm = nlm;
+    if (rv <= tol) { it++; break; }
+  }
+  if (clamp) {
+#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
+    if (lane == 0) fprintf(stderr, "affine fallback at sweep %d (nlim %d)\n", it, NL);
+#endif
+    return -1;
+  }
+#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
+  if (lane == 0) fprintf(stderr, "affine ok: %d sweeps (nlim %d)\n", it, NL);
+#endif
+  lam_m = lm;
+#pragma unroll
+  for (int l = 0; l < 3; l++) lam_l[l] = ll[l];
+  return it;
+}
 
 // Arm island made of the position-motor rows and (optionally) joint-limit rows, no arm contact: every row acts
 // through one generalised coordinate (J = e_d, or -+e_d for a limit of dof d), so the island's state is the
@@ -294,83 +384,17 @@ __device__ __noinline__ int tree_arm_affine(TreeSmem& sm, int lane, int nd, int 
   }
   if (nlim > 1) x10 = Minv[ld[1] * 33 + ld[0]];
   if (nlim > 2) { x20 = Minv[ld[2] * 33 + ld[0]]; x21 = Minv[ld[2] * 33 + ld[1]]; }
-  float p = 0.f, lm = 0.f, ll[3] = {0.f, 0.f, 0.f};
-  int it = 0;
-  bool clamp = false;
-  for (; it < max_iters; it++) {
-    float a0 = c, a1 = 0.f;
+  AffineLim L;
 #pragma unroll
-    for (int k = 1; k < 32; k += 2) a0 = fmaf(G[k], SHW(p, k), a0);
-#pragma unroll
-    for (int k = 2; k < 32; k += 2) a1 = fmaf(G[k], SHW(p, k), a1);
-    float p1 = a0 + a1;                      // G[0] = 0: nothing of the previous iterate enters row 0 from before it
-    const float dm = row ? p1 - p : 0.f;     // impulse change of this lane's motor row
-    if (!row) p1 = 0.f;
-    const float nlm = lm + dm;
-    const bool cl = row && !(nlm >= lo && nlm <= hi);   // a motor force bound would activate: not affine any more
-    float rv = dm * diag;
-    rv = rv * rv;
-    if (nlim > 0) {
-      // limit rows, one after the other, with their exact projection lambda >= 0 (a speculative row of a joint that
-      // is merely close to its limit stays at 0).  (M^-1 p)_d of the three rows: one interleaved butterfly, then
-      // the scalar corrections for the rows handled before.
-      float d0 = lrow[0] * p1, d1 = lrow[1] * p1, d2 = lrow[2] * p1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        d0 += __shfl_xor_sync(FULL, d0, o);
-        d1 += __shfl_xor_sync(FULL, d1, o);
-        d2 += __shfl_xor_sync(FULL, d2, o);
-      }
-      float dp0, dp1 = 0.f, dp2 = 0.f;   // generalised impulse changes s_l * dlambda_l
-      {
-        const float nl = fmaxf(fmaf(lrhs[0] - ls[0] * d0, lidg[0], ll[0]), 0.f);
-        const float dl = nl - ll[0];
-        ll[0] = nl;
-        dp0 = ls[0] * dl;
-        const float r2 = dl * ldiag[0];
-        rv = fmaxf(rv, r2 * r2);
-      }
-      if (nlim > 1) {
-        d1 = fmaf(x10, dp0, d1);
-        const float nl = fmaxf(fmaf(lrhs[1] - ls[1] * d1, lidg[1], ll[1]), 0.f);
-        const float dl = nl - ll[1];
-        ll[1] = nl;
-        dp1 = ls[1] * dl;
-        const float r2 = dl * ldiag[1];
-        rv = fmaxf(rv, r2 * r2);
-      }
-      if (nlim > 2) {
-        d2 = fmaf(x20, dp0, fmaf(x21, dp1, d2));
-        const float nl = fmaxf(fmaf(lrhs[2] - ls[2] * d2, lidg[2], ll[2]), 0.f);
-        const float dl = nl - ll[2];
-        ll[2] = nl;
-        dp2 = ls[2] * dl;
-        const float r2 = dl * ldiag[2];
-        rv = fmaxf(rv, r2 * r2);
-      }
-      if (lane == ld[0]) p1 += dp0;
-      if (nlim > 1 && lane == ld[1]) p1 += dp1;
-      if (nlim > 2 && lane == ld[2]) p1 += dp2;
-    }
-    if (__any_sync(FULL, cl)) { clamp = true; break; }
-    p = p1;
-    lm = nlm;
-    rv = wmaxf(rv);
-    if (rv <= tol) { it++; break; }
+  for (int l = 0; l < 3; l++) { L.ld[l] = ld[l]; L.ls[l] = ls[l]; L.lrow[l] = lrow[l]; L.lidg[l] = lidg[l]; L.ldiag[l] = ldiag[l]; L.lrhs[l] = lrhs[l]; }
+  L.x10 = x10; L.x20 = x20; L.x21 = x21;
+  float* pb = sm.mlam;   // the iterate p, broadcast through shared memory (free until the impulses are stored)
+  switch (nlim) {
+    case 0: return tree_affine_sweeps<0>(pb, lane, row, G, c, diag, lo, hi, L, max_iters, tol, lam_m, lam_l);
+    case 1: return tree_affine_sweeps<1>(pb, lane, row, G, c, diag, lo, hi, L, max_iters, tol, lam_m, lam_l);
+    case 2: return tree_affine_sweeps<2>(pb, lane, row, G, c, diag, lo, hi, L, max_iters, tol, lam_m, lam_l);
+    default: return tree_affine_sweeps<3>(pb, lane, row, G, c, diag, lo, hi, L, max_iters, tol, lam_m, lam_l);
   }
-  if (clamp) {
-#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
-    if (lane == 0) fprintf(stderr, "affine fallback at sweep %d (nlim %d)\n", it, nlim);
-#endif
-    return -1;
-  }
-#if defined(B2E_EMU) && defined(EMU_TRACE_AFFINE)
-  if (lane == 0) fprintf(stderr, "affine ok: %d sweeps (nlim %d)\n", it, nlim);
-#endif
-  lam_m = lm;
-#pragma unroll
-  for (int l = 0; l < 3; l++) lam_l[l] = ll[l];
-  return it;
 }
 
 // Projected Gauss-Seidel on the Delassus form: rows in Bullet's order (motors, limits, contact normals, then the
@@ -392,7 +416,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
     r.base = r.lam * r.gg;
     if (!done0) {
       for (int i = 0; i < nd; i++) {   // motor rows: Delassus column i = [M^-1[:, i] ; W_g[i]]
-        const float cm = Minv[i * 33 + lane], cg = sm.WT[i * 32 + lane];
+        const float cm = Minv[i * 33 + lane], cg = sm.W[lane * TREE_WS + i];   // column i of W (rows >= RG are zero)
         float nl = fmaf(m.u, m.invd, m.lam);
         nl = fminf(fmaxf(nl, m.lo), m.hi);
         const float dli = SHW(nl - m.lam, i);
@@ -909,7 +933,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       m.prev = 0.f;
     }
     TreeRow rr;
-    bool coupled, has_cube, arm_part;
+    bool coupled, has_cube, arm_part, arm_contact;
     float Jc[6];   // cube part of this row's Jacobian
     {
       const int gi = lane;
@@ -922,10 +946,15 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       float desired = 0.f, cfm = 0.f, lo = 0.f, hi = 0.f, mu = 0.f;
       int type = ROW_LIMIT, isl = 0, nidx = 0;
       bool sphere_cube_normal = false;
+      const bool is_lim = valid && gi < nlim;
+      int lim_dof = 0;
+      float lim_sg = 0.f;
       if (valid) {
         if (gi < nlim) {
           const int code = sm.lim_d[gi];
           const int d = code & 0xff, side = code >> 8;
+          lim_dof = d;
+          lim_sg = side ? -1.f : 1.f;
 #pragma unroll
           for (int k = 0; k < 32; k++) J[k] = (k == d) ? (side ? -1.f : 1.f) : 0.f;
           const float pen = sm.lim_dist[gi] + P.slop;
@@ -987,23 +1016,33 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       }
       arm_part = valid && isl == 0;
       // W = M^-1 J^T (rows of cube-table contacts have no arm part)
+      // Without a proxy contact (the common case) the only rows with an arm part are the limit rows, J = -+e_d:
+      // their W row is a signed column of M^-1 and every J . x below is one signed element (the same bits as the
+      // dense sums, whose other terms are exact zeros).
       float diag = 0.f, jv = 0.f;
-      const bool any_arm = __any_sync(FULL, arm_part);
+      arm_contact = __any_sync(FULL, arm_part && gi >= nlim);
+      if (arm_contact) {
 #pragma unroll 4
-      for (int d = 0; d < 32; d++) {
-        float acc = 0.f;
-        if (any_arm) {
+        for (int d = 0; d < 32; d++) {
+          float acc = 0.f;
 #pragma unroll
           for (int e = 0; e < 32; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
+          sm.W[gi * TREE_WS + d] = acc;
         }
-        sm.W[gi * TREE_WS + d] = acc;
-        sm.WT[d * 32 + gi] = valid ? acc : 0.f;
-      }
-      __syncwarp();
+        __syncwarp();
 #pragma unroll
-      for (int d = 0; d < 32; d++) {
-        diag = fmaf(J[d], sm.W[gi * TREE_WS + d], diag);
-        jv = fmaf(J[d], sm.vstar[d], jv);
+        for (int d = 0; d < 32; d++) {
+          diag = fmaf(J[d], sm.W[gi * TREE_WS + d], diag);
+          jv = fmaf(J[d], sm.vstar[d], jv);
+        }
+      } else {
+#pragma unroll 4
+        for (int d = 0; d < 32; d++) sm.W[gi * TREE_WS + d] = is_lim ? lim_sg * sm.Minv[d][lim_dof] : 0.f;
+        __syncwarp();
+        if (is_lim) {
+          diag = lim_sg * sm.W[gi * TREE_WS + lim_dof];
+          jv = lim_sg * sm.vstar[lim_dof];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 6; k++) {
@@ -1012,7 +1051,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         diag = fmaf(Jc[k], wv, diag);
         jv = fmaf(Jc[k], sm.vstar[32 + k], jv);
       }
-      sm.W[gi * TREE_WS + 38] = 0.f; sm.W[gi * TREE_WS + 39] = 0.f;
+      sm.W[gi * TREE_WS + 38] = 0.f; sm.W[gi * TREE_WS + 39] = 0.f; sm.W[gi * TREE_WS + 40] = 0.f;
       rr.type = type; rr.isl = isl; rr.nidx = nidx;
       rr.lo = lo; rr.hi = hi; rr.mu = mu;
       rr.diag = valid ? diag + cfm : 0.f;
@@ -1026,8 +1065,12 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       // generic x generic block: A[c][r] = J_r . W_c
       for (int c = 0; c < RG; c++) {
         float acc = 0.f;
+        if (arm_contact) {
 #pragma unroll
-        for (int k = 0; k < 32; k++) acc = fmaf(J[k], sm.W[c * TREE_WS + k], acc);
+          for (int k = 0; k < 32; k++) acc = fmaf(J[k], sm.W[c * TREE_WS + k], acc);
+        } else if (is_lim) {
+          acc = lim_sg * sm.W[c * TREE_WS + lim_dof];
+        }
 #pragma unroll
         for (int k = 0; k < 6; k++) acc = fmaf(Jc[k], sm.W[c * TREE_WS + 32 + k], acc);
         sm.A[c * 32 + gi] = valid ? acc : 0.f;
@@ -1057,7 +1100,6 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     int iters_arm = 0;
     {
       // arm island = motor rows + limit rows only (no proxy contact): affine Gauss-Seidel
-      const bool arm_contact = __any_sync(FULL, arm_part && lane >= nlim);
       if (!coupled && !arm_contact) {
         float lam_m = 0.f, lam_l[3];
         const float r0 = SHW(rr.u, 0), r1 = SHW(rr.u, 1), r2 = SHW(rr.u, 2);
