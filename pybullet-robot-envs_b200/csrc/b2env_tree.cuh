@@ -12,17 +12,25 @@
 // row per lane, Delassus-form projected Gauss-Seidel with lane = constraint row (32 motor rows = one row per
 // lane, then up to 32 "generic" rows: joint limits and contact normals / frictions).
 
-#define TREE_WPB 4      // warps (= environments) per block
+#define TREE_WPB 4      // warps (= environments) per block; 3 blocks per SM = 12 warps (168 registers, 17.4 KB of shared memory per env)
 #define TREE_MAXC 8     // contacts kept per env (4 cube-table + 4 proxy contacts): 3 + 3*8 = 27 generic rows <= 32
 #define TREE_WS 41      // row stride of the W table (32 arm dofs + 6 cube components; odd: rows AND columns are conflict-free)
 #define TREE_ROUNDS 24  // child -> parent accumulation rounds the host schedule may use
 #define SHW(v, src) __shfl_sync(FULL, (v), (src))
+#ifndef TREE_PHASE_SYNC
+#define TREE_PHASE_SYNC 1   // block barriers between the stages (and per IK iteration): the warps of a block walk the
+#endif                      // code together and share instruction-cache lines (the kernel is instruction-fetch bound)
+#if TREE_PHASE_SYNC
+#define TREE_BARRIER() __syncthreads()
+#else
+#define TREE_BARRIER() __syncwarp()
+#endif
 
 struct TreeSmem {
-  float Minv[32][33];        // joint-space inertia, then its inverse (row stride 33: conflict-free column reads)
+  float Mi[32 * 32];         // joint-space inertia, then its inverse, SKEWED: element (r, c) at r*32 + ((r-c) & 31) —
+                             // rows and columns are both conflict-free, rows are 16-byte aligned (see MI())
   float A[32 * 32];          // generic x generic Delassus block, A[c*32 + r]
   float W[32 * TREE_WS];     // W[g][k] = (M^-1 J_g^T)_k; k < 32 arm dofs, 32..37 cube (lin, ang)
-  float X[32 * 32];          // tree_arm_affine: rows of the motor Delassus block, rotated (16-byte aligned)
   float T[32][12];           // body world transforms: R (9) + p (3)
   float S[32][6];            // world spatial axes about O = base position: (w ; v_O)
   float vstar[44];           // unconstrained velocities (32 arm + 6 cube)
@@ -36,8 +44,9 @@ struct TreeSmem {
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
 };
-static_assert(sizeof(TreeSmem) % 16 == 0 && offsetof(TreeSmem, X) % 16 == 0 && offsetof(TreeSmem, mlam) % 16 == 0,
-              "TreeSmem: X and mlam are read with 16-byte loads");
+static_assert(sizeof(TreeSmem) % 16 == 0 && offsetof(TreeSmem, Mi) % 16 == 0 && offsetof(TreeSmem, mlam) % 16 == 0,
+              "TreeSmem: Mi and mlam are read with 16-byte loads");
+#define MI(r, c) ((r) * 32 + (((r) - (c)) & 31))
 
 __device__ __forceinline__ float wmaxf(float v) {   // max of non-negative floats over the warp
   return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
@@ -141,7 +150,15 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
   const int jt = __ldg(&M->jtype[li]);
   const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
   float qv = my_q;
+#if TREE_PHASE_SYNC
+  bool done = false;
+  for (int it = 0;; it++) {
+    // the loop is shared by the block: every warp takes part in the barrier of every pass until all are done
+    if (!__syncthreads_or(!done && it < max_iters)) break;
+    if (done || it >= max_iters) continue;
+#else
   for (int it = 0; it < max_iters; it++) {
+#endif
     float R[9], p[3];
     tree_fk(M, U, lane, lane < nl ? qv : 0.f, R, p);
     float pe[3], Re[9];
@@ -150,7 +167,11 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
 #pragma unroll
     for (int k = 0; k < 9; k++) Re[k] = SHW(R[k], ee);
     const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
+#if TREE_PHASE_SYNC
+    if (sqrtf(dot3(dp, dp)) <= residual) { done = true; continue; }   // warp-uniform
+#else
     if (sqrtf(dot3(dp, dp)) <= residual) break;   // warp-uniform
+#endif
     float cq[4], eq[4], er[3];
     mat_to_quat(Re, cq);
     {
@@ -325,7 +346,7 @@ __device__ __noinline__ int tree_arm_affine(TreeSmem& sm, int lane, int nd, int 
                                             float lo, float hi, float rl0, float rl1, float rl2, int max_iters, float tol,
                                             float& lam_m, float* lam_l) {
   const bool row = lane < nd;
-  const float* Minv = &sm.Minv[0][0];
+  const float* Mi = sm.Mi;
   float G[32];
   float c = 0.f;
   {
@@ -335,15 +356,10 @@ __device__ __noinline__ int tree_arm_affine(TreeSmem& sm, int lane, int nd, int 
     // y_j = T[r][j] is consumed at once: G[r][k] -= y_j A_jk for k > j, c_r += y_j b_j.  Both register files rotate one
     // place per step (z[m] = rhs[j-m]; G[m] = G_r[j+1+m] on entry, natural order after j = 0), so all indices
     // are static; slots that rotate in from outside the triangle only ever feed slots outside the triangle.
-    // X[j][m] = A[j][(j-m) mod 32]: m = 1..j is the lower part of row j (the solve), m = j+1..31 the upper part
+    // The skewed table IS what this loop wants, X[j][m] = A[j][(j-m) mod 32] (zero outside the n_dof block):
+    // m = 1..j is the lower part of row j (the solve), m = j+1..31 the upper part
     // reversed (the G update), read as lane-uniform 16-byte loads.
-    float* X = sm.X;
-#pragma unroll 1
-    for (int j = 0; j < 32; j++) {
-      const int cc = (j - lane) & 31;
-      X[j * 32 + lane] = (j < nd && cc < nd) ? Minv[j * 33 + cc] : 0.f;
-    }
-    __syncwarp();
+    const float* X = Mi;
     const float idg = row ? invd : 1.f;
     const float bb = row ? b : 0.f;
     float z[32];
@@ -377,13 +393,13 @@ __device__ __noinline__ int tree_arm_affine(TreeSmem& sm, int lane, int nd, int 
       const int code = sm.lim_d[l];
       ld[l] = code & 0xff;
       ls[l] = (code >> 8) ? -1.f : 1.f;
-      lrow[l] = Minv[ld[l] * 33 + lane];
-      ldiag[l] = Minv[ld[l] * 33 + ld[l]];
+      lrow[l] = Mi[MI(ld[l], lane)];
+      ldiag[l] = Mi[MI(ld[l], ld[l])];
       lidg[l] = 1.0f / ldiag[l];
     }
   }
-  if (nlim > 1) x10 = Minv[ld[1] * 33 + ld[0]];
-  if (nlim > 2) { x20 = Minv[ld[2] * 33 + ld[0]]; x21 = Minv[ld[2] * 33 + ld[1]]; }
+  if (nlim > 1) x10 = Mi[MI(ld[1], ld[0])];
+  if (nlim > 2) { x20 = Mi[MI(ld[2], ld[0])]; x21 = Mi[MI(ld[2], ld[1])]; }
   AffineLim L;
 #pragma unroll
   for (int l = 0; l < 3; l++) { L.ld[l] = ld[l]; L.ls[l] = ls[l]; L.lrow[l] = lrow[l]; L.lidg[l] = lidg[l]; L.ldiag[l] = ldiag[l]; L.lrhs[l] = lrhs[l]; }
@@ -406,7 +422,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
   const bool cube = !coupled && r.isl == 1;
   const unsigned arm_nf = __ballot_sync(FULL, valid && !cube && !fr), arm_f = __ballot_sync(FULL, valid && !cube && fr);
   const unsigned cube_nf = __ballot_sync(FULL, valid && cube && !fr), cube_f = __ballot_sync(FULL, valid && cube && fr);
-  const float* Minv = &sm.Minv[0][0];
+  const float* Mi = sm.Mi;
   bool done0 = arm_done, done1 = !has_cube_rows || coupled;   // arm_done: the arm island was solved by tree_arm_affine
   int it = 0;
   for (; it < max_iters; it++) {
@@ -416,7 +432,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
     r.base = r.lam * r.gg;
     if (!done0) {
       for (int i = 0; i < nd; i++) {   // motor rows: Delassus column i = [M^-1[:, i] ; W_g[i]]
-        const float cm = Minv[i * 33 + lane], cg = sm.W[lane * TREE_WS + i];   // column i of W (rows >= RG are zero)
+        const float cm = Mi[MI(i, lane)], cg = sm.W[lane * TREE_WS + i];   // column i of W (rows >= RG are zero)
         float nl = fmaf(m.u, m.invd, m.lam);
         nl = fminf(fmaxf(nl, m.lo), m.hi);
         const float dli = SHW(nl - m.lam, i);
@@ -464,7 +480,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
 }
 
 template <bool IK>
-__global__ void __launch_bounds__(32 * TREE_WPB, 2)
+__global__ void __launch_bounds__(32 * TREE_WPB, 3)
 tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P,
                  DevState st, const float* __restrict__ action, float* __restrict__ obs_out, float* __restrict__ reward_out,
                  float* __restrict__ done_out, int nsub, int mode, int record_contacts, const int* __restrict__ env_ids,
@@ -600,6 +616,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
                               tq[1], tq[2], tq[3]);
       if (is_dof && !ghost) my_target = (P.n_obs_joints > 0 && !is_ctrl) ? my_home : t;
     }
+    TREE_BARRIER();
     if (is_dof) {
 #pragma unroll
       for (int k = 0; k < 9; k++) sm.T[lane][k] = Rm[k];
@@ -719,7 +736,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     }
     const float tau_b = S[0] * Iw[0] + S[1] * Iw[1] + S[2] * Iw[2] + S[3] * Iw[3] + S[4] * Iw[4] + S[5] * Iw[5];
     // joint-space inertia: M[d][e] = S_e . F_d for every e on the path base..d; symmetric fill through smem
-    for (int k = lane; k < 32 * 33; k += 32) (&sm.Minv[0][0])[k] = 0.f;
+    for (int k = lane; k < 32 * 32; k += 32) sm.Mi[k] = 0.f;
     __syncwarp();
     {
       unsigned pm = is_dof ? __ldg(&M->link_dofmask[li]) : 0u;
@@ -728,14 +745,14 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         pm &= pm - 1;
         const float val = sm.S[e][0] * F[0] + sm.S[e][1] * F[1] + sm.S[e][2] * F[2] + sm.S[e][3] * F[3] + sm.S[e][4] * F[4] +
                           sm.S[e][5] * F[5];
-        sm.Minv[lane][e] = val;
-        sm.Minv[e][lane] = val;
+        sm.Mi[MI(lane, e)] = val;
+        sm.Mi[MI(e, lane)] = val;
       }
     }
-    __syncwarp();
+    TREE_BARRIER();
     float a[32];
 #pragma unroll
-    for (int e = 0; e < 32; e++) a[e] = (is_dof && e < nd) ? sm.Minv[lane][e] : ((e == lane) ? 1.f : 0.f);
+    for (int e = 0; e < 32; e++) a[e] = (is_dof && e < nd) ? sm.Mi[MI(lane, e)] : ((e == lane) ? 1.f : 0.f);
     // in-place Gauss-Jordan inverse (M is symmetric positive definite: no pivoting), lane = row.  The loop over the
     // pivots is ROLLED (the kernel is instruction-fetch bound when it is not): the row registers rotate one place per
     // step, so the pivot column is always a[0] — the FFMA that updates column j writes it to slot j-1, the finished
@@ -755,8 +772,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     }
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; e++) sm.Minv[lane][e] = (is_dof && e < nd) ? a[e] : 0.f;
-    sm.Minv[lane][32] = 0.f;
+    for (int e = 0; e < 32; e++) sm.Mi[MI(lane, e)] = (is_dof && e < nd) ? a[e] : 0.f;
     // unconstrained acceleration and v*
     const float rhs_d = is_dof ? (-tau_b - __ldg(&M->joint_damping[li]) * my_qd) : 0.f;
     float qdd = 0.f;
@@ -774,7 +790,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     }
     sm.vstar[lane] = vstar_d;
     if (lane < 8) sm.vstar[32 + lane] = lane < 3 ? cvs[lane] : (lane < 6 ? cws[lane - 3] : 0.f);
-    __syncwarp();
+    TREE_BARRIER();
 
     // ---- collision detection (pre-step poses): same canonical order and keys as the Panda kernel ----
     float Rc[9];
@@ -910,7 +926,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       const int ls = __popc(blo & lt) + __popc(bup & lt) + (lo_hit ? 1 : 0);
       if (ls < B2E_MAX_LIMROWS) { sm.lim_d[ls] = lane | (1 << 8); sm.lim_dist[ls] = dup; }
     }
-    __syncwarp();
+    TREE_BARRIER();
 
     // ---- constraint rows: motor row of dof `lane`, generic row `lane` ----
     const int fric_start = nlim + nc;
@@ -923,7 +939,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       float desired = my_kp * (my_target - my_q) * inv_dt;
       const float mv = __ldg(&M->max_vel[li]);
       if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
-      const float diag = is_dof ? sm.Minv[lane][lane] : 1.f;
+      const float diag = is_dof ? sm.Mi[MI(lane, lane)] : 1.f;
       m.diag = diag;
       m.invd = is_dof ? 1.0f / diag : 0.f;
       m.u = is_dof ? desired - vstar_d : 0.f;
@@ -1026,7 +1042,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         for (int d = 0; d < 32; d++) {
           float acc = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; e++) acc = fmaf(sm.Minv[d][e], J[e], acc);
+          for (int e = 0; e < 32; e++) acc = fmaf(sm.Mi[MI(d, e)], J[e], acc);
           sm.W[gi * TREE_WS + d] = acc;
         }
         __syncwarp();
@@ -1037,7 +1053,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         }
       } else {
 #pragma unroll 4
-        for (int d = 0; d < 32; d++) sm.W[gi * TREE_WS + d] = is_lim ? lim_sg * sm.Minv[d][lim_dof] : 0.f;
+        for (int d = 0; d < 32; d++) sm.W[gi * TREE_WS + d] = is_lim ? lim_sg * sm.Mi[MI(d, lim_dof)] : 0.f;
         __syncwarp();
         if (is_lim) {
           diag = lim_sg * sm.W[gi * TREE_WS + lim_dof];
@@ -1096,6 +1112,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         }
       }
     }
+    TREE_BARRIER();
     bool arm_done = false;
     int iters_arm = 0;
     {
@@ -1117,7 +1134,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     if (iters_arm > iters) iters = iters_arm;
     sm.mlam[lane] = is_dof ? m.lam : 0.f;
     sm.glam[lane] = lane < RG ? rr.lam : 0.f;
-    __syncwarp();
+    TREE_BARRIER();
 
     // ---- delta velocities dv = sum_r W_r lambda_r ----
     float dvk = 0.f, dvc = 0.f;
@@ -1127,7 +1144,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       if (lane < 6) dvc = fmaf(sm.W[g2 * TREE_WS + 32 + lane], lg, dvc);
     }
 #pragma unroll 8
-    for (int d = 0; d < 32; d++) dvk = fmaf(sm.Minv[lane][d], sm.mlam[d], dvk);
+    for (int d = 0; d < 32; d++) dvk = fmaf(sm.Mi[MI(lane, d)], sm.mlam[d], dvk);
     // ---- integrate (semi-implicit Euler) ----
     if (is_dof && !ghost) {
       my_qd = vstar_d + dvk;

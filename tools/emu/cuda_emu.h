@@ -67,6 +67,7 @@ struct Warp {
 struct Block {
   unsigned gen = 0;
   int arrived = 0, alive = 0;
+  int orflag[3] = {0, 0, 0};
 };
 
 extern thread_local Fiber* g_cur;
@@ -203,6 +204,15 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) {
   emu::warp_enter(6, 0u);
 }
 inline void __syncthreads() { emu::block_barrier(); }
+inline int __syncthreads_or(int pred) {   // three rotating accumulators keyed by the barrier generation (see block_barrier)
+  int* acc = emu::g_block.orflag;
+  const unsigned g = emu::g_block.gen;
+  if (pred) acc[g % 3] = 1;
+  emu::block_barrier();
+  const int r = acc[g % 3];
+  acc[(g + 2) % 3] = 0;   // not written before every fiber has left this call and arrived at the next barrier
+  return r;
+}
 
 // ------------------------------------------------------------------ scalar intrinsics
 template <class T>
