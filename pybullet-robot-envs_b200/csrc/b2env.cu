@@ -34,6 +34,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b2env.h"
@@ -67,6 +68,18 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #define NSLOT 2           // overflow slots per block for environments with more than 16 generic rows
 #endif
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
+// Slow-first scheduling (full-batch launches of the group kernel): a launch lasts as long as its slowest environment
+// (a jammed contact runs all solver sweeps over ~45 rows, ~0.5 ms), so it matters WHEN that environment starts.  The
+// kernel lists the blocks whose last solve was expensive, and the NEXT launch steps those blocks first: the grid has
+// SCHED_FRONT extra positions at its head, head position i steps listed block i, and the home position of a listed
+// block exits at once.  Block composition, code and results are unchanged — only the start order.
+#define SCHED_FRONT 128                     // extra grid positions at the head = blocks that can be listed
+#ifndef SCHED_COST
+#define SCHED_COST 2500                     // sweeps x rows of the last solve that makes an environment "slow"
+#endif
+#define SCHED_LIST(k) (4 + (k) * SCHED_FRONT)   // int sched[]: 4 counters (ring) | 2 lists | 2 x per-block tag (written / read
+#define SCHED_TAGS (4 + 2 * SCHED_FRONT)        // by alternate launches: a head position may re-list its block before the
+                                                // home position looks)
 #define SCRATCH_PER_ENV (BIGS * BIGS + BIGS * WSTRIDE + NDMAX * BIGS)   // A | W | W^T(arm part), same layout as a slot
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
@@ -133,6 +146,8 @@ struct b2e_sim {
   int record_contacts;
   cudaEvent_t ev0, ev1;
   cudaStream_t pstream[2];   // chunk pipeline of the page-locked host path
+  int* d_sched;              // slow-first scheduling state (see SCHED_FRONT)
+  int sched_seq;
 };
 
 static thread_local char g_err[512] = "";
@@ -959,14 +974,26 @@ template <bool IK>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
-            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset) {
+            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset, int* sched, int seq) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
   const int half = wl >> 4, lane = wl & (GL - 1);          // two environments per warp, 16 lanes each
   const Grp g = {0xffffu << (GL * half), GL * half, lane};
   // slot -> environment: the whole batch, or the subset listed in env_ids (per-env resets, row f1)
   const int n_slots = n_ids;   // env_ids: listed envs; else the contiguous range [env_offset, env_offset + n_ids)
-  const int slot = (blockIdx.x * WPB + warp) * 2 + half;
+  const int nhome = (n_slots + 2 * WPB - 1) / (2 * WPB);   // blocks of the batch
+  int hblock = blockIdx.x;                                  // the block of environments this grid position steps
+  if (sched) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) sched[(seq + 1) & 3] = 0;   // the next launch's counter (unused by this one)
+    if ((int)blockIdx.x < SCHED_FRONT) {   // head of the grid: the blocks the previous launch listed as slow
+      if ((int)blockIdx.x >= min(sched[(seq - 1) & 3], SCHED_FRONT)) return;
+      hblock = sched[SCHED_LIST((seq - 1) & 1) + blockIdx.x];
+    } else {
+      hblock = blockIdx.x - SCHED_FRONT;
+      if (sched[SCHED_TAGS + ((seq - 1) & 1) * nhome + hblock] == seq - 1) return;   // stepped by a head position
+    }
+  }
+  const int slot = (hblock * WPB + warp) * 2 + half;
   const bool live_env = slot < n_slots;      // padding warps of the last block shadow the last slot, stores masked
   const int slot_c = live_env ? slot : n_slots - 1;
   const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
@@ -1519,6 +1546,16 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 
   }
 
+  if (sched) {   // list this block for the head of the next launch (once per block: the tag is the claim)
+    if (lane == 0 && live_env && iters * R >= SCHED_COST) {
+      int* tag = &sched[SCHED_TAGS + (seq & 1) * nhome + hblock];
+      if (atomicExch(tag, seq) != seq) {
+        const int i = atomicAdd(&sched[seq & 3], 1);
+        if (i < SCHED_FRONT) sched[SCHED_LIST(seq & 1) + i] = hblock;
+        else *tag = 0;   // list full: stays at home
+      }
+    }
+  }
   // ---- store state (padding groups shadow the last env: they keep pace but store nothing) ----
   if (is_dof && live_env) {
     st.q[env * nd + lane] = my_q;
@@ -1860,15 +1897,18 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
-  const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
+  // slow-first scheduling only for launches over the whole batch (they all run on the caller's stream, in order)
+  int* sched = (!env_ids && env_offset == 0 && n == s->B && s->d_sched) ? s->d_sched : nullptr;
+  const int seq = sched ? s->sched_seq++ : 0;
+  const int blocks = (n + 2 * WPB - 1) / (2 * WPB) + (sched ? SCHED_FRONT : 0);
   if (s->params.use_ik)
     B2E_LAUNCH(step_kernel<true>, blocks, 32 * WPB, SMEM_BYTES, stream,
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-        env_offset);
+        env_offset, sched, seq);
   else
     B2E_LAUNCH(step_kernel<false>, blocks, 32 * WPB, SMEM_BYTES, stream,
         s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-        env_offset);
+        env_offset, sched, seq);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1938,6 +1978,15 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
   s->st.shaping = (float*)s->fields[B2E_F_SHAPING];
   CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
+  {
+    const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches slow-first scheduling off (A/B measurements)
+    if (!tree && !(e && e[0] == '0')) {
+      const size_t sb = (size_t)(SCHED_TAGS + 2 * ((num_envs + 2 * WPB - 1) / (2 * WPB))) * sizeof(int);
+      CUDA_TRY(cudaMalloc(&s->d_sched, sb));
+      CUDA_TRY(cudaMemset(s->d_sched, 0, sb));
+      s->sched_seq = 2;   // tags are 0-initialised: no environment is listed for the first launch
+    }
+  }
   const size_t na = (size_t)num_envs * (params->n_act > 0 ? params->n_act : 1) * 4, no = (size_t)num_envs * params->n_obs * 4;
   CUDA_TRY(cudaMalloc(&s->d_action, na)); CUDA_TRY(cudaMalloc(&s->d_obs, no));
   CUDA_TRY(cudaMalloc(&s->d_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMalloc(&s->d_done, (size_t)num_envs * 4));
@@ -1958,6 +2007,7 @@ void b2e_destroy(b2e_sim* s) {
   cudaSetDevice(s->device);
   for (int f = 0; f < B2E_F_COUNT; f++) cudaFree(s->fields[f]);
   cudaFree(s->st.scratch);
+  cudaFree(s->d_sched);
   cudaFree(s->d_model); cudaFree(s->d_action); cudaFree(s->d_obs); cudaFree(s->d_reward); cudaFree(s->d_done);
   cudaFreeHost(s->h_action); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_reward); cudaFreeHost(s->h_done);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);

@@ -12,7 +12,12 @@
 // row per lane, Delassus-form projected Gauss-Seidel with lane = constraint row (32 motor rows = one row per
 // lane, then up to 32 "generic" rows: joint limits and contact normals / frictions).
 
-#define TREE_WPB 4      // warps (= environments) per block; 3 blocks per SM = 12 warps (168 registers, 17.4 KB of shared memory per env)
+#ifndef TREE_WPB
+#define TREE_WPB 4      // warps (= environments) per block
+#endif
+#ifndef TREE_MINB
+#define TREE_MINB 3     // blocks per SM: 12 warps (168 registers, 17.4 KB of shared memory per env)
+#endif
 #define TREE_MAXC 8     // contacts kept per env (4 cube-table + 4 proxy contacts): 3 + 3*8 = 27 generic rows <= 32
 #define TREE_WS 41      // row stride of the W table (32 arm dofs + 6 cube components; odd: rows AND columns are conflict-free)
 #define TREE_ROUNDS 24  // child -> parent accumulation rounds the host schedule may use
@@ -20,6 +25,12 @@
 #ifndef TREE_PHASE_SYNC
 #define TREE_PHASE_SYNC 1   // block barriers between the stages (and per IK iteration): the warps of a block walk the
 #endif                      // code together and share instruction-cache lines (the kernel is instruction-fetch bound)
+#ifndef TREE_BAR_POST_SOLVE
+#define TREE_BAR_POST_SOLVE 1
+#endif
+#ifndef TREE_BAR_IK_ITER
+#define TREE_BAR_IK_ITER 1
+#endif
 #if TREE_PHASE_SYNC
 #define TREE_BARRIER() __syncthreads()
 #else
@@ -150,7 +161,7 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
   const int jt = __ldg(&M->jtype[li]);
   const float ax[3] = {__ldg(&M->axis[li][0]), __ldg(&M->axis[li][1]), __ldg(&M->axis[li][2])};
   float qv = my_q;
-#if TREE_PHASE_SYNC
+#if TREE_PHASE_SYNC && TREE_BAR_IK_ITER
   bool done = false;
   for (int it = 0;; it++) {
     // the loop is shared by the block: every warp takes part in the barrier of every pass until all are done
@@ -167,7 +178,7 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
 #pragma unroll
     for (int k = 0; k < 9; k++) Re[k] = SHW(R[k], ee);
     const float dp[3] = {tpx - pe[0], tpy - pe[1], tpz - pe[2]};
-#if TREE_PHASE_SYNC
+#if TREE_PHASE_SYNC && TREE_BAR_IK_ITER
     if (sqrtf(dot3(dp, dp)) <= residual) { done = true; continue; }   // warp-uniform
 #else
     if (sqrtf(dot3(dp, dp)) <= residual) break;   // warp-uniform
@@ -480,7 +491,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
 }
 
 template <bool IK>
-__global__ void __launch_bounds__(32 * TREE_WPB, 3)
+__global__ void __launch_bounds__(32 * TREE_WPB, TREE_MINB)
 tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P,
                  DevState st, const float* __restrict__ action, float* __restrict__ obs_out, float* __restrict__ reward_out,
                  float* __restrict__ done_out, int nsub, int mode, int record_contacts, const int* __restrict__ env_ids,
@@ -756,8 +767,8 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     // in-place Gauss-Jordan inverse (M is symmetric positive definite: no pivoting), lane = row.  The loop over the
     // pivots is ROLLED (the kernel is instruction-fetch bound when it is not): the row registers rotate one place per
     // step, so the pivot column is always a[0] — the FFMA that updates column j writes it to slot j-1, the finished
-    // pivot column enters at slot 31, and after 32 steps every column is back in its own slot.  Same arithmetic,
-    // same bits as the unrolled form; body = 32 SHFL + 31 FSEL + 31 FFMA.
+    // pivot column enters at slot 31, and after 32 steps every column is back in its own slot.
+    // Body = 32 SHFL + 31 FFMA.
 #pragma unroll 1
     for (int k = 0; k < 32; k++) {
       float rk[32];
@@ -765,10 +776,12 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       for (int j = 0; j < 32; j++) rk[j] = SHW(a[j], k);
       const float pinv = 1.0f / rk[0];
       const bool piv = lane == k;
-      const float coef = piv ? pinv : -a[0] * pinv;
+      // the pivot lane holds the pivot row itself (a[j] == rk[j]): a[j] * pinv = a[j] + (pinv - 1) * rk[j], so one FFMA
+      // form serves every lane
+      const float coef = piv ? pinv - 1.0f : -a[0] * pinv;
 #pragma unroll
-      for (int j = 1; j < 32; j++) a[j - 1] = fmaf(coef, rk[j], piv ? 0.f : a[j]);
-      a[31] = coef;
+      for (int j = 1; j < 32; j++) a[j - 1] = fmaf(coef, rk[j], a[j]);
+      a[31] = piv ? pinv : coef;
     }
     __syncwarp();
 #pragma unroll
@@ -1134,7 +1147,11 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     if (iters_arm > iters) iters = iters_arm;
     sm.mlam[lane] = is_dof ? m.lam : 0.f;
     sm.glam[lane] = lane < RG ? rr.lam : 0.f;
+#if TREE_BAR_POST_SOLVE
     TREE_BARRIER();
+#else
+    __syncwarp();
+#endif
 
     // ---- delta velocities dv = sum_r W_r lambda_r ----
     float dvk = 0.f, dvc = 0.f;

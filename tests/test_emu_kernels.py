@@ -67,6 +67,45 @@ def test_panda_push_kernel_matches_oracle(make_sim, oracle_lib):
     np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
 
 
+def test_panda_slow_first_scheduling_is_transparent(oracle_lib):
+    """Slow-first scheduling (SCHED_FRONT head positions of the grid) with the cost threshold forced to 0: after the first
+    launch EVERY block is listed and stepped by a head position while its home position exits — results must not change."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    so = os.path.join(EMU_DIR, "libb2env_emu_sched0.so")
+    srcs = [os.path.join(ROOT, "pybullet-robot-envs_b200", "csrc", f) for f in ("b2env.cu", "b2env_tree.cuh")]
+    srcs += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "b2env.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        subprocess.check_call(["bash", os.path.join(EMU_DIR, "build.sh"), "-DSCHED_COST=0"],
+                              env=dict(os.environ, OUT=os.path.basename(so)))
+    from pybullet_robot_envs.b2env import binding
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    lib = binding.load_library(so)
+    B = 37   # three blocks, the last one with padding groups
+    m, p = panda_task_setup(TASK_PUSH)
+    sim = B2Sim(m, p, B, 0, lib=lib)
+    try:
+        orc = oracle_lib.Oracle(m, p, B, nthreads=4)
+        pose = sample_object_poses(B)
+        orc.reset(pose, targets_for(pose))
+        orc.step(None, 60, 1, want_obs=False)
+        copy_state_to_gpu(orc, sim)
+        rng = np.random.RandomState(3)
+        for i in range(5):
+            a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+            g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+            o_obs, o_rew, o_done = orc.step(a, 1, 0)
+            np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
+            np.testing.assert_allclose(g_obs, o_obs, atol=2e-3)
+            np.testing.assert_array_equal(g_done, o_done)
+        assert np.abs(sim.get("q") - orc.state["q"]).max() < 1e-5
+        assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max() < 1e-5
+        np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
+        np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
+    finally:
+        sim.close()
+
+
 def test_icub_joint_mode(make_sim, oracle_lib):
     icub_cases.single_step_parity(make_sim, oracle_lib, B=5, use_ik=0, n_hold=2, n_act=4)
 

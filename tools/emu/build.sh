@@ -7,4 +7,4 @@ cd "$(dirname "$0")"
 CXX=${CXX:-g++}
 $CXX -O2 -g -std=c++17 -fPIC -shared -march=x86-64-v3 -ffp-contract=fast -Wno-unused-result \
   -DB2E_EMU_IMPL -include cuda_emu.h -x c++ ../../pybullet-robot-envs_b200/csrc/b2env.cu \
-  -o libb2env_emu.so -lpthread "$@"
+  -o ${OUT:-libb2env_emu.so} -lpthread "$@"

@@ -233,6 +233,7 @@ inline int atomicCAS(int* addr, int compare, int val) {
   return old;
 }
 inline int atomicAdd(int* addr, int val) { const int old = *addr; *addr += val; return old; }
+inline int atomicExch(int* addr, int val) { const int old = *addr; *addr = val; return old; }
 inline long long clock64() { return 0; }
 
 // ------------------------------------------------------------------ runtime API (host memory stands in for HBM)
