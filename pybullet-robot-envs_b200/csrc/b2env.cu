@@ -304,6 +304,7 @@ struct EnvSmem {
   float T[TLMAX][12];          // link world transforms: R (9) + p (3)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
+  float TL[NDMAX][GL];         // (D+L)^-1 of the motor block of the Delassus matrix, TL[k][row] (pgs_solve)
   float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
   float mlam[16];              // motor-row impulses (lane = dof)
   float glam[GMAX];            // generic-row impulses
@@ -517,6 +518,28 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
 // table),  generic x generic = A (shared memory when <= 16 generic rows, else global scratch).
 // Per-row state: u = rhs - (A lambda)_r is the running velocity error, base = lambda*(1 - cfm*invd),
 // so the dependent chain of one row update is FFMA -> FMNMX -> FMNMX -> FADD -> SHFL -> FFMA.
+// T = (D+L)^-1 of the motor block M^-1 = L + D + U of the Delassus matrix by forward substitution, lane = row
+// (T[k] = T[lane][k]); Ar = row `lane` of M^-1 (identity outside the n_dof block).  Both groups of the warp together.
+__device__ __forceinline__ void motor_block_T(const Grp& g, const float* Minv, int nd, float invd, float* Ar, float* T) {
+  const int lane = g.lane;
+  const bool row = lane < nd;
+  const int lc = lane < NDMAX ? lane : NDMAX;
+#pragma unroll
+  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? Minv[k * (NDMAX + 1) + lc] : ((k == lane) ? 1.f : 0.f);
+  const float idg = row ? invd : 1.f;
+#pragma unroll
+  for (int k = 0; k < NDMAX; k++) T[k] = (k == lane) ? 1.f : 0.f;
+#pragma unroll
+  for (int j = 0; j < NDMAX; j++) {
+#pragma unroll
+    for (int k = 0; k <= j; k++) {
+      const float tj = SHF(T[k] * idg, j);       // final row j of T
+      if (lane == j) T[k] = tj;
+      else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
+    }
+  }
+}
+
 struct MotorRegs {
   float u, invd, diag, lo, hi, lam, prev;
 };
@@ -594,8 +617,19 @@ __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowReg
 
 template <int NSG>
 __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                         const float* WT, int AS, const float* Minv, int nd, int RG, int fric_start, bool coupled,
-                                         bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
+                                         const float* WT, int AS, const float* Minv, float* TL, int nd, int RG, int fric_start,
+                                         bool coupled, bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
+  // The motor rows have no active bound in practice (|lambda| <= 1e5 dt), so their part of a sweep — n_dof serial,
+  // shuffle-dependent row updates — is the triangular solve dlambda = (D+L)^-1 u followed by u -= M^-1 dlambda (and
+  // the same for the generic rows' u through W^T): two 9-wide mat-vecs.  Same iterates in exact arithmetic; a sweep in
+  // which a bound WOULD activate (the 10 N finger rows of the grasp task) takes the serial rows instead.
+  if (__any_sync(FULL, arm_sweep)) {
+    float Ar[NDMAX], T[NDMAX];
+    motor_block_T(g, Minv, nd, m.invd, Ar, T);
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) TL[k * GL + g.lane] = T[k];
+    gsync(g);
+  }
   // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
   unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
 #pragma unroll
@@ -617,7 +651,25 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
     if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
-      for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
+      float dl = 0.f;
+#pragma unroll
+      for (int j = 0; j < NDMAX; j++) dl = fmaf(TL[j * GL + g.lane], SHF(m.u, j), dl);
+      const float nl = m.lam + dl;
+      const bool viol = !done0 && g.lane < nd && !(nl >= m.lo && nl <= m.hi);
+      if (__any_sync(FULL, viol)) {
+        for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
+      } else {
+        dl = done0 ? 0.f : dl;
+        m.lam += dl;
+        const int lc = g.lane < NDMAX ? g.lane : NDMAX;
+#pragma unroll
+        for (int i = 0; i < NDMAX; i++) {
+          const float di = SHF(dl, i);
+          m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], di, m.u);
+#pragma unroll
+          for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], di, r.u[s]);
+        }
+      }
     }
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
                        (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
@@ -673,24 +725,8 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
                                                 float lo, float hi, int max_iters, float tol, float& lam_out) {
   const int lane = g.lane;
   const bool row = lane < nd;
-  const int lc = lane < NDMAX ? lane : NDMAX;
-  float Ar[NDMAX];
-#pragma unroll
-  for (int k = 0; k < NDMAX; k++) Ar[k] = (row && k < nd) ? Minv[k * (NDMAX + 1) + lc] : ((k == lane) ? 1.f : 0.f);
-  const float idg = row ? invd : 1.f;
-  // T = (D+L)^-1 by forward substitution, lane = row
-  float T[NDMAX];
-#pragma unroll
-  for (int k = 0; k < NDMAX; k++) T[k] = (k == lane) ? 1.f : 0.f;
-#pragma unroll
-  for (int j = 0; j < NDMAX; j++) {
-#pragma unroll
-    for (int k = 0; k <= j; k++) {
-      const float tj = SHF(T[k] * idg, j);       // final row j of T
-      if (lane == j) T[k] = tj;
-      else if (lane > j) T[k] = fmaf(-Ar[j], tj, T[k]);
-    }
-  }
+  float Ar[NDMAX], T[NDMAX];
+  motor_block_T(g, Minv, nd, invd, Ar, T);
   // G = -T U, c = T b
   float G[NDMAX];
 #pragma unroll
@@ -955,7 +991,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, &sm.TL[0][0], nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
