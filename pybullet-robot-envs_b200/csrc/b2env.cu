@@ -318,6 +318,7 @@ struct EnvSmem {
 
 // Storage of one big constraint system (17..39 generic rows): block-level overflow slot in shared memory,
 // or — when the block's slots are taken — the environment's global scratch (same layout).
+static_assert(offsetof(EnvSmem, T) % 16 == 0 && sizeof(EnvSmem) % 16 == 0, "EnvSmem: A | W | WT are zeroed with 16-byte stores");
 struct BigSlot {
   float A[BIGS * BIGS];      // generic x generic Delassus block, A[c*BIGS + r]
   float W[BIGS * WSTRIDE];   // W[g][k]
@@ -325,6 +326,7 @@ struct BigSlot {
                              // third row set run to g = 47)
 };
 
+static_assert(sizeof(BigSlot) % 16 == 0, "BigSlot is zeroed with 16-byte stores");
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
 __device__ __forceinline__ void fk_lanes(const DevModel* __restrict__ M, const DevModelU& U, const Grp& g, float qi,
@@ -551,7 +553,8 @@ struct RowRegs {
 
 // Row updates are branch-free: the table entries are loaded first (their latency hides under the dependent
 // FFMA -> FMNMX -> FMNMX -> FADD -> SHFL chain), and a group that does not visit the row (`active` false)
-// multiplies zero coefficients by a zero impulse change (never 0 * stale-NaN).
+// broadcasts a zero impulse change; its table entries may be stale but are always finite (step_kernel zeroes the
+// tables of the block at its start; the global scratch is zeroed at create), so 0 * entry = 0.
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
                                            const float* W, const float* WT, int AS, int i, bool active) {
@@ -565,9 +568,9 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
   const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
   const float dli = SHF(dl, i);
   m.lam = (g.lane == i && active) ? nl : m.lam;
-  m.u = fmaf(active ? -cm : 0.f, dli, m.u);
+  m.u = fmaf(-cm, dli, m.u);                    // inactive: dli = 0 and the tables are finite (zeroed at kernel start)
 #pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -cg[s] : 0.f, dli, r.u[s]);
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-cg[s], dli, r.u[s]);
 }
 
 template <int NSG, int SI>
@@ -582,9 +585,13 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
   const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits this row in this pass
   const float dli = SHF(dl, li);
   r.lam[SI] = (g.lane == li && active) ? nl : r.lam[SI];  // base/prev are refreshed once per sweep
-  m.u = fmaf((active && arm_sweep) ? -cw : 0.f, dli, m.u);
+  // a group that does not visit the row broadcasts dli = 0; every table entry is finite (the tables are zeroed at kernel
+  // start, rows are only ever written with finite values), so no coefficient needs masking.  m.u of a finished arm
+  // island is dead.
+  (void)arm_sweep;
+  m.u = fmaf(-cw, dli, m.u);
 #pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(active ? -ca[s] : 0.f, dli, r.u[s]);
+  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
 }
 
 // Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
@@ -594,7 +601,7 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
 template <int NSG, int SI>
 __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
                                           int AS, unsigned mk, bool arm_sweep) {
-  const unsigned w = mk | __shfl_xor_sync(FULL, mk, GL);
+  const unsigned w = __reduce_or_sync(FULL, mk);   // union of the two groups' masks, PROVABLY warp-uniform (no BRA.DIV in the loop)
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
   const float* Arow = A + (GL * SI + lo) * AS;
@@ -790,7 +797,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   const float* Minv = &sm.Minv[0][0];
   const int fric_start = nlim + nc;   // generic index of the first friction row
   const int RG = nlim + 3 * nc;       // generic rows
-  const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));   // larger count of the two groups: shared loop bounds
+  const int RGw = (int)__reduce_max_sync(FULL, (unsigned)RG);   // larger count of the two groups: shared loop bounds (uniform)
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
 
@@ -991,8 +998,14 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
+#ifdef PROFILE_CYCLES
+  const long long t_pgs0 = clock64();
+#endif
   int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, &sm.TL[0][0], nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
+#ifdef PROFILE_CYCLES
+  if (lane == 0) sm.lim_dist[3] = (float)(clock64() - t_pgs0);   // instrumentation build only: cycles of the sweeps
+#endif
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
 #pragma unroll
@@ -1070,7 +1083,17 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
                       : ((ctrl_gains && P.task == B2E_TASK_GRASP && lane >= P.n_ctrl) ? P.kp_grip : P.kp_hold);
   const float grip_cmd = SHF(my_act, P.n_ctrl & (GL - 1));   // GRASP: action[n_ctrl] = gripper command
   int iters = 0, nc = 0, R = 0;
+#ifdef PROFILE_CYCLES
+  int prof_pgs = 0;
+#endif
   bool stop = false;
+  {
+    // solver tables start finite (see motor_step / generic_step): A | W | WT of this environment and the overflow slots
+    float4* t4 = reinterpret_cast<float4*>(&sm);
+    for (int k = lane; k < (int)(offsetof(EnvSmem, T) / 16); k += GL) t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* s4 = reinterpret_cast<float4*>(slots);
+    for (int k = threadIdx.x; k < (int)(sizeof(BigSlot) * NSLOT / 16); k += 32 * WPB) s4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   gsync(g);
 
   const int li = lane < nl ? lane : 0;
@@ -1485,7 +1508,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     // generic rows (limits + contacts) come in sets of 16; both envs of the warp take the same
     // instantiation (the larger need) so the warp does not execute two instantiations back to back
     const int RG = nlim + 3 * nc;
-    const int RGw = max(RG, __shfl_xor_sync(FULL, RG, GL));
+    const int RGw = (int)__reduce_max_sync(FULL, (unsigned)RG);
     // storage of a big system (> 16 generic rows): an overflow slot of the block if one is free, else global scratch
     float* gscratch = st.scratch + (size_t)env * SCRATCH_PER_ENV;
     int got = -1;
@@ -1507,6 +1530,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 
 #ifdef PROFILE_CYCLES
     R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (got < 0 ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
+    prof_pgs = (int)sm.lim_dist[3];   // cycles of the sweeps alone (replaces the contact count in B2E_F_STATUS)
 #endif
     PHASE_BARRIER();
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
@@ -1736,7 +1760,11 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     st.status[env * 4 + 0] = flags;
     if (nsub > 0) {   // solver diagnostics of the last physics step survive pure observation calls
       st.status[env * 4 + 1] = iters;
+#ifdef PROFILE_CYCLES
+      st.status[env * 4 + 2] = prof_pgs;
+#else
       st.status[env * 4 + 2] = nc;
+#endif
       st.status[env * 4 + 3] = R;
     }
   }
@@ -2014,6 +2042,7 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
   s->st.shaping = (float*)s->fields[B2E_F_SHAPING];
   CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
+  CUDA_TRY(cudaMemset(s->st.scratch, 0, (size_t)num_envs * SCRATCH_PER_ENV * 4));   // tables are finite from the start
   {
     const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches slow-first scheduling off (A/B measurements)
     if (!tree && !(e && e[0] == '0')) {

@@ -43,6 +43,7 @@ struct dim3 {
 };
 struct float3 { float x, y, z; };
 struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 using std::max;
 using std::min;
