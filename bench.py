@@ -38,8 +38,17 @@ WORKLOAD = "pandaPush-v0 joint mode, random policy U(-1,1)^7, post-reset state, 
 # --workload icubpush: BASELINE.json config 4 (iCubPush-v0 as registered: Cartesian control through the DLS IK,
 # 32-dof tree), an extra line next to the headline; 1492 algorithmic bytes per env-step
 WORKLOADS = {
-    "pandapush": dict(metric=METRIC, workload=WORKLOAD, n_act=7, n_obs=33, b_alg=B_ALG_PUSH, kernel="step_kernel"),
+    "pandapush": dict(metric=METRIC, workload=WORKLOAD, n_act=7, n_obs=33, b_alg=B_ALG_PUSH, kernel="step_kernel",
+                      traffic=TRAFFIC_BYTES_PER_LAUNCH_16384,
+                      note="latency-bound by construction: ~40 sequential PGS sweeps per step, and a launch lasts as long as its "
+                           "slowest environment (a jammed contact: 150 sweeps x ~45 rows x ~100 cycles, DESIGN.md 4c); DRAM "
+                           "traffic per launch (ncu, profiles/) stays below the 15.9 MB algorithmic figure: state is "
+                           "written back lazily from L2"),
     "icubpush": dict(metric="env-steps/sec iCubPush-v0", n_act=3, n_obs=34, b_alg=1492, kernel="tree_step_kernel<IK>",
+                     traffic=12.67e6,   # profiles/r1_ncu_icub_tree_kernel_phase_locked.csv: 12.67 MB read + 0.5 KB write
+                     note="instruction-issue / latency-bound: ~33 k warp instructions per env-step (32x32 inverse, DLS IK, "
+                          "affine Gauss-Seidel sweeps), IPC 1.9 of 4 after phase-locking the blocks (DESIGN.md 4b); "
+                          "DRAM traffic per launch 12.7 MB vs 24.4 MB algorithmic",
                      workload="iCubPush-v0 as registered (left arm, Cartesian xyz actions -> DLS IK -> 32 position motors), "
                               "random policy U(-1,1)^3, post-reset state, done ignored"),
 }
@@ -369,9 +378,9 @@ def main():
                        "rollout_depth_per_replica": (W + K) // NREP, "protocol": "BASELINE.md: 50 warm-up + 1000 timed steps after reset per batch, done ignored",
                        "wall_ms_per_step": 1e3 * t_wall / K, "kernel_ms_at_final_depth": kernel_ms, "mean_episode_return": mean_return},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (TRAFFIC_BYTES_PER_LAUNCH_16384 if (B == 16384 and args.workload == "pandapush") else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG,
+                         "traffic": (WL["traffic"] if B == 16384 else None), "traffic_unit": "bytes per launch (ncu)", "peak_source": which, "alg_bytes_per_env_step": B_ALG,
                          "kernel": WL["kernel"], "kernel_ms_avg": dev_ms_max / K, "kernel_ms_at_final_depth": kernel_ms,
-                         "note": "latency/issue-bound by construction: ~40 sequential PGS sweeps per step; the average launch is dominated by the tail of a few jammed envs (DESIGN.md §4); DRAM traffic per launch (ncu, profiles/): 8.3 MB read + 0.3 MB write vs 15.9 MB algorithmic"},
+                         "note": WL["note"]},
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * NA * 4,
                     "d2h_bytes_per_step": B * (NO + 2) * 4, "steps": Ke, "warmup": n_warm_e,
                     "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays"},
