@@ -301,10 +301,10 @@ struct EnvSmem {
   float WT[NDMAX * GL];        // WT[d][g] = W[g][d]: what a motor row reads (unit stride over g).  A 16-row system
                                // solved in a 2/3-set instantiation (its warp mate is big) reads up to 31 floats past
                                // the end for its non-existent rows: T follows, which nobody writes during the solve
-  float T[TLMAX][12];          // link world transforms: R (9) + p (3)
+  float T[TLMAX][12];          // link world transforms: R (9) + p (3); dead after collision detection: pgs_solve keeps
+                               // (D+L)^-1 of the motor block here, TL[k][row] = T[k*16 + row] (NDMAX*GL = TLMAX*12 floats)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
-  float TL[NDMAX][GL];         // (D+L)^-1 of the motor block of the Delassus matrix, TL[k][row] (pgs_solve)
   float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
   float mlam[16];              // motor-row impulses (lane = dof)
   float glam[GMAX];            // generic-row impulses
@@ -326,6 +326,7 @@ struct BigSlot {
                              // third row set run to g = 47)
 };
 
+static_assert(NDMAX * GL <= TLMAX * 12, "pgs_solve keeps its 9 x 16 triangular table in EnvSmem::T");
 static_assert(sizeof(BigSlot) % 16 == 0, "BigSlot is zeroed with 16-byte stores");
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
@@ -1001,7 +1002,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 #ifdef PROFILE_CYCLES
   const long long t_pgs0 = clock64();
 #endif
-  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, &sm.TL[0][0], nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
+  int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, &sm.T[0][0], nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
                             P.residual_tol);
 #ifdef PROFILE_CYCLES
   if (lane == 0) sm.lim_dist[3] = (float)(clock64() - t_pgs0);   // instrumentation build only: cycles of the sweeps
