@@ -225,7 +225,10 @@ int b2e_reset(b2e_sim* sim, const uint8_t* env_mask, const float* obj_init_pose 
  * with scale_gym_data, utils.py:78-91), reward [B], done [B] (float 0/1).
  * obs/reward/done may be NULL (settle steps).  All device pointers.
  * n_substeps == 0 with mode HOLD only evaluates observation / reward / done on
- * the current state (get_extended_observation, _termination, _compute_reward). */
+ * the current state (get_extended_observation, _termination, _compute_reward).
+ * Launches over the whole batch of a Panda-class model reorder their blocks by the
+ * cost of the previous solve (slow blocks first); results do not depend
+ * on it.  Environment variable B2ENV_SCHED=0 (read at b2e_create) switches it off.  */
 int b2e_step(b2e_sim* sim, const float* action, float* obs, float* reward, float* done,
              int n_substeps, int mode, void* stream);
 

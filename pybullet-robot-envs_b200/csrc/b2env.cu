@@ -1992,9 +1992,9 @@ extern "C" {
 
 const char* b2e_last_error(void) { return g_err; }
 #ifdef B2E_EMU
-const char* b2e_version(void) { return "b2env 0.3 EMULATION (host build of the CUDA source: test infrastructure, not the product)"; }
+const char* b2e_version(void) { return "b2env 0.4 EMULATION (host build of the CUDA source: test infrastructure, not the product)"; }
 #else
-const char* b2e_version(void) { return "b2env 0.3 (sm_100a; Panda: two environments per warp, iCub: one warp per environment)"; }
+const char* b2e_version(void) { return "b2env 0.4 (sm_100a; Panda: two environments per warp, slow-first block order; iCub: one warp per environment, phase-locked blocks)"; }
 #endif
 
 int b2e_field_elem_size(int field) {
