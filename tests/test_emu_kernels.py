@@ -102,6 +102,25 @@ def test_panda_slow_first_scheduling_is_transparent(oracle_lib):
         assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max() < 1e-5
         np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
         np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
+        # launches that do not take part (a subset step, an observe-only call) between two that do: the lists written
+        # two launches ago must still be consistent (every environment stepped exactly once)
+        ids = np.array([3, 17, 36], np.int32)
+        sim.step_subset(ids, 2, 1)
+        mask = np.zeros(B, np.uint8)
+        mask[ids] = 1
+        q_before = orc.state["q"].copy()
+        for _ in range(2):   # the oracle advances the same three environments (HOLD mode, no action)
+            full = {k: v.copy() for k, v in orc.state.items()}
+            orc.step(None, 1, 1, want_obs=False)
+            for k, v in orc.state.items():
+                v[mask == 0] = full[k][mask == 0]
+        assert np.abs(orc.state["q"] - q_before)[mask == 0].max() == 0
+        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)
+        np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
+        assert np.abs(sim.get("q") - orc.state["q"]).max() < 1e-5
+        np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
     finally:
         sim.close()
 
