@@ -2181,6 +2181,19 @@ int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, f
   // (measured on B200: splitting a 16384-env batch costs more kernel efficiency than the overlap returns;
   //  chunks only start to pay once every chunk still fills the GPU)
   int chunks = s->B / 32768 > 1 ? (s->B / 32768 > 4 ? 4 : s->B / 32768) : 1;
+  // EXPERIMENT (off by default, not yet measured on a B200): B2ENV_ZEROCOPY=1 lets the kernel store observation /
+  // reward / done straight into the caller's page-locked arrays (device-accessible under unified addressing), so the
+  // 2.3 MB of results cross PCIe while the launch's long tail is still running instead of in a copy after it.
+  static const bool zero_copy = [] { const char* e = getenv("B2ENV_ZEROCOPY"); return e && e[0] == '1'; }();
+  if (zero_copy && chunks == 1) {
+    cudaStream_t st = s->pstream[0];
+    if (mode == B2E_MODE_ACTION)
+      CUDA_TRY(cudaMemcpyAsync(s->d_action, action_pinned, (size_t)s->B * na * 4, cudaMemcpyHostToDevice, st));
+    int rc = launch_step(s, s->d_action, obs_pinned, reward_pinned, done_pinned, n_substeps, mode, nullptr, s->B, st, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+  }
   const int per = ((s->B + chunks - 1) / chunks + align - 1) / align * align;
   for (int c = 0; c * per < s->B; c++) {
     const int lo = c * per, n = (lo + per <= s->B) ? per : s->B - lo;
