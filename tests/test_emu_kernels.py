@@ -125,6 +125,27 @@ def test_panda_slow_first_scheduling_is_transparent(oracle_lib):
         sim.close()
 
 
+def test_host_paths_agree(make_sim):
+    """b2e_step_host (staging copies) and b2e_step_pinned (results written straight into the page-locked arrays):
+    identical outputs and states (the GPU twin is tests/test_gpu_parity.py::test_full_batch_properties)."""
+    B = 37
+    m, p = panda_task_setup(TASK_PUSH)
+    pose = sample_object_poses(B, 11)
+    tg = targets_for(pose, z=0.65)
+    outs = []
+    for rep in range(2):
+        sim = make_sim(m, p, B)
+        sim.reset_host(pose, tg)
+        sim.step_host(None, 30, 1, want_obs=False)
+        rng = np.random.RandomState(5)
+        for i in range(6):
+            a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
+            obs, rew, done = sim.step_host(a, 1, 0) if rep == 0 else sim.step_pinned(a, 1, 0)
+        outs.append((sim.get("q").copy(), np.array(obs), np.array(rew), np.array(done)))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_icub_joint_mode(make_sim, oracle_lib):
     icub_cases.single_step_parity(make_sim, oracle_lib, B=5, use_ik=0, n_hold=2, n_act=4)
 
