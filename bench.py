@@ -383,7 +383,7 @@ def main():
                          "note": WL["note"]},
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * NA * 4,
                     "d2h_bytes_per_step": B * (NO + 2) * 4, "steps": Ke, "warmup": n_warm_e,
-                    "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays"},
+                    "note": "fresh reset, then warm-up + timed steps through env.step() with host arrays: H2D copy of the actions, results stored by the kernel straight into page-locked host arrays (zero-copy D2H; B2ENV_ZEROCOPY=0 for explicit copies)"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }
