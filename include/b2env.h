@@ -241,6 +241,12 @@ int b2e_step_subset(b2e_sim* sim, const int32_t* env_ids, int n_ids, const float
 int b2e_set_rows(b2e_sim* sim, int field, const int32_t* env_ids, int n, const void* rows, void* stream);
 int b2e_get_rows(b2e_sim* sim, int field, const int32_t* env_ids, int n, void* rows, void* stream);
 
+/* Stream contract: every entry point that takes `stream` enqueues its work there; the host-buffer entry
+ * points below use the library's own streams.  Calls on one b2e_sim are ORDERED whatever streams they use:
+ * each launch records an event that the next entry point's stream waits on, so a caller on a non-blocking
+ * (e.g. torch side) stream may freely mix b2e_step, b2e_step_pinned, b2e_set_rows, ...  A b2e_sim is still
+ * not thread-safe: drive it from one host thread at a time.                      */
+
 /* Host-buffer convenience used by the single-env compatibility path and the
  * end-to-end benchmark: copies action H2D, steps, copies results D2H, syncs.    */
 int b2e_step_host(b2e_sim* sim, const float* action_host, float* obs_host, float* reward_host,

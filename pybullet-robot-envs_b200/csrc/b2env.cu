@@ -148,6 +148,8 @@ struct b2e_sim {
   cudaStream_t pstream[2];   // chunk pipeline of the page-locked host path
   int* d_sched;              // slow-first scheduling state (see SCHED_FRONT)
   int sched_seq;
+  cudaEvent_t ev_order;      // recorded after every launch: the next entry point's stream waits on it, so calls on
+                             // DIFFERENT streams (a torch side stream, the library's own copy streams) stay ordered
 };
 
 static thread_local char g_err[512] = "";
@@ -160,6 +162,17 @@ static int fail(int code, const char* fmt, const char* detail) {
     cudaError_t e_ = (x);                                                      \
     if (e_ != cudaSuccess) return fail(B2E_ECUDA, #x ": %s", cudaGetErrorString(e_)); \
   } while (0)
+
+// Entry points are ordered with respect to each other whatever stream they are given: every launch is followed by
+// order_end (event record on its stream), every entry point starts with order_begin (its stream waits on that event).
+// On one and the same stream both are no-ops for the GPU.
+#ifdef B2E_EMU
+#define ORDER_BEGIN(s, stream) do { } while (0)
+#define ORDER_END(s, stream) do { } while (0)
+#else
+#define ORDER_BEGIN(s, stream) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)(stream), (s)->ev_order, 0))
+#define ORDER_END(s, stream) CUDA_TRY(cudaEventRecord((s)->ev_order, (cudaStream_t)(stream)))
+#endif
 
 // ------------------------------------------------------------------------------------------
 // small device math (all on register arrays with static indexing)
@@ -1945,9 +1958,10 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
 #define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
 #define TREE_SMEM_BYTES (sizeof(TreeSmem) * TREE_WPB)
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
-                       const int* env_ids, int n_ids, void* stream, int env_offset = 0) {
+                       const int* env_ids, int n_ids, void* stream, int env_offset = 0, bool ordered = true) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
   if (n <= 0) return 0;
+  if (ordered) ORDER_BEGIN(s, stream);
   if (s->tree) {
     const int tb = (n + TREE_WPB - 1) / TREE_WPB;
     if (s->params.use_ik)
@@ -1960,6 +1974,7 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
           env_offset);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (ordered) ORDER_END(s, stream);
     return 0;
   }
   // slow-first scheduling only for launches over the whole batch (they all run on the caller's stream, in order)
@@ -1976,6 +1991,7 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
         env_offset, sched, seq);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
+  if (ordered) ORDER_END(s, stream);
   return 0;
 }
 
@@ -2005,6 +2021,8 @@ int b2e_field_width(const b2e_sim* sim, int field) { return sim ? field_width(si
 int b2e_num_envs(const b2e_sim* sim) { return sim ? sim->B : -1; }
 int64_t b2e_launch_count(const b2e_sim* sim) { return sim ? sim->launches : -1; }
 
+static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params, int num_envs, int tree);
+
 int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, int device, b2e_sim** out) {
   if (!model || !params || !out || num_envs < 1) return fail(B2E_EINVAL, "b2e_create: bad argument%s", "");
   if (params->n_obs > B2E_MAX_OBS || params->n_obs < 1) return fail(B2E_EINVAL, "b2e_create: bad n_obs%s", "");
@@ -2025,6 +2043,19 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   b2e_sim* s = new b2e_sim();
   memset(s, 0, sizeof(*s));
   s->B = num_envs; s->device = device; s->model = *model; s->params = *params; s->umodel = hu; s->tree = tree;
+  rc = create_impl(s, hm, params, num_envs, tree);
+  if (rc) {   // nothing allocated so far survives a failed create (g_err keeps the first error)
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    b2e_destroy(s);
+    memcpy(g_err, keep, sizeof(keep));
+    return rc;
+  }
+  *out = s;
+  return 0;
+}
+
+static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params, int num_envs, int tree) {
   CUDA_TRY(cudaMalloc(&s->d_model, sizeof(DevModel)));
   CUDA_TRY(cudaMemcpy(s->d_model, &hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   for (int f = 0; f < B2E_F_COUNT; f++) {
@@ -2059,12 +2090,13 @@ int b2e_create(const b2e_model* model, const b2e_params* params, int num_envs, i
   CUDA_TRY(cudaMallocHost(&s->h_action, na)); CUDA_TRY(cudaMallocHost(&s->h_obs, no));
   CUDA_TRY(cudaMallocHost(&s->h_reward, (size_t)num_envs * 4)); CUDA_TRY(cudaMallocHost(&s->h_done, (size_t)num_envs * 4));
   CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
+  CUDA_TRY(cudaEventCreateWithFlags(&s->ev_order, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(s->ev_order, 0));
   CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
-  *out = s;
   return 0;
 }
 
@@ -2076,8 +2108,12 @@ void b2e_destroy(b2e_sim* s) {
   cudaFree(s->d_sched);
   cudaFree(s->d_model); cudaFree(s->d_action); cudaFree(s->d_obs); cudaFree(s->d_reward); cudaFree(s->d_done);
   cudaFreeHost(s->h_action); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_reward); cudaFreeHost(s->h_done);
-  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
-  cudaStreamDestroy(s->pstream[0]); cudaStreamDestroy(s->pstream[1]);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev_order) cudaEventDestroy(s->ev_order);
+  if (s->pstream[0]) cudaStreamDestroy(s->pstream[0]);
+  if (s->pstream[1]) cudaStreamDestroy(s->pstream[1]);
+  cudaGetLastError();   // a partially created sim frees null handles: leave no sticky error behind
   delete s;
 }
 
@@ -2099,10 +2135,12 @@ int b2e_reset(b2e_sim* s, const uint8_t* env_mask, const float* obj_init_pose, c
   if (!s || !obj_init_pose || !target) return fail(B2E_EINVAL, "b2e_reset: null argument%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
   const int tpb = 128;
+  ORDER_BEGIN(s, stream);
   B2E_LAUNCH(reset_kernel, (s->B + tpb - 1) / tpb, tpb, 0, stream, s->d_model, s->params, s->st, env_mask, obj_init_pose,
              target);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
+  ORDER_END(s, stream);
   return 0;
 }
 
@@ -2129,9 +2167,11 @@ int b2e_set_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, const voi
   if (n == 0) return 0;
   CUDA_TRY(cudaSetDevice(s->device));
   const int w = field_width(s, field), tot = n * w;
+  ORDER_BEGIN(s, stream);
   B2E_LAUNCH(rows_kernel, (tot + 255) / 256, 256, 0, stream, (float*)s->fields[field], env_ids, n, w, (float*)rows, 0);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
+  ORDER_END(s, stream);
   return 0;
 }
 int b2e_get_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, void* rows, void* stream) {
@@ -2139,9 +2179,11 @@ int b2e_get_rows(b2e_sim* s, int field, const int32_t* env_ids, int n, void* row
   if (n == 0) return 0;
   CUDA_TRY(cudaSetDevice(s->device));
   const int w = field_width(s, field), tot = n * w;
+  ORDER_BEGIN(s, stream);
   B2E_LAUNCH(rows_kernel, (tot + 255) / 256, 256, 0, stream, (float*)s->fields[field], env_ids, n, w, (float*)rows, 1);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
+  ORDER_END(s, stream);
   return 0;
 }
 
@@ -2153,6 +2195,7 @@ int b2e_step_host(b2e_sim* s, const float* action_host, float* obs_host, float* 
   if (mode == B2E_MODE_ACTION) {
     if (!action_host) return fail(B2E_EINVAL, "b2e_step_host: action required%s", "");
     memcpy(s->h_action, action_host, na);
+    ORDER_BEGIN(s, 0);   // d_action may still be read by a launch on another stream
     CUDA_TRY(cudaMemcpyAsync(s->d_action, s->h_action, na, cudaMemcpyHostToDevice, 0));
   }
   int rc = b2e_step(s, s->d_action, obs_host ? s->d_obs : nullptr, reward_host ? s->d_reward : nullptr,
@@ -2188,6 +2231,7 @@ int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, f
   static const bool zero_copy = [] { const char* e = getenv("B2ENV_ZEROCOPY"); return !(e && e[0] == '0'); }();
   if (zero_copy && chunks == 1) {
     cudaStream_t st = s->pstream[0];
+    ORDER_BEGIN(s, st);
     if (mode == B2E_MODE_ACTION)
       CUDA_TRY(cudaMemcpyAsync(s->d_action, action_pinned, (size_t)s->B * na * 4, cudaMemcpyHostToDevice, st));
     int rc = launch_step(s, s->d_action, obs_pinned, reward_pinned, done_pinned, n_substeps, mode, nullptr, s->B, st, 0);
@@ -2196,6 +2240,8 @@ int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, f
     return 0;
   }
   const int per = ((s->B + chunks - 1) / chunks + align - 1) / align * align;
+  ORDER_BEGIN(s, s->pstream[0]);   // the chunks touch disjoint environments: ordered against earlier calls, not each other
+  ORDER_BEGIN(s, s->pstream[1]);
   for (int c = 0; c * per < s->B; c++) {
     const int lo = c * per, n = (lo + per <= s->B) ? per : s->B - lo;
     cudaStream_t st = s->pstream[c & 1];
@@ -2203,14 +2249,14 @@ int b2e_step_pinned(b2e_sim* s, const float* action_pinned, float* obs_pinned, f
       CUDA_TRY(cudaMemcpyAsync(s->d_action + (size_t)lo * na, action_pinned + (size_t)lo * na, (size_t)n * na * 4,
                                cudaMemcpyHostToDevice, st));
     int rc = launch_step(s, s->d_action, obs_pinned ? s->d_obs : nullptr, reward_pinned ? s->d_reward : nullptr,
-                         done_pinned ? s->d_done : nullptr, n_substeps, mode, nullptr, n, st, lo);
+                         done_pinned ? s->d_done : nullptr, n_substeps, mode, nullptr, n, st, lo, false);
     if (rc) return rc;
     if (obs_pinned) CUDA_TRY(cudaMemcpyAsync(obs_pinned + (size_t)lo * no, s->d_obs + (size_t)lo * no, (size_t)n * no * 4, cudaMemcpyDeviceToHost, st));
     if (reward_pinned) CUDA_TRY(cudaMemcpyAsync(reward_pinned + lo, s->d_reward + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (done_pinned) CUDA_TRY(cudaMemcpyAsync(done_pinned + lo, s->d_done + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   }
   CUDA_TRY(cudaStreamSynchronize(s->pstream[0]));
-  CUDA_TRY(cudaStreamSynchronize(s->pstream[1]));
+  CUDA_TRY(cudaStreamSynchronize(s->pstream[1]));   // both drained: the chunks are ordered before whatever comes next
   return 0;
 }
 
@@ -2227,15 +2273,19 @@ int b2e_host_free(void* p) {
 int b2e_get(b2e_sim* s, int field, void* dst_dev, void* stream) {
   if (!s || !dst_dev || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_get: bad argument%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
+  ORDER_BEGIN(s, stream);
   CUDA_TRY(cudaMemcpyAsync(dst_dev, s->fields[field], (size_t)s->B * field_width(s, field) * 4, cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
+  ORDER_END(s, stream);
   return 0;
 }
 int b2e_set(b2e_sim* s, int field, const void* src_dev, void* stream) {
   if (!s || !src_dev || field < 0 || field >= B2E_F_COUNT) return fail(B2E_EINVAL, "b2e_set: bad argument%s", "");
   CUDA_TRY(cudaSetDevice(s->device));
+  ORDER_BEGIN(s, stream);
   CUDA_TRY(cudaMemcpyAsync(s->fields[field], src_dev, (size_t)s->B * field_width(s, field) * 4, cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
+  ORDER_END(s, stream);
   return 0;
 }
 int b2e_get_host(b2e_sim* s, int field, void* dst_host) {

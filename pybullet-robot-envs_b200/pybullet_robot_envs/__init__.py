@@ -2,12 +2,27 @@
 (Panda ids) and :7-44 (iCub ids).  The reference registers
 ``renders: True``; the CUDA backend has no GUI, so ids register with ``renders: False``.
 BASELINE.json spells the ids with a capital P: both spellings are registered."""
-try:  # a real gym wins if present
+from pybullet_robot_envs import gym_compat
+from pybullet_robot_envs.gym_compat import register as _register_compat
+
+try:  # a real gym, when present, gets the same ids (the env classes subclass gym_compat.Env: duck-typed gym API)
     import gym  # noqa: F401
-    from gym.envs.registration import register
-except Exception:  # this image: use the bundled shim
-    from pybullet_robot_envs import gym_compat as gym  # noqa: F401
-    from pybullet_robot_envs.gym_compat import register
+    from gym.envs.registration import register as _register_gym
+except Exception:  # this image: only the bundled shim
+    gym = gym_compat
+    _register_gym = None
+
+
+def register(**kw):
+    """Every id is registered with the bundled shim (``gym_compat.make`` always works) and, when a real ``gym`` is
+    importable, with its registry as well."""
+    _register_compat(**kw)
+    if _register_gym is not None:
+        try:
+            _register_gym(**kw)
+        except Exception:   # e.g. the id is already taken in a long-lived interpreter
+            pass
+
 
 _REACH_KW = {'numControlledJoints': 7, 'use_IK': 0, 'obj_pose_rnd_std': 0.05, 'includeVelObs': True,
              'max_steps': 1000, 'renders': False}

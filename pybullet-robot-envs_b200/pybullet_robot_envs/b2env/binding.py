@@ -216,6 +216,15 @@ class B2Sim:
         self._check(self.lib.b2e_get_host(self.h, f, _ptr(out)))
         return out
 
+    def get_device(self, name, like):
+        """Device-side copy of a state field into a new torch tensor on ``like``'s device / current stream."""
+        import torch
+        f = FIELD_NAMES[name]
+        w = self.lib.b2e_field_width(self.h, f)
+        out = torch.empty((self.B, w), device=like.device, dtype=torch.int32 if f in INT_FIELDS else torch.float32)
+        self._check(self.lib.b2e_get(self.h, f, _ptr(out), C.c_void_p(torch.cuda.current_stream(like.device).cuda_stream)))
+        return out
+
     def set(self, name, value):
         f = FIELD_NAMES[name]
         w = self.lib.b2e_field_width(self.h, f)

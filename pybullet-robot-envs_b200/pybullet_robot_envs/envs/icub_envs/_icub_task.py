@@ -56,6 +56,7 @@ class ICubTaskBase(PandaTaskBase):
         self._fused = all(getattr(type(self), h) is getattr(self._base_cls(), h) for h in self._hooks)
         self._torch_out = None
         self.auto_reset = False
+        self.zero_copy_results = False   # see PandaTaskBase._setup
         self.seed()
 
     @property

@@ -33,6 +33,13 @@ class iCubPushGymEnv(ICubTaskBase):
             self._physics_client_id.set("shaping", sh)
         else:
             self._physics_client_id.set_rows("shaping", ids, sh[ids])
+            if self.num_envs == 1:
+                self._init_dist_hand_obj, self._max_dist_obj_tg = d0[0], dm[0]
+            else:   # keep the host-side attributes (read by subclasses that override _compute_reward) in step
+                self._init_dist_hand_obj = np.array(np.broadcast_to(self._init_dist_hand_obj, (self.num_envs,)), np.float32)
+                self._max_dist_obj_tg = np.array(np.broadcast_to(self._max_dist_obj_tg, (self.num_envs,)), np.float32)
+                self._init_dist_hand_obj[ids] = d0[ids]
+                self._max_dist_obj_tg[ids] = dm[ids]
 
     def sample_tg_pose(self, obj_pos):
         """Target = object + (0.05, 0.05, 0), or object + N(0, tg_pose_rnd_std) from the GLOBAL numpy generator

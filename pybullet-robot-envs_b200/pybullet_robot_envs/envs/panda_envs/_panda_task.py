@@ -67,6 +67,9 @@ class PandaTaskBase(gym.Env):
         self._fused = all(getattr(type(self), h) is getattr(self._base_cls(), h) for h in self._hooks)
         self._torch_out = None
         self.auto_reset = False   # set True for auto-resetting vectorised rollouts (host-array step path)
+        # step() returns fresh arrays like the reference.  True: return VIEWS of the library's page-locked result
+        # buffers instead (no copy; overwritten by the next step(), dangling after close()) — see INTEGRATION.md
+        self.zero_copy_results = False
         self.seed()
 
     @classmethod
@@ -146,7 +149,7 @@ class PandaTaskBase(gym.Env):
         c = self._physics_client_id
         n = len(ids)
         if n == 0:
-            return np.zeros((0, self.observation_space.shape[0]), np.float32)
+            return np.zeros((0, self._sim.params.n_obs), np.float64)
         c.set_rows("counters", ids, np.zeros((n, 2), np.int32))
         c.set_rows("status", ids, np.zeros((n, 4), np.int32))
         c.set_rows("obj_pose", ids, np.tile(np.array(_PARK_POSE, np.float32), (n, 1)))
@@ -170,7 +173,7 @@ class PandaTaskBase(gym.Env):
             c.set_rows("target", ids, tg)
             self._after_target(ids)
         scaled = c.observe()[0]
-        return scaled[ids]
+        return scaled[ids].astype(np.float64)
 
     def _sync_target(self):
         tp = np.asarray(self._target_pose, np.float32).reshape(-1, 3)
@@ -212,6 +215,10 @@ class PandaTaskBase(gym.Env):
             done = self._termination()
             reward = self._compute_reward()
             return scaled_obs, np.array(reward), np.array(done), {}
+        return self._step_fused(action)
+
+    def _step_fused(self, action):
+        """apply_action + stepSimulation + observation + termination + reward in ONE launch."""
         if hasattr(action, "is_cuda") and action.is_cuda:
             return self._step_device(action)
         a = np.asarray(action, np.float32)
@@ -220,10 +227,12 @@ class PandaTaskBase(gym.Env):
             obs, rew, done = self._sim.step_host(self._as_batch(a), self._action_repeat, binding.MODE_ACTION)
             self._physics_client_id.invalidate()
             return obs[0].astype(np.float64), np.array(rew[0]), np.array(done[0]), {}
-        # batched host path: page-locked staging, results are views valid until the next step()
+        # batched host path: page-locked staging; the results land in page-locked arrays owned by the library
         obs, rew, done = self._sim.step_pinned(a if a.ndim == 2 else self._as_batch(a), self._action_repeat,
                                                binding.MODE_ACTION)
         self._physics_client_id.invalidate()
+        if not getattr(self, "zero_copy_results", False):
+            obs, rew, done = np.array(obs), np.array(rew), np.array(done)   # fresh arrays, like the reference
         if self.auto_reset and done.any():
             # vectorised-env convention: finished envs restart at once, their row of `obs` is the first
             # observation of the new episode; reward / done still describe the finished episode

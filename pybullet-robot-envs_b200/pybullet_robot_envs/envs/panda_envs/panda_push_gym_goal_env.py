@@ -4,7 +4,6 @@ import numpy as np
 
 from pybullet_robot_envs import gym_compat as gym
 from pybullet_robot_envs.gym_compat import spaces
-from pybullet_robot_envs.b2env import binding
 from pybullet_robot_envs.b2env.client import squeeze1
 from pybullet_robot_envs.envs.utils import goal_distance, scale_gym_data
 from pybullet_robot_envs.envs.world_envs.world_env import get_objects_list
@@ -24,10 +23,11 @@ class GoalMixin:
             observation=box))
         return observation_space, action_space
 
-    def _goal_dict(self, scaled, raw):
-        B = self.num_envs
+    def _goal_dict(self, scaled, raw, squeeze=True):
+        B = self.num_envs if squeeze else 0
         nr = self._n_robot_obs   # robot obs | object pose (6) | relative pose (6) | target (3)
-        return {'observation': squeeze1(np.asarray(scaled, np.float64), B),
+        scaled = np.asarray(scaled, np.float64).reshape(-1, raw.shape[-1])
+        return {'observation': squeeze1(scaled, B),
                 'achieved_goal': squeeze1(np.asarray(raw[:, nr:nr + 3], np.float64), B),
                 'desired_goal': squeeze1(np.asarray(raw[:, nr + 12:nr + 15], np.float64), B)}
 
@@ -37,27 +37,34 @@ class GoalMixin:
         d['observation'] = squeeze1(raw.astype(np.float64), self.num_envs)   # unscaled, like the reference
         return d
 
-    def reset(self):
+    def reset(self, env_ids=None):
+        """``reset()`` as the reference (:74-87); ``reset(env_ids)`` resets the listed environments only and returns
+        their dict observation (batched extension, same contract as the Box envs)."""
         gym.GoalEnv.reset(self)
-        self.reset_simulation()
-        world_obs, _ = self._world.get_observation()
-        self._target_pose = self.sample_tg_pose(np.asarray(world_obs).reshape(self.num_envs, 6)[:, :3])
-        self._sync_target()
-        self._after_target()
+        if env_ids is not None:
+            ids = np.asarray(env_ids, np.int32)
+            scaled = self._box_cls.reset(self, ids)
+            raw = self._physics_client_id.observe()[3][ids]
+            return self._goal_dict(scaled, raw, squeeze=False)
+        self._box_cls.reset(self)
         scaled, _, _, raw = self._physics_client_id.observe()
         return self._goal_dict(scaled, raw)
 
     def step(self, action):
-        a = np.asarray(action, np.float32)
-        assert a.shape[-1:] == self.action_space.shape
-        obs, rew, done = self._sim.step_host(self._as_batch(a), self._action_repeat, binding.MODE_ACTION)
-        raw = self._sim.get("raw_obs")
-        self._physics_client_id.invalidate()
+        """One fused launch like the Box envs (same host / CUDA-tensor / auto_reset paths), results re-packed as the
+        GoalEnv dict (reference :89-104)."""
+        nr = self._n_robot_obs
+        if hasattr(action, "is_cuda") and action.is_cuda:
+            obs, rew, done, _ = self._step_fused(action)
+            raw = self._sim.get_device("raw_obs", obs)
+            out = {'observation': obs, 'achieved_goal': raw[:, nr:nr + 3], 'desired_goal': raw[:, nr + 12:nr + 15]}
+            d = (out['achieved_goal'] - out['desired_goal']).norm(dim=1)
+            return out, rew, done > 0, {'is_success': d <= self._target_dist_min}
+        obs, rew, done, _ = self._step_fused(action)
+        raw = self._sim.get("raw_obs")      # after an auto-reset: rows of the restarted envs describe the new episode, like obs
         out = self._goal_dict(obs, raw)
         success = self._is_success(out['achieved_goal'], out['desired_goal'])
-        info = {'is_success': success}
-        B = self.num_envs
-        return out, squeeze1(rew, B), squeeze1(done.astype(bool), B), info
+        return out, rew, np.asarray(done).astype(bool), {'is_success': success}
 
     def _termination(self):
         c = self._physics_client_id.get("counters")[:, 0]

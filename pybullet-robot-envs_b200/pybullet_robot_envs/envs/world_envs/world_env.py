@@ -63,12 +63,12 @@ class WorldEnv:
     def load_object(self, obj_name, env_ids=None):
         if obj_name not in get_objects_list():
             raise NotImplementedError("unknown object '%s'" % obj_name)
-        if obj_name != 'cube_small' and not WorldEnv._warned_proxy:
+        if obj_name != 'cube_small' and not self._warned_proxy:
             # the mesh objects (duck_vhacd is the reference default of iCubReachGymEnv) live in the un-vendored
             # pybullet_data package: they are simulated with the cube_small collision model (documented deviation)
             import warnings
             warnings.warn("object '%s' is simulated with the 'cube_small' collision proxy (mesh assets are not available)" % obj_name)
-            WorldEnv._warned_proxy = True
+            self._warned_proxy = True   # once per WorldEnv object (every construction warns)
         self._obj_name = obj_name
         c = self._client
         B = c.num_envs

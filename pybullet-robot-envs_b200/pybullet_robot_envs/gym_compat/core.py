@@ -85,7 +85,9 @@ class Wrapper(Env):
 
 
 class TimeLimit(Wrapper):
-    """``register(max_episode_steps=1000)`` (reference __init__.py:10) wraps every env in this."""
+    """``register(max_episode_steps=1000)`` (reference __init__.py:10) wraps every env in this.  Batched envs return
+    per-env ``done`` arrays: the limit then raises every entry, and with ``auto_reset`` the elapsed steps are counted
+    per environment (an env that restarted inside ``step()`` starts from 0 again)."""
 
     def __init__(self, env, max_episode_steps=None):
         super().__init__(env)
@@ -93,12 +95,23 @@ class TimeLimit(Wrapper):
         self._elapsed_steps = 0
 
     def step(self, action):
+        import numpy as np
         observation, reward, done, info = self.env.step(action)
+        batched = hasattr(done, "shape") and getattr(done, "shape", ()) != ()
+        if batched and getattr(self.env.unwrapped, "auto_reset", False) and not hasattr(done, "is_cuda"):
+            if np.isscalar(self._elapsed_steps):
+                self._elapsed_steps = np.full(done.shape, self._elapsed_steps, np.int64)
+            self._elapsed_steps += 1
+            over = self._elapsed_steps >= self._max_episode_steps if self._max_episode_steps is not None else np.zeros(done.shape, bool)
+            finished = np.asarray(done).astype(bool)
+            done = np.where(over, np.ones_like(done), done)
+            self._elapsed_steps[finished] = 0     # restarted by the env itself
+            return observation, reward, done, info
         self._elapsed_steps += 1
-        if self._max_episode_steps is not None and self._elapsed_steps >= self._max_episode_steps:
-            try:
-                done = done | True if hasattr(done, "shape") and getattr(done, "shape", ()) != () else True
-            except TypeError:
+        if self._max_episode_steps is not None and np.all(self._elapsed_steps >= self._max_episode_steps):
+            if batched:
+                done = done.clone().fill_(1) if hasattr(done, "is_cuda") else np.ones_like(done)
+            else:
                 done = True
         return observation, reward, done, info
 
