@@ -266,6 +266,11 @@ int b2e_set(b2e_sim* sim, int field, const void* src_dev, void* stream);
 int b2e_get_host(b2e_sim* sim, int field, void* dst_host);
 int b2e_set_host(b2e_sim* sim, int field, const void* src_host);
 
+/* Diagnostics (tests): the scheduling lists written by the last scheduled full-batch step — the environments of the
+ * main launch's cost classes (lightest class first), then those of the tail launch.  Every environment appears exactly
+ * once.  n_main = n_tail = 0 when the simulation is not scheduled (small batches, the tree kernel).               */
+int b2e_debug_sched(b2e_sim* sim, int32_t* envs_out, int cap, int32_t* n_main_out, int32_t* n_tail_out);
+
 /* Width (elements per env) and element size of a field.                        */
 int b2e_field_width(const b2e_sim* sim, int field);
 int b2e_field_elem_size(int field);

@@ -68,18 +68,29 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #define NSLOT 2           // overflow slots per block for environments with more than 16 generic rows
 #endif
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
-// Slow-first scheduling (full-batch launches of the group kernel): a launch lasts as long as its slowest environment
-// (a jammed contact runs all solver sweeps over ~45 rows, ~0.5 ms), so it matters WHEN that environment starts.  The
-// kernel lists the blocks whose last solve was expensive, and the NEXT launch steps those blocks first: the grid has
-// SCHED_FRONT extra positions at its head, head position i steps listed block i, and the home position of a listed
-// block exits at once.  Block composition, code and results are unchanged — only the start order.
-#define SCHED_FRONT 128                     // extra grid positions at the head = blocks that can be listed
-#ifndef SCHED_COST
-#define SCHED_COST 2500                     // sweeps x rows of the last solve that makes an environment "slow"
+// Cost-ordered scheduling (full-batch launches of the group kernel).  The environments of a block advance in phase
+// (block barriers between the stages), so a block lasts as long as its slowest environment, and a launch as long as its
+// slowest block: with contiguous blocks, one jammed contact (all solver sweeps over ~45 rows, ~0.4 ms) held 15 ordinary
+// environments and half an SM's registers / shared memory for the whole launch.  Instead, every environment files itself,
+// at the end of a step, under a cost class estimated from its own solve (sweeps x rows); the NEXT full-batch step is
+//   * a TAIL launch on the library's own high-priority stream: the heavy class (big constraint systems, or an estimated
+//     cost above SCHED_TAIL_COST), in lean blocks (TAIL_WPB warps, one overflow slot per environment) that start first, and
+//   * the MAIN launch: everything else, slot -> environment taken from the class lists, heaviest class first, so that
+//     blocks are cost-homogeneous.
+// Both run concurrently; results do not depend on which slot steps an environment (tests/test_emu_kernels.py).
+#define NBK_MAIN 16                         // cost classes of the main launch
+#define NBK (NBK_MAIN + 1)                  // + the tail class
+#define TAIL_CAP 1024                       // environments the tail launch can take (overflow: heaviest main class)
+#ifndef SCHED_TAIL_COST
+#define SCHED_TAIL_COST 160000              // estimated solve cycles that send an environment to the tail launch
 #endif
-#define SCHED_LIST(k) (4 + (k) * SCHED_FRONT)   // int sched[]: 4 counters (ring) | 2 lists | 2 x per-block tag (written / read
-#define SCHED_TAGS (4 + 2 * SCHED_FRONT)        // by alternate launches: a head position may re-list its block before the
-                                                // home position looks)
+#define SCHED_CNT(q, b) ((q) * NBK + (b))                                        // int sched[]: 4 x NBK counters (ring),
+#define SCHED_LIST(par, b, B) (4 * NBK + ((par) * NBK_MAIN + (b)) * (B))         // 2 x NBK_MAIN class lists of capacity B,
+#define SCHED_TAIL(par, B) (4 * NBK + 2 * NBK_MAIN * (B) + (par) * TAIL_CAP)      // 2 x tail list
+#define SCHED_INTS(B) (4 * NBK + 2 * NBK_MAIN * (B) + 2 * TAIL_CAP)
+#define ROLE_PLAIN 0                        // slot -> environment: identity / env_ids (subset launches, no scheduling)
+#define ROLE_MAIN 1
+#define ROLE_TAIL 2
 #define SCRATCH_PER_ENV (BIGS * BIGS + BIGS * WSTRIDE + NDMAX * BIGS)   // A | W | W^T(arm part), same layout as a slot
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
@@ -146,8 +157,11 @@ struct b2e_sim {
   int record_contacts;
   cudaEvent_t ev0, ev1;
   cudaStream_t pstream[2];   // chunk pipeline of the page-locked host path
-  int* d_sched;              // slow-first scheduling state (see SCHED_FRONT)
+  int* d_sched;              // cost-ordered scheduling state (see NBK_MAIN)
   int sched_seq;
+  int tail_wpb;              // warps per block of the tail launch
+  cudaStream_t tstream;      // the tail launch's stream (high priority)
+  cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev_order;      // recorded after every launch: the next entry point's stream waits on it, so calls on
                              // DIFFERENT streams (a torch side stream, the library's own copy streams) stay ordered
 };
@@ -325,6 +339,7 @@ struct EnvSmem {
   float con_cfm[B2E_MAX_CONTACTS];
   int lim_d[4];                // limit rows: dof | side << 8
   float lim_dist[4];
+  float cost[4];               // [0]: estimated cycles of this environment's last solve (scheduling class)
   int ckey[B2E_CACHE_SLOTS];
   float clam[B2E_CACHE_SLOTS][3];
 };
@@ -561,7 +576,8 @@ struct MotorRegs {
 };
 template <int NSG>
 struct RowRegs {
-  float lam[NSG], u[NSG], base[NSG], gg[NSG], invd[NSG], diag[NSG], lo[NSG], hi[NSG], mu[NSG], prev[NSG];
+  float lam[NSG], u[NSG], gm1[NSG], invd[NSG], diag[NSG], lo[NSG], hi[NSG], mu[NSG], prev[NSG];
+  float cc[NSG], lo2[NSG], hi2[NSG];   // per-phase constants of the delta-form row update (rows_prepare)
   int type[NSG], isl[NSG], nidx[NSG];
 };
 
@@ -587,23 +603,35 @@ __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<N
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-cg[s], dli, r.u[s]);
 }
 
+// Delta form of the row update.  With c = lambda (gg - 1), lo' = lo - lambda, hi' = hi - lambda prepared once per sweep
+// phase (a row is visited once per phase, so its lambda is constant until then):
+//     dlambda = clamp(u invd + c, lo', hi')        [ = clamp(u invd + lambda gg, lo, hi) - lambda ]
+// which leaves FFMA -> FMNMX -> FMNMX -> SHFL -> FFMA on the dependent chain (tools/micro/row_chain2.cu: 50 instead of 68
+// cycles per row for a lone warp).  A row this group does not visit in the phase has lo' = hi' = 0, i.e. broadcasts 0; every
+// table entry is finite (tables are zeroed at kernel start), so no coefficient needs masking.
+template <int NSG>
+__device__ __forceinline__ void rows_prepare(const Grp& g, RowRegs<NSG>& r, unsigned m0, unsigned m1, unsigned m2) {
+#pragma unroll
+  for (int s = 0; s < NSG; s++) {
+    const unsigned mk = s == 0 ? m0 : (s == 1 ? m1 : m2);
+    const bool act = (mk >> g.lane) & 1u;
+    r.cc[s] = r.lam[s] * r.gm1[s];
+    r.lo2[s] = act ? r.lo[s] - r.lam[s] : 0.f;
+    r.hi2[s] = act ? r.hi[s] - r.lam[s] : 0.f;
+  }
+}
+
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
-                                             const float* Wrow, int li, bool arm_sweep, bool active) {
+                                             const float* Wrow, int li) {
   float ca[NSG];
 #pragma unroll
   for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
   const float cw = Wrow[g.lane];
-  float nl = fmaf(r.u[SI], r.invd[SI], r.base[SI]);
-  nl = fminf(fmaxf(nl, r.lo[SI]), r.hi[SI]);
-  const float dl = active ? nl - r.lam[SI] : 0.f;   // `active`: this group visits this row in this pass
+  const float dl = fminf(fmaxf(fmaf(r.u[SI], r.invd[SI], r.cc[SI]), r.lo2[SI]), r.hi2[SI]);
   const float dli = SHF(dl, li);
-  r.lam[SI] = (g.lane == li && active) ? nl : r.lam[SI];  // base/prev are refreshed once per sweep
-  // a group that does not visit the row broadcasts dli = 0; every table entry is finite (the tables are zeroed at kernel
-  // start, rows are only ever written with finite values), so no coefficient needs masking.  m.u of a finished arm
-  // island is dead.
-  (void)arm_sweep;
-  m.u = fmaf(-cw, dli, m.u);
+  r.lam[SI] += (g.lane == li) ? dl : 0.f;
+  m.u = fmaf(-cw, dli, m.u);                    // m.u of a finished arm island is dead
 #pragma unroll
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
 }
@@ -614,14 +642,14 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
 // a group skips (dl = 0, no table access) the rows it does not visit itself.
 template <int NSG, int SI>
 __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                          int AS, unsigned mk, bool arm_sweep) {
+                                          int AS, unsigned mk) {
   const unsigned w = __reduce_or_sync(FULL, mk);   // union of the two groups' masks, PROVABLY warp-uniform (no BRA.DIV in the loop)
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
   const float* Arow = A + (GL * SI + lo) * AS;
   const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
   for (int i = lo; i < hi; i++) {
-    generic_step<NSG, SI>(g, m, r, Arow, Wrow, i, arm_sweep, (mk >> i) & 1u);
+    generic_step<NSG, SI>(g, m, r, Arow, Wrow, i);
     Arow += AS;
     Wrow += WSTRIDE;
   }
@@ -629,11 +657,12 @@ __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NS
 
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, bool arm_sweep) {
+                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2) {
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
-  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0, arm_sweep);
-  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1, arm_sweep);
-  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2, arm_sweep);
+  rows_prepare<NSG>(g, r, m0, m1, m2);
+  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0);
+  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1);
+  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2);
 }
 
 template <int NSG>
@@ -669,7 +698,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     if (__all_sync(FULL, my_it >= 0)) break;
     m.prev = m.lam;
 #pragma unroll
-    for (int s = 0; s < NSG; s++) { r.prev[s] = r.lam[s]; r.base[s] = r.lam[s] * r.gg[s]; }
+    for (int s = 0; s < NSG; s++) r.prev[s] = r.lam[s];
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
     if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
       float dl = 0.f;
@@ -693,7 +722,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
       }
     }
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
-                       (arm_nf[2] & a0) | (cube_nf[2] & c0), !done0);
+                       (arm_nf[2] & a0) | (cube_nf[2] & c0));
     const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
                    f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
     if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
@@ -712,7 +741,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2, !done0);
+      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2);
     }
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
@@ -793,7 +822,7 @@ template <int NSG, bool GB>   // GB: some group of the warp keeps its big system
 __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U,
                                             const b2e_params& P, unsigned hm, int sh, int lane, int nd, int nlim, int nc,
                                             float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
-                                            int slot, float* gscratch) {
+                                            int big_off, float* gscratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp g = {hm, sh, lane};
   const float cpos[3] = {cpx, cpy, cpz};
@@ -803,8 +832,8 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   const int AS = use_big ? BIGS : GL;
   // the slot address is formed here from the shared-memory base so that, in the GB = false instantiations,
   // every table access is a shared-memory access (no generic loads in the row loops)
-  float* big = reinterpret_cast<float*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * (slot < 0 ? 0 : slot));
-  if (GB && slot < 0) big = gscratch;
+  float* big = reinterpret_cast<float*>(smem_raw + (big_off < 0 ? 0 : big_off));   // byte offset of the claimed overflow slot
+  if (GB && big_off < 0) big = gscratch;
   float* A = use_big ? big : sm.A;
   float* W = use_big ? big + BIGS * BIGS : sm.W;
   float* WT = use_big ? big + BIGS * BIGS + BIGS * WSTRIDE : sm.WT;
@@ -939,9 +968,10 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     rr.lo[s] = lo; rr.hi[s] = hi; rr.mu[s] = mu;
     rr.diag[s] = valid ? diag + cfm : 0.f;
     rr.invd[s] = valid ? 1.0f / (diag + cfm) : 0.f;
-    rr.gg[s] = 1.0f - cfm * rr.invd[s];
+    rr.gm1[s] = -cfm * rr.invd[s];
     rr.u[s] = valid ? desired - jv : 0.f;
-    rr.lam[s] = 0.f; rr.base[s] = 0.f; rr.prev[s] = 0.f;
+    rr.lam[s] = 0.f; rr.prev[s] = 0.f;
+    rr.cc[s] = 0.f; rr.lo2[s] = 0.f; rr.hi2[s] = 0.f;
     {  // votes are collectives: evaluate them unconditionally (no short-circuit), then combine
       const bool v1 = gany(g, sphere_cube_normal), v2 = gany(g, valid && isl == 1), v3 = gany(g, arm_part);
       coupled = coupled || v1;
@@ -984,7 +1014,6 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       for (int sl = 0; sl < B2E_CACHE_SLOTS; sl++)
         if (sm.ckey[sl] == key) { l0 = sm.clam[sl][j] * P.warmstart; break; }
       rr.lam[s] = l0;
-      rr.base[s] = l0 * rr.gg[s];
     }
   }
   for (int c = 0; c < RGw; c++) {
@@ -1020,6 +1049,11 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 #ifdef PROFILE_CYCLES
   if (lane == 0) sm.lim_dist[3] = (float)(clock64() - t_pgs0);   // instrumentation build only: cycles of the sweeps
 #endif
+  // estimated cycles of this environment's own solve (the class it files itself under for the next step): fixed build
+  // cost + affine arm iterations + serial sweeps x (motor block + generic rows)
+  if (lane == 0)
+    sm.cost[0] = 20000.f + 150.f * (float)(iters_arm > 0 ? iters_arm : 0) +
+                 (float)iters * ((arm_sweep ? 400.f : 0.f) + 55.f * (float)RG);
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
 #pragma unroll
@@ -1037,32 +1071,54 @@ template <bool IK>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
-            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset, int* sched, int seq) {
+            int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset, int* sched, int seq,
+            int role, int nslot) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wpb = blockDim.x >> 5;                          // warps per block: WPB (main / plain launches) or the tail's
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
   const int half = wl >> 4, lane = wl & (GL - 1);          // two environments per warp, 16 lanes each
   const Grp g = {0xffffu << (GL * half), GL * half, lane};
-  // slot -> environment: the whole batch, or the subset listed in env_ids (per-env resets, row f1)
-  const int n_slots = n_ids;   // env_ids: listed envs; else the contiguous range [env_offset, env_offset + n_ids)
-  const int nhome = (n_slots + 2 * WPB - 1) / (2 * WPB);   // blocks of the batch
-  int hblock = blockIdx.x;                                  // the block of environments this grid position steps
-  if (sched) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) sched[(seq + 1) & 3] = 0;   // the next launch's counter (unused by this one)
-    if ((int)blockIdx.x < SCHED_FRONT) {   // head of the grid: the blocks the previous launch listed as slow
-      if ((int)blockIdx.x >= min(sched[(seq - 1) & 3], SCHED_FRONT)) return;
-      hblock = sched[SCHED_LIST((seq - 1) & 1) + blockIdx.x];
+  // slot -> environment: the whole batch in cost order (ROLE_MAIN / ROLE_TAIL, see NBK_MAIN), or identity / the subset
+  // listed in env_ids (ROLE_PLAIN: per-env resets (row f1), chunked host path)
+  int n_slots = n_ids;   // env_ids: listed envs; else the contiguous range [env_offset, env_offset + n_ids)
+  const int slot = (blockIdx.x * wpb + warp) * 2 + half;
+  int env;
+  if (role == ROLE_PLAIN) {
+    const int sc = slot < n_slots ? slot : n_slots - 1;
+    env = env_ids ? env_ids[sc] : env_offset + sc;
+  } else {
+    const int qp = (seq - 1) & 3, pp = (seq - 1) & 1, B = st.B;
+    if (role == ROLE_MAIN && blockIdx.x == 0 && (int)threadIdx.x < NBK)
+      sched[SCHED_CNT((seq + 1) & 3, threadIdx.x)] = 0;   // the next step's counters (not used by this step's launches)
+    if (role == ROLE_TAIL) {
+      n_slots = min(sched[SCHED_CNT(qp, NBK_MAIN)], TAIL_CAP);
+      if ((int)blockIdx.x * 2 * wpb >= n_slots) return;
+      env = sched[SCHED_TAIL(pp, B) + (slot < n_slots ? slot : n_slots - 1)];
     } else {
-      hblock = blockIdx.x - SCHED_FRONT;
-      if (sched[SCHED_TAGS + ((seq - 1) & 1) * nhome + hblock] == seq - 1) return;   // stepped by a head position
+      int cnt[NBK_MAIN];
+#pragma unroll
+      for (int b = 0; b < NBK_MAIN; b++) cnt[b] = sched[SCHED_CNT(qp, b)];
+      n_slots = 0;
+#pragma unroll
+      for (int b = 0; b < NBK_MAIN; b++) n_slots += cnt[b];
+      if ((int)blockIdx.x * 2 * wpb >= n_slots) return;
+      int rem = slot < n_slots ? slot : n_slots - 1, cls = 0;   // heaviest class first
+#pragma unroll
+      for (int b = NBK_MAIN - 1; b >= 0; b--) {
+        if (rem >= 0 && rem < cnt[b]) { cls = b; break; }
+        rem -= cnt[b];
+      }
+      env = sched[SCHED_LIST(pp, cls, B) + rem];
     }
   }
-  const int slot = (hblock * WPB + warp) * 2 + half;
   const bool live_env = slot < n_slots;      // padding warps of the last block shadow the last slot, stores masked
-  const int slot_c = live_env ? slot : n_slots - 1;
-  const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
   EnvSmem& sm = reinterpret_cast<EnvSmem*>(smem_raw)[warp * 2 + half];
-  BigSlot* slots = reinterpret_cast<BigSlot*>(smem_raw + sizeof(EnvSmem) * 2 * WPB);
-  int* slot_owner = reinterpret_cast<int*>(smem_raw + sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT);
+  const int slots_off = (int)sizeof(EnvSmem) * 2 * wpb;
+  BigSlot* slots = reinterpret_cast<BigSlot*>(smem_raw + slots_off);
+  int* slot_owner = reinterpret_cast<int*>(smem_raw + slots_off + sizeof(BigSlot) * nslot);   // [16] owners | [NBK] class
+  int* cls_hist = slot_owner + 16;                                                              // histogram | [NBK] bases
+  int* cls_base = cls_hist + NBK;
+  if ((int)threadIdx.x < NBK) cls_hist[threadIdx.x] = 0;   // ordered before its use by the barriers of the step loop
   const int nd = U.n_dof, nl = U.n_links;
   const float dt = P.dt;
 
@@ -1101,12 +1157,19 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   int prof_pgs = 0;
 #endif
   bool stop = false;
+#ifdef PROFILE_STAGES   // instrumentation build only: cycle stamps of the stages of the last sub-step -> B2E_F_CONTACTS[env][0..7]
+  long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_T(k) prof_t[k] = clock64()
+#else
+#define PROF_T(k) do { } while (0)
+#endif
+  PROF_T(0);
   {
     // solver tables start finite (see motor_step / generic_step): A | W | WT of this environment and the overflow slots
     float4* t4 = reinterpret_cast<float4*>(&sm);
     for (int k = lane; k < (int)(offsetof(EnvSmem, T) / 16); k += GL) t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* s4 = reinterpret_cast<float4*>(slots);
-    for (int k = threadIdx.x; k < (int)(sizeof(BigSlot) * NSLOT / 16); k += 32 * WPB) s4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = threadIdx.x; k < (int)(sizeof(BigSlot) / 16) * nslot; k += blockDim.x) s4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   gsync(g);
 
@@ -1149,8 +1212,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       }
     }
     if (sub >= nsub) break;
+    PROF_T(1);   // start of the sub-step (after FK + termination bookkeeping)
     const bool ghost = stop;   // terminated mid-repeat (panda_push_gym_env.py:239-240): keep pace with the block, change nothing
-    if ((int)threadIdx.x < NSLOT) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
+    if ((int)threadIdx.x < nslot) slot_owner[threadIdx.x] = -1;   // overflow slots are free again (claimed after the barriers below)
     __syncthreads();
 
     // ---- action -> motor targets (panda_push_gym_env.py:225-230, panda_env.py:303) ----
@@ -1374,6 +1438,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     if (lane < NDMAX && !is_dof) sm.vstar[lane] = 0.f;
 
+    PROF_T(2);   // dynamics done
     PHASE_BARRIER();
     // ---- collision detection (pre-step poses) ----
     float Rc[9];
@@ -1516,6 +1581,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
     gsync(g);
 
+    PROF_T(3);   // collision done
     PHASE_BARRIER();
     // ---- rows + PGS ----
     R = nd + nlim + 3 * nc;
@@ -1527,26 +1593,30 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     float* gscratch = st.scratch + (size_t)env * SCRATCH_PER_ENV;
     int got = -1;
     if (lane == 0 && RG > GL) {
-      for (int k = 0; k < NSLOT && got < 0; k++)
+      for (int k = 0; k < nslot && got < 0; k++)
         if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
     }
     got = SHF(got, 0);
     const bool need_global = __any_sync(FULL, RG > GL && got < 0);   // rare: more big systems in the block than slots
     const float* big = (RG > GL && got < 0) ? gscratch : reinterpret_cast<const float*>(&slots[got < 0 ? 0 : got]);
+    PROF_T(4);   // past the pre-solve barrier
 #ifdef PROFILE_CYCLES
     const long long t_solve0 = clock64();
 #endif
-#define B2E_SOLVE(N, G) build_and_solve<N, G>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], got, gscratch)
+    const int big_off = got < 0 ? -1 : slots_off + (int)sizeof(BigSlot) * got;
+#define B2E_SOLVE(N, G) build_and_solve<N, G>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big_off, gscratch)
     if (RGw <= GL) iters = B2E_SOLVE(1, false);
     else if (!need_global) iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, false) : B2E_SOLVE(3, false);
     else iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, true) : B2E_SOLVE(3, true);
 #undef B2E_SOLVE
+    PROF_T(5);   // solve done (this warp)
 
 #ifdef PROFILE_CYCLES
     R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (got < 0 ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
     prof_pgs = (int)sm.lim_dist[3];   // cycles of the sweeps alone (replaces the contact count in B2E_F_STATUS)
 #endif
     PHASE_BARRIER();
+    PROF_T(6);   // past the post-solve barrier
     // ---- delta velocities dv = sum_r W_r * lambda_r (lane = velocity component) ----
     float dvk = 0.f;
     {
@@ -1620,14 +1690,27 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 
   }
 
-  if (sched) {   // list this block for the head of the next launch (once per block: the tag is the claim)
-    if (lane == 0 && live_env && iters * R >= SCHED_COST) {
-      int* tag = &sched[SCHED_TAGS + (seq & 1) * nhome + hblock];
-      if (atomicExch(tag, seq) != seq) {
-        const int i = atomicAdd(&sched[seq & 3], 1);
-        if (i < SCHED_FRONT) sched[SCHED_LIST(seq & 1) + i] = hblock;
-        else *tag = 0;   // list full: stays at home
+  if (role != ROLE_PLAIN) {   // file this environment under its cost class for the next full-batch step
+    int cls = -1, rank = 0;
+    if (lane == 0 && live_env) {
+      const float c = sm.cost[0];
+      cls = (R - nd > GL || c >= (float)SCHED_TAIL_COST) ? NBK_MAIN : min(NBK_MAIN - 1, (int)(c * (1.0f / 8192.0f)));
+      rank = atomicAdd(&cls_hist[cls], 1);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NBK) {
+      const int h = cls_hist[threadIdx.x];
+      cls_base[threadIdx.x] = h ? atomicAdd(&sched[SCHED_CNT(seq & 3, threadIdx.x)], h) : 0;
+    }
+    __syncthreads();
+    if (cls >= 0) {
+      const int B = st.B;
+      int pos = cls_base[cls] + rank;
+      if (cls == NBK_MAIN && pos >= TAIL_CAP) {   // tail list full: the heaviest class of the main launch takes it
+        cls = NBK_MAIN - 1;
+        pos = atomicAdd(&sched[SCHED_CNT(seq & 3, cls)], 1);
       }
+      sched[(cls == NBK_MAIN ? SCHED_TAIL(seq & 1, B) : SCHED_LIST(seq & 1, cls, B)) + pos] = env;
     }
   }
   // ---- store state (padding groups shadow the last env: they keep pace but store nothing) ----
@@ -1768,6 +1851,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       if (done_out) done_out[env] = (float)dn;
     }
   }
+#ifdef PROFILE_STAGES
+  if (lane == 0 && live_env && nsub > 0) {
+    const long long t_end = clock64();
+    float* o = st.contacts + (size_t)env * B2E_MAX_CONTACTS * 8;
+    for (int k = 1; k < 7; k++) o[k - 1] = (float)(prof_t[k] - prof_t[0]);
+    o[6] = (float)(t_end - prof_t[0]);
+    o[7] = (float)blockIdx.x;
+  }
+#endif
   if (lane == 0 && mode != B2E_MODE_OBSERVE && live_env) {
     st.counters[env * 2] = counter;
     st.counters[env * 2 + 1] = terminated;
@@ -1955,8 +2047,16 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
   return 0;
 }
 
-#define SMEM_BYTES (sizeof(EnvSmem) * 2 * WPB + sizeof(BigSlot) * NSLOT + 16)
+#define SMEM_BYTES_FOR(wpb, nslot) (sizeof(EnvSmem) * 2 * (wpb) + sizeof(BigSlot) * (nslot) + (16 + 2 * NBK + 2) * sizeof(int))
+#define SMEM_BYTES SMEM_BYTES_FOR(WPB, NSLOT)
 #define TREE_SMEM_BYTES (sizeof(TreeSmem) * TREE_WPB)
+template <bool IK>
+static void launch_group(b2e_sim* s, int blocks, int threads, size_t smem, void* stream, const float* action, float* obs, float* reward,
+                         float* done, int n_substeps, int mode, const int* env_ids, int n, int env_offset, int* sched, int seq, int role,
+                         int nslot) {
+  B2E_LAUNCH(step_kernel<IK>, blocks, threads, smem, stream, s->d_model, s->umodel, s->params, s->st, action, obs, reward, done,
+             n_substeps, mode, s->record_contacts, env_ids, n, env_offset, sched, seq, role, nslot);
+}
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0, bool ordered = true) {
   const int n = (env_ids || n_ids > 0) ? n_ids : s->B;
@@ -1977,20 +2077,42 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
     if (ordered) ORDER_END(s, stream);
     return 0;
   }
-  // slow-first scheduling only for launches over the whole batch (they all run on the caller's stream, in order)
-  int* sched = (!env_ids && env_offset == 0 && n == s->B && s->d_sched) ? s->d_sched : nullptr;
-  const int seq = sched ? s->sched_seq++ : 0;
-  const int blocks = (n + 2 * WPB - 1) / (2 * WPB) + (sched ? SCHED_FRONT : 0);
-  if (s->params.use_ik)
-    B2E_LAUNCH(step_kernel<true>, blocks, 32 * WPB, SMEM_BYTES, stream,
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-        env_offset, sched, seq);
-  else
-    B2E_LAUNCH(step_kernel<false>, blocks, 32 * WPB, SMEM_BYTES, stream,
-        s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-        env_offset, sched, seq);
-  s->launches++;
+  // cost-ordered scheduling only for physics launches over the whole batch
+  int* sched = (!env_ids && env_offset == 0 && n == s->B && n_substeps > 0 && s->d_sched) ? s->d_sched : nullptr;
+  const bool ik = s->params.use_ik != 0;
+  if (!sched) {
+    const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
+    if (ik) launch_group<true>(s, blocks, 32 * WPB, SMEM_BYTES, stream, action, obs, reward, done, n_substeps, mode, env_ids, n, env_offset, nullptr, 0, ROLE_PLAIN, NSLOT);
+    else launch_group<false>(s, blocks, 32 * WPB, SMEM_BYTES, stream, action, obs, reward, done, n_substeps, mode, env_ids, n, env_offset, nullptr, 0, ROLE_PLAIN, NSLOT);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (ordered) ORDER_END(s, stream);
+    return 0;
+  }
+  const int seq = s->sched_seq++;
+  // fork: the tail launch (heavy class, lean blocks, own high-priority stream) is enqueued FIRST so that its blocks are
+  // resident when the main launch starts filling the machine; join: the caller's stream waits for it
+  const int twpb = s->tail_wpb, tslots = 2 * twpb;
+  const int tblocks = (TAIL_CAP + 2 * twpb - 1) / (2 * twpb);
+#ifndef B2E_EMU
+  CUDA_TRY(cudaEventRecord(s->ev_fork, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(s->tstream, s->ev_fork, 0));
+#endif
+  void* ts = (void*)s->tstream;
+  if (ik) launch_group<true>(s, tblocks, 32 * twpb, SMEM_BYTES_FOR(twpb, tslots), ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
+  else launch_group<false>(s, tblocks, 32 * twpb, SMEM_BYTES_FOR(twpb, tslots), ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
   CUDA_TRY(cudaGetLastError());
+#ifndef B2E_EMU
+  CUDA_TRY(cudaEventRecord(s->ev_join, s->tstream));
+#endif
+  const int blocks = (n + 2 * WPB - 1) / (2 * WPB);
+  if (ik) launch_group<true>(s, blocks, 32 * WPB, SMEM_BYTES, stream, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_MAIN, NSLOT);
+  else launch_group<false>(s, blocks, 32 * WPB, SMEM_BYTES, stream, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_MAIN, NSLOT);
+  CUDA_TRY(cudaGetLastError());
+#ifndef B2E_EMU
+  CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_join, 0));
+#endif
+  s->launches += 2;
   if (ordered) ORDER_END(s, stream);
   return 0;
 }
@@ -2076,12 +2198,29 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
   CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
   CUDA_TRY(cudaMemset(s->st.scratch, 0, (size_t)num_envs * SCRATCH_PER_ENV * 4));   // tables are finite from the start
   {
-    const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches slow-first scheduling off (A/B measurements)
-    if (!tree && !(e && e[0] == '0')) {
-      const size_t sb = (size_t)(SCHED_TAGS + 2 * ((num_envs + 2 * WPB - 1) / (2 * WPB))) * sizeof(int);
-      CUDA_TRY(cudaMalloc(&s->d_sched, sb));
-      CUDA_TRY(cudaMemset(s->d_sched, 0, sb));
-      s->sched_seq = 2;   // tags are 0-initialised: no environment is listed for the first launch
+    const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches cost-ordered scheduling off (A/B measurements)
+    const char* mn = getenv("B2ENV_SCHED_MIN");   // smallest batch that is scheduled (tests lower it)
+    if (!tree && num_envs >= (mn ? atoi(mn) : 2048) && !(e && e[0] == '0')) {
+      // every environment starts in class 0, in index order (as the lists of "step 1", read by the first step, seq = 2)
+      const size_t ni = (size_t)SCHED_INTS(num_envs);
+      int* h = (int*)calloc(ni, sizeof(int));
+      if (!h) return fail(B2E_EINVAL, "b2e_create: out of host memory%s", "");
+      h[SCHED_CNT(1, 0)] = num_envs;
+      for (int i = 0; i < num_envs; i++) h[SCHED_LIST(1, 0, num_envs) + i] = i;
+      cudaError_t e1 = cudaMalloc(&s->d_sched, ni * sizeof(int));
+      if (e1 == cudaSuccess) e1 = cudaMemcpy(s->d_sched, h, ni * sizeof(int), cudaMemcpyHostToDevice);
+      free(h);
+      CUDA_TRY(e1);
+      s->sched_seq = 2;
+      const char* w = getenv("B2ENV_TAIL_WPB");   // warps per block of the tail launch (1, 2 or 4)
+      s->tail_wpb = (w && (w[0] == '1' || w[0] == '2' || w[0] == '4')) ? (w[0] - '0') : 4;
+#ifndef B2E_EMU
+      int lo_p = 0, hi_p = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+      CUDA_TRY(cudaStreamCreateWithPriority(&s->tstream, cudaStreamNonBlocking, hi_p));
+      CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+#endif
     }
   }
   const size_t na = (size_t)num_envs * (params->n_act > 0 ? params->n_act : 1) * 4, no = (size_t)num_envs * params->n_obs * 4;
@@ -2093,8 +2232,9 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
   CUDA_TRY(cudaEventCreateWithFlags(&s->ev_order, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(s->ev_order, 0));
   CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int smem_max = (int)(SMEM_BYTES > SMEM_BYTES_FOR(4, 8) ? SMEM_BYTES : SMEM_BYTES_FOR(4, 8));   // main / largest tail block
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));
   return 0;
@@ -2111,6 +2251,9 @@ void b2e_destroy(b2e_sim* s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev_order) cudaEventDestroy(s->ev_order);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->tstream) cudaStreamDestroy(s->tstream);
   if (s->pstream[0]) cudaStreamDestroy(s->pstream[0]);
   if (s->pstream[1]) cudaStreamDestroy(s->pstream[1]);
   cudaGetLastError();   // a partially created sim frees null handles: leave no sticky error behind
@@ -2300,6 +2443,29 @@ int b2e_set_host(b2e_sim* s, int field, const void* src_host) {
   CUDA_TRY(cudaSetDevice(s->device));
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(s->fields[field], src_host, (size_t)s->B * field_width(s, field) * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2e_debug_sched(b2e_sim* s, int32_t* envs_out, int cap, int32_t* n_main_out, int32_t* n_tail_out) {
+  if (!s || !envs_out || !n_main_out || !n_tail_out) return fail(B2E_EINVAL, "b2e_debug_sched: null%s", "");
+  *n_main_out = 0; *n_tail_out = 0;
+  if (!s->d_sched) return 0;
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t ni = (size_t)SCHED_INTS(s->B);
+  int* h = (int*)malloc(ni * sizeof(int));
+  if (!h) return fail(B2E_EINVAL, "b2e_debug_sched: out of host memory%s", "");
+  cudaError_t e = cudaMemcpy(h, s->d_sched, ni * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(h); CUDA_TRY(e); }
+  const int q = (s->sched_seq - 1) & 3, par = (s->sched_seq - 1) & 1;
+  int n = 0;
+  for (int b = 0; b < NBK_MAIN; b++)
+    for (int i = 0; i < h[SCHED_CNT(q, b)] && n < cap; i++) envs_out[n++] = h[SCHED_LIST(par, b, s->B) + i];
+  *n_main_out = n;
+  const int nt = h[SCHED_CNT(q, NBK_MAIN)] < TAIL_CAP ? h[SCHED_CNT(q, NBK_MAIN)] : TAIL_CAP;
+  for (int i = 0; i < nt && n < cap; i++) envs_out[n++] = h[SCHED_TAIL(par, s->B) + i];
+  *n_tail_out = n - *n_main_out;
+  free(h);
   return 0;
 }
 

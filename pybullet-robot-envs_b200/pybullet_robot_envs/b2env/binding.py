@@ -30,7 +30,7 @@ EXPORTS = [
     "b2e_step_subset", "b2e_set_rows", "b2e_get_rows",
     "b2e_step_host", "b2e_step_pinned", "b2e_host_alloc", "b2e_host_free", "b2e_get", "b2e_set", "b2e_get_host", "b2e_set_host", "b2e_field_width",
     "b2e_field_elem_size", "b2e_num_envs", "b2e_launch_count", "b2e_timer_start", "b2e_timer_stop",
-    "b2e_last_error", "b2e_version",
+    "b2e_last_error", "b2e_version", "b2e_debug_sched",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library(path=None):
     lib.b2e_launch_count.restype = C.c_int64
     lib.b2e_timer_start.argtypes = [vp, vp]
     lib.b2e_timer_stop.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    lib.b2e_debug_sched.argtypes = [vp, vp, ci, C.POINTER(ci), C.POINTER(ci)]
     lib.b2e_last_error.restype = C.c_char_p
     lib.b2e_version.restype = C.c_char_p
     if path is None:
@@ -280,6 +281,13 @@ class B2Sim:
         self._check(self.lib.b2e_get_rows(self.h, f, _ptr(d), int(len(d)), _ptr(out), C.c_void_p(0)))
         self._sync()
         return out if self._host_mem else out.cpu().numpy()
+
+    def debug_sched_lists(self):
+        """(environments in scheduling order, how many of them are in the tail list) — diagnostics for the tests."""
+        out = np.zeros(self.B, np.int32)
+        nm, nt = C.c_int(), C.c_int()
+        self._check(self.lib.b2e_debug_sched(self.h, _ptr(out), self.B, C.byref(nm), C.byref(nt)))
+        return [int(x) for x in out[:nm.value + nt.value]], nt.value
 
     def launch_count(self):
         return int(self.lib.b2e_launch_count(self.h))

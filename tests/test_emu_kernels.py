@@ -67,60 +67,97 @@ def test_panda_push_kernel_matches_oracle(make_sim, oracle_lib):
     np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
 
 
-def test_panda_slow_first_scheduling_is_transparent(oracle_lib):
-    """Slow-first scheduling (SCHED_FRONT head positions of the grid) with the cost threshold forced to 0: after the first
-    launch EVERY block is listed and stepped by a head position while its home position exits — results must not change."""
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    so = os.path.join(EMU_DIR, "libb2env_emu_sched0.so")
+def _sched_variant_lib():
+    """Emulation build with a LOW tail threshold: a good part of the ordinary environments then travels through the tail
+    launch, the others are spread over several cost classes of the main launch."""
+    so = os.path.join(EMU_DIR, "libb2env_emu_tail.so")
     srcs = [os.path.join(ROOT, "pybullet-robot-envs_b200", "csrc", f) for f in ("b2env.cu", "b2env_tree.cuh")]
     srcs += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "b2env.h")]
     if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
-        subprocess.check_call(["bash", os.path.join(EMU_DIR, "build.sh"), "-DSCHED_COST=0"],
+        subprocess.check_call(["bash", os.path.join(EMU_DIR, "build.sh"), "-DSCHED_TAIL_COST=27500"],
                               env=dict(os.environ, OUT=os.path.basename(so)))
     from pybullet_robot_envs.b2env import binding
+    return binding.load_library(so)
+
+
+def _mk_sched(lib, m, p, B, sched, tail_wpb="4"):
     from pybullet_robot_envs.b2env.binding import B2Sim
-    lib = binding.load_library(so)
-    B = 37   # three blocks, the last one with padding groups
+    old = {k: os.environ.get(k) for k in ("B2ENV_SCHED", "B2ENV_SCHED_MIN", "B2ENV_TAIL_WPB")}
+    os.environ.update({"B2ENV_SCHED": "1" if sched else "0", "B2ENV_SCHED_MIN": "1", "B2ENV_TAIL_WPB": tail_wpb})
+    try:
+        return B2Sim(m, p, B, 0, lib=lib)   # the switches are read by b2e_create
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("tail_wpb", ["1", "4"])
+def test_panda_cost_ordered_scheduling_is_transparent(oracle_lib, tail_wpb):
+    """Cost-ordered scheduling (class lists + concurrent tail launch): which slot / block / launch steps an environment,
+    and next to which warp mate, must not change a single bit of its results.  Same batch stepped with scheduling on
+    (low tail threshold: both launches and several classes are populated) and off; contact-rich states included so that
+    big constraint systems go through the tail launch's per-environment overflow slots."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import test_gpu_parity as T
+    lib = _sched_variant_lib()
+    B = 45   # three main blocks, the last one with padding groups
     m, p = panda_task_setup(TASK_PUSH)
-    sim = B2Sim(m, p, B, 0, lib=lib)
+    sims = [_mk_sched(lib, m, p, B, True, tail_wpb), _mk_sched(lib, m, p, B, False)]
     try:
         orc = oracle_lib.Oracle(m, p, B, nthreads=4)
-        pose = sample_object_poses(B)
-        orc.reset(pose, targets_for(pose))
-        orc.step(None, 60, 1, want_obs=False)
-        copy_state_to_gpu(orc, sim)
+        qs, poses = T._contact_rich_states(oracle_lib, m, p, B, 5)
+        poses[::2] = sample_object_poses(B)[::2]          # every other environment: arm at home, cube at rest
+        qs[::2] = np.array([m.home[i] for i in range(9)], np.float32)
+        orc.reset(poses, targets_for(poses) + np.array([0.3, 0, 0], np.float32))
+        orc.state["q"][:] = qs
+        orc.state["mtarget"][:] = qs
+        orc.step(None, 3, 1, want_obs=False)
+        for sim in sims:
+            copy_state_to_gpu(orc, sim)
         rng = np.random.RandomState(3)
-        for i in range(5):
+        seen_tail, seen_classes = 0, set()
+        for i in range(6):
             a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
-            g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
-            o_obs, o_rew, o_done = orc.step(a, 1, 0)
-            np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
-            np.testing.assert_allclose(g_obs, o_obs, atol=2e-3)
-            np.testing.assert_array_equal(g_done, o_done)
-        assert np.abs(sim.get("q") - orc.state["q"]).max() < 1e-5
-        assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max() < 1e-5
-        np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
-        np.testing.assert_array_equal(sim.get("status")[:, 2:], orc.state["status"][:, 2:])
-        # launches that do not take part (a subset step, an observe-only call) between two that do: the lists written
-        # two launches ago must still be consistent (every environment stepped exactly once)
-        ids = np.array([3, 17, 36], np.int32)
-        sim.step_subset(ids, 2, 1)
-        mask = np.zeros(B, np.uint8)
-        mask[ids] = 1
-        q_before = orc.state["q"].copy()
-        for _ in range(2):   # the oracle advances the same three environments (HOLD mode, no action)
-            full = {k: v.copy() for k, v in orc.state.items()}
-            orc.step(None, 1, 1, want_obs=False)
-            for k, v in orc.state.items():
-                v[mask == 0] = full[k][mask == 0]
-        assert np.abs(orc.state["q"] - q_before)[mask == 0].max() == 0
-        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32)
-        g_obs, g_rew, g_done = sim.step_host(a, 1, 0)
-        o_obs, o_rew, o_done = orc.step(a, 1, 0)
-        np.testing.assert_allclose(g_rew, o_rew, atol=1e-3)
-        assert np.abs(sim.get("q") - orc.state["q"]).max() < 1e-5
-        np.testing.assert_array_equal(sim.get("counters"), orc.state["counters"])
+            outs = [sim.step_host(a, 1, 0) for sim in sims]
+            for x, y in zip(outs[0], outs[1]):
+                np.testing.assert_array_equal(x, y, err_msg="step %d" % i)
+            for f in ("q", "qd", "obj_pose", "obj_vel", "mtarget", "counters", "cache_key", "cache_lam", "status", "raw_obs"):
+                np.testing.assert_array_equal(sims[0].get(f), sims[1].get(f), err_msg="%s step %d" % (f, i))
+            if i == 2:   # launches that do not take part (a subset step, an observe-only call) between two that do
+                ids = np.array([3, 17, 36], np.int32)
+                for sim in sims:
+                    sim.step_subset(ids, 2, 1)
+                    sim.step_host(None, 0, 4)
+        o_obs, o_rew, o_done = orc.step(a, 1, 0)   # sanity against the oracle: the last step from the emulated state
+    finally:
+        for sim in sims:
+            sim.close()
+
+
+def test_panda_scheduling_lists_partition_the_batch(oracle_lib):
+    """After every scheduled step the class lists + tail list hold every environment exactly once."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    lib = _sched_variant_lib()
+    B = 45
+    m, p = panda_task_setup(TASK_PUSH)
+    sim = _mk_sched(lib, m, p, B, True)
+    try:
+        pose = sample_object_poses(B)
+        sim.reset_host(pose, targets_for(pose))
+        sim.step_host(None, 40, 1, want_obs=False)
+        rng = np.random.RandomState(4)
+        total_tail = 0
+        for i in range(4):
+            sim.step_host(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+            envs, n_tail = sim.debug_sched_lists()
+            assert sorted(envs) == list(range(B)), (i, sorted(envs))
+            total_tail += n_tail
+        assert total_tail > 0   # the low threshold of this build sends ordinary environments through the tail launch
     finally:
         sim.close()
 

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Stage timing of the Panda kernel (instrumentation build -DPROFILE_STAGES, selected with B2ENV_LIB): rolls a
+16384-env batch to the given depths and prints, per depth, the per-environment cycle stamps of one launch:
+dynamics / collision / solve / wait at the post-solve barrier / rest, as mean, p50, p99 and max over the environments.
+usage: B2ENV_LIB=variants/libb2env_stages.so python tools/stage_profile.py [depths=50,300,600,1000]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pybullet-robot-envs_b200"))
+from pybullet_robot_envs.b2env import binding  # noqa: E402
+from pybullet_robot_envs.envs import pandaPushGymEnv  # noqa: E402
+
+depths = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "50,300,600,1000").split(",")]
+B = 16384
+dev = torch.device("cuda", 0)
+env = pandaPushGymEnv(num_envs=B, device=0, renders=False, obj_pose_rnd_std=0.05, tg_pose_rnd_std=0, max_steps=100000)
+env.seed(0)
+env.reset()
+sim = env._sim
+gen = torch.Generator(device=dev)
+gen.manual_seed(1234)
+obs_t = torch.empty((B, sim.params.n_obs), device=dev)
+rew_t = torch.empty(B, device=dev)
+done_t = torch.empty(B, device=dev)
+stream = torch.cuda.current_stream(dev).cuda_stream
+d = 0
+names = ["fk+term", "dynamics", "collision", "barrier1", "solve", "barrier2(wait)", "rest"]
+for D in depths:
+    while d < D:
+        a = torch.rand((B, 7), generator=gen, device=dev) * 2 - 1
+        sim.step(a, obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
+        d += 1
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a = torch.rand((B, 7), generator=gen, device=dev) * 2 - 1
+    ev0.record()
+    sim.step(a, obs_t, rew_t, done_t, 1, binding.MODE_ACTION, stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    d += 1
+    c = sim.get("contacts").reshape(B, -1)[:, :8].astype(np.float64)
+    st = sim.get("status")
+    t = np.concatenate([c[:, :1], np.diff(c[:, :7], axis=1)], axis=1)   # per-stage cycles
+    print("depth %d: launch %.3f ms (%d cycles at 1.965 GHz), mean iters %.1f, capped %d" % (
+        d, ev0.elapsed_time(ev1), int(ev0.elapsed_time(ev1) * 1.965e6), st[:, 1].mean(), int((st[:, 1] >= 150).sum())))
+    for k, n in enumerate(names):
+        v = t[:, k]
+        print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % (n, v.mean(), np.percentile(v, 50), np.percentile(v, 99), v.max()))
+    tot = c[:, 6]
+    print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % ("block lifetime", tot.mean(), np.percentile(tot, 50), np.percentile(tot, 99), tot.max()))
+    # solve cycles vs (iters, rows)
+    it, R = st[:, 1], st[:, 3]
+    simple = (R == 21)
+    if simple.any():
+        cyc = t[simple, 4]; its = it[simple]
+        A = np.stack([its, np.ones_like(its)], axis=1).astype(np.float64)
+        coef = np.linalg.lstsq(A, cyc, rcond=None)[0]
+        print("   resting-cube envs (21 rows): solve cycles ~ %.0f + %.1f * sweeps  (=> %.1f cycles per row update over 12 cube rows)" % (coef[1], coef[0], coef[0] / 12))
