@@ -68,6 +68,18 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #define NSLOT 2           // overflow slots per block for environments with more than 16 generic rows
 #endif
 #define WSTRIDE 16        // row stride of the W = M^-1 J^T table
+// The solver's sweep loop must stay SMALL: a sweep-capped environment walks it 150 times, alone or next to other heavy warps,
+// and once the loop bodies of the warps on an SM outgrow the instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB per SM)
+// every row update waits for instruction fetches (measured with four heavy warps per tail block: 550-640 cycles per row
+// update with the row loops unrolled by 2 or 4, 120-130 with rolled loops).  Row loops are therefore NOT unrolled.
+#ifndef SWEEP_UNROLL
+#define SWEEP_UNROLL 1
+#endif
+#ifndef MOTOR_UNROLL
+#define MOTOR_UNROLL 3
+#endif
+#define B2E_PRAGMA(x) _Pragma(#x)
+#define B2E_UNROLL(n) B2E_PRAGMA(unroll n)
 // Cost-ordered scheduling (full-batch launches of the group kernel).  The environments of a block advance in phase
 // (block barriers between the stages), so a block lasts as long as its slowest environment, and a launch as long as its
 // slowest block: with contiguous blocks, one jammed contact (all solver sweeps over ~45 rows, ~0.4 ms) held 15 ordinary
@@ -642,12 +654,13 @@ __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs
 // a group skips (dl = 0, no table access) the rows it does not visit itself.
 template <int NSG, int SI>
 __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                          int AS, unsigned mk) {
-  const unsigned w = __reduce_or_sync(FULL, mk);   // union of the two groups' masks, PROVABLY warp-uniform (no BRA.DIV in the loop)
+                                          int AS, unsigned w) {
+  // w: union of the two groups' row masks of this set (__reduce_or_sync: provably warp-uniform trip count)
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
   const float* Arow = A + (GL * SI + lo) * AS;
   const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
+  B2E_UNROLL(SWEEP_UNROLL)
   for (int i = lo; i < hi; i++) {
     generic_step<NSG, SI>(g, m, r, Arow, Wrow, i);
     Arow += AS;
@@ -657,12 +670,14 @@ __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NS
 
 template <int NSG>
 __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A,
-                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2) {
+                                              const float* W, int AS, unsigned m0, unsigned m1, unsigned m2, unsigned w0,
+                                              unsigned w1, unsigned w2) {
+  // m*: rows of each set THIS group visits in the phase; w*: their unions over the two groups of the warp (loop bounds)
   constexpr int S1 = NSG > 1 ? 1 : 0, S2 = NSG > 2 ? 2 : 0;
   rows_prepare<NSG>(g, r, m0, m1, m2);
-  sweep_set<NSG, 0>(g, m, r, A, W, AS, m0);
-  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, m1);
-  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, m2);
+  sweep_set<NSG, 0>(g, m, r, A, W, AS, w0);
+  if (NSG > 1) sweep_set<NSG, S1>(g, m, r, A, W, AS, w1);
+  if (NSG > 2) sweep_set<NSG, S2>(g, m, r, A, W, AS, w2);
 }
 
 template <int NSG>
@@ -692,17 +707,35 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     cube_nf[s] = gballot(g, valid && cube && !fr);
     cube_f[s] = gballot(g, valid && cube && fr);
   }
+  // Control state of the shared sweep loop is kept warp-uniform: "island finished" flags of BOTH groups (A = lanes 0-15,
+  // B = lanes 16-31), maintained from two ballots per sweep; the unions of the row masks (loop bounds) are recomputed only
+  // when a flag flips.
   bool done0 = !arm_sweep, done1 = !has_cube_rows || coupled;
+  bool dA0, dB0, dA1, dB1;
+  {
+    const unsigned b0 = __ballot_sync(FULL, done0), b1 = __ballot_sync(FULL, done1);
+    dA0 = b0 & 1u; dB0 = (b0 >> GL) & 1u; dA1 = b1 & 1u; dB1 = (b1 >> GL) & 1u;
+  }
   int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
+  unsigned wn[3] = {0, 0, 0}, wf[3] = {0, 0, 0};
+  bool fresh = true;
   for (int it = 0; it < max_iters; it++) {
-    if (__all_sync(FULL, my_it >= 0)) break;
+    if (dA0 && dB0 && dA1 && dB1) break;
+    const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
+    if (fresh) {
+#pragma unroll
+      for (int s = 0; s < NSG; s++) {
+        wn[s] = __reduce_or_sync(FULL, (arm_nf[s] & a0) | (cube_nf[s] & c0));
+        wf[s] = __reduce_or_sync(FULL, (arm_f[s] & a0) | (cube_f[s] & c0));
+      }
+      fresh = false;
+    }
     m.prev = m.lam;
 #pragma unroll
     for (int s = 0; s < NSG; s++) r.prev[s] = r.lam[s];
-    const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
-    if (__any_sync(FULL, !done0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
+    if (!(dA0 && dB0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
       float dl = 0.f;
-#pragma unroll
+      B2E_UNROLL(MOTOR_UNROLL)
       for (int j = 0; j < NDMAX; j++) dl = fmaf(TL[j * GL + g.lane], SHF(m.u, j), dl);
       const float nl = m.lam + dl;
       const bool viol = !done0 && g.lane < nd && !(nl >= m.lo && nl <= m.hi);
@@ -712,7 +745,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
         dl = done0 ? 0.f : dl;
         m.lam += dl;
         const int lc = g.lane < NDMAX ? g.lane : NDMAX;
-#pragma unroll
+        B2E_UNROLL(MOTOR_UNROLL)
         for (int i = 0; i < NDMAX; i++) {
           const float di = SHF(dl, i);
           m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], di, m.u);
@@ -722,10 +755,8 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
       }
     }
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
-                       (arm_nf[2] & a0) | (cube_nf[2] & c0));
-    const unsigned f0 = (arm_f[0] & a0) | (cube_f[0] & c0), f1 = (arm_f[1] & a0) | (cube_f[1] & c0),
-                   f2 = (arm_f[2] & a0) | (cube_f[2] & c0);
-    if (__any_sync(FULL, (f0 | f1 | f2) != 0u)) {
+                       (arm_nf[2] & a0) | (cube_nf[2] & c0), wn[0], wn[1], wn[2]);
+    if ((wf[0] | wf[1] | wf[2]) != 0u) {
       // friction bounds from the current normal impulses (mu * lambda_n)
 #pragma unroll
       for (int s = 0; s < NSG; s++) {
@@ -741,7 +772,8 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
-      sweep_generic<NSG>(g, m, r, A, W, AS, f0, f1, f2);
+      sweep_generic<NSG>(g, m, r, A, W, AS, (arm_f[0] & a0) | (cube_f[0] & c0), (arm_f[1] & a0) | (cube_f[1] & c0),
+                         (arm_f[2] & a0) | (cube_f[2] & c0), wf[0], wf[1], wf[2]);
     }
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
@@ -756,10 +788,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
         if (coupled || r.isl[s] == 0) ra = fmaxf(ra, rv); else rc = fmaxf(rc, rv);
       }
     }
-    ra = gmaxf(g, ra);
-    rc = gmaxf(g, rc);
-    if (!done0 && ra <= tol) done0 = true;
-    if (!done1 && rc <= tol) done1 = true;
+    // an island is finished when the largest squared velocity change of the sweep is <= tol: "no lane above tol"
+    const unsigned ba = __ballot_sync(FULL, !(ra <= tol)), bc = __ballot_sync(FULL, !(rc <= tol));
+    const bool nA0 = dA0 || !(ba & 0xffffu), nB0 = dB0 || !(ba >> GL), nA1 = dA1 || !(bc & 0xffffu), nB1 = dB1 || !(bc >> GL);
+    fresh = (nA0 != dA0) || (nB0 != dB0) || (nA1 != dA1) || (nB1 != dB1);
+    dA0 = nA0; dB0 = nB0; dA1 = nA1; dB1 = nB1;
+    done0 = g.sh ? dB0 : dA0;
+    done1 = g.sh ? dB1 : dA1;
     if (my_it < 0 && done0 && done1) my_it = it + 1;
   }
   return my_it < 0 ? max_iters : my_it;
@@ -791,24 +826,27 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
   }
   float lam = 0.f;
   int my_it = -1;          // >= 0: converged after that many sweeps; -2: a bound would activate (fallback)
+  bool openA = true, openB = true;   // warp-uniform: group A / B still iterating (two ballots per sweep)
   for (int it = 0; it < max_iters; it++) {
-    if (__all_sync(FULL, my_it != -1)) break;   // the loop is shared by both groups of the warp
+    if (!openA && !openB) break;   // the loop is shared by both groups of the warp
     float a0 = c, a1 = 0.f;
 #pragma unroll
     for (int k = 1; k < NDMAX; k += 2) a0 = fmaf(G[k], SHF(lam, k), a0);
 #pragma unroll
     for (int k = 2; k < NDMAX; k += 2) a1 = fmaf(G[k], SHF(lam, k), a1);
     const float nl = a0 + a1;
-    const bool clamp = gany(g, row && !(nl >= lo && nl <= hi));
-    float rv = row ? (nl - lam) * diag : 0.f;
-    rv = gmaxf(g, rv * rv);
+    const float rv = row ? (nl - lam) * diag : 0.f;
+    const unsigned bcl = __ballot_sync(FULL, row && !(nl >= lo && nl <= hi)), bres = __ballot_sync(FULL, !(rv * rv <= tol));
+    const bool clamp = (bcl & g.hm) != 0u, conv = (bres & g.hm) == 0u;
     if (my_it == -1) {
       if (clamp) my_it = -2;
       else {
         lam = nl;
-        if (rv <= tol) my_it = it + 1;
+        if (conv) my_it = it + 1;
       }
     }
+    openA = openA && !(bcl & 0xffffu) && (bres & 0xffffu);
+    openB = openB && !(bcl >> GL) && (bres >> GL);
   }
   if (my_it == -2) return -1;
   lam_out = lam;
@@ -2213,7 +2251,7 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
       CUDA_TRY(e1);
       s->sched_seq = 2;
       const char* w = getenv("B2ENV_TAIL_WPB");   // warps per block of the tail launch (1, 2 or 4)
-      s->tail_wpb = (w && (w[0] == '1' || w[0] == '2' || w[0] == '4')) ? (w[0] - '0') : 4;
+      s->tail_wpb = (w && (w[0] == '1' || w[0] == '2' || w[0] == '4')) ? (w[0] - '0') : 1;
 #ifndef B2E_EMU
       int lo_p = 0, hi_p = 0;
       CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));

@@ -53,6 +53,20 @@ for D in depths:
         print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % (n, v.mean(), np.percentile(v, 50), np.percentile(v, 99), v.max()))
     tot = c[:, 6]
     print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % ("block lifetime", tot.mean(), np.percentile(tot, 50), np.percentile(tot, 99), tot.max()))
+    top = np.argsort(-t[:, 4])[:6]
+    envs, n_tail = sim.debug_sched_lists()
+    print("   tail list: %d envs; slowest solves: %s" % (n_tail, ", ".join("env %d: %d cycles, %d sweeps x %d rows (%.0f cycles/row), block %d" % (
+        e, t[e, 4], st[e, 1], st[e, 3], t[e, 4] / max(1, st[e, 1] * st[e, 3]), c[e, 7]) for e in top)))
+    cs = sim.get("contacts").reshape(B, -1)[:, 8:13].astype(np.float64)
+    if cs.any():   # -DPROFILE_SWEEP build: cycles per part of the sweeps
+        for e in top[:4]:
+            n = max(1, st[e, 1])
+            print("   env %d sweep parts, cycles per sweep: motor+masks %.0f | non-friction rows %.0f | friction bounds %.0f | friction rows %.0f | residual %.0f  (rows %d, nc %d)" % (
+                e, cs[e, 0] / n, cs[e, 1] / n, cs[e, 2] / n, cs[e, 3] / n, cs[e, 4] / n, st[e, 3], st[e, 2]))
+        simple_e = np.nonzero(st[:, 3] == 21)[0][:3]
+        for e in simple_e:
+            print("   resting env %d: totals motor+masks %.0f | nf rows %.0f | fric bounds %.0f | fric rows %.0f | residual %.0f (status iters %d)" % (
+                e, cs[e, 0], cs[e, 1], cs[e, 2], cs[e, 3], cs[e, 4], st[e, 1]))
     # solve cycles vs (iters, rows)
     it, R = st[:, 1], st[:, 3]
     simple = (R == 21)
