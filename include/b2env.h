@@ -39,6 +39,9 @@ extern "C" {
 #define B2E_MAX_SPHERES 16
 #define B2E_MAX_OBS 40
 #define B2E_MAX_CONTACTS 12 /* contact points kept per env per step            */
+#define B2E_MAX_BOXES 4     /* box collision proxies of robot links (finger pads) */
+#define B2E_MAX_SELF_PAIRS 32 /* sphere pairs tested for robot self-collision    */
+#define B2E_MAX_SBOXES 6    /* static world boxes (table top, legs)             */
 #define B2E_MAX_LIMROWS 3   /* joint-limit rows kept per env per step          */
 #define B2E_CACHE_SLOTS 16  /* warm-start cache slots (key + 3 impulses each)  */
 
@@ -86,6 +89,20 @@ typedef struct b2e_model {
   float sph_mu[B2E_MAX_SPHERES];     /* lateral friction of the owning link     */
   float sph_erp[B2E_MAX_SPHERES];    /* <0: use global erp                      */
   float sph_cfm[B2E_MAX_SPHERES];
+  /* box proxies (finger pads): collided with the object and the static world by box-box SAT + face clipping
+   * (include/b2env_narrowphase.h), the narrowphase Bullet runs for box shapes                                  */
+  int32_t n_boxes;
+  int32_t box_link[B2E_MAX_BOXES];
+  float box_c[B2E_MAX_BOXES][3];     /* centre in link frame                      */
+  float box_h[B2E_MAX_BOXES][3];     /* half extents along the link axes          */
+  float box_mu[B2E_MAX_BOXES];
+  float box_erp[B2E_MAX_BOXES];      /* <0: use global erp                        */
+  float box_cfm[B2E_MAX_BOXES];
+  /* robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): candidate pairs of sphere proxies on links that
+   * are neither the same nor parent / child (Bullet's default filter), built on the host                       */
+  int32_t n_self_pairs;
+  int32_t self_a[B2E_MAX_SELF_PAIRS];
+  int32_t self_b[B2E_MAX_SELF_PAIRS];
 } b2e_model;
 
 #define B2E_TASK_REACH 0
@@ -152,6 +169,12 @@ typedef struct b2e_params {
                               this translation (icub_env.py:251-257, :303-305)                             */
   int32_t reward_kind;     /* B2E_REWARD_*                                                                 */
   int32_t max_contacts;    /* contact points kept per env per step; <= 0: B2E_MAX_CONTACTS                 */
+  /* ---- static world boxes (world_env.py:62-66: table/table.urdf = top slab + four legs; [0] is the top slab and
+   *      equals table_min / table_max); the ground plane z = 0 is implicit.  n_sboxes = 0: top slab only          */
+  int32_t n_sboxes;
+  float sbox_c[B2E_MAX_SBOXES][3];   /* centre (world, axis aligned)             */
+  float sbox_h[B2E_MAX_SBOXES][3];   /* half extents                             */
+  float sbox_mu[B2E_MAX_SBOXES];
 } b2e_params;
 
 #define B2E_REWARD_PANDA 0       /* panda_push_gym_env.py:318-331 / panda_reach_gym_env.py:303-313 (bonus replaces) */
@@ -178,6 +201,31 @@ enum b2e_field {
                                             (icub_push_gym_env.py:126-127)       */
   B2E_F_COUNT = 14
 };
+
+/* Contact feature keys (B2E_F_CACHE_KEY, B2E_F_CONTACTS): stable ids used by the warm-start cache.
+ *   0..7    cube vertex v vs table top (cube fully over the table: vertex-face manifold)
+ *   8..15   cube vertex v vs ground plane
+ *   16..31  robot sphere s vs cube
+ *   32..47  robot sphere s vs table top
+ *   64..95  robot box b vertex v vs table top (64 + 8 b + v);  96..127 the same vs the ground plane
+ *   128..255 robot sphere s vs static box k other than through the table top (128 + 8 s + k)
+ *   256..271 robot sphere s vs ground plane
+ *   512..543 robot self-collision, sphere pair p
+ *   4096 + 1024 k + id   cube vs static box k, general box-box (rim, legs; id: include/b2env_narrowphase.h)
+ *   12288 + 1024 b + id  robot box b vs cube, box-box
+ *   16384 + 1024 (8 b + k) + id  robot box b vs static box k, general box-box                                   */
+#define B2E_KEY_CUBE_TABLE 0
+#define B2E_KEY_CUBE_PLANE 8
+#define B2E_KEY_SPHERE_CUBE 16
+#define B2E_KEY_SPHERE_TABLE 32
+#define B2E_KEY_BOXV_TABLE 64
+#define B2E_KEY_BOXV_PLANE 96
+#define B2E_KEY_SPHERE_SBOX 128
+#define B2E_KEY_SPHERE_PLANE 256
+#define B2E_KEY_SELF 512
+#define B2E_KEY_CUBE_SBOX 4096
+#define B2E_KEY_BOX_CUBE 12288
+#define B2E_KEY_BOX_SBOX 16384
 
 /* status flag bits */
 #define B2E_ST_NAN 1

@@ -457,54 +457,143 @@ static void minv_mul(const b2e_model* m, const fk_t* fk, const aba_t* w, const r
   }
 }
 
-/* ------------------------------------------------------------------ collision */
+/* ------------------------------------------------------------------ collision
+ * Broadphase: a static candidate-pair list (object x static world, robot proxies x object, robot proxies x static
+ * world, robot self pairs) culled by bounding spheres.  Narrowphase: closed forms where they are exact (cube vertices on
+ * the table top when the cube is wholly over it, sphere-box, sphere-plane, sphere-sphere), box-box SAT + face clipping
+ * (include/b2env_narrowphase.h, shared with the CUDA kernel and pinned by tests/test_narrowphase.py) for everything
+ * else: the cube at the table rim or against a leg, the finger-pad boxes against the cube and the table.            */
 #define CT_CUBE_STATIC 0
-#define CT_SPHERE_CUBE 1
-#define CT_SPHERE_STATIC 2
-#define KEY_CUBE_TABLE 0
-#define KEY_CUBE_PLANE 8
-#define KEY_SPHERE_CUBE 16
-#define KEY_SPHERE_TABLE 32
+#define CT_ARM_CUBE 1
+#define CT_ARM_STATIC 2
+#define CT_ARM_ARM 3
+
+#define B2N_REAL real
+#define B2N_FN static
+#define B2N_SQRT(x) RSQRT(x)
+#define B2N_FABS(x) RFABS(x)
+#include "../include/b2env_narrowphase.h"
 
 typedef struct {
-  int key, type, link;
-  real pA[3], pB[3], n[3]; /* n points from B towards A; A = cube (cube-static) or the arm sphere */
+  int key, type, link, link2;
+  real pA[3], pB[3], n[3]; /* n points from B towards A; A = cube (cube-static) or the arm proxy (link); B = cube / world /
+                              the second arm proxy (link2, self-collision) */
   real dist, mu, erp, cfm;
 } contact_t;
 
+typedef struct { contact_t* out; int nc, maxc, overflow; } clist_t;
+static contact_t* push_contact(clist_t* L) {
+  if (L->nc >= L->maxc) { L->overflow = 1; return NULL; }
+  return &L->out[L->nc++];
+}
+static void sbox_get(const b2e_params* P, int k, real* c, real* h) {
+  if (P->n_sboxes > 0) {
+    for (int j = 0; j < 3; j++) { c[j] = P->sbox_c[k][j]; h[j] = P->sbox_h[k][j]; }
+  } else {
+    for (int j = 0; j < 3; j++) { c[j] = (real)0.5 * (P->table_min[j] + P->table_max[j]); h[j] = (real)0.5 * (P->table_max[j] - P->table_min[j]); }
+  }
+}
+static const real IDENT3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+/* sphere (centre c, radius r) vs axis-aligned box: 1 if within margin; n from the box towards the sphere */
+static int sphere_aabox(const real* c, real r, const real* bc, const real* bh, real margin, real* n, real* pB, real* dist, int* top) {
+  real l[3], cl[3];
+  int inside = 1;
+  for (int j = 0; j < 3; j++) {
+    l[j] = c[j] - bc[j];
+    cl[j] = l[j] < -bh[j] ? -bh[j] : (l[j] > bh[j] ? bh[j] : l[j]);
+    if (cl[j] != l[j]) inside = 0;
+  }
+  *top = 0;
+  if (!inside) {
+    real dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+    if (dv[0] == 0 && dv[1] == 0 && dv[2] > 0) { /* over the top face: the round-1 closed form, bit for bit */
+      *dist = c[2] - r - (bc[2] + bh[2]);
+      if (!(*dist < margin)) return 0;
+      n[0] = 0; n[1] = 0; n[2] = 1;
+      pB[0] = c[0]; pB[1] = c[1]; pB[2] = bc[2] + bh[2];
+      *top = 1;
+      return 1;
+    }
+    real d = RSQRT(dot3(dv, dv));
+    *dist = d - r;
+    if (!(*dist < margin)) return 0;
+    for (int j = 0; j < 3; j++) { n[j] = dv[j] / d; pB[j] = bc[j] + cl[j]; }
+    return 1;
+  }
+  int ax = 0;
+  real best = bh[0] - RFABS(l[0]);
+  for (int j = 1; j < 3; j++) {
+    real pen = bh[j] - RFABS(l[j]);
+    if (pen < best) { best = pen; ax = j; }
+  }
+  n[0] = n[1] = n[2] = 0;
+  n[ax] = l[ax] >= 0 ? 1 : -1;
+  cl[ax] = n[ax] * bh[ax];
+  *dist = -best - r;
+  for (int j = 0; j < 3; j++) pB[j] = bc[j] + cl[j];
+  return 1;
+}
+
 static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, const real* cpos, const real* cquat,
                    contact_t* out, int* overflow) {
-  int nc = 0;
-  const int maxc = (P->max_contacts > 0 && P->max_contacts < MAXC) ? P->max_contacts : MAXC;
-  *overflow = 0;
+  clist_t L = {out, 0, (P->max_contacts > 0 && P->max_contacts < MAXC) ? P->max_contacts : MAXC, 0};
   real Rc[9];
   quat_to_mat(cquat, Rc);
-  real a = P->cube_half, margin = P->contact_margin;
-  /* cube vertices vs table-top slab / ground plane (vertex-face manifold; equals Bullet's
-   * box-box face clipping result for a face-down cube) */
+  const real a = P->cube_half, margin = P->contact_margin;
+  const real ch[3] = {a, a, a};
+  const real rb = a * (real)1.7320508075688772;   /* bounding sphere of the cube */
+  const int nsb = P->n_sboxes > 0 ? P->n_sboxes : 1;
+  real verts[8][3];
   for (int k = 0; k < 8; k++) {
-    real l[3] = {(k & 1) ? a : -a, (k & 2) ? a : -a, (k & 4) ? a : -a}, v[3];
-    m3_vec(Rc, l, v);
-    for (int j = 0; j < 3; j++) v[j] += cpos[j];
-    int over_table = v[0] >= P->table_min[0] && v[0] <= P->table_max[0] && v[1] >= P->table_min[1] &&
-                     v[1] <= P->table_max[1] && v[2] > P->table_min[2];
-    real dist, mu;
-    int key;
-    real top;
-    if (over_table) { top = P->table_max[2]; mu = P->cube_mu * P->table_mu; key = KEY_CUBE_TABLE + k; }
-    else { top = 0; mu = P->cube_mu * P->plane_mu; key = KEY_CUBE_PLANE + k; }
-    dist = v[2] - top;
-    if (dist < margin) {
-      if (nc >= maxc) { *overflow = 1; continue; }
-      contact_t* c = &out[nc++];
-      c->key = key; c->type = CT_CUBE_STATIC; c->link = -1;
-      for (int j = 0; j < 3; j++) { c->pA[j] = v[j]; c->pB[j] = v[j]; }
+    real l[3] = {(k & 1) ? a : -a, (k & 2) ? a : -a, (k & 4) ? a : -a};
+    m3_vec(Rc, l, verts[k]);
+    for (int j = 0; j < 3; j++) verts[k][j] += cpos[j];
+  }
+  /* ---- 1. cube vs static world ---- */
+  const real top = P->table_max[2];
+  const int cube_fast = cpos[0] - rb >= P->table_min[0] && cpos[0] + rb <= P->table_max[0] && cpos[1] - rb >= P->table_min[1] &&
+                        cpos[1] + rb <= P->table_max[1] && cpos[2] >= top;
+  if (cube_fast) { /* wholly over the table: vertex-face manifold (= box-box face clipping for a face-down cube) */
+    for (int k = 0; k < 8; k++) {
+      real dist = verts[k][2] - top;
+      if (!(dist < margin)) continue;
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = B2E_KEY_CUBE_TABLE + k; c->type = CT_CUBE_STATIC; c->link = -1; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = verts[k][j]; c->pB[j] = verts[k][j]; }
       c->pB[2] = top;
       c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
-      c->dist = dist; c->mu = mu; c->erp = P->erp; c->cfm = 0;
+      c->dist = dist; c->mu = P->cube_mu * P->table_mu; c->erp = P->erp; c->cfm = 0;
     }
   }
-  /* robot spheres vs cube */
+  for (int k = cube_fast ? 1 : 0; k < nsb; k++) { /* rim of the top slab, legs: general box-box behind a bounding-sphere cull */
+    real bc[3], bh[3];
+    sbox_get(P, k, bc, bh);
+    real d[3] = {cpos[0] - bc[0], cpos[1] - bc[1], cpos[2] - bc[2]};
+    if (RSQRT(dot3(d, d)) - (rb + RSQRT(dot3(bh, bh))) >= margin) continue;
+    real n[3];
+    b2n_contact pts[B2N_MAX_POINTS];
+    int np = b2n_box_box(cpos, Rc, ch, bc, IDENT3, bh, margin, n, pts);
+    for (int q = 0; q < np; q++) {
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = B2E_KEY_CUBE_SBOX + B2N_ID_STRIDE * k + pts[q].id; c->type = CT_CUBE_STATIC; c->link = -1; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = pts[q].pa[j]; c->pB[j] = pts[q].pb[j]; c->n[j] = n[j]; }
+      c->dist = pts[q].dist; c->mu = P->cube_mu * (P->n_sboxes > 0 ? P->sbox_mu[k] : P->table_mu); c->erp = P->erp; c->cfm = 0;
+    }
+  }
+  for (int k = 0; k < 8; k++) { /* ground plane z = 0 */
+    if (cube_fast || !(verts[k][2] < margin)) continue;
+    contact_t* c = push_contact(&L);
+    if (!c) continue;
+    c->key = B2E_KEY_CUBE_PLANE + k; c->type = CT_CUBE_STATIC; c->link = -1; c->link2 = -1;
+    for (int j = 0; j < 3; j++) { c->pA[j] = verts[k][j]; c->pB[j] = verts[k][j]; }
+    c->pB[2] = 0;
+    c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
+    c->dist = verts[k][2]; c->mu = P->cube_mu * P->plane_mu; c->erp = P->erp; c->cfm = 0;
+  }
+  /* ---- robot proxies in world coordinates ---- */
   real sc[B2E_MAX_SPHERES][3];
   for (int s = 0; s < m->n_spheres; s++) {
     int li = m->sph_link[s];
@@ -512,6 +601,15 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
     m3_vec(fk->R[li], lc, o);
     for (int j = 0; j < 3; j++) sc[s][j] = fk->p[li][j] + o[j];
   }
+  real bxc[B2E_MAX_BOXES][3], bxh[B2E_MAX_BOXES][3], bxr[B2E_MAX_BOXES];
+  for (int b = 0; b < m->n_boxes; b++) {
+    int li = m->box_link[b];
+    real lc[3] = {m->box_c[b][0], m->box_c[b][1], m->box_c[b][2]}, o[3];
+    m3_vec(fk->R[li], lc, o);
+    for (int j = 0; j < 3; j++) { bxc[b][j] = fk->p[li][j] + o[j]; bxh[b][j] = m->box_h[b][j]; }
+    bxr[b] = RSQRT(dot3(bxh[b], bxh[b]));
+  }
+  /* ---- 2. robot vs cube: spheres (closest point on the box), finger-pad boxes (box-box) ---- */
   for (int s = 0; s < m->n_spheres; s++) {
     real rel[3] = {sc[s][0] - cpos[0], sc[s][1] - cpos[1], sc[s][2] - cpos[2]}, l[3], cl[3];
     m3t_vec(Rc, rel, l);
@@ -540,9 +638,9 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
       cl[ax] = nl[ax] * a;
       dist = -best - r;
     }
-    if (nc >= maxc) { *overflow = 1; continue; }
-    contact_t* c = &out[nc++];
-    c->key = KEY_SPHERE_CUBE + s; c->type = CT_SPHERE_CUBE; c->link = m->sph_link[s];
+    contact_t* c = push_contact(&L);
+    if (!c) continue;
+    c->key = B2E_KEY_SPHERE_CUBE + s; c->type = CT_ARM_CUBE; c->link = m->sph_link[s]; c->link2 = -1;
     real nw[3], pw[3];
     m3_vec(Rc, nl, nw);
     m3_vec(Rc, cl, pw);
@@ -555,26 +653,137 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
     c->erp = m->sph_erp[s] >= 0 ? m->sph_erp[s] : P->erp;
     c->cfm = m->sph_cfm[s];
   }
-  /* robot spheres vs table top */
+  for (int b = 0; b < m->n_boxes; b++) {
+    real d[3] = {bxc[b][0] - cpos[0], bxc[b][1] - cpos[1], bxc[b][2] - cpos[2]};
+    if (RSQRT(dot3(d, d)) - (rb + bxr[b]) >= margin) continue;
+    real n[3];
+    b2n_contact pts[B2N_MAX_POINTS];
+    int np = b2n_box_box(bxc[b], fk->R[m->box_link[b]], bxh[b], cpos, Rc, ch, margin, n, pts);
+    for (int q = 0; q < np; q++) {
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = B2E_KEY_BOX_CUBE + B2N_ID_STRIDE * b + pts[q].id; c->type = CT_ARM_CUBE; c->link = m->box_link[b]; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = pts[q].pa[j]; c->pB[j] = pts[q].pb[j]; c->n[j] = n[j]; }
+      c->dist = pts[q].dist; c->mu = P->cube_mu * m->box_mu[b];
+      c->erp = m->box_erp[b] >= 0 ? m->box_erp[b] : P->erp;
+      c->cfm = m->box_cfm[b];
+    }
+  }
+  /* ---- 3. robot vs static world ---- */
   for (int s = 0; s < m->n_spheres; s++) {
     real r = m->sph_r[s];
-    if (!(sc[s][0] >= P->table_min[0] && sc[s][0] <= P->table_max[0] && sc[s][1] >= P->table_min[1] &&
-          sc[s][1] <= P->table_max[1] && sc[s][2] > P->table_min[2]))
-      continue;
-    real dist = sc[s][2] - r - P->table_max[2];
+    int kept = 0;
+    for (int k = 0; k < nsb && kept < 3; k++) { /* at most three static boxes per sphere */
+      real bc[3], bh[3], n[3], pB[3], dist;
+      int is_top;
+      sbox_get(P, k, bc, bh);
+      real d[3] = {sc[s][0] - bc[0], sc[s][1] - bc[1], sc[s][2] - bc[2]};
+      if (RSQRT(dot3(d, d)) - (r + RSQRT(dot3(bh, bh))) >= margin) continue;
+      if (!sphere_aabox(sc[s], r, bc, bh, margin, n, pB, &dist, &is_top)) continue;
+      kept++;
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = (k == 0 && is_top) ? B2E_KEY_SPHERE_TABLE + s : B2E_KEY_SPHERE_SBOX + 8 * s + k;
+      c->type = CT_ARM_STATIC; c->link = m->sph_link[s]; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->n[j] = n[j]; c->pB[j] = pB[j]; c->pA[j] = sc[s][j] - n[j] * r; }
+      c->dist = dist; c->mu = (P->n_sboxes > 0 ? P->sbox_mu[k] : P->table_mu) * m->sph_mu[s];
+      c->erp = m->sph_erp[s] >= 0 ? m->sph_erp[s] : P->erp;
+      c->cfm = m->sph_cfm[s];
+    }
+  }
+  for (int s = 0; s < m->n_spheres; s++) { /* ground plane */
+    real r = m->sph_r[s], dist = sc[s][2] - r;
     if (!(dist < margin)) continue;
-    if (nc >= maxc) { *overflow = 1; continue; }
-    contact_t* c = &out[nc++];
-    c->key = KEY_SPHERE_TABLE + s; c->type = CT_SPHERE_STATIC; c->link = m->sph_link[s];
+    contact_t* c = push_contact(&L);
+    if (!c) continue;
+    c->key = B2E_KEY_SPHERE_PLANE + s; c->type = CT_ARM_STATIC; c->link = m->sph_link[s]; c->link2 = -1;
     c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
     for (int j = 0; j < 3; j++) { c->pA[j] = sc[s][j]; c->pB[j] = sc[s][j]; }
-    c->pA[2] = sc[s][2] - r;
-    c->pB[2] = P->table_max[2];
-    c->dist = dist; c->mu = P->table_mu * m->sph_mu[s];
+    c->pA[2] = dist; c->pB[2] = 0;
+    c->dist = dist; c->mu = P->plane_mu * m->sph_mu[s];
     c->erp = m->sph_erp[s] >= 0 ? m->sph_erp[s] : P->erp;
     c->cfm = m->sph_cfm[s];
   }
-  return nc;
+  /* finger-pad boxes: family by family (the CUDA kernel compacts each family with one ballot): vertices on the table top
+   * (pad wholly over the table), general box-box against the static boxes, vertices on the ground plane */
+  int bfast[B2E_MAX_BOXES];
+  real bv[B2E_MAX_BOXES][8][3];
+  for (int b = 0; b < m->n_boxes; b++) {
+    const real* Rb = fk->R[m->box_link[b]];
+    bfast[b] = bxc[b][0] - bxr[b] >= P->table_min[0] && bxc[b][0] + bxr[b] <= P->table_max[0] &&
+               bxc[b][1] - bxr[b] >= P->table_min[1] && bxc[b][1] + bxr[b] <= P->table_max[1] && bxc[b][2] >= top;
+    for (int k = 0; k < 8; k++) {
+      real l[3] = {(k & 1) ? bxh[b][0] : -bxh[b][0], (k & 2) ? bxh[b][1] : -bxh[b][1], (k & 4) ? bxh[b][2] : -bxh[b][2]};
+      m3_vec(Rb, l, bv[b][k]);
+      for (int j = 0; j < 3; j++) bv[b][k][j] += bxc[b][j];
+    }
+  }
+  for (int b = 0; b < m->n_boxes; b++) {
+    const real erp = m->box_erp[b] >= 0 ? m->box_erp[b] : P->erp;
+    for (int k = 0; k < 8; k++) {
+      real dist = bv[b][k][2] - top;
+      if (!bfast[b] || !(dist < margin)) continue;
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = B2E_KEY_BOXV_TABLE + 8 * b + k; c->type = CT_ARM_STATIC; c->link = m->box_link[b]; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = bv[b][k][j]; c->pB[j] = bv[b][k][j]; }
+      c->pB[2] = top;
+      c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
+      c->dist = dist; c->mu = P->table_mu * m->box_mu[b]; c->erp = erp; c->cfm = m->box_cfm[b];
+    }
+  }
+  for (int b = 0; b < m->n_boxes; b++) {
+    const real* Rb = fk->R[m->box_link[b]];
+    const real erp = m->box_erp[b] >= 0 ? m->box_erp[b] : P->erp;
+    for (int k = bfast[b] ? 1 : 0; k < nsb; k++) {
+      real bc[3], bh[3];
+      sbox_get(P, k, bc, bh);
+      real d[3] = {bxc[b][0] - bc[0], bxc[b][1] - bc[1], bxc[b][2] - bc[2]};
+      if (RSQRT(dot3(d, d)) - (bxr[b] + RSQRT(dot3(bh, bh))) >= margin) continue;
+      real n[3];
+      b2n_contact pts[B2N_MAX_POINTS];
+      int np = b2n_box_box(bxc[b], Rb, bxh[b], bc, IDENT3, bh, margin, n, pts);
+      for (int q = 0; q < np; q++) {
+        contact_t* c = push_contact(&L);
+        if (!c) continue;
+        c->key = B2E_KEY_BOX_SBOX + B2N_ID_STRIDE * (8 * b + k) + pts[q].id; c->type = CT_ARM_STATIC; c->link = m->box_link[b]; c->link2 = -1;
+        for (int j = 0; j < 3; j++) { c->pA[j] = pts[q].pa[j]; c->pB[j] = pts[q].pb[j]; c->n[j] = n[j]; }
+        c->dist = pts[q].dist; c->mu = (P->n_sboxes > 0 ? P->sbox_mu[k] : P->table_mu) * m->box_mu[b]; c->erp = erp; c->cfm = m->box_cfm[b];
+      }
+    }
+  }
+  for (int b = 0; b < m->n_boxes; b++) {
+    const real erp = m->box_erp[b] >= 0 ? m->box_erp[b] : P->erp;
+    for (int k = 0; k < 8; k++) { /* ground plane */
+      if (bfast[b] || !(bv[b][k][2] < margin)) continue;
+      contact_t* c = push_contact(&L);
+      if (!c) continue;
+      c->key = B2E_KEY_BOXV_PLANE + 8 * b + k; c->type = CT_ARM_STATIC; c->link = m->box_link[b]; c->link2 = -1;
+      for (int j = 0; j < 3; j++) { c->pA[j] = bv[b][k][j]; c->pB[j] = bv[b][k][j]; }
+      c->pB[2] = 0;
+      c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
+      c->dist = bv[b][k][2]; c->mu = P->plane_mu * m->box_mu[b]; c->erp = erp; c->cfm = m->box_cfm[b];
+    }
+  }
+  /* ---- 4. robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): sphere pairs of non-neighbouring links ---- */
+  for (int p = 0; p < m->n_self_pairs; p++) {
+    const int sa = m->self_a[p], sb = m->self_b[p];
+    real d[3] = {sc[sa][0] - sc[sb][0], sc[sa][1] - sc[sb][1], sc[sa][2] - sc[sb][2]};
+    real dn = RSQRT(dot3(d, d));
+    real dist = dn - (m->sph_r[sa] + m->sph_r[sb]);
+    if (!(dist < margin) || !(dn > (real)1e-9)) continue;
+    contact_t* c = push_contact(&L);
+    if (!c) continue;
+    c->key = B2E_KEY_SELF + p; c->type = CT_ARM_ARM; c->link = m->sph_link[sa]; c->link2 = m->sph_link[sb];
+    for (int j = 0; j < 3; j++) {
+      c->n[j] = d[j] / dn;
+      c->pA[j] = sc[sa][j] - c->n[j] * m->sph_r[sa];
+      c->pB[j] = sc[sb][j] + c->n[j] * m->sph_r[sb];
+    }
+    c->dist = dist; c->mu = m->sph_mu[sa] * m->sph_mu[sb]; c->erp = P->erp; c->cfm = 0;
+  }
+  *overflow = L.overflow;
+  return L.nc;
 }
 
 /* btPlaneSpace1 [EXT-recalled]: deterministic tangent basis of a unit normal */
@@ -641,7 +850,11 @@ static void contact_J(const rowctx_t* cx, const contact_t* c, const real* cpos, 
     real Jl[ND][3], Ja[ND][3];
     point_jacobian(cx->m, cx->fk, c->link, c->pA, Jl, Ja);
     for (int d = 0; d < nd; d++) J[d] = dot3(Jl[d], dir);
-    if (c->type == CT_SPHERE_CUBE) {
+    if (c->type == CT_ARM_ARM) { /* self-collision: velocity of the point on link minus that of the point on link2 */
+      point_jacobian(cx->m, cx->fk, c->link2, c->pB, Jl, Ja);
+      for (int d = 0; d < nd; d++) J[d] -= dot3(Jl[d], dir);
+    }
+    if (c->type == CT_ARM_CUBE) {
       real rel[3] = {c->pB[0] - cpos[0], c->pB[1] - cpos[1], c->pB[2] - cpos[2]}, t[3];
       cross3(rel, dir, t);
       for (int k = 0; k < 3; k++) { J[nd + k] = -dir[k]; J[nd + 3 + k] = -t[k]; }
@@ -860,7 +1073,7 @@ static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int 
     memset(r, 0, sizeof(*r));
     r->type = ROW_NORMAL;
     r->island = con[c].type == CT_CUBE_STATIC ? ISL_CUBE : ISL_ARM;
-    if (con[c].type == CT_SPHERE_CUBE) coupled = 1;
+    if (con[c].type == CT_ARM_CUBE) coupled = 1;
     contact_J(&cx, &con[c], e->cpos, con[c].n, r->J);
     real pen = con[c].dist + P->slop;
     real desired = pen > 0 ? -pen / dt : -pen * con[c].erp / dt;
@@ -1313,5 +1526,39 @@ int b2o_ik(const b2e_model* m, const b2e_params* P, const float* q0, const float
   int it = ik_dls(m, P, q, tp, tq, o);
   for (int d = 0; d < m->n_dof; d++) qout[d] = (float)o[d];
   return it;
+}
+/* box-box narrowphase (include/b2env_narrowphase.h) on its own: out = [n][8] = pa(3) pb(3) dist id, normal[3] */
+int b2o_box_box(const float* cA, const float* RA, const float* hA, const float* cB, const float* RB, const float* hB, float margin,
+                float* normal, float* out) {
+  real a[3], ra[9], ha[3], b[3], rb[9], hb[3], n[3];
+  for (int k = 0; k < 3; k++) { a[k] = cA[k]; ha[k] = hA[k]; b[k] = cB[k]; hb[k] = hB[k]; }
+  for (int k = 0; k < 9; k++) { ra[k] = RA[k]; rb[k] = RB[k]; }
+  b2n_contact pts[B2N_MAX_POINTS];
+  int np = b2n_box_box(a, ra, ha, b, rb, hb, (real)margin, n, pts);
+  for (int q = 0; q < np; q++) {
+    for (int k = 0; k < 3; k++) { out[8 * q + k] = (float)pts[q].pa[k]; out[8 * q + 3 + k] = (float)pts[q].pb[k]; }
+    out[8 * q + 6] = (float)pts[q].dist;
+    out[8 * q + 7] = (float)pts[q].id;
+  }
+  if (np > 0) for (int k = 0; k < 3; k++) normal[k] = (float)n[k];
+  return np;
+}
+/* the contact set of one configuration: out = [n][16] = key type link link2 pA(3) pB(3) n(3) dist mu erp */
+int b2o_collide(const b2e_model* m, const b2e_params* P, const float* q, const float* obj_pose, float* out, int* overflow) {
+  real qq[ND] = {0}, cp[3], cq[4];
+  for (int d = 0; d < m->n_dof; d++) qq[d] = q[d];
+  for (int k = 0; k < 3; k++) cp[k] = obj_pose[k];
+  for (int k = 0; k < 4; k++) cq[k] = obj_pose[3 + k];
+  fk_t fk;
+  forward_kinematics(m, qq, &fk);
+  contact_t con[MAXC];
+  int nc = collide(m, P, &fk, cp, cq, con, overflow);
+  for (int c = 0; c < nc; c++) {
+    float* o = out + 16 * c;
+    o[0] = (float)con[c].key; o[1] = (float)con[c].type; o[2] = (float)con[c].link; o[3] = (float)con[c].link2;
+    for (int k = 0; k < 3; k++) { o[4 + k] = (float)con[c].pA[k]; o[7 + k] = (float)con[c].pB[k]; o[10 + k] = (float)con[c].n[k]; }
+    o[13] = (float)con[c].dist; o[14] = (float)con[c].mu; o[15] = (float)con[c].erp;
+  }
+  return nc;
 }
 int b2o_real_size(void) { return (int)sizeof(real); }

@@ -107,13 +107,10 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
 
-#define KEY_CUBE_TABLE 0
-#define KEY_CUBE_PLANE 8
-#define KEY_SPHERE_CUBE 16
-#define KEY_SPHERE_TABLE 32
-#define CT_CUBE_STATIC 0
-#define CT_SPHERE_CUBE 1
-#define CT_SPHERE_STATIC 2
+#define CT_CUBE_STATIC 0     // object vs static world: rows act on the object only
+#define CT_ARM_CUBE 1        // robot proxy (point on `link`) vs object
+#define CT_ARM_STATIC 2      // robot proxy vs static world
+#define CT_ARM_ARM 3         // robot self-collision: point on `link` vs point on `link2`
 #define ROW_MOTOR 0
 #define ROW_LIMIT 1
 #define ROW_NORMAL 2
@@ -136,11 +133,15 @@ struct DevModel {
   int sph_link[B2E_MAX_SPHERES];
   float sph_c[B2E_MAX_SPHERES][3], sph_r[B2E_MAX_SPHERES], sph_mu[B2E_MAX_SPHERES], sph_erp[B2E_MAX_SPHERES],
       sph_cfm[B2E_MAX_SPHERES];
+  int n_boxes, n_self_pairs;
+  int box_link[B2E_MAX_BOXES];
+  float box_c[B2E_MAX_BOXES][3], box_h[B2E_MAX_BOXES][3], box_mu[B2E_MAX_BOXES], box_erp[B2E_MAX_BOXES], box_cfm[B2E_MAX_BOXES];
+  int self_a[B2E_MAX_SELF_PAIRS], self_b[B2E_MAX_SELF_PAIRS];
 };
 
 // warp-uniform part of the model: passed by value (constant bank), no loads on the critical path
 struct DevModelU {
-  int n_links, n_dof, ee_link, n_spheres, fk_rounds, acc_rounds;
+  int n_links, n_dof, ee_link, n_spheres, fk_rounds, acc_rounds, n_boxes, n_self_pairs;
   unsigned ee_dofmask;
   float base_pos[3], base_rot[9], ee_com[3];
   int parent[TLMAX];
@@ -329,7 +330,7 @@ __device__ __forceinline__ void gsync(const Grp& g) { (void)g; __syncwarp(); }
 
 // per-environment shared memory (4.6 KB)
 struct Contact {   // 16 words
-  int key, type, link, pad;
+  int key, type, link, link2;
   float pA[3], pB[3], n[3];
   float dist, mu, erp;
 };
@@ -953,7 +954,18 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
                       sm.S[d][4] * dir[1] + sm.S[d][5] * dir[2];
             J[d] = ((mask >> d) & 1) ? v : 0.f;
           }
-          if (ct.type == CT_SPHERE_CUBE) {
+          if (ct.type == CT_ARM_ARM) {   // self-collision: minus the velocity of the point on link2
+            const unsigned mask2 = __ldg(&M->link_dofmask[ct.link2]);
+            float rel2[3] = {ct.pB[0] - U.base_pos[0], ct.pB[1] - U.base_pos[1], ct.pB[2] - U.base_pos[2]}, wn2[3];
+            cross3(rel2, dir, wn2);
+#pragma unroll
+            for (int d = 0; d < NDMAX; d++) {
+              float v = sm.S[d][0] * wn2[0] + sm.S[d][1] * wn2[1] + sm.S[d][2] * wn2[2] + sm.S[d][3] * dir[0] +
+                        sm.S[d][4] * dir[1] + sm.S[d][5] * dir[2];
+              J[d] -= ((mask2 >> d) & 1) ? v : 0.f;
+            }
+          }
+          if (ct.type == CT_ARM_CUBE) {
             float relc[3] = {ct.pB[0] - cpos[0], ct.pB[1] - cpos[1], ct.pB[2] - cpos[2]}, t[3];
             cross3(relc, dir, t);
 #pragma unroll
@@ -1101,6 +1113,444 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   }
   gsync(g);
   return iters;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Collision stage.  Broadphase: a static candidate-pair list (object x static world, robot proxies x object, robot
+// proxies x static world, robot self pairs) culled by bounding spheres.  Narrowphase: closed forms where they are exact
+// (cube vertices on the table top while the cube is wholly over it, sphere-box, sphere-plane, sphere-sphere), box-box
+// SAT + face clipping (include/b2env_narrowphase.h) for the rest: the cube at the table rim or against a leg, the
+// finger-pad boxes against the cube and the table.  Lanes = candidates of one family (cube vertices, spheres, box
+// vertices, box pairs, self pairs); every family is compacted into the contact list by ballots, in the canonical order
+// of oracle/b2oracle.c collide().  The box-box routine is scalar code run by the lane that owns the pair (rare).
+#define B2N_REAL float
+#define B2N_FN __device__ __noinline__
+#define B2N_SQRT(x) sqrtf(x)
+#define B2N_FABS(x) fabsf(x)
+#include "../../include/b2env_narrowphase.h"
+
+struct ContactOut {   // what a lane hands to emit_contact
+  float pA[3], pB[3], n[3], dist, mu, erp, cfm;
+  int key, type, link, link2;
+};
+__device__ __forceinline__ void emit_contact(EnvSmem& sm, int slot, int maxc, const ContactOut& o) {
+  if (slot >= maxc) return;
+  Contact& c = sm.con[slot];
+  c.key = o.key; c.type = o.type; c.link = o.link; c.link2 = o.link2;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { c.pA[j] = o.pA[j]; c.pB[j] = o.pB[j]; c.n[j] = o.n[j]; }
+  c.dist = o.dist; c.mu = o.mu; c.erp = o.erp;
+  sm.con_cfm[slot] = o.cfm;
+}
+// exclusive prefix over the lanes of the group of a small per-lane count (0..7), and the group total
+__device__ __forceinline__ int gprefix3(const Grp& g, int cnt, int& total) {
+  const unsigned lt = (1u << g.lane) - 1u;
+  const unsigned b0 = gballot(g, cnt & 1), b1 = gballot(g, cnt & 2), b2 = gballot(g, cnt & 4);
+  total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+  return __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+}
+__device__ __forceinline__ void sbox_get(const b2e_params& P, int k, float* c, float* h) {
+  if (P.n_sboxes > 0) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { c[j] = P.sbox_c[k][j]; h[j] = P.sbox_h[k][j]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { c[j] = 0.5f * (P.table_min[j] + P.table_max[j]); h[j] = 0.5f * (P.table_max[j] - P.table_min[j]); }
+  }
+}
+// sphere vs axis-aligned box (same decisions as oracle sphere_aabox)
+__device__ __forceinline__ bool sphere_aabox(const float* c, float r, const float* bc, const float* bh, float margin, float* n,
+                                             float* pB, float& dist, bool& top) {
+  float l[3], cl[3];
+  bool inside = true;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    l[j] = c[j] - bc[j];
+    cl[j] = l[j] < -bh[j] ? -bh[j] : (l[j] > bh[j] ? bh[j] : l[j]);
+    if (cl[j] != l[j]) inside = false;
+  }
+  top = false;
+  if (!inside) {
+    const float dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+    if (dv[0] == 0.f && dv[1] == 0.f && dv[2] > 0.f) {   // over the top face: the closed form of round 1, bit for bit
+      dist = c[2] - r - (bc[2] + bh[2]);
+      if (!(dist < margin)) return false;
+      n[0] = 0.f; n[1] = 0.f; n[2] = 1.f;
+      pB[0] = c[0]; pB[1] = c[1]; pB[2] = bc[2] + bh[2];
+      top = true;
+      return true;
+    }
+    const float d = sqrtf(dot3(dv, dv));
+    dist = d - r;
+    if (!(dist < margin)) return false;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { n[j] = dv[j] / d; pB[j] = bc[j] + cl[j]; }
+    return true;
+  }
+  int ax = 0;
+  float best = bh[0] - fabsf(l[0]);
+#pragma unroll
+  for (int j = 1; j < 3; j++) {
+    const float pen = bh[j] - fabsf(l[j]);
+    if (pen < best) { best = pen; ax = j; }
+  }
+  n[0] = n[1] = n[2] = 0.f;
+  const float sg = ((ax == 0 ? l[0] : (ax == 1 ? l[1] : l[2])) >= 0.f) ? 1.f : -1.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) if (j == ax) { n[j] = sg; cl[j] = sg * bh[j]; }
+  dist = -best - r;
+#pragma unroll
+  for (int j = 0; j < 3; j++) pB[j] = bc[j] + cl[j];
+  return true;
+}
+
+// Returns the contact count (<= B2E_MAX_CONTACTS) | overflow << 8.  Reads the link transforms of sm.T; sm.W is scratch here
+// (left finite).  Both groups of the warp run every collective together.
+__device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U, const b2e_params& P,
+                                          unsigned hm, int sh, int lane, float cpx, float cpy, float cpz, float cqx, float cqy,
+                                          float cqz, float cqw) {
+  const Grp g = {hm, sh, lane};
+  const unsigned lt = (1u << lane) - 1u;
+  const int maxc = B2E_MAX_CONTACTS;
+  const float cpos[3] = {cpx, cpy, cpz}, cquat[4] = {cqx, cqy, cqz, cqw};
+  float Rc[9];
+  quat_to_mat(cquat, Rc);
+  const float ca = P.cube_half, margin = P.contact_margin, top = P.table_max[2];
+  const float chh[3] = {ca, ca, ca};
+  const float rb = ca * 1.7320508075688772f;
+  const int nsb = P.n_sboxes > 0 ? P.n_sboxes : 1;
+  const float ident[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  int base = 0, total;
+  ContactOut o;
+  // ---- 1. cube vs static world ----
+  const bool cube_fast = cpos[0] - rb >= P.table_min[0] && cpos[0] + rb <= P.table_max[0] && cpos[1] - rb >= P.table_min[1] &&
+                         cpos[1] + rb <= P.table_max[1] && cpos[2] >= top;
+  float v_pos[3] = {0.f, 0.f, 0.f};
+  if (lane < 8) {
+    const float l[3] = {(lane & 1) ? ca : -ca, (lane & 2) ? ca : -ca, (lane & 4) ? ca : -ca};
+    m3vec(Rc, l, v_pos);
+    v_pos[0] += cpos[0]; v_pos[1] += cpos[1]; v_pos[2] += cpos[2];
+  }
+  {
+    const bool hit = cube_fast && lane < 8 && (v_pos[2] - top) < margin;
+    const unsigned b = gballot(g, hit);
+    if (hit) {
+      o.key = B2E_KEY_CUBE_TABLE + lane; o.type = CT_CUBE_STATIC; o.link = -1; o.link2 = -1;
+      o.pA[0] = v_pos[0]; o.pA[1] = v_pos[1]; o.pA[2] = v_pos[2];
+      o.pB[0] = v_pos[0]; o.pB[1] = v_pos[1]; o.pB[2] = top;
+      o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+      o.dist = v_pos[2] - top; o.mu = P.cube_mu * P.table_mu; o.erp = P.erp; o.cfm = 0.f;
+      emit_contact(sm, base + __popc(b & lt), maxc, o);
+    }
+    base += __popc(b);
+  }
+  {  // rim of the top slab, legs: lane = static box, general box-box behind a bounding-sphere cull
+    int cnt = 0;
+    float nrm[3] = {0.f, 0.f, 1.f};
+    b2n_contact pts[B2N_MAX_POINTS];
+    const int k = lane;
+    if (k < nsb && k >= (cube_fast ? 1 : 0)) {
+      float bc[3], bh[3];
+      sbox_get(P, k, bc, bh);
+      const float d[3] = {cpos[0] - bc[0], cpos[1] - bc[1], cpos[2] - bc[2]};
+      if (!(sqrtf(dot3(d, d)) - (rb + sqrtf(dot3(bh, bh))) >= margin)) cnt = b2n_box_box(cpos, Rc, chh, bc, ident, bh, margin, nrm, pts);
+    }
+    __syncwarp();
+    const int off = gprefix3(g, cnt, total);
+    for (int q = 0; q < cnt; q++) {
+      o.key = B2E_KEY_CUBE_SBOX + B2N_ID_STRIDE * k + pts[q].id; o.type = CT_CUBE_STATIC; o.link = -1; o.link2 = -1;
+#pragma unroll
+      for (int j = 0; j < 3; j++) { o.pA[j] = pts[q].pa[j]; o.pB[j] = pts[q].pb[j]; o.n[j] = nrm[j]; }
+      o.dist = pts[q].dist; o.mu = P.cube_mu * (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu); o.erp = P.erp; o.cfm = 0.f;
+      emit_contact(sm, base + off + q, maxc, o);
+    }
+    base += total;
+  }
+  {
+    const bool hit = !cube_fast && lane < 8 && v_pos[2] < margin;
+    const unsigned b = gballot(g, hit);
+    if (hit) {
+      o.key = B2E_KEY_CUBE_PLANE + lane; o.type = CT_CUBE_STATIC; o.link = -1; o.link2 = -1;
+      o.pA[0] = v_pos[0]; o.pA[1] = v_pos[1]; o.pA[2] = v_pos[2];
+      o.pB[0] = v_pos[0]; o.pB[1] = v_pos[1]; o.pB[2] = 0.f;
+      o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+      o.dist = v_pos[2]; o.mu = P.cube_mu * P.plane_mu; o.erp = P.erp; o.cfm = 0.f;
+      emit_contact(sm, base + __popc(b & lt), maxc, o);
+    }
+    base += __popc(b);
+  }
+  // ---- robot proxies in world coordinates: sphere centres (lane = sphere, also staged in sm.W for the self pairs) ----
+  const int ns = U.n_spheres;
+  float s_c[3] = {0.f, 0.f, 0.f}, s_r = 0.f, s_mu = 0.f, s_erp = P.erp, s_cfm = 0.f;
+  int s_link = 0;
+  float* scr = sm.W;
+  if (lane < ns) {
+    s_link = __ldg(&M->sph_link[lane]);
+    s_r = __ldg(&M->sph_r[lane]);
+    s_mu = __ldg(&M->sph_mu[lane]);
+    const float se = __ldg(&M->sph_erp[lane]);
+    s_erp = se >= 0.f ? se : P.erp;
+    s_cfm = __ldg(&M->sph_cfm[lane]);
+    const float lc[3] = {__ldg(&M->sph_c[lane][0]), __ldg(&M->sph_c[lane][1]), __ldg(&M->sph_c[lane][2])};
+    float Rl[9], oo[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = sm.T[s_link][k];
+    m3vec(Rl, lc, oo);
+    s_c[0] = sm.T[s_link][9] + oo[0]; s_c[1] = sm.T[s_link][10] + oo[1]; s_c[2] = sm.T[s_link][11] + oo[2];
+  }
+  scr[lane * 4 + 0] = s_c[0]; scr[lane * 4 + 1] = s_c[1]; scr[lane * 4 + 2] = s_c[2]; scr[lane * 4 + 3] = s_r;
+  // ---- 2. robot vs cube: spheres (closest point on the box) ----
+  {
+    bool hit = false;
+    if (lane < ns) {
+      const float rel[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]};
+      float l[3], cl[3], nloc[3];
+      m3tvec(Rc, rel, l);
+      bool inside = true;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        cl[j] = l[j] < -ca ? -ca : (l[j] > ca ? ca : l[j]);
+        if (cl[j] != l[j]) inside = false;
+      }
+      if (!inside) {
+        const float dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
+        const float d = sqrtf(dot3(dv, dv));
+        o.dist = d - s_r;
+        hit = o.dist < margin;
+        nloc[0] = dv[0] / d; nloc[1] = dv[1] / d; nloc[2] = dv[2] / d;
+      } else {
+        int axm = 0;
+        float best = ca - fabsf(l[0]);
+#pragma unroll
+        for (int j = 1; j < 3; j++) {
+          const float pen = ca - fabsf(l[j]);
+          if (pen < best) { best = pen; axm = j; }
+        }
+        nloc[0] = nloc[1] = nloc[2] = 0.f;
+        const float sgn = ((axm == 0 ? l[0] : (axm == 1 ? l[1] : l[2])) >= 0) ? 1.f : -1.f;
+        if (axm == 0) { nloc[0] = sgn; cl[0] = sgn * ca; }
+        else if (axm == 1) { nloc[1] = sgn; cl[1] = sgn * ca; }
+        else { nloc[2] = sgn; cl[2] = sgn * ca; }
+        o.dist = -best - s_r;
+        hit = true;
+      }
+      if (hit) {
+        float pwl[3];
+        m3vec(Rc, nloc, o.n);
+        m3vec(Rc, cl, pwl);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { o.pB[j] = cpos[j] + pwl[j]; o.pA[j] = s_c[j] - o.n[j] * s_r; }
+      }
+    }
+    const unsigned b = gballot(g, hit);
+    if (hit) {
+      o.key = B2E_KEY_SPHERE_CUBE + lane; o.type = CT_ARM_CUBE; o.link = s_link; o.link2 = -1;
+      o.mu = P.cube_mu * s_mu; o.erp = s_erp; o.cfm = s_cfm;
+      emit_contact(sm, base + __popc(b & lt), maxc, o);
+    }
+    base += __popc(b);
+  }
+  // finger-pad boxes: world pose (lanes 0..n_boxes-1 own a box; every lane can read them from scratch)
+  const int nbx = U.n_boxes;
+  float* bscr = scr + 64;     // per box: centre (3) | bounding radius | R (9) | half extents (3)
+  if (lane < nbx) {
+    const int li = __ldg(&M->box_link[lane]);
+    const float lc[3] = {__ldg(&M->box_c[lane][0]), __ldg(&M->box_c[lane][1]), __ldg(&M->box_c[lane][2])};
+    float Rl[9], oo[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
+    m3vec(Rl, lc, oo);
+    const float h[3] = {__ldg(&M->box_h[lane][0]), __ldg(&M->box_h[lane][1]), __ldg(&M->box_h[lane][2])};
+    float* bs = bscr + 16 * lane;
+    bs[0] = sm.T[li][9] + oo[0]; bs[1] = sm.T[li][10] + oo[1]; bs[2] = sm.T[li][11] + oo[2];
+    bs[3] = sqrtf(dot3(h, h));
+#pragma unroll
+    for (int k = 0; k < 9; k++) bs[4 + k] = Rl[k];
+    bs[13] = h[0]; bs[14] = h[1]; bs[15] = h[2];
+  }
+  gsync(g);
+  if (__any_sync(FULL, nbx > 0)) {  // robot boxes vs cube: lane = box, box-box behind a bounding-sphere cull
+    int cnt = 0;
+    float nrm[3] = {0.f, 0.f, 1.f};
+    b2n_contact pts[B2N_MAX_POINTS];
+    if (lane < nbx) {
+      const float* bs = bscr + 16 * lane;
+      const float bc[3] = {bs[0], bs[1], bs[2]}, bh[3] = {bs[13], bs[14], bs[15]};
+      float Rl[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rl[k] = bs[4 + k];
+      const float d[3] = {bc[0] - cpos[0], bc[1] - cpos[1], bc[2] - cpos[2]};
+      if (!(sqrtf(dot3(d, d)) - (rb + bs[3]) >= margin)) cnt = b2n_box_box(bc, Rl, bh, cpos, Rc, chh, margin, nrm, pts);
+    }
+    __syncwarp();
+    const int off = gprefix3(g, cnt, total);
+    for (int q = 0; q < cnt; q++) {
+      const float be = __ldg(&M->box_erp[lane]);
+      o.key = B2E_KEY_BOX_CUBE + B2N_ID_STRIDE * lane + pts[q].id; o.type = CT_ARM_CUBE; o.link = __ldg(&M->box_link[lane]); o.link2 = -1;
+#pragma unroll
+      for (int j = 0; j < 3; j++) { o.pA[j] = pts[q].pa[j]; o.pB[j] = pts[q].pb[j]; o.n[j] = nrm[j]; }
+      o.dist = pts[q].dist; o.mu = P.cube_mu * __ldg(&M->box_mu[lane]); o.erp = be >= 0.f ? be : P.erp; o.cfm = __ldg(&M->box_cfm[lane]);
+      emit_contact(sm, base + off + q, maxc, o);
+    }
+    base += total;
+  }
+  // ---- 3. robot vs static world: spheres vs static boxes (lane = sphere, at most three boxes each), vs the ground plane ----
+  {
+    int cnt = 0, kk[3] = {0, 0, 0};
+    float nn[3][3], pb[3][3], dd[3] = {0.f, 0.f, 0.f};
+    bool tp[3] = {false, false, false};
+    if (lane < ns) {
+      for (int k = 0; k < nsb && cnt < 3; k++) {
+        float bc[3], bh[3], n[3], pB[3], dist;
+        bool is_top;
+        sbox_get(P, k, bc, bh);
+        const float d[3] = {s_c[0] - bc[0], s_c[1] - bc[1], s_c[2] - bc[2]};
+        if (sqrtf(dot3(d, d)) - (s_r + sqrtf(dot3(bh, bh))) >= margin) continue;
+        if (!sphere_aabox(s_c, s_r, bc, bh, margin, n, pB, dist, is_top)) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          if (c == cnt) {
+            kk[c] = k; dd[c] = dist; tp[c] = is_top;
+#pragma unroll
+            for (int j = 0; j < 3; j++) { nn[c][j] = n[j]; pb[c][j] = pB[j]; }
+          }
+        cnt++;
+      }
+    }
+    __syncwarp();
+    const int off = gprefix3(g, cnt, total);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (c < cnt) {
+        const int k = kk[c];
+        o.key = (k == 0 && tp[c]) ? B2E_KEY_SPHERE_TABLE + lane : B2E_KEY_SPHERE_SBOX + 8 * lane + k;
+        o.type = CT_ARM_STATIC; o.link = s_link; o.link2 = -1;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { o.n[j] = nn[c][j]; o.pB[j] = pb[c][j]; o.pA[j] = s_c[j] - nn[c][j] * s_r; }
+        o.dist = dd[c]; o.mu = (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu) * s_mu; o.erp = s_erp; o.cfm = s_cfm;
+        emit_contact(sm, base + off + c, maxc, o);
+      }
+    }
+    base += total;
+  }
+  {
+    const float dist = s_c[2] - s_r;
+    const bool hit = lane < ns && dist < margin;
+    const unsigned b = gballot(g, hit);
+    if (hit) {
+      o.key = B2E_KEY_SPHERE_PLANE + lane; o.type = CT_ARM_STATIC; o.link = s_link; o.link2 = -1;
+      o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+      o.pA[0] = s_c[0]; o.pA[1] = s_c[1]; o.pA[2] = dist;
+      o.pB[0] = s_c[0]; o.pB[1] = s_c[1]; o.pB[2] = 0.f;
+      o.dist = dist; o.mu = P.plane_mu * s_mu; o.erp = s_erp; o.cfm = s_cfm;
+      emit_contact(sm, base + __popc(b & lt), maxc, o);
+    }
+    base += __popc(b);
+  }
+  if (__any_sync(FULL, nbx > 0)) {
+    // finger-pad boxes: lane = 8 * box + vertex for the vertex families, lane = 8 * box + static box for the general pairs
+    const int bxi = lane >> 3, sub = lane & 7;
+    const bool has = bxi < nbx;
+    const float* bs = bscr + 16 * (has ? bxi : 0);
+    const float bc[3] = {bs[0], bs[1], bs[2]}, bh[3] = {bs[13], bs[14], bs[15]}, br = bs[3];
+    float Rl[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = bs[4 + k];
+    const bool bfast = bc[0] - br >= P.table_min[0] && bc[0] + br <= P.table_max[0] && bc[1] - br >= P.table_min[1] &&
+                       bc[1] + br <= P.table_max[1] && bc[2] >= top;
+    float bv[3];
+    {
+      const float l[3] = {(sub & 1) ? bh[0] : -bh[0], (sub & 2) ? bh[1] : -bh[1], (sub & 4) ? bh[2] : -bh[2]};
+      m3vec(Rl, l, bv);
+      bv[0] += bc[0]; bv[1] += bc[1]; bv[2] += bc[2];
+    }
+    const int blink = has ? __ldg(&M->box_link[bxi]) : 0;
+    const float bmu = has ? __ldg(&M->box_mu[bxi]) : 0.f, bcfm = has ? __ldg(&M->box_cfm[bxi]) : 0.f;
+    const float be = has ? __ldg(&M->box_erp[bxi]) : -1.f, berp = be >= 0.f ? be : P.erp;
+    {
+      const bool hit = has && bfast && (bv[2] - top) < margin;
+      const unsigned b = gballot(g, hit);
+      if (hit) {
+        o.key = B2E_KEY_BOXV_TABLE + lane; o.type = CT_ARM_STATIC; o.link = blink; o.link2 = -1;
+        o.pA[0] = bv[0]; o.pA[1] = bv[1]; o.pA[2] = bv[2];
+        o.pB[0] = bv[0]; o.pB[1] = bv[1]; o.pB[2] = top;
+        o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+        o.dist = bv[2] - top; o.mu = P.table_mu * bmu; o.erp = berp; o.cfm = bcfm;
+        emit_contact(sm, base + __popc(b & lt), maxc, o);
+      }
+      base += __popc(b);
+    }
+    {
+      int cnt = 0;
+      float nrm[3] = {0.f, 0.f, 1.f};
+      b2n_contact pts[B2N_MAX_POINTS];
+      const int k = sub;
+      if (has && k < nsb && k >= (bfast ? 1 : 0)) {
+        float sc2[3], sh2[3];
+        sbox_get(P, k, sc2, sh2);
+        const float d[3] = {bc[0] - sc2[0], bc[1] - sc2[1], bc[2] - sc2[2]};
+        if (!(sqrtf(dot3(d, d)) - (br + sqrtf(dot3(sh2, sh2))) >= margin)) cnt = b2n_box_box(bc, Rl, bh, sc2, ident, sh2, margin, nrm, pts);
+      }
+      __syncwarp();
+      const int off = gprefix3(g, cnt, total);
+      for (int q = 0; q < cnt; q++) {
+        o.key = B2E_KEY_BOX_SBOX + B2N_ID_STRIDE * lane + pts[q].id; o.type = CT_ARM_STATIC; o.link = blink; o.link2 = -1;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { o.pA[j] = pts[q].pa[j]; o.pB[j] = pts[q].pb[j]; o.n[j] = nrm[j]; }
+        o.dist = pts[q].dist; o.mu = (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu) * bmu; o.erp = berp; o.cfm = bcfm;
+        emit_contact(sm, base + off + q, maxc, o);
+      }
+      base += total;
+    }
+    {
+      const bool hit = has && !bfast && bv[2] < margin;
+      const unsigned b = gballot(g, hit);
+      if (hit) {
+        o.key = B2E_KEY_BOXV_PLANE + lane; o.type = CT_ARM_STATIC; o.link = blink; o.link2 = -1;
+        o.pA[0] = bv[0]; o.pA[1] = bv[1]; o.pA[2] = bv[2];
+        o.pB[0] = bv[0]; o.pB[1] = bv[1]; o.pB[2] = 0.f;
+        o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+        o.dist = bv[2]; o.mu = P.plane_mu * bmu; o.erp = berp; o.cfm = bcfm;
+        emit_contact(sm, base + __popc(b & lt), maxc, o);
+      }
+      base += __popc(b);
+    }
+  }
+  // ---- 4. robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): sphere pairs of non-neighbouring links ----
+  {
+    const int nsp = U.n_self_pairs;
+    for (int p0 = 0; p0 < nsp; p0 += GL) {   // warp-uniform trip count: both groups share the model
+      const int p = p0 + lane;
+      bool hit = false;
+      if (p < nsp) {
+        const int sa = __ldg(&M->self_a[p]), sb = __ldg(&M->self_b[p]);
+        const float ra = scr[sa * 4 + 3], rbb = scr[sb * 4 + 3];
+        const float d[3] = {scr[sa * 4] - scr[sb * 4], scr[sa * 4 + 1] - scr[sb * 4 + 1], scr[sa * 4 + 2] - scr[sb * 4 + 2]};
+        const float dn = sqrtf(dot3(d, d));
+        o.dist = dn - (ra + rbb);
+        hit = o.dist < margin && dn > 1e-9f;
+        if (hit) {
+          o.key = B2E_KEY_SELF + p; o.type = CT_ARM_ARM; o.link = __ldg(&M->sph_link[sa]); o.link2 = __ldg(&M->sph_link[sb]);
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            o.n[j] = d[j] / dn;
+            o.pA[j] = scr[sa * 4 + j] - o.n[j] * ra;
+            o.pB[j] = scr[sb * 4 + j] + o.n[j] * rbb;
+          }
+          o.mu = __ldg(&M->sph_mu[sa]) * __ldg(&M->sph_mu[sb]); o.erp = P.erp; o.cfm = 0.f;
+        }
+      }
+      const unsigned b = gballot(g, hit);
+      if (hit) emit_contact(sm, base + __popc(b & lt), maxc, o);
+      base += __popc(b);
+    }
+  }
+  gsync(g);
+  // leave the scratch finite for the solver tables (they are zeroed at kernel start and must stay finite)
+  for (int k = lane; k < 64 + 16 * B2E_MAX_BOXES; k += GL) scr[k] = 0.f;
+  gsync(g);
+  return (base > maxc ? maxc : base) | (base > maxc ? 256 : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1478,130 +1928,13 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 
     PROF_T(2);   // dynamics done
     PHASE_BARRIER();
-    // ---- collision detection (pre-step poses) ----
-    float Rc[9];
-    quat_to_mat(cquat, Rc);
-    const float ca = P.cube_half, margin = P.contact_margin;
-    // cube vertices vs table slab / ground plane: lane = vertex
-    bool v_hit = false;
-    float v_pos[3] = {0, 0, 0}, v_dist = 0.f, v_top = 0.f, v_mu = 0.f;
-    int v_key = 0;
-    if (lane < 8) {
-      float l[3] = {(lane & 1) ? ca : -ca, (lane & 2) ? ca : -ca, (lane & 4) ? ca : -ca};
-      m3vec(Rc, l, v_pos);
-      v_pos[0] += cpos[0]; v_pos[1] += cpos[1]; v_pos[2] += cpos[2];
-      const bool over = v_pos[0] >= P.table_min[0] && v_pos[0] <= P.table_max[0] && v_pos[1] >= P.table_min[1] &&
-                        v_pos[1] <= P.table_max[1] && v_pos[2] > P.table_min[2];
-      if (over) { v_top = P.table_max[2]; v_mu = P.cube_mu * P.table_mu; v_key = KEY_CUBE_TABLE + lane; }
-      else { v_top = 0.f; v_mu = P.cube_mu * P.plane_mu; v_key = KEY_CUBE_PLANE + lane; }
-      v_dist = v_pos[2] - v_top;
-      v_hit = v_dist < margin;
+    // ---- collision detection (pre-step poses): broadphase + narrowphase, see collide_stage ----
+    {
+      const int cr = collide_stage(sm, M, U, P, g.hm, g.sh, lane, cpos[0], cpos[1], cpos[2], cquat[0], cquat[1], cquat[2], cquat[3]);
+      nc = cr & 255;
+      if (cr & 256) flags |= B2E_ST_CONTACT_OVERFLOW;
     }
-    // spheres: lane = sphere
-    const int ns = U.n_spheres;
-    bool sc_hit = false, st_hit = false;
-    float s_c[3] = {0, 0, 0}, sc_n[3] = {0, 0, 0}, sc_pB[3] = {0, 0, 0}, sc_dist = 0.f, st_dist = 0.f, s_r = 0.f;
-    int s_link = 0;
-    gsync(g);
-    if (lane < ns) {
-      s_link = __ldg(&M->sph_link[lane]);
-      s_r = __ldg(&M->sph_r[lane]);
-      float lc[3] = {__ldg(&M->sph_c[lane][0]), __ldg(&M->sph_c[lane][1]), __ldg(&M->sph_c[lane][2])}, o[3];
-      float Rl[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) Rl[k] = sm.T[s_link][k];
-      m3vec(Rl, lc, o);
-      s_c[0] = sm.T[s_link][9] + o[0]; s_c[1] = sm.T[s_link][10] + o[1]; s_c[2] = sm.T[s_link][11] + o[2];
-      // vs cube
-      float rel[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]}, l[3], cl[3];
-      m3tvec(Rc, rel, l);
-      bool inside = true;
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        cl[j] = l[j] < -ca ? -ca : (l[j] > ca ? ca : l[j]);
-        if (cl[j] != l[j]) inside = false;
-      }
-      float nloc[3];
-      if (!inside) {
-        float dv[3] = {l[0] - cl[0], l[1] - cl[1], l[2] - cl[2]};
-        const float d = sqrtf(dot3(dv, dv));
-        sc_dist = d - s_r;
-        sc_hit = sc_dist < margin;
-        nloc[0] = dv[0] / d; nloc[1] = dv[1] / d; nloc[2] = dv[2] / d;
-      } else {
-        int axm = 0;
-        float best = ca - fabsf(l[0]);
-#pragma unroll
-        for (int j = 1; j < 3; j++) {
-          const float pen = ca - fabsf(l[j]);
-          if (pen < best) { best = pen; axm = j; }
-        }
-        nloc[0] = nloc[1] = nloc[2] = 0.f;
-        const float sgn = ((axm == 0 ? l[0] : (axm == 1 ? l[1] : l[2])) >= 0) ? 1.f : -1.f;
-        if (axm == 0) { nloc[0] = sgn; cl[0] = sgn * ca; }
-        else if (axm == 1) { nloc[1] = sgn; cl[1] = sgn * ca; }
-        else { nloc[2] = sgn; cl[2] = sgn * ca; }
-        sc_dist = -best - s_r;
-        sc_hit = true;
-      }
-      if (sc_hit) {
-        float pwl[3];
-        m3vec(Rc, nloc, sc_n);
-        m3vec(Rc, cl, pwl);
-        sc_pB[0] = cpos[0] + pwl[0]; sc_pB[1] = cpos[1] + pwl[1]; sc_pB[2] = cpos[2] + pwl[2];
-      }
-      // vs table top
-      const bool over = s_c[0] >= P.table_min[0] && s_c[0] <= P.table_max[0] && s_c[1] >= P.table_min[1] &&
-                        s_c[1] <= P.table_max[1] && s_c[2] > P.table_min[2];
-      st_dist = s_c[2] - s_r - P.table_max[2];
-      st_hit = over && (st_dist < margin);
-    }
-    // canonical order: cube-static by vertex, sphere-cube by sphere, sphere-table by sphere
-    const unsigned bv = gballot(g, v_hit), bsc = gballot(g, sc_hit), bst = gballot(g, st_hit);
     const unsigned lt = (1u << lane) - 1u;
-    const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
-    const int total = n_v + n_sc + n_st;
-    if (total > B2E_MAX_CONTACTS) flags |= B2E_ST_CONTACT_OVERFLOW;
-    nc = total > B2E_MAX_CONTACTS ? B2E_MAX_CONTACTS : total;
-    if (v_hit) {
-      const int slot = __popc(bv & lt);
-      if (slot < B2E_MAX_CONTACTS) {
-        Contact& c = sm.con[slot];
-        c.key = v_key; c.type = CT_CUBE_STATIC; c.link = -1;
-        c.pA[0] = v_pos[0]; c.pA[1] = v_pos[1]; c.pA[2] = v_pos[2];
-        c.pB[0] = v_pos[0]; c.pB[1] = v_pos[1]; c.pB[2] = v_top;
-        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
-        c.dist = v_dist; c.mu = v_mu; c.erp = P.erp;
-        sm.con_cfm[slot] = 0.f;
-      }
-    }
-    if (sc_hit) {
-      const int slot = n_v + __popc(bsc & lt);
-      if (slot < B2E_MAX_CONTACTS) {
-        Contact& c = sm.con[slot];
-        const float serp = __ldg(&M->sph_erp[lane]);
-        c.key = KEY_SPHERE_CUBE + lane; c.type = CT_SPHERE_CUBE; c.link = s_link;
-#pragma unroll
-        for (int j = 0; j < 3; j++) { c.n[j] = sc_n[j]; c.pB[j] = sc_pB[j]; c.pA[j] = s_c[j] - sc_n[j] * s_r; }
-        c.dist = sc_dist; c.mu = P.cube_mu * __ldg(&M->sph_mu[lane]);
-        c.erp = serp >= 0 ? serp : P.erp;
-        sm.con_cfm[slot] = __ldg(&M->sph_cfm[lane]);
-      }
-    }
-    if (st_hit) {
-      const int slot = n_v + n_sc + __popc(bst & lt);
-      if (slot < B2E_MAX_CONTACTS) {
-        Contact& c = sm.con[slot];
-        const float serp = __ldg(&M->sph_erp[lane]);
-        c.key = KEY_SPHERE_TABLE + lane; c.type = CT_SPHERE_STATIC; c.link = s_link;
-        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
-        c.pA[0] = s_c[0]; c.pA[1] = s_c[1]; c.pA[2] = s_c[2] - s_r;
-        c.pB[0] = s_c[0]; c.pB[1] = s_c[1]; c.pB[2] = P.table_max[2];
-        c.dist = st_dist; c.mu = P.table_mu * __ldg(&M->sph_mu[lane]);
-        c.erp = serp >= 0 ? serp : P.erp;
-        sm.con_cfm[slot] = __ldg(&M->sph_cfm[lane]);
-      }
-    }
     // joint-limit rows near a limit (lane = dof): order (dof, lower) then (dof, upper)
     const float dlo = my_q - my_lower, dup = my_upper - my_q;
     const float lmar = is_dof ? __ldg(&M->limit_margin[lane]) : 0.f;
@@ -1914,6 +2247,15 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   }
 }
 
+// The tree kernel (iCub) keeps the closed-form contact set (cube vertices vs table top / ground plane, spheres vs cube /
+// table top): its arms cannot reach the table rim, the legs or the floor in the pinned pose; box-box families, static
+// boxes and self pairs are group-kernel (Panda) features.
+#define KEY_CUBE_TABLE B2E_KEY_CUBE_TABLE
+#define KEY_CUBE_PLANE B2E_KEY_CUBE_PLANE
+#define KEY_SPHERE_CUBE B2E_KEY_SPHERE_CUBE
+#define KEY_SPHERE_TABLE B2E_KEY_SPHERE_TABLE
+#define CT_SPHERE_CUBE CT_ARM_CUBE
+#define CT_SPHERE_STATIC CT_ARM_STATIC
 #include "b2env_tree.cuh"
 
 // masked reset: home joint state, object pose, target, counters, empty cache
@@ -2081,6 +2423,21 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
     d->sph_link[s] = m->sph_link[s];
     for (int k = 0; k < 3; k++) d->sph_c[s][k] = m->sph_c[s][k];
     d->sph_r[s] = m->sph_r[s]; d->sph_mu[s] = m->sph_mu[s]; d->sph_erp[s] = m->sph_erp[s]; d->sph_cfm[s] = m->sph_cfm[s];
+  }
+  if (m->n_boxes < 0 || m->n_boxes > B2E_MAX_BOXES || m->n_self_pairs < 0 || m->n_self_pairs > B2E_MAX_SELF_PAIRS)
+    return fail(B2E_EINVAL, "bad n_boxes / n_self_pairs%s", "");
+  if (!tree && m->n_boxes > 2) return fail(B2E_EUNSUPPORTED, "group kernel: at most two box proxies%s", "");
+  d->n_boxes = u->n_boxes = tree ? 0 : m->n_boxes;
+  d->n_self_pairs = u->n_self_pairs = tree ? 0 : m->n_self_pairs;
+  for (int b = 0; b < m->n_boxes; b++) {
+    d->box_link[b] = m->box_link[b];
+    for (int k = 0; k < 3; k++) { d->box_c[b][k] = m->box_c[b][k]; d->box_h[b][k] = m->box_h[b][k]; }
+    d->box_mu[b] = m->box_mu[b]; d->box_erp[b] = m->box_erp[b]; d->box_cfm[b] = m->box_cfm[b];
+  }
+  for (int k = 0; k < m->n_self_pairs; k++) {
+    if (m->self_a[k] < 0 || m->self_a[k] >= m->n_spheres || m->self_b[k] < 0 || m->self_b[k] >= m->n_spheres)
+      return fail(B2E_EINVAL, "self-collision pair names a sphere that does not exist%s", "");
+    d->self_a[k] = m->self_a[k]; d->self_b[k] = m->self_b[k];
   }
   return 0;
 }

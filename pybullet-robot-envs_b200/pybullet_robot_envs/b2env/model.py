@@ -25,6 +25,9 @@ MAX_SPHERES = 16
 MAX_OBS = 40
 MAX_CONTACTS = 12
 CACHE_SLOTS = 16
+MAX_BOXES = 4
+MAX_SELF_PAIRS = 32
+MAX_SBOXES = 6
 
 JOINT_REVOLUTE = 0
 JOINT_PRISMATIC = 1
@@ -55,6 +58,9 @@ class B2EModel(C.Structure):
         ("sph_link", _i * MAX_SPHERES), ("sph_c", (_f * 3) * MAX_SPHERES),
         ("sph_r", _f * MAX_SPHERES), ("sph_mu", _f * MAX_SPHERES),
         ("sph_erp", _f * MAX_SPHERES), ("sph_cfm", _f * MAX_SPHERES),
+        ("n_boxes", _i), ("box_link", _i * MAX_BOXES), ("box_c", (_f * 3) * MAX_BOXES), ("box_h", (_f * 3) * MAX_BOXES),
+        ("box_mu", _f * MAX_BOXES), ("box_erp", _f * MAX_BOXES), ("box_cfm", _f * MAX_BOXES),
+        ("n_self_pairs", _i), ("self_a", _i * MAX_SELF_PAIRS), ("self_b", _i * MAX_SELF_PAIRS),
     ]
 
 
@@ -76,6 +82,7 @@ class B2EParams(C.Structure):
         ("kp_grip", _f), ("grasp_lift", _f), ("grasp_rest_z", _f), ("goal_env", _i),
         ("n_obs_joints", _i), ("obs_dof", _i * 16), ("ctrl_dof", _i * 16), ("ctrl_mask", C.c_uint32),
         ("ik_link_offset", _f * 3), ("reward_kind", _i), ("max_contacts", _i),
+        ("n_sboxes", _i), ("sbox_c", (_f * 3) * MAX_SBOXES), ("sbox_h", (_f * 3) * MAX_SBOXES), ("sbox_mu", _f * MAX_SBOXES),
     ]
 
 
@@ -169,7 +176,7 @@ def parse_urdf(path):
                 links=[links[j["child"]] for j in order])
 
 
-def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres):
+def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres, boxes=(), self_pairs=()):
     """Flatten the parsed URDF dict into a ``B2EModel``."""
     m = B2EModel()
     n = len(d["joints"])
@@ -242,13 +249,14 @@ PANDA_JSON = os.path.join(_HERE, "..", "robot_data", "franka_panda", "panda_mode
 def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
     """Build the Panda ``B2EModel``.  ``urdf_path`` (e.g. the reference's own
     ``robot_data/franka_panda/panda_model.urdf``) overrides the committed JSON."""
-    from .proxies import PANDA_SPHERES
+    from .proxies import PANDA_BOXES, PANDA_SELF_PAIRS, PANDA_SPHERES
     if urdf_path is not None:
         d = parse_urdf(urdf_path)
     else:
         with open(PANDA_JSON) as f:
             d = json.load(f)
-    m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES)
+    m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES, boxes=PANDA_BOXES,
+                                  self_pairs=PANDA_SELF_PAIRS)
     # soft finger contacts: <stiffness>/<damping> (URDF:256-263) -> per-contact erp/cfm the way
     # Bullet derives them: denom = dt*k + d, erp = dt*k/denom, cfm = 1/(denom*dt) [EXT-recalled]
     names = [l["name"] for l in d["links"]]
@@ -260,6 +268,14 @@ def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
             denom = dt * k + dmp
             m.sph_erp[s] = dt * k / denom
             m.sph_cfm[s] = 1.0 / (denom * dt)
+    for b in range(m.n_boxes):
+        ct = d["links"][m.box_link[b]]["contact"]
+        if "stiffness" in ct:
+            k = ct["stiffness"]
+            dmp = ct.get("damping", 0.0) + 0.1
+            denom = dt * k + dmp
+            m.box_erp[b] = dt * k / denom
+            m.box_cfm[b] = 1.0 / (denom * dt)
     del names
     return m, d
 
@@ -282,6 +298,15 @@ def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orie
     p.table_max[0], p.table_max[1], p.table_max[2] = 0.85 + 0.75, 0.5, 0.625
     p.table_mu = 1.0
     p.plane_mu = 1.0
+    # static boxes: [0] the top slab, [1..4] the legs 0.1 x 0.1 x 0.58 at (0.85 +- 0.65, +- 0.4, 0.29) [EXT-recalled, App. B.3]
+    boxes = [((0.85, 0.0, 0.6), (0.75, 0.5, 0.025))]
+    boxes += [((0.85 + sx * 0.65, sy * 0.4, 0.29), (0.05, 0.05, 0.29)) for sx in (-1, 1) for sy in (-1, 1)]
+    p.n_sboxes = len(boxes)
+    for k, (c, h) in enumerate(boxes):
+        for j in range(3):
+            p.sbox_c[k][j] = c[j]
+            p.sbox_h[k][j] = h[j]
+        p.sbox_mu[k] = 1.0
     p.cube_half = 0.025
     p.cube_mass = 0.1
     p.cube_inertia = 0.1 * (0.05 ** 2) / 6.0
