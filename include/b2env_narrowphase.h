@@ -265,4 +265,374 @@ B2N_FN int b2n_box_box(const B2N_REAL* cA, const B2N_REAL* RA, const B2N_REAL* h
   return nk;
 }
 
+/* ---------------------------------------------------------------------------------------------- GJK / EPA */
+/* Convex shapes given by a support mapping of a CORE (point, segment, box) plus a rounding radius r: sphere = point + r,
+ * capsule = segment + r, rounded box = box + r.  GJK finds the closest points of the two cores; while the cores are apart
+ * the contact of the rounded shapes follows directly (this is also how Bullet treats collision margins).  When the cores
+ * themselves overlap, EPA expands a polytope inside the Minkowski difference to the nearest boundary face: penetration
+ * depth, direction and witness points.  One contact point per pair.                                                       */
+#define B2N_POINT 0
+#define B2N_SEGMENT 1 /* endpoints c -+ h[2] * (column 2 of R) */
+#define B2N_BOX 2
+typedef struct b2n_shape {
+  int type;
+  B2N_REAL c[3]; /* centre (world)                                                            */
+  B2N_REAL R[9]; /* world <- body, row-major (box axes = columns; segment axis = column 2)    */
+  B2N_REAL h[3]; /* box: half extents; segment: h[2] = half length                            */
+  B2N_REAL r;    /* rounding radius                                                           */
+} b2n_shape;
+
+#define B2N_GJK_ITERS 32
+#define B2N_EPA_ITERS 24
+#define B2N_EPA_MAXV (4 + B2N_EPA_ITERS)
+#define B2N_EPA_MAXF (4 + 2 * B2N_EPA_ITERS)
+#define B2N_EPA_MAXE 32
+
+B2N_FN void b2n_support(const b2n_shape* s, const B2N_REAL* d, B2N_REAL* out) {
+  int k, j;
+  out[0] = s->c[0]; out[1] = s->c[1]; out[2] = s->c[2];
+  if (s->type == B2N_POINT) return;
+  for (k = (s->type == B2N_SEGMENT ? 2 : 0); k < 3; k++) {
+    const B2N_REAL dk = d[0] * s->R[k] + d[1] * s->R[3 + k] + d[2] * s->R[6 + k];
+    const B2N_REAL e = dk >= 0 ? s->h[k] : -s->h[k];
+    for (j = 0; j < 3; j++) out[j] += e * s->R[3 * j + k];
+  }
+}
+
+#define B2N_DOT(a, b) ((a)[0] * (b)[0] + (a)[1] * (b)[1] + (a)[2] * (b)[2])
+#define B2N_CROSS(o, a, b)                                                                                             \
+  {                                                                                                                    \
+    (o)[0] = (a)[1] * (b)[2] - (a)[2] * (b)[1];                                                                       \
+    (o)[1] = (a)[2] * (b)[0] - (a)[0] * (b)[2];                                                                       \
+    (o)[2] = (a)[0] * (b)[1] - (a)[1] * (b)[0];                                                                       \
+  }
+
+/* closest point to the origin on the triangle (a, b, c): barycentric coordinates l[3] (Voronoi-region tests) */
+B2N_FN void b2n_closest_triangle(const B2N_REAL* a, const B2N_REAL* b, const B2N_REAL* c, B2N_REAL* l) {
+  typedef B2N_REAL real;
+  real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+  const real d1 = -B2N_DOT(ab, a), d2 = -B2N_DOT(ac, a);
+  l[0] = l[1] = l[2] = 0;
+  if (d1 <= 0 && d2 <= 0) { l[0] = 1; return; }
+  const real d3 = -B2N_DOT(ab, b), d4 = -B2N_DOT(ac, b);
+  if (d3 >= 0 && d4 <= d3) { l[1] = 1; return; }
+  const real vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { const real v = d1 / (d1 - d3); l[0] = 1 - v; l[1] = v; return; }
+  const real d5 = -B2N_DOT(ab, c), d6 = -B2N_DOT(ac, c);
+  if (d6 >= 0 && d5 <= d6) { l[2] = 1; return; }
+  const real vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { const real w = d2 / (d2 - d6); l[0] = 1 - w; l[2] = w; return; }
+  const real va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { const real w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); l[1] = 1 - w; l[2] = w; return; }
+  {
+    const real den = 1 / (va + vb + vc), v = vb * den, w = vc * den;
+    l[0] = 1 - v - w; l[1] = v; l[2] = w;
+  }
+}
+
+/* Closest point of the simplex W[0..n-1] (n <= 4) to the origin: barycentric coordinates l[]; returns 1 if the origin is
+ * inside the tetrahedron.                                                                                              */
+B2N_FN int b2n_closest_simplex(B2N_REAL W[4][3], int n, B2N_REAL* l) {
+  typedef B2N_REAL real;
+  int i, f;
+  l[0] = l[1] = l[2] = l[3] = 0;
+  if (n == 1) { l[0] = 1; return 0; }
+  if (n == 2) {
+    real ab[3] = {W[1][0] - W[0][0], W[1][1] - W[0][1], W[1][2] - W[0][2]};
+    const real den = B2N_DOT(ab, ab);
+    real t = den > 0 ? -B2N_DOT(W[0], ab) / den : 0;
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    l[0] = 1 - t; l[1] = t;
+    return 0;
+  }
+  if (n == 3) { b2n_closest_triangle(W[0], W[1], W[2], l); return 0; }
+  {
+    /* tetrahedron: the origin is inside if, for every face, it lies on the same side of the face plane as the 4th vertex
+     * (strictly, and the tetrahedron is not flat); otherwise the closest point is the nearest of the closest points of the
+     * four faces (all four are evaluated: sign tests of a nearly flat tetrahedron are not reliable)                      */
+    const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
+    real best = (real)1e30;
+    int inside = 1;
+    for (f = 0; f < 4; f++) {
+      const real* a = W[F[f][0]]; const real* b = W[F[f][1]]; const real* c = W[F[f][2]]; const real* d = W[F[f][3]];
+      real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nn[3];
+      B2N_CROSS(nn, ab, ac);
+      real ad[3] = {d[0] - a[0], d[1] - a[1], d[2] - a[2]};
+      const real sp = -B2N_DOT(a, nn), sd = B2N_DOT(ad, nn);
+      const real flat = (real)1e-6 * B2N_SQRT(B2N_DOT(nn, nn) * B2N_DOT(ad, ad));
+      if (!(sp * sd > 0) || B2N_FABS(sd) <= flat) inside = 0;
+    }
+    if (inside) return 1;
+    for (f = 0; f < 4; f++) {
+      const real* a = W[F[f][0]]; const real* b = W[F[f][1]]; const real* c = W[F[f][2]];
+      real lf[3], p[3];
+      b2n_closest_triangle(a, b, c, lf);
+      for (i = 0; i < 3; i++) p[i] = lf[0] * a[i] + lf[1] * b[i] + lf[2] * c[i];
+      const real dd = B2N_DOT(p, p);
+      if (dd < best) {
+        best = dd;
+        l[0] = l[1] = l[2] = l[3] = 0;
+        l[F[f][0]] = lf[0]; l[F[f][1]] = lf[1]; l[F[f][2]] = lf[2];
+      }
+    }
+    return 0;
+  }
+}
+
+/* GJK on the cores.  Returns 1 with the closest points pa / pb and their distance when the cores are apart; 0 when they
+ * touch or overlap, leaving the last simplex (Minkowski points W, support points on A in SA, n_simplex) for EPA.         */
+B2N_FN int b2n_gjk(const b2n_shape* A, const b2n_shape* B, B2N_REAL* pa, B2N_REAL* pb, B2N_REAL* dist, B2N_REAL W[4][3],
+                   B2N_REAL SA[4][3], int* n_simplex) {
+  typedef B2N_REAL real;
+  real v[3] = {A->c[0] - B->c[0], A->c[1] - B->c[1], A->c[2] - B->c[2]}, l[4] = {1, 0, 0, 0};
+  int n = 0, it, i, k;
+  if (B2N_DOT(v, v) < (real)1e-12) { v[0] = 1; v[1] = 0; v[2] = 0; }
+  for (it = 0; it < B2N_GJK_ITERS; it++) {
+    real d[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
+    b2n_support(A, d, sa);
+    b2n_support(B, v, sb);
+    for (k = 0; k < 3; k++) w[k] = sa[k] - sb[k];
+    const real vv = B2N_DOT(v, v), vw = B2N_DOT(v, w);
+    if (n > 0 && vv - vw <= (real)1e-5 * vv) break;       /* no point of A - B is closer along v */
+    {
+      int dup = 0;
+      for (i = 0; i < n; i++) {
+        real e[3] = {w[0] - W[i][0], w[1] - W[i][1], w[2] - W[i][2]};
+        if (B2N_DOT(e, e) <= (real)1e-14) dup = 1;
+      }
+      if (dup) break;
+    }
+    if (n == 4) break;   /* cannot happen after a reduction; guards the arrays */
+    real Wb[4][3], SAb[4][3], lb[4];   /* the simplex so far: restored if the new vertex brings no progress (rounding) */
+    const int nb = n;
+    for (i = 0; i < 4; i++) {
+      lb[i] = l[i];
+      for (k = 0; k < 3; k++) { Wb[i][k] = W[i][k]; SAb[i][k] = SA[i][k]; }
+    }
+    for (k = 0; k < 3; k++) { W[n][k] = w[k]; SA[n][k] = sa[k]; }
+    n++;
+    if (b2n_closest_simplex(W, n, l)) { *n_simplex = n; return 0; }
+    {
+      /* drop the vertices with zero weight, recompute v */
+      int m = 0;
+      real nv[3] = {0, 0, 0};
+      for (i = 0; i < n; i++)
+        if (l[i] > 0) {
+          for (k = 0; k < 3; k++) { W[m][k] = W[i][k]; SA[m][k] = SA[i][k]; nv[k] += l[i] * W[i][k]; }
+          l[m] = l[i];
+          m++;
+        }
+      n = m;
+      const real nvv = B2N_DOT(nv, nv);
+      if (nvv <= (real)1e-10) { *n_simplex = n; return 0; }                 /* cores touch */
+      if (it > 0 && nvv >= vv) {                                            /* no progress (rounding): keep the previous simplex */
+        n = nb;
+        for (i = 0; i < 4; i++) {
+          l[i] = lb[i];
+          for (k = 0; k < 3; k++) { W[i][k] = Wb[i][k]; SA[i][k] = SAb[i][k]; }
+        }
+        break;
+      }
+      v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
+    }
+  }
+  {
+    real a[3] = {0, 0, 0};
+    for (i = 0; i < n; i++)
+      for (k = 0; k < 3; k++) a[k] += l[i] * SA[i][k];
+    /* v was recomputed from the same weights unless the loop stopped on "no progress"; the witness on B follows from it */
+    real vs[3] = {0, 0, 0};
+    for (i = 0; i < n; i++)
+      for (k = 0; k < 3; k++) vs[k] += l[i] * W[i][k];
+    for (k = 0; k < 3; k++) { pa[k] = a[k]; pb[k] = a[k] - vs[k]; }
+    *dist = B2N_SQRT(B2N_DOT(vs, vs));
+  }
+  *n_simplex = n;
+  return 1;
+}
+
+/* EPA from the simplex GJK ended with.  Returns 1 with the unit normal nf of the nearest boundary face of A - B (pointing
+ * away from the origin), the depth and the witness points on the cores; 0 if no polytope could be built (cores touching in
+ * a point: depth 0).                                                                                                      */
+B2N_FN int b2n_epa(const b2n_shape* A, const b2n_shape* B, B2N_REAL W4[4][3], B2N_REAL SA4[4][3], int n, B2N_REAL* nf,
+                   B2N_REAL* depth, B2N_REAL* pa, B2N_REAL* pb) {
+  typedef B2N_REAL real;
+  real V[B2N_EPA_MAXV][3], VA[B2N_EPA_MAXV][3];
+  unsigned char F[B2N_EPA_MAXF][3], E[B2N_EPA_MAXE][2];
+  int nv = 0, nfc = 0, i, k, it;
+  for (i = 0; i < n; i++)
+    for (k = 0; k < 3; k++) { V[i][k] = W4[i][k]; VA[i][k] = SA4[i][k]; }
+  nv = n;
+  /* complete the simplex to a tetrahedron with support points off its affine hull */
+  for (it = 0; it < 8 && nv < 4; it++) {
+    real d[3] = {0, 0, 0}, md[3], sa[3], sb[3], w[3];
+    if (nv == 1) { d[it % 3] = (it & 1) ? (real)-1 : (real)1; }
+    else if (nv == 2) {
+      real e[3] = {V[1][0] - V[0][0], V[1][1] - V[0][1], V[1][2] - V[0][2]}, ax[3] = {0, 0, 0};
+      int mi = B2N_FABS(e[0]) <= B2N_FABS(e[1]) ? (B2N_FABS(e[0]) <= B2N_FABS(e[2]) ? 0 : 2) : (B2N_FABS(e[1]) <= B2N_FABS(e[2]) ? 1 : 2);
+      ax[(mi + it) % 3] = 1;
+      B2N_CROSS(d, e, ax);
+      if (it & 1) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+    } else {
+      real e1[3] = {V[1][0] - V[0][0], V[1][1] - V[0][1], V[1][2] - V[0][2]}, e2[3] = {V[2][0] - V[0][0], V[2][1] - V[0][1], V[2][2] - V[0][2]};
+      B2N_CROSS(d, e1, e2);
+      if (it & 1) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+    }
+    if (B2N_DOT(d, d) <= (real)1e-30) continue;
+    md[0] = -d[0]; md[1] = -d[1]; md[2] = -d[2];
+    b2n_support(A, d, sa);
+    b2n_support(B, md, sb);
+    for (k = 0; k < 3; k++) w[k] = sa[k] - sb[k];
+    {
+      /* accept only if it enlarges the hull: distinct from the vertices and off the line / plane */
+      int ok = 1;
+      for (i = 0; i < nv; i++) {
+        real e[3] = {w[0] - V[i][0], w[1] - V[i][1], w[2] - V[i][2]};
+        if (B2N_DOT(e, e) <= (real)1e-14) ok = 0;
+      }
+      if (ok && nv >= 2) {
+        real e[3] = {w[0] - V[0][0], w[1] - V[0][1], w[2] - V[0][2]};
+        const real off = B2N_DOT(e, d);
+        if (off * off <= (real)1e-12 * B2N_DOT(d, d)) ok = 0;
+      }
+      if (!ok) continue;
+    }
+    for (k = 0; k < 3; k++) { V[nv][k] = w[k]; VA[nv][k] = sa[k]; }
+    nv++;
+  }
+  if (nv < 4) return 0;
+  {
+    /* orient the four faces outwards (away from the opposite vertex) */
+    const int T[4][4] = {{0, 1, 2, 3}, {0, 3, 1, 2}, {0, 2, 3, 1}, {1, 3, 2, 0}};
+    for (i = 0; i < 4; i++) {
+      const real* a = V[T[i][0]]; const real* b = V[T[i][1]]; const real* c = V[T[i][2]]; const real* o = V[T[i][3]];
+      real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nn[3];
+      real ao[3] = {o[0] - a[0], o[1] - a[1], o[2] - a[2]};
+      B2N_CROSS(nn, ab, ac);
+      F[nfc][0] = (unsigned char)T[i][0];
+      if (B2N_DOT(nn, ao) > 0) { F[nfc][1] = (unsigned char)T[i][2]; F[nfc][2] = (unsigned char)T[i][1]; }
+      else { F[nfc][1] = (unsigned char)T[i][1]; F[nfc][2] = (unsigned char)T[i][2]; }
+      nfc++;
+    }
+  }
+  {
+    int bf = 0;
+    real bn[3] = {0, 0, 1}, bd = 0;
+    for (it = 0;; it++) {
+      /* nearest face */
+      bd = (real)1e30; bf = -1;
+      for (i = 0; i < nfc; i++) {
+        const real* a = V[F[i][0]]; const real* b = V[F[i][1]]; const real* c = V[F[i][2]];
+        real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nn[3];
+        B2N_CROSS(nn, ab, ac);
+        const real l2 = B2N_DOT(nn, nn);
+        if (l2 <= (real)1e-30) continue;
+        const real il = 1 / B2N_SQRT(l2);
+        real dd = B2N_DOT(nn, a) * il;
+        if (dd < 0) dd = 0;   /* origin marginally outside (rounding) */
+        if (dd < bd) { bd = dd; bf = i; bn[0] = nn[0] * il; bn[1] = nn[1] * il; bn[2] = nn[2] * il; }
+      }
+      if (bf < 0) return 0;
+      if (it >= B2N_EPA_ITERS || nv >= B2N_EPA_MAXV || nfc + 2 > B2N_EPA_MAXF) break;
+      real mb[3] = {-bn[0], -bn[1], -bn[2]}, sa[3], sb[3], w[3];
+      b2n_support(A, bn, sa);
+      b2n_support(B, mb, sb);
+      for (k = 0; k < 3; k++) w[k] = sa[k] - sb[k];
+      if (B2N_DOT(w, bn) - bd <= (real)1e-6 + (real)1e-4 * bd) break;   /* the face is on the boundary */
+      /* remove the faces seen from w, collect the horizon */
+      int ne = 0, j, e, found, overflow = 0;
+      for (i = 0; i < nfc;) {
+        const real* a = V[F[i][0]]; const real* b = V[F[i][1]]; const real* c = V[F[i][2]];
+        real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nn[3];
+        real aw[3] = {w[0] - a[0], w[1] - a[1], w[2] - a[2]};
+        B2N_CROSS(nn, ab, ac);
+        if (B2N_DOT(nn, aw) > 0) {
+          for (j = 0; j < 3; j++) {
+            const unsigned char ea = F[i][j], eb = F[i][(j + 1) % 3];
+            found = 0;
+            for (e = 0; e < ne; e++)
+              if (E[e][0] == eb && E[e][1] == ea) { E[e][0] = E[ne - 1][0]; E[e][1] = E[ne - 1][1]; ne--; found = 1; break; }
+            if (!found) {
+              if (ne < B2N_EPA_MAXE) { E[ne][0] = ea; E[ne][1] = eb; ne++; }
+              else overflow = 1;
+            }
+          }
+          F[i][0] = F[nfc - 1][0]; F[i][1] = F[nfc - 1][1]; F[i][2] = F[nfc - 1][2];
+          nfc--;
+        } else i++;
+      }
+      if (overflow || ne == 0 || nfc + ne > B2N_EPA_MAXF) break;   /* keep the answer of the last complete polytope */
+      for (k = 0; k < 3; k++) { V[nv][k] = w[k]; VA[nv][k] = sa[k]; }
+      for (e = 0; e < ne; e++) { F[nfc][0] = E[e][0]; F[nfc][1] = E[e][1]; F[nfc][2] = (unsigned char)nv; nfc++; }
+      nv++;
+    }
+    if (bf >= nfc) {   /* the loop left after removing faces: take the nearest face of what remains */
+      bd = (real)1e30; bf = -1;
+      for (i = 0; i < nfc; i++) {
+        const real* a = V[F[i][0]]; const real* b = V[F[i][1]]; const real* c = V[F[i][2]];
+        real ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nn[3];
+        B2N_CROSS(nn, ab, ac);
+        const real l2 = B2N_DOT(nn, nn);
+        if (l2 <= (real)1e-30) continue;
+        const real il = 1 / B2N_SQRT(l2);
+        real dd = B2N_DOT(nn, a) * il;
+        if (dd < 0) dd = 0;
+        if (dd < bd) { bd = dd; bf = i; bn[0] = nn[0] * il; bn[1] = nn[1] * il; bn[2] = nn[2] * il; }
+      }
+      if (bf < 0) return 0;
+    }
+    {
+      /* witness: barycentric coordinates of the foot of the origin on the face */
+      const int ia = F[bf][0], ib = F[bf][1], ic = F[bf][2];
+      real a[3], b[3], c[3], l[3];
+      for (k = 0; k < 3; k++) { a[k] = V[ia][k] - bd * bn[k]; b[k] = V[ib][k] - bd * bn[k]; c[k] = V[ic][k] - bd * bn[k]; }
+      b2n_closest_triangle(a, b, c, l);
+      for (k = 0; k < 3; k++) {
+        pa[k] = l[0] * VA[ia][k] + l[1] * VA[ib][k] + l[2] * VA[ic][k];
+        const real pk = l[0] * V[ia][k] + l[1] * V[ib][k] + l[2] * V[ic][k];
+        pb[k] = pa[k] - pk;
+      }
+      nf[0] = bn[0]; nf[1] = bn[1]; nf[2] = bn[2];
+      *depth = bd;
+    }
+  }
+  return 1;
+}
+
+/* One contact of two rounded convex shapes: 1 if their surfaces are closer than `margin` (n from B towards A, points on the
+ * two surfaces, dist < 0 = penetration).  id: 0 = cores apart (GJK), 1 = cores overlapping (EPA).                            */
+B2N_FN int b2n_convex_contact(const b2n_shape* A, const b2n_shape* B, B2N_REAL margin, B2N_REAL* n_out, b2n_contact* out) {
+  typedef B2N_REAL real;
+  real W[4][3], SA[4][3], pa[3], pb[3], d = 0, n[3] = {0, 0, 1};
+  int ns = 0, k, id = 0;
+  if (b2n_gjk(A, B, pa, pb, &d, W, SA, &ns)) {
+    if (!(d - A->r - B->r < margin)) return 0;
+    for (k = 0; k < 3; k++) n[k] = (pa[k] - pb[k]) / d;
+  } else {
+    real nfc[3], depth = 0;
+    id = 1;
+    if (b2n_epa(A, B, W, SA, ns, nfc, &depth, pa, pb)) {
+      for (k = 0; k < 3; k++) n[k] = -nfc[k];
+      d = -depth;
+    } else {
+      /* touching in a point: no direction from the cores; separate along the line of centres */
+      real cc[3] = {A->c[0] - B->c[0], A->c[1] - B->c[1], A->c[2] - B->c[2]};
+      const real l = B2N_SQRT(B2N_DOT(cc, cc));
+      if (l > (real)1e-9) { n[0] = cc[0] / l; n[1] = cc[1] / l; n[2] = cc[2] / l; }
+      real a[3] = {0, 0, 0};
+      for (k = 0; k < 3; k++) a[k] = ns > 0 ? SA[0][k] : A->c[k];
+      for (k = 0; k < 3; k++) { pa[k] = a[k]; pb[k] = a[k]; }
+      d = 0;
+    }
+  }
+  for (k = 0; k < 3; k++) {
+    out->pa[k] = pa[k] - n[k] * A->r;
+    out->pb[k] = pb[k] + n[k] * B->r;
+    n_out[k] = n[k];
+  }
+  out->dist = d - A->r - B->r;
+  out->id = id;
+  return 1;
+}
+
 #endif /* B2ENV_NARROWPHASE_H */

@@ -1543,6 +1543,25 @@ int b2o_box_box(const float* cA, const float* RA, const float* hA, const float* 
   if (np > 0) for (int k = 0; k < 3; k++) normal[k] = (float)n[k];
   return np;
 }
+/* GJK / EPA contact of two rounded convex shapes (include/b2env_narrowphase.h) on its own.  shape = [type, c(3), R(9), h(3), r]
+ * as 17 floats; out = pa(3) pb(3) dist id, normal[3]; returns 1 when within margin                                        */
+int b2o_convex_contact(const float* shapeA, const float* shapeB, float margin, float* normal, float* out) {
+  b2n_shape S[2];
+  const float* src[2] = {shapeA, shapeB};
+  for (int i = 0; i < 2; i++) {
+    S[i].type = (int)src[i][0];
+    for (int k = 0; k < 3; k++) { S[i].c[k] = src[i][1 + k]; S[i].h[k] = src[i][13 + k]; }
+    for (int k = 0; k < 9; k++) S[i].R[k] = src[i][4 + k];
+    S[i].r = src[i][16];
+  }
+  real n[3];
+  b2n_contact c;
+  if (!b2n_convex_contact(&S[0], &S[1], (real)margin, n, &c)) return 0;
+  for (int k = 0; k < 3; k++) { out[k] = (float)c.pa[k]; out[3 + k] = (float)c.pb[k]; normal[k] = (float)n[k]; }
+  out[6] = (float)c.dist;
+  out[7] = (float)c.id;
+  return 1;
+}
 /* the contact set of one configuration: out = [n][16] = key type link link2 pA(3) pB(3) n(3) dist mu erp */
 int b2o_collide(const b2e_model* m, const b2e_params* P, const float* q, const float* obj_pose, float* out, int* overflow) {
   real qq[ND] = {0}, cp[3], cq[4];

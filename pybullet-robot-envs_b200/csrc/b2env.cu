@@ -173,6 +173,9 @@ struct b2e_sim {
   int* d_sched;              // cost-ordered scheduling state (see NBK_MAIN)
   int sched_seq;
   int tail_wpb;              // warps per block of the tail launch
+  int tail_blocks;           // blocks of the tail launch (capacity = blocks x warps x 2 environments, <= TAIL_CAP)
+  int tail_excl;             // tail blocks ask for enough shared memory to have their SM to themselves
+  int tail_cost;             // estimated solve cycles from which an environment is stepped by the tail launch
   cudaStream_t tstream;      // the tail launch's stream (high priority)
   cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev_order;      // recorded after every launch: the next entry point's stream waits on it, so calls on
@@ -1560,7 +1563,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB)
 step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P, DevState st, const float* __restrict__ action,
             float* __restrict__ obs_out, float* __restrict__ reward_out, float* __restrict__ done_out, int nsub,
             int mode, int record_contacts, const int* __restrict__ env_ids, int n_ids, int env_offset, int* sched, int seq,
-            int role, int nslot) {
+            int role, int nslot, int tail_cap, int tail_cost) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wpb = blockDim.x >> 5;                          // warps per block: WPB (main / plain launches) or the tail's
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
@@ -1569,7 +1572,10 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   // slot -> environment: the whole batch in cost order (ROLE_MAIN / ROLE_TAIL, see NBK_MAIN), or identity / the subset
   // listed in env_ids (ROLE_PLAIN: per-env resets (row f1), chunked host path)
   int n_slots = n_ids;   // env_ids: listed envs; else the contiguous range [env_offset, env_offset + n_ids)
-  const int slot = (blockIdx.x * wpb + warp) * 2 + half;
+  // main / plain launches: consecutive slots per block.  Tail launch: slot s -> block s % grid, warp (s / grid) % wpb, group
+  // s / (grid * wpb), so that a short tail list is spread one environment per block (each block has an SM to itself, see
+  // launch_step) before a second warp of any block is used, and the second group of a warp last of all
+  const int slot = role == ROLE_TAIL ? (half * wpb + warp) * (int)gridDim.x + (int)blockIdx.x : (blockIdx.x * wpb + warp) * 2 + half;
   int env;
   if (role == ROLE_PLAIN) {
     const int sc = slot < n_slots ? slot : n_slots - 1;
@@ -1579,9 +1585,12 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     if (role == ROLE_MAIN && blockIdx.x == 0 && (int)threadIdx.x < NBK)
       sched[SCHED_CNT((seq + 1) & 3, threadIdx.x)] = 0;   // the next step's counters (not used by this step's launches)
     if (role == ROLE_TAIL) {
-      n_slots = min(sched[SCHED_CNT(qp, NBK_MAIN)], TAIL_CAP);
-      if ((int)blockIdx.x * 2 * wpb >= n_slots) return;
-      env = sched[SCHED_TAIL(pp, B) + (slot < n_slots ? slot : n_slots - 1)];
+      n_slots = min(sched[SCHED_CNT(qp, NBK_MAIN)], tail_cap);
+      // a warp whose first group has no environment leaves (block barriers count the warps that are left); a second group
+      // without one shadows the first (stores masked)
+      const int slot_a = warp * (int)gridDim.x + (int)blockIdx.x;
+      if (slot_a >= n_slots) return;
+      env = sched[SCHED_TAIL(pp, B) + (slot < n_slots ? slot : slot_a)];
     } else {
       int cnt[NBK_MAIN];
 #pragma unroll
@@ -2065,7 +2074,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     int cls = -1, rank = 0;
     if (lane == 0 && live_env) {
       const float c = sm.cost[0];
-      cls = (R - nd > GL || c >= (float)SCHED_TAIL_COST) ? NBK_MAIN : min(NBK_MAIN - 1, (int)(c * (1.0f / 8192.0f)));
+      cls = (R - nd > GL || c >= (float)tail_cost) ? NBK_MAIN : min(NBK_MAIN - 1, (int)(c * (1.0f / 8192.0f)));
       rank = atomicAdd(&cls_hist[cls], 1);
     }
     __syncthreads();
@@ -2077,7 +2086,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     if (cls >= 0) {
       const int B = st.B;
       int pos = cls_base[cls] + rank;
-      if (cls == NBK_MAIN && pos >= TAIL_CAP) {   // tail list full: the heaviest class of the main launch takes it
+      if (cls == NBK_MAIN && pos >= tail_cap) {   // tail list full: the heaviest class of the main launch takes it
         cls = NBK_MAIN - 1;
         pos = atomicAdd(&sched[SCHED_CNT(seq & 3, cls)], 1);
       }
@@ -2444,13 +2453,16 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
 
 #define SMEM_BYTES_FOR(wpb, nslot) (sizeof(EnvSmem) * 2 * (wpb) + sizeof(BigSlot) * (nslot) + (16 + 2 * NBK + 2) * sizeof(int))
 #define SMEM_BYTES SMEM_BYTES_FOR(WPB, NSLOT)
+// 228 KB per SM, 1 KB reserved per resident block: a tail block of this size leaves < SMEM_BYTES + 1 KB free
+#define TAIL_EXCL_SMEM (228 * 1024 - 2 * 1024 - SMEM_BYTES + 512)
 #define TREE_SMEM_BYTES (sizeof(TreeSmem) * TREE_WPB)
 template <bool IK>
 static void launch_group(b2e_sim* s, int blocks, int threads, size_t smem, void* stream, const float* action, float* obs, float* reward,
                          float* done, int n_substeps, int mode, const int* env_ids, int n, int env_offset, int* sched, int seq, int role,
                          int nslot) {
   B2E_LAUNCH(step_kernel<IK>, blocks, threads, smem, stream, s->d_model, s->umodel, s->params, s->st, action, obs, reward, done,
-             n_substeps, mode, s->record_contacts, env_ids, n, env_offset, sched, seq, role, nslot);
+             n_substeps, mode, s->record_contacts, env_ids, n, env_offset, sched, seq, role, nslot,
+             s->tail_blocks * s->tail_wpb * 2, s->tail_cost);
 }
 static int launch_step(b2e_sim* s, const float* action, float* obs, float* reward, float* done, int n_substeps, int mode,
                        const int* env_ids, int n_ids, void* stream, int env_offset = 0, bool ordered = true) {
@@ -2488,14 +2500,19 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
   // fork: the tail launch (heavy class, lean blocks, own high-priority stream) is enqueued FIRST so that its blocks are
   // resident when the main launch starts filling the machine; join: the caller's stream waits for it
   const int twpb = s->tail_wpb, tslots = 2 * twpb;
-  const int tblocks = (TAIL_CAP + 2 * twpb - 1) / (2 * twpb);
+  const int tblocks = s->tail_blocks;
+  // shared memory of a tail block: what it uses, or (tail_excl) enough that no block of the main launch fits next to it — the
+  // few environments that decide how long the step lasts then run without other warps competing for issue slots and for
+  // the shared-memory / shuffle pipe (tools/micro/row_chain3.cu: 56 cycles per row update alone, 125 next to 16 busy warps)
+  size_t tsmem = SMEM_BYTES_FOR(twpb, tslots);
+  if (s->tail_excl && tsmem < (size_t)TAIL_EXCL_SMEM) tsmem = TAIL_EXCL_SMEM;
 #ifndef B2E_EMU
   CUDA_TRY(cudaEventRecord(s->ev_fork, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(s->tstream, s->ev_fork, 0));
 #endif
   void* ts = (void*)s->tstream;
-  if (ik) launch_group<true>(s, tblocks, 32 * twpb, SMEM_BYTES_FOR(twpb, tslots), ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
-  else launch_group<false>(s, tblocks, 32 * twpb, SMEM_BYTES_FOR(twpb, tslots), ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
+  if (ik) launch_group<true>(s, tblocks, 32 * twpb, tsmem, ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
+  else launch_group<false>(s, tblocks, 32 * twpb, tsmem, ts, action, obs, reward, done, n_substeps, mode, nullptr, n, 0, sched, seq, ROLE_TAIL, tslots);
   CUDA_TRY(cudaGetLastError());
 #ifndef B2E_EMU
   CUDA_TRY(cudaEventRecord(s->ev_join, s->tstream));
@@ -2608,7 +2625,15 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
       CUDA_TRY(e1);
       s->sched_seq = 2;
       const char* w = getenv("B2ENV_TAIL_WPB");   // warps per block of the tail launch (1, 2 or 4)
-      s->tail_wpb = (w && (w[0] == '1' || w[0] == '2' || w[0] == '4')) ? (w[0] - '0') : 1;
+      s->tail_wpb = (w && (w[0] == '1' || w[0] == '2' || w[0] == '4')) ? (w[0] - '0') : 4;
+      const char* tb = getenv("B2ENV_TAIL_BLOCKS");
+      s->tail_blocks = tb ? atoi(tb) : 64;
+      if (s->tail_blocks < 1) s->tail_blocks = 1;
+      if (s->tail_blocks * s->tail_wpb * 2 > TAIL_CAP) s->tail_blocks = TAIL_CAP / (s->tail_wpb * 2);
+      const char* te = getenv("B2ENV_TAIL_EXCL");   // 0: tail blocks share their SM with the main launch (A/B runs)
+      s->tail_excl = !(te && te[0] == '0');
+      const char* tc = getenv("B2ENV_TAIL_COST");
+      s->tail_cost = tc ? atoi(tc) : SCHED_TAIL_COST;
 #ifndef B2E_EMU
       int lo_p = 0, hi_p = 0;
       CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -2627,7 +2652,9 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
   CUDA_TRY(cudaEventCreateWithFlags(&s->ev_order, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(s->ev_order, 0));
   CUDA_TRY(cudaStreamCreate(&s->pstream[0])); CUDA_TRY(cudaStreamCreate(&s->pstream[1]));
-  const int smem_max = (int)(SMEM_BYTES > SMEM_BYTES_FOR(4, 8) ? SMEM_BYTES : SMEM_BYTES_FOR(4, 8));   // main / largest tail block
+  int smem_max = (int)(SMEM_BYTES > SMEM_BYTES_FOR(4, 8) ? SMEM_BYTES : SMEM_BYTES_FOR(4, 8));   // main / largest tail block
+  if (smem_max < (int)TAIL_EXCL_SMEM) smem_max = (int)TAIL_EXCL_SMEM;                             // SM-exclusive tail block
+  static_assert(TAIL_EXCL_SMEM <= 227 * 1024 && SMEM_BYTES_FOR(4, 8) <= 227 * 1024, "tail block within the 227 KB a block can have");
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   CUDA_TRY(cudaFuncSetAttribute(tree_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM_BYTES));

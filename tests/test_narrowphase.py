@@ -219,3 +219,185 @@ def test_world_contact_sets(lib):
     ln = c[[k in leg for k in keys], 10:13]
     np.testing.assert_allclose(ln, [[0, 1, 0]] * 4, atol=1e-6)       # from the leg towards the cube
     np.testing.assert_allclose(c[[k in leg for k in keys], 13], -0.0005, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ GJK / EPA
+B2N_POINT, B2N_SEGMENT, B2N_BOX = 0, 1, 2
+
+
+def _shape(kind, c, R=np.eye(3), h=(0, 0, 0), r=0.0):
+    return np.concatenate([[kind], np.asarray(c, np.float64), np.asarray(R, np.float64).reshape(9), np.asarray(h, np.float64),
+                           [r]]).astype(np.float32)
+
+
+def convex_contact(o, A, B, margin=0.01):
+    o.lib.b2o_convex_contact.restype = C.c_int
+    n = np.zeros(3, np.float32)
+    out = np.zeros(8, np.float32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    k = o.lib.b2o_convex_contact(p(A), p(B), C.c_float(margin), p(n), p(out))
+    return k, n.astype(np.float64), out.astype(np.float64)
+
+
+def _point_box_dist(x, c, R, h):
+    """Signed distance of point x to a box (negative inside) and the closest surface point."""
+    l = np.asarray(R).T @ (x - c)
+    cl = np.clip(l, -h, h)
+    if np.all(cl == l):
+        pen = h - np.abs(l)
+        ax = int(np.argmin(pen))
+        cl = l.copy()
+        cl[ax] = np.sign(l[ax] if l[ax] != 0 else 1.0) * h[ax]
+        return -pen[ax], c + np.asarray(R) @ cl
+    return np.linalg.norm(l - cl), c + np.asarray(R) @ cl
+
+
+def _points_box_dist(X, R, h):
+    """Signed distances of the points X (rows) to a box centred at the origin (vectorised _point_box_dist)."""
+    l = X @ np.asarray(R)
+    cl = np.clip(l, -h, h)
+    inside = np.all(cl == l, axis=1)
+    return np.where(inside, -(h - np.abs(l)).min(axis=1), np.linalg.norm(l - cl, axis=1))
+
+
+def test_gjk_sphere_box_matches_the_closed_form(lib):
+    """Sphere (point core + radius) against a rotated box: distance, normal and witness points equal the closest-point
+    closed form used by the sphere families of collide(), both apart (GJK) and with the centre inside the box (EPA)."""
+    rng = np.random.RandomState(1)
+    n_epa = 0
+    for it in range(400):
+        h = rng.uniform(0.01, 0.2, 3)
+        R = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        r = rng.uniform(0.005, 0.06)
+        l = rng.uniform(-1, 1, 3) * h * (1.6 if it % 4 else 0.95)      # every fourth centre inside the box
+        x = R @ l
+        sd, foot = _point_box_dist(x, np.zeros(3), R, h)
+        k, n, out = convex_contact(lib, _shape(B2N_POINT, x, r=r), _shape(B2N_BOX, np.zeros(3), R, h), margin=10.0)
+        assert k == 1
+        assert abs(out[6] - (sd - r)) < 2e-5, (it, out[6], sd - r)
+        n_epa += int(out[7]) == 1
+        if abs(sd) > 1e-3:
+            if sd < 0:
+                # inside: the least-penetration face may be tied within rounding; check the depth and that n is a face normal
+                assert np.abs(np.abs(R.T @ n)).max() > 1 - 1e-4
+            else:
+                np.testing.assert_allclose(n, (x - foot) / sd, atol=2e-4)
+                np.testing.assert_allclose(out[3:6], foot, atol=2e-5)
+            np.testing.assert_allclose(out[0:3], x - n * r, atol=2e-5)
+    assert n_epa > 50
+
+
+def test_gjk_capsule_box_against_brute_force(lib):
+    """Capsule (segment core + radius) against a box: the distance equals the minimum over the segment of the closed-form
+    point-box distance (dense sampling + local refinement), the witness points lie on the two surfaces, and n is the
+    direction between them."""
+    rng = np.random.RandomState(2)
+    n_hit = n_deep = 0
+    for it in range(300):
+        h = rng.uniform(0.02, 0.3, 3) if it % 2 else np.array([0.025] * 3)
+        R = _rot(rng.normal(size=3), rng.uniform(0, np.pi)) if it % 3 else np.eye(3)
+        Rs = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        hl, r = rng.uniform(0.03, 0.15), rng.uniform(0.02, 0.06)
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        # centre placed so that the capsule is between 3 cm of overlap and 3 cm of gap
+        ts = np.linspace(-hl, hl, 801)
+
+        def surf_dist(c):
+            return _points_box_dist(c[None] + ts[:, None] * Rs[:, 2][None], R, h).min() - r
+        lo, hi = 0.0, 1.0
+        while surf_dist(u * hi) < 0.03:
+            hi *= 1.5
+        target = rng.uniform(-0.03, 0.03) if it % 4 else -(r + rng.uniform(0.002, 0.02))   # every fourth: the segment enters
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            if surf_dist(u * mid) < target:
+                lo = mid
+            else:
+                hi = mid
+        c = u * hi
+        ref = surf_dist(c)
+        k, n, out = convex_contact(lib, _shape(B2N_SEGMENT, c, Rs, (0, 0, hl), r), _shape(B2N_BOX, np.zeros(3), R, h), margin=0.05)
+        assert k == 1, (it, ref)
+        n_hit += 1
+        core = ref + r
+        if core > 1e-3:        # cores apart: GJK is exact
+            assert int(out[7]) == 0
+            assert abs(out[6] - ref) < 5e-5, (it, out[6], ref)
+            pa, pb = out[0:3], out[3:6]
+            np.testing.assert_allclose((pa - pb) @ n, out[6], atol=2e-5)
+            assert abs(_point_box_dist(pb, np.zeros(3), R, h)[0]) < 3e-5          # on the box
+            t = (pa + n * r - c) @ Rs[:, 2]
+            assert abs(t) <= hl + 1e-4 and np.linalg.norm(pa + n * r - c - t * Rs[:, 2]) < 3e-5   # r away from the segment
+        elif core < -1e-3:     # the segment itself enters the box: EPA depth = least translation that frees the segment
+            n_deep += 1
+            assert int(out[7]) == 1
+            depth = -(out[6] + r)
+            # separating translation along n: afterwards the segment no longer penetrates (brute force), and no sampled
+            # direction does it with a clearly shorter translation
+            moved = c + n * (depth + 1e-4)
+            assert _points_box_dist(moved[None] + ts[:, None] * Rs[:, 2][None], R, h).min() > -2e-4, it
+            assert depth <= -core * 3 + 0.02
+    assert n_hit == 300 and n_deep > 20, (n_hit, n_deep)
+
+
+def _sat_depth(cA, RA, hA, cB, RB, hB):
+    """Largest separation over the 15 SAT axes (negative = overlap depth): exact for two boxes."""
+    axes = [RA[:, i] for i in range(3)] + [RB[:, j] for j in range(3)]
+    axes += [np.cross(RA[:, i], RB[:, j]) for i in range(3) for j in range(3)]
+    best = -1e9
+    for a in axes:
+        l = np.linalg.norm(a)
+        if l < 1e-6:
+            continue
+        a = a / l
+        best = max(best, max(_support_gap(cA, RA, hA, cB, RB, hB, s * a) for s in (-1, 1)))
+    return best
+
+
+def test_epa_depth_of_overlapping_boxes_equals_the_sat_depth(lib):
+    """Two sharp boxes through GJK / EPA (no rounding): for overlapping pairs the EPA depth is the minimum translation
+    distance, which for boxes is the best of the 15 separating axes (an independent, closed-form answer); for separated pairs
+    the GJK distance is bounded below by the best axis separation and the witness points realise it."""
+    rng = np.random.RandomState(3)
+    n_over = n_sep = 0
+    for it in range(400):
+        hA, hB = rng.uniform(0.01, 0.05, 3), rng.uniform(0.01, 0.2, 3)
+        RA = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        RB = _rot(rng.normal(size=3), rng.uniform(0, np.pi)) if it % 3 else np.eye(3)
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        g0 = _support_gap(np.zeros(3), RA, hA, np.zeros(3), RB, hB, u)
+        cA = u * (-g0 + (rng.uniform(-0.06, -0.005) if it % 2 else rng.uniform(0.0, 0.03)))
+        sat = _sat_depth(cA, RA, hA, np.zeros(3), RB, hB)
+        k, n, out = convex_contact(lib, _shape(B2N_BOX, cA, RA, hA), _shape(B2N_BOX, np.zeros(3), RB, hB), margin=1.0)
+        assert k == 1
+        if sat < -1e-3:
+            n_over += 1
+            assert int(out[7]) == 1
+            assert abs(out[6] - sat) < 1e-4 + 0.01 * abs(sat), (it, out[6], sat)
+            gap_n = _support_gap(cA, RA, hA, np.zeros(3), RB, hB, n)
+            assert abs(gap_n - sat) < 1e-4 + 0.01 * abs(sat), (it, gap_n, sat)      # n IS a least-penetration direction
+        elif sat > 1e-3:
+            n_sep += 1
+            assert int(out[7]) == 0
+            assert out[6] >= sat - 2e-5, (it, out[6], sat)
+            gap_n = _support_gap(cA, RA, hA, np.zeros(3), RB, hB, n)
+            assert abs(gap_n - out[6]) < 5e-5, (it, gap_n, out[6])                  # the distance is realised along n
+            la = np.abs(RA.T @ (out[0:3] - cA)) - hA
+            lb = np.abs(RB.T @ out[3:6]) - hB
+            assert abs(la.max()) < 3e-5 and abs(lb.max()) < 3e-5                    # witnesses on the two surfaces
+    assert n_over > 60 and n_sep > 100, (n_over, n_sep)
+
+
+def test_gjk_degenerate_configurations(lib):
+    """Symmetric / degenerate inputs: concentric shapes, a segment through the box centre along an axis, touching cores."""
+    box = _shape(B2N_BOX, [0, 0, 0], np.eye(3), [0.1, 0.2, 0.3])
+    k, n, out = convex_contact(lib, _shape(B2N_POINT, [0, 0, 0], r=0.01), box, margin=1.0)
+    assert k == 1 and abs(out[6] - (-0.1 - 0.01)) < 1e-5 and abs(abs(n[0]) - 1) < 1e-5
+    k, n, out = convex_contact(lib, _shape(B2N_SEGMENT, [0, 0, 0], np.eye(3), (0, 0, 0.5), 0.02), box, margin=1.0)
+    assert k == 1 and abs(out[6] - (-0.1 - 0.02)) < 1e-4 and abs(n[2]) < 1e-4 and np.isfinite(out).all()
+    k, n, out = convex_contact(lib, _shape(B2N_POINT, [0.1, 0, 0], r=0.01), box, margin=1.0)       # centre exactly on a face
+    assert k == 1 and abs(out[6] + 0.01) < 1e-5 and np.isfinite(n).all()
+    k, n, out = convex_contact(lib, _shape(B2N_POINT, [0.5, 0, 0], r=0.01), box, margin=0.01)       # far: no contact
+    assert k == 0
