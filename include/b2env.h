@@ -42,6 +42,7 @@ extern "C" {
 #define B2E_MAX_BOXES 4     /* box collision proxies of robot links (finger pads) */
 #define B2E_MAX_SELF_PAIRS 32 /* sphere pairs tested for robot self-collision    */
 #define B2E_MAX_SBOXES 6    /* static world boxes (table top, legs)             */
+#define B2E_MAX_CAPS 4      /* capsule collision proxies of robot links          */
 #define B2E_MAX_LIMROWS 3   /* joint-limit rows kept per env per step          */
 #define B2E_CACHE_SLOTS 16  /* warm-start cache slots (key + 3 impulses each)  */
 
@@ -103,6 +104,18 @@ typedef struct b2e_model {
   int32_t n_self_pairs;
   int32_t self_a[B2E_MAX_SELF_PAIRS];
   int32_t self_b[B2E_MAX_SELF_PAIRS];
+  /* sphere flags: bit 0 = self-collision partner only (not tested against the object or the static world: the link's
+   * world contacts come from another proxy, or the link cannot reach the world)                                  */
+  int32_t sph_flags[B2E_MAX_SPHERES];
+  /* capsule proxies (segment p0-p1 in the link frame + radius): collided with the object and the static boxes by GJK /
+   * EPA on the segment core (include/b2env_narrowphase.h: b2n_convex_contact), with the ground plane in closed form.
+   * This is the convex-convex narrowphase Bullet runs for hull / capsule shapes (btGjkPairDetector + EPA)          */
+  int32_t n_caps;
+  int32_t cap_link[B2E_MAX_CAPS];
+  float cap_p0[B2E_MAX_CAPS][3];
+  float cap_p1[B2E_MAX_CAPS][3];
+  float cap_r[B2E_MAX_CAPS];
+  float cap_mu[B2E_MAX_CAPS];
 } b2e_model;
 
 #define B2E_TASK_REACH 0
@@ -211,6 +224,8 @@ enum b2e_field {
  *   128..255 robot sphere s vs static box k other than through the table top (128 + 8 s + k)
  *   256..271 robot sphere s vs ground plane
  *   512..543 robot self-collision, sphere pair p
+ *   576..579 robot capsule c vs cube (GJK / EPA);  592..623 capsule c vs static box k (592 + 8 c + k);
+ *   624..631 capsule c end e vs ground plane (624 + 2 c + e)
  *   4096 + 1024 k + id   cube vs static box k, general box-box (rim, legs; id: include/b2env_narrowphase.h)
  *   12288 + 1024 b + id  robot box b vs cube, box-box
  *   16384 + 1024 (8 b + k) + id  robot box b vs static box k, general box-box                                   */
@@ -223,6 +238,9 @@ enum b2e_field {
 #define B2E_KEY_SPHERE_SBOX 128
 #define B2E_KEY_SPHERE_PLANE 256
 #define B2E_KEY_SELF 512
+#define B2E_KEY_CAP_CUBE 576
+#define B2E_KEY_CAP_SBOX 592
+#define B2E_KEY_CAP_PLANE 624
 #define B2E_KEY_CUBE_SBOX 4096
 #define B2E_KEY_BOX_CUBE 12288
 #define B2E_KEY_BOX_SBOX 16384

@@ -609,8 +609,31 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
     for (int j = 0; j < 3; j++) { bxc[b][j] = fk->p[li][j] + o[j]; bxh[b][j] = m->box_h[b][j]; }
     bxr[b] = RSQRT(dot3(bxh[b], bxh[b]));
   }
-  /* ---- 2. robot vs cube: spheres (closest point on the box), finger-pad boxes (box-box) ---- */
+  b2n_shape caps[B2E_MAX_CAPS];
+  real cap_e[B2E_MAX_CAPS][2][3];   /* world end points */
+  for (int c = 0; c < m->n_caps; c++) {
+    int li = m->cap_link[c];
+    for (int e = 0; e < 2; e++) {
+      real lc[3], o[3];
+      for (int j = 0; j < 3; j++) lc[j] = e ? m->cap_p1[c][j] : m->cap_p0[c][j];
+      m3_vec(fk->R[li], lc, o);
+      for (int j = 0; j < 3; j++) cap_e[c][e][j] = fk->p[li][j] + o[j];
+    }
+    real ax[3] = {cap_e[c][1][0] - cap_e[c][0][0], cap_e[c][1][1] - cap_e[c][0][1], cap_e[c][1][2] - cap_e[c][0][2]};
+    real len = RSQRT(dot3(ax, ax));
+    caps[c].type = B2N_SEGMENT;
+    for (int j = 0; j < 9; j++) caps[c].R[j] = 0;
+    for (int j = 0; j < 3; j++) {
+      caps[c].c[j] = (real)0.5 * (cap_e[c][0][j] + cap_e[c][1][j]);
+      caps[c].R[3 * j + 2] = len > 0 ? ax[j] / len : (j == 2 ? (real)1 : (real)0);
+      caps[c].h[j] = 0;
+    }
+    caps[c].h[2] = (real)0.5 * len;
+    caps[c].r = m->cap_r[c];
+  }
+  /* ---- 2. robot vs cube: spheres (closest point on the box), finger-pad boxes (box-box), capsules (GJK / EPA) ---- */
   for (int s = 0; s < m->n_spheres; s++) {
+    if (m->sph_flags[s] & 1) continue; /* self-collision partner only */
     real rel[3] = {sc[s][0] - cpos[0], sc[s][1] - cpos[1], sc[s][2] - cpos[2]}, l[3], cl[3];
     m3t_vec(Rc, rel, l);
     int inside = 1;
@@ -669,8 +692,25 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
       c->cfm = m->box_cfm[b];
     }
   }
+  for (int c = 0; c < m->n_caps; c++) {
+    real d[3] = {caps[c].c[0] - cpos[0], caps[c].c[1] - cpos[1], caps[c].c[2] - cpos[2]};
+    if (RSQRT(dot3(d, d)) - (rb + caps[c].h[2] + caps[c].r) >= margin) continue;
+    b2n_shape cube;
+    cube.type = B2N_BOX; cube.r = 0;
+    for (int j = 0; j < 3; j++) { cube.c[j] = cpos[j]; cube.h[j] = a; }
+    for (int j = 0; j < 9; j++) cube.R[j] = Rc[j];
+    real n[3];
+    b2n_contact pt;
+    if (!b2n_convex_contact(&caps[c], &cube, margin, n, &pt)) continue;
+    contact_t* ct = push_contact(&L);
+    if (!ct) continue;
+    ct->key = B2E_KEY_CAP_CUBE + c; ct->type = CT_ARM_CUBE; ct->link = m->cap_link[c]; ct->link2 = -1;
+    for (int j = 0; j < 3; j++) { ct->pA[j] = pt.pa[j]; ct->pB[j] = pt.pb[j]; ct->n[j] = n[j]; }
+    ct->dist = pt.dist; ct->mu = P->cube_mu * m->cap_mu[c]; ct->erp = P->erp; ct->cfm = 0;
+  }
   /* ---- 3. robot vs static world ---- */
   for (int s = 0; s < m->n_spheres; s++) {
+    if (m->sph_flags[s] & 1) continue;
     real r = m->sph_r[s];
     int kept = 0;
     for (int k = 0; k < nsb && kept < 3; k++) { /* at most three static boxes per sphere */
@@ -693,7 +733,7 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
   }
   for (int s = 0; s < m->n_spheres; s++) { /* ground plane */
     real r = m->sph_r[s], dist = sc[s][2] - r;
-    if (!(dist < margin)) continue;
+    if ((m->sph_flags[s] & 1) || !(dist < margin)) continue;
     contact_t* c = push_contact(&L);
     if (!c) continue;
     c->key = B2E_KEY_SPHERE_PLANE + s; c->type = CT_ARM_STATIC; c->link = m->sph_link[s]; c->link2 = -1;
@@ -763,6 +803,45 @@ static int collide(const b2e_model* m, const b2e_params* P, const fk_t* fk, cons
       c->pB[2] = 0;
       c->n[0] = 0; c->n[1] = 0; c->n[2] = 1;
       c->dist = bv[b][k][2]; c->mu = P->plane_mu * m->box_mu[b]; c->erp = erp; c->cfm = m->box_cfm[b];
+    }
+  }
+  /* capsules vs static boxes (GJK / EPA behind an axis-aligned bounding-box cull), vs the ground plane (end spheres) */
+  for (int c = 0; c < m->n_caps; c++) {
+    for (int k = 0; k < nsb; k++) {
+      real bc[3], bh[3];
+      sbox_get(P, k, bc, bh);
+      int apart = 0;
+      for (int j = 0; j < 3; j++) {
+        real lo = cap_e[c][0][j] < cap_e[c][1][j] ? cap_e[c][0][j] : cap_e[c][1][j];
+        real hi = cap_e[c][0][j] < cap_e[c][1][j] ? cap_e[c][1][j] : cap_e[c][0][j];
+        if (lo - caps[c].r - (bc[j] + bh[j]) >= margin || (bc[j] - bh[j]) - (hi + caps[c].r) >= margin) apart = 1;
+      }
+      if (apart) continue;
+      b2n_shape box;
+      box.type = B2N_BOX; box.r = 0;
+      for (int j = 0; j < 3; j++) { box.c[j] = bc[j]; box.h[j] = bh[j]; }
+      for (int j = 0; j < 9; j++) box.R[j] = IDENT3[j];
+      real n[3];
+      b2n_contact pt;
+      if (!b2n_convex_contact(&caps[c], &box, margin, n, &pt)) continue;
+      contact_t* ct = push_contact(&L);
+      if (!ct) continue;
+      ct->key = B2E_KEY_CAP_SBOX + 8 * c + k; ct->type = CT_ARM_STATIC; ct->link = m->cap_link[c]; ct->link2 = -1;
+      for (int j = 0; j < 3; j++) { ct->pA[j] = pt.pa[j]; ct->pB[j] = pt.pb[j]; ct->n[j] = n[j]; }
+      ct->dist = pt.dist; ct->mu = (P->n_sboxes > 0 ? P->sbox_mu[k] : P->table_mu) * m->cap_mu[c]; ct->erp = P->erp; ct->cfm = 0;
+    }
+  }
+  for (int c = 0; c < m->n_caps; c++) {
+    for (int e = 0; e < 2; e++) {
+      real dist = cap_e[c][e][2] - caps[c].r;
+      if (!(dist < margin)) continue;
+      contact_t* ct = push_contact(&L);
+      if (!ct) continue;
+      ct->key = B2E_KEY_CAP_PLANE + 2 * c + e; ct->type = CT_ARM_STATIC; ct->link = m->cap_link[c]; ct->link2 = -1;
+      ct->n[0] = 0; ct->n[1] = 0; ct->n[2] = 1;
+      for (int j = 0; j < 3; j++) { ct->pA[j] = cap_e[c][e][j]; ct->pB[j] = cap_e[c][e][j]; }
+      ct->pA[2] = dist; ct->pB[2] = 0;
+      ct->dist = dist; ct->mu = P->plane_mu * m->cap_mu[c]; ct->erp = P->erp; ct->cfm = 0;
     }
   }
   /* ---- 4. robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): sphere pairs of non-neighbouring links ---- */

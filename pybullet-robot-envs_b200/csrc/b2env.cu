@@ -137,11 +137,14 @@ struct DevModel {
   int box_link[B2E_MAX_BOXES];
   float box_c[B2E_MAX_BOXES][3], box_h[B2E_MAX_BOXES][3], box_mu[B2E_MAX_BOXES], box_erp[B2E_MAX_BOXES], box_cfm[B2E_MAX_BOXES];
   int self_a[B2E_MAX_SELF_PAIRS], self_b[B2E_MAX_SELF_PAIRS];
+  int sph_flags[B2E_MAX_SPHERES];
+  int n_caps, cap_link[B2E_MAX_CAPS];
+  float cap_p0[B2E_MAX_CAPS][3], cap_p1[B2E_MAX_CAPS][3], cap_r[B2E_MAX_CAPS], cap_mu[B2E_MAX_CAPS];
 };
 
 // warp-uniform part of the model: passed by value (constant bank), no loads on the critical path
 struct DevModelU {
-  int n_links, n_dof, ee_link, n_spheres, fk_rounds, acc_rounds, n_boxes, n_self_pairs;
+  int n_links, n_dof, ee_link, n_spheres, fk_rounds, acc_rounds, n_boxes, n_self_pairs, n_caps;
   unsigned ee_dofmask;
   float base_pos[3], base_rot[9], ee_com[3];
   int parent[TLMAX];
@@ -1208,6 +1211,22 @@ __device__ __forceinline__ bool sphere_aabox(const float* c, float r, const floa
   return true;
 }
 
+// capsule shape from its scratch record: p0 (3) | radius | p1 (3) | friction  (same arithmetic as oracle collide())
+__device__ __forceinline__ void cap_shape(const float* cs, b2n_shape& cap) {
+  const float ax[3] = {cs[4] - cs[0], cs[5] - cs[1], cs[6] - cs[2]};
+  const float len = sqrtf(dot3(ax, ax));
+  cap.type = B2N_SEGMENT;
+#pragma unroll
+  for (int j = 0; j < 9; j++) cap.R[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    cap.c[j] = 0.5f * (cs[j] + cs[4 + j]);
+    cap.R[3 * j + 2] = len > 0.f ? ax[j] / len : (j == 2 ? 1.f : 0.f);
+    cap.h[j] = 0.f;
+  }
+  cap.h[2] = 0.5f * len;
+  cap.r = cs[3];
+}
 // Returns the contact count (<= B2E_MAX_CONTACTS) | overflow << 8.  Reads the link transforms of sm.T; sm.W is scratch here
 // (left finite).  Both groups of the warp run every collective together.
 __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U, const b2e_params& P,
@@ -1288,7 +1307,9 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
   float s_c[3] = {0.f, 0.f, 0.f}, s_r = 0.f, s_mu = 0.f, s_erp = P.erp, s_cfm = 0.f;
   int s_link = 0;
   float* scr = sm.W;
+  bool s_world = false;   // this lane's sphere is tested against the object and the static world
   if (lane < ns) {
+    s_world = !(__ldg(&M->sph_flags[lane]) & 1);
     s_link = __ldg(&M->sph_link[lane]);
     s_r = __ldg(&M->sph_r[lane]);
     s_mu = __ldg(&M->sph_mu[lane]);
@@ -1306,7 +1327,7 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
   // ---- 2. robot vs cube: spheres (closest point on the box) ----
   {
     bool hit = false;
-    if (lane < ns) {
+    if (s_world) {
       const float rel[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]};
       float l[3], cl[3], nloc[3];
       m3tvec(Rc, rel, l);
@@ -1398,12 +1419,63 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
     }
     base += total;
   }
+  // capsules: world end points (lanes 0..n_caps-1 own one; every lane can read them from scratch), then capsule vs cube:
+  // lane = capsule, GJK / EPA on the segment core behind a bounding-sphere cull
+  const int ncap = U.n_caps;
+  float* cscr = bscr + 16 * B2E_MAX_BOXES;   // per capsule: p0 (3) | radius | p1 (3) | friction
+  if (lane < ncap) {
+    const int li = __ldg(&M->cap_link[lane]);
+    float Rl[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
+    float* cs = cscr + 8 * lane;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float lc[3] = {e ? __ldg(&M->cap_p1[lane][0]) : __ldg(&M->cap_p0[lane][0]), e ? __ldg(&M->cap_p1[lane][1]) : __ldg(&M->cap_p0[lane][1]),
+                           e ? __ldg(&M->cap_p1[lane][2]) : __ldg(&M->cap_p0[lane][2])};
+      float oo[3];
+      m3vec(Rl, lc, oo);
+      cs[4 * e + 0] = sm.T[li][9] + oo[0]; cs[4 * e + 1] = sm.T[li][10] + oo[1]; cs[4 * e + 2] = sm.T[li][11] + oo[2];
+    }
+    cs[3] = __ldg(&M->cap_r[lane]); cs[7] = __ldg(&M->cap_mu[lane]);
+  }
+  gsync(g);
+  if (__any_sync(FULL, ncap > 0)) {
+    bool hit = false;
+    if (lane < ncap) {
+      b2n_shape cap, cube;
+      cap_shape(cscr + 8 * lane, cap);
+      const float d[3] = {cap.c[0] - cpos[0], cap.c[1] - cpos[1], cap.c[2] - cpos[2]};
+      if (!(sqrtf(dot3(d, d)) - (rb + cap.h[2] + cap.r) >= margin)) {
+        cube.type = B2N_BOX; cube.r = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { cube.c[j] = cpos[j]; cube.h[j] = ca; }
+#pragma unroll
+        for (int j = 0; j < 9; j++) cube.R[j] = Rc[j];
+        b2n_contact pt;
+        float nn[3];
+        if (b2n_convex_contact(&cap, &cube, margin, nn, &pt)) {
+          hit = true;
+#pragma unroll
+          for (int j = 0; j < 3; j++) { o.pA[j] = pt.pa[j]; o.pB[j] = pt.pb[j]; o.n[j] = nn[j]; }
+          o.dist = pt.dist;
+        }
+      }
+    }
+    const unsigned b = gballot(g, hit);
+    if (hit) {
+      o.key = B2E_KEY_CAP_CUBE + lane; o.type = CT_ARM_CUBE; o.link = __ldg(&M->cap_link[lane]); o.link2 = -1;
+      o.mu = P.cube_mu * cscr[8 * lane + 7]; o.erp = P.erp; o.cfm = 0.f;
+      emit_contact(sm, base + __popc(b & lt), maxc, o);
+    }
+    base += __popc(b);
+  }
   // ---- 3. robot vs static world: spheres vs static boxes (lane = sphere, at most three boxes each), vs the ground plane ----
   {
     int cnt = 0, kk[3] = {0, 0, 0};
     float nn[3][3], pb[3][3], dd[3] = {0.f, 0.f, 0.f};
     bool tp[3] = {false, false, false};
-    if (lane < ns) {
+    if (s_world) {
       for (int k = 0; k < nsb && cnt < 3; k++) {
         float bc[3], bh[3], n[3], pB[3], dist;
         bool is_top;
@@ -1439,7 +1511,7 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
   }
   {
     const float dist = s_c[2] - s_r;
-    const bool hit = lane < ns && dist < margin;
+    const bool hit = s_world && dist < margin;
     const unsigned b = gballot(g, hit);
     if (hit) {
       o.key = B2E_KEY_SPHERE_PLANE + lane; o.type = CT_ARM_STATIC; o.link = s_link; o.link2 = -1;
@@ -1520,6 +1592,66 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
       base += __popc(b);
     }
   }
+  if (__any_sync(FULL, ncap > 0)) {
+    // capsules vs static boxes: lane = 8 * capsule + static box (two capsules per pass of 16 lanes), GJK / EPA behind an
+    // axis-aligned bounding-box cull; then vs the ground plane: lane = 2 * capsule + end (closed form)
+    for (int c0 = 0; c0 < ncap; c0 += 2) {   // warp-uniform trip count: both groups share the model
+      const int c = c0 + (lane >> 3), k = lane & 7;
+      bool hit = false;
+      if (c < ncap && k < nsb) {
+        const float* cs = cscr + 8 * c;
+        float bc[3], bh[3];
+        sbox_get(P, k, bc, bh);
+        bool apart = false;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float lo = fminf(cs[j], cs[4 + j]), hi = fmaxf(cs[j], cs[4 + j]);
+          if (lo - cs[3] - (bc[j] + bh[j]) >= margin || (bc[j] - bh[j]) - (hi + cs[3]) >= margin) apart = true;
+        }
+        if (!apart) {
+          b2n_shape cap, box;
+          cap_shape(cs, cap);
+          box.type = B2N_BOX; box.r = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; j++) { box.c[j] = bc[j]; box.h[j] = bh[j]; }
+#pragma unroll
+          for (int j = 0; j < 9; j++) box.R[j] = ident[j];
+          b2n_contact pt;
+          float nn[3];
+          if (b2n_convex_contact(&cap, &box, margin, nn, &pt)) {
+            hit = true;
+#pragma unroll
+            for (int j = 0; j < 3; j++) { o.pA[j] = pt.pa[j]; o.pB[j] = pt.pb[j]; o.n[j] = nn[j]; }
+            o.dist = pt.dist;
+          }
+        }
+      }
+      const unsigned b = gballot(g, hit);
+      if (hit) {
+        o.key = B2E_KEY_CAP_SBOX + 8 * c + k; o.type = CT_ARM_STATIC; o.link = __ldg(&M->cap_link[c]); o.link2 = -1;
+        o.mu = (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu) * cscr[8 * c + 7]; o.erp = P.erp; o.cfm = 0.f;
+        emit_contact(sm, base + __popc(b & lt), maxc, o);
+      }
+      base += __popc(b);
+    }
+    {
+      const int c = lane >> 1, e = lane & 1;
+      const bool has = c < ncap;
+      const float* cs = cscr + 8 * (has ? c : 0);
+      const float dist = cs[4 * e + 2] - cs[3];
+      const bool hit = has && dist < margin;
+      const unsigned b = gballot(g, hit);
+      if (hit) {
+        o.key = B2E_KEY_CAP_PLANE + lane; o.type = CT_ARM_STATIC; o.link = __ldg(&M->cap_link[c]); o.link2 = -1;
+        o.n[0] = 0.f; o.n[1] = 0.f; o.n[2] = 1.f;
+        o.pA[0] = cs[4 * e]; o.pA[1] = cs[4 * e + 1]; o.pA[2] = dist;
+        o.pB[0] = cs[4 * e]; o.pB[1] = cs[4 * e + 1]; o.pB[2] = 0.f;
+        o.dist = dist; o.mu = P.plane_mu * cs[7]; o.erp = P.erp; o.cfm = 0.f;
+        emit_contact(sm, base + __popc(b & lt), maxc, o);
+      }
+      base += __popc(b);
+    }
+  }
   // ---- 4. robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): sphere pairs of non-neighbouring links ----
   {
     const int nsp = U.n_self_pairs;
@@ -1551,7 +1683,7 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
   }
   gsync(g);
   // leave the scratch finite for the solver tables (they are zeroed at kernel start and must stay finite)
-  for (int k = lane; k < 64 + 16 * B2E_MAX_BOXES; k += GL) scr[k] = 0.f;
+  for (int k = lane; k < 64 + 16 * B2E_MAX_BOXES + 8 * B2E_MAX_CAPS; k += GL) scr[k] = 0.f;
   gsync(g);
   return (base > maxc ? maxc : base) | (base > maxc ? 256 : 0);
 }
@@ -2447,6 +2579,15 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
     if (m->self_a[k] < 0 || m->self_a[k] >= m->n_spheres || m->self_b[k] < 0 || m->self_b[k] >= m->n_spheres)
       return fail(B2E_EINVAL, "self-collision pair names a sphere that does not exist%s", "");
     d->self_a[k] = m->self_a[k]; d->self_b[k] = m->self_b[k];
+  }
+  for (int s = 0; s < m->n_spheres; s++) d->sph_flags[s] = tree ? 0 : m->sph_flags[s];
+  if (m->n_caps < 0 || m->n_caps > B2E_MAX_CAPS) return fail(B2E_EINVAL, "bad n_caps%s", "");
+  d->n_caps = u->n_caps = tree ? 0 : m->n_caps;
+  for (int c = 0; c < m->n_caps; c++) {
+    if (m->cap_link[c] < 0 || m->cap_link[c] >= m->n_links) return fail(B2E_EINVAL, "capsule on a link that does not exist%s", "");
+    d->cap_link[c] = m->cap_link[c];
+    for (int k = 0; k < 3; k++) { d->cap_p0[c][k] = m->cap_p0[c][k]; d->cap_p1[c][k] = m->cap_p1[c][k]; }
+    d->cap_r[c] = m->cap_r[c]; d->cap_mu[c] = m->cap_mu[c];
   }
   return 0;
 }

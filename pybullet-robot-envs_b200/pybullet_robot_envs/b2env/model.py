@@ -28,6 +28,7 @@ CACHE_SLOTS = 16
 MAX_BOXES = 4
 MAX_SELF_PAIRS = 32
 MAX_SBOXES = 6
+MAX_CAPS = 4
 
 JOINT_REVOLUTE = 0
 JOINT_PRISMATIC = 1
@@ -61,6 +62,9 @@ class B2EModel(C.Structure):
         ("n_boxes", _i), ("box_link", _i * MAX_BOXES), ("box_c", (_f * 3) * MAX_BOXES), ("box_h", (_f * 3) * MAX_BOXES),
         ("box_mu", _f * MAX_BOXES), ("box_erp", _f * MAX_BOXES), ("box_cfm", _f * MAX_BOXES),
         ("n_self_pairs", _i), ("self_a", _i * MAX_SELF_PAIRS), ("self_b", _i * MAX_SELF_PAIRS),
+        ("sph_flags", _i * MAX_SPHERES),
+        ("n_caps", _i), ("cap_link", _i * MAX_CAPS), ("cap_p0", (_f * 3) * MAX_CAPS), ("cap_p1", (_f * 3) * MAX_CAPS),
+        ("cap_r", _f * MAX_CAPS), ("cap_mu", _f * MAX_CAPS),
     ]
 
 
@@ -176,7 +180,7 @@ def parse_urdf(path):
                 links=[links[j["child"]] for j in order])
 
 
-def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres, boxes=(), self_pairs=()):
+def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres, boxes=(), self_pairs=(), capsules=()):
     """Flatten the parsed URDF dict into a ``B2EModel``."""
     m = B2EModel()
     n = len(d["joints"])
@@ -233,6 +237,34 @@ def descriptor_from_urdf_dict(d, base_position, home, ee_link, spheres, boxes=()
         m.sph_mu[s] = ct.get("lateral_friction", 0.5)  # Bullet default link friction 0.5 [EXT-recalled]
         m.sph_erp[s] = -1.0
         m.sph_cfm[s] = 0.0
+        m.sph_flags[s] = 1 if sp.get("self_only") else 0
+    assert len(boxes) <= MAX_BOXES
+    m.n_boxes = len(boxes)
+    for b, bx in enumerate(boxes):
+        li = names.index(bx["link"])
+        m.box_link[b] = li
+        for k in range(3):
+            m.box_c[b][k] = bx["c"][k]
+            m.box_h[b][k] = bx["h"][k]
+        m.box_mu[b] = d["links"][li]["contact"].get("lateral_friction", 0.5)
+        m.box_erp[b] = -1.0
+        m.box_cfm[b] = 0.0
+    assert len(self_pairs) <= MAX_SELF_PAIRS
+    m.n_self_pairs = len(self_pairs)
+    for k, (a, b) in enumerate(self_pairs):
+        assert 0 <= a < len(spheres) and 0 <= b < len(spheres)
+        m.self_a[k] = a
+        m.self_b[k] = b
+    assert len(capsules) <= MAX_CAPS
+    m.n_caps = len(capsules)
+    for c, cp in enumerate(capsules):
+        li = names.index(cp["link"])
+        m.cap_link[c] = li
+        for k in range(3):
+            m.cap_p0[c][k] = cp["p0"][k]
+            m.cap_p1[c][k] = cp["p1"][k]
+        m.cap_r[c] = cp["r"]
+        m.cap_mu[c] = d["links"][li]["contact"].get("lateral_friction", 0.5)
     return m
 
 
@@ -249,14 +281,14 @@ PANDA_JSON = os.path.join(_HERE, "..", "robot_data", "franka_panda", "panda_mode
 def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
     """Build the Panda ``B2EModel``.  ``urdf_path`` (e.g. the reference's own
     ``robot_data/franka_panda/panda_model.urdf``) overrides the committed JSON."""
-    from .proxies import PANDA_BOXES, PANDA_SELF_PAIRS, PANDA_SPHERES
+    from .proxies import PANDA_BOXES, PANDA_CAPSULES, PANDA_SELF_PAIRS, PANDA_SPHERES
     if urdf_path is not None:
         d = parse_urdf(urdf_path)
     else:
         with open(PANDA_JSON) as f:
             d = json.load(f)
     m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES, boxes=PANDA_BOXES,
-                                  self_pairs=PANDA_SELF_PAIRS)
+                                  self_pairs=PANDA_SELF_PAIRS, capsules=PANDA_CAPSULES)
     # soft finger contacts: <stiffness>/<damping> (URDF:256-263) -> per-contact erp/cfm the way
     # Bullet derives them: denom = dt*k + d, erp = dt*k/denom, cfm = 1/(denom*dt) [EXT-recalled]
     names = [l["name"] for l in d["links"]]

@@ -235,3 +235,37 @@ def test_icub_gym_surface(emu_lib, monkeypatch):
     with pytest.raises(AssertionError):
         env.step(np.zeros(4, np.float32))
     env.close()
+
+
+def test_panda_contact_families_parity(emu_lib, oracle_lib):
+    """Every contact family of the collision stage (cube at the rim / against a leg / on the ground plane, finger-pad boxes vs
+    cube / table / static boxes, spheres vs cube / table / rim, robot self-collision, forearm capsule vs cube / static boxes
+    through GJK / EPA): emulated kernel vs oracle from identical states, contact keys and counts exact."""
+    from common import FAMILIES, family_states
+    m, p = panda_task_setup(TASK_PUSH)
+    qs, poses, fam = family_states(oracle_lib, m, p, list(FAMILIES), per_family=2, seed=3)
+    B = len(fam)
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    sim = B2Sim(m, p, B, 0, lib=emu_lib)
+    try:
+        orc = oracle_lib.Oracle(m, p, B, nthreads=4)
+        orc.reset(poses, targets_for(poses))
+        orc.state["q"][:] = qs
+        orc.state["mtarget"][:] = qs
+        seen = set()
+        for i in range(3):
+            copy_state_to_gpu(orc, sim)
+            orc.step(None, 1, 1, want_obs=False)
+            sim.step_host(None, 1, 1, want_obs=False)
+            g_st, o_st = sim.get("status"), orc.state["status"]
+            np.testing.assert_array_equal(g_st[:, 2:], o_st[:, 2:], err_msg="n_contacts / n_rows, step %d" % i)
+            np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="contact keys, step %d" % i)
+            for k in orc.state["cache_key"].ravel():
+                seen |= {f for f, (a, b) in FAMILIES.items() if a <= k < b}
+            conv = o_st[:, 1] < 150
+            assert np.abs(sim.get("q") - orc.state["q"])[conv].max() < 2e-4
+            assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"])[conv].max() < 2e-4
+            assert np.isfinite(sim.get("q")).all() and np.isfinite(sim.get("obj_pose")).all()
+        assert seen == set(FAMILIES), set(FAMILIES) - seen
+    finally:
+        sim.close()

@@ -224,3 +224,45 @@ def test_contact_rich_single_step_parity(oracle_lib):
     assert seen_coupled > 50 and seen_limit > 0, (seen_coupled, seen_limit)
     print("contact-rich: max rows %d, coupled env-steps %d, limit-row env-steps %d; sweep-capped env-steps %d of which %d within 2e-3; "
           "worst motor-residual disagreement %.3f of its bound" % (seen_rows, seen_coupled, seen_limit, n_lim, n_lim_close, res_worst))
+
+
+def test_contact_families_parity(oracle_lib):
+    """N1: every contact family of the collision stage on hardware — cube at the table rim / against a leg / on the ground
+    plane (box-box SAT + clipping), finger-pad boxes vs cube / table / static boxes, spheres vs cube / table / rim, robot
+    self-collision, forearm capsule vs cube / static boxes (GJK / EPA) — GPU vs oracle from identical states: contact keys,
+    contact and row counts exact; converged environments within the single-step tolerances."""
+    from common import FAMILIES, family_states
+    from pybullet_robot_envs.b2env.binding import B2Sim, OPT_RECORD_CONTACTS
+    m, p = panda_task_setup(TASK_PUSH)
+    qs, poses, fam = family_states(oracle_lib, m, p, list(FAMILIES), per_family=24, seed=11)
+    B = len(fam)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=8)
+    sim = B2Sim(m, p, B, 0)
+    sim.set_option(OPT_RECORD_CONTACTS, 1)
+    orc.reset(poses, targets_for(poses))
+    orc.state["q"][:] = qs
+    orc.state["mtarget"][:] = qs
+    seen = {f: 0 for f in FAMILIES}
+    rng = np.random.RandomState(2)
+    worst = 0.0
+    for i in range(12):
+        copy_state_to_gpu(orc, sim)
+        a = rng.uniform(-1, 1, (B, 7)).astype(np.float32) * (0.2 if i < 6 else 1.0)
+        orc.step(a, 1, 0)
+        sim.step_host(a, 1, 0)
+        g_st, o_st = sim.get("status"), orc.state["status"]
+        np.testing.assert_array_equal(g_st[:, 2:], o_st[:, 2:], err_msg="n_contacts / n_rows, step %d" % i)
+        np.testing.assert_array_equal(g_st[:, 0] & 6, o_st[:, 0] & 6, err_msg="overflow flags, step %d" % i)
+        np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="contact keys, step %d" % i)
+        keys = orc.state["cache_key"]
+        for f, (lo, hi) in FAMILIES.items():
+            seen[f] += int(((keys >= lo) & (keys < hi)).any(axis=1).sum())
+        conv = o_st[:, 1] < 150
+        dq = np.abs(sim.get("q") - orc.state["q"]).max(axis=1)
+        dc = np.abs(sim.get("obj_pose") - orc.state["obj_pose"]).max(axis=1)
+        assert np.isfinite(sim.get("q")).all() and np.isfinite(sim.get("obj_pose")).all()
+        assert dq[conv].max() < 2e-4 and dc[conv].max() < 2e-4, (i, dq[conv].max(), dc[conv].max())
+        assert dq.max() < 5e-2 and dc.max() < 5e-2, (i, dq.max(), dc.max())
+        worst = max(worst, float(dq[conv].max()), float(dc[conv].max()))
+    assert all(v >= 12 for v in seen.values()), seen
+    print("contact families (env-steps with the family present):", seen, "worst converged |dq|, |dpose| %.1e" % worst)
