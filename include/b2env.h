@@ -188,6 +188,11 @@ typedef struct b2e_params {
   float sbox_c[B2E_MAX_SBOXES][3];   /* centre (world, axis aligned)             */
   float sbox_h[B2E_MAX_SBOXES][3];   /* half extents                             */
   float sbox_mu[B2E_MAX_SBOXES];
+  /* ---- Cartesian control with a velocity cap: robot.apply_action(action, max_vel) with max_vel != -1 (panda_env.py:285-291,
+   *      icub_env.py:331-337) drives the n_ctrl controlled joints through setJointMotorControl2(maxVelocity = max_vel) with
+   *      PyBullet's DEFAULT position gain instead of setJointMotorControlArray(positionGains = 0.2).  <= 0: off          */
+  float ik_max_vel;
+  float kp_ik_max_vel;     /* PyBullet default positionGain 0.1 [EXT-recalled]                                       */
 } b2e_params;
 
 #define B2E_REWARD_PANDA 0       /* panda_push_gym_env.py:318-331 / panda_reach_gym_env.py:303-313 (bonus replaces) */

@@ -223,7 +223,10 @@ B2N_FN int b2n_box_box(const B2N_REAL* cA, const B2N_REAL* RA, const B2N_REAL* h
   if (m <= B2N_MAX_POINTS) {
     for (i = 0; i < m; i++) keep[nk++] = i;
   } else {
-    const real tol = (real)1e-5;
+    /* ties (symmetric configurations: a square face seen from one of its corners) are decided by the lowest label; "equal"
+     * means within 1e-5 m for depths and within 1e-4 relative for squared distances / areas, far above rounding, so that
+     * both builds of this header (CPU oracle, CUDA with contracted FMAs) take the same decisions                       */
+    const real tol = (real)1e-5, rtol = (real)1e-4, atol = (real)1e-12;
     int b0 = 0;
     for (i = 1; i < m; i++)
       if (ph[i] < ph[b0] - tol || (B2N_FABS(ph[i] - ph[b0]) <= tol && lab[i] < lab[b0])) b0 = i;
@@ -231,15 +234,21 @@ B2N_FN int b2n_box_box(const B2N_REAL* cA, const B2N_REAL* RA, const B2N_REAL* h
     for (i = 0; i < m; i++) {
       if (i == b0) continue;
       real d2 = (px[i] - px[b0]) * (px[i] - px[b0]) + (py[i] - py[b0]) * (py[i] - py[b0]);
-      if (b1 < 0 || d2 > v1 + tol * tol || (B2N_FABS(d2 - v1) <= tol * tol && lab[i] < lab[b1])) { b1 = i; v1 = d2; }
+      const real eq = rtol * (d2 > v1 ? d2 : v1) + atol;
+      if (b1 < 0 || d2 > v1 + eq || (B2N_FABS(d2 - v1) <= eq && lab[i] < lab[b1])) { b1 = i; v1 = d2; }
     }
     const real ex = px[b1] - px[b0], ey = py[b1] - py[b0];
     int b2 = -1, b3 = -1; real v2 = tol * B2N_SQRT(v1 > 0 ? v1 : 0), v3 = v2;
     for (i = 0; i < m; i++) {
       if (i == b0 || i == b1) continue;
       real cr = ex * (py[i] - py[b0]) - ey * (px[i] - px[b0]);
-      if (cr > 0) { if (b2 < 0 ? cr > v2 : (cr > v2 + tol * tol || (B2N_FABS(cr - v2) <= tol * tol && lab[i] < lab[b2]))) { b2 = i; v2 = cr; } }
-      else { if (b3 < 0 ? -cr > v3 : (-cr > v3 + tol * tol || (B2N_FABS(-cr - v3) <= tol * tol && lab[i] < lab[b3]))) { b3 = i; v3 = -cr; } }
+      if (cr > 0) {
+        const real eq = rtol * (cr > v2 ? cr : v2) + atol;
+        if (b2 < 0 ? cr > v2 : (cr > v2 + eq || (B2N_FABS(cr - v2) <= eq && lab[i] < lab[b2]))) { b2 = i; v2 = cr; }
+      } else {
+        const real eq = rtol * (-cr > v3 ? -cr : v3) + atol;
+        if (b3 < 0 ? -cr > v3 : (-cr > v3 + eq || (B2N_FABS(-cr - v3) <= eq && lab[i] < lab[b3]))) { b3 = i; v3 = -cr; }
+      }
     }
     keep[nk++] = b0; keep[nk++] = b1;
     if (b2 >= 0) keep[nk++] = b2;

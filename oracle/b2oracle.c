@@ -1083,7 +1083,7 @@ typedef struct {
   real contact_out[MAXC][8];
 } env_t;
 
-static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int kp_ctrl_active, int grip_active) {
+static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int kp_ctrl_active, int grip_active, int ik_active) {
   int nd = m->n_dof, nv = nd + 6;
   real dt = P->dt;
   fk_t fk;
@@ -1118,10 +1118,12 @@ static void physics_step(const b2e_model* m, const b2e_params* P, env_t* e, int 
     r->type = ROW_MOTOR; r->island = ISL_ARM;
     r->J[d] = 1;
     real kp = (kp_ctrl_active && is_ctrl_dof(P, d)) ? P->kp_ctrl : ((grip_active && d >= P->n_ctrl) ? P->kp_grip : P->kp_hold);
+    real mv = m->max_vel[d];
+    if (ik_active && P->ik_max_vel > 0 && (is_ctrl_dof(P, d) || P->n_obs_joints > 0)) { kp = P->kp_ik_max_vel; mv = P->ik_max_vel; } /* panda_env.py:285-291 */
     real desired = kp * (e->mtarget[d] - e->q[d]) / dt;
-    if (m->max_vel[d] > 0) {
-      if (desired > m->max_vel[d]) desired = m->max_vel[d];
-      if (desired < -m->max_vel[d]) desired = -m->max_vel[d];
+    if (mv > 0) {
+      if (desired > mv) desired = mv;
+      if (desired < -mv) desired = -mv;
     }
     r->cfm = 0;
     r->hi = m->max_force[d] * dt;
@@ -1394,7 +1396,8 @@ static void step_env(const b2e_model* m, const b2e_params* P, b2o_state* S, int 
       for (int d = 0; d < m->n_dof; d++) /* blocked joints keep the rest pose (icub_env.py:314-317) */
         e.mtarget[d] = (P->n_obs_joints > 0 && !is_ctrl_dof(P, d)) ? (real)m->home[d] : qik[d];
     }
-    physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik, mode != B2E_MODE_HOLD && P->task == B2E_TASK_GRASP);
+    physics_step(m, P, &e, mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE && !P->use_ik, mode != B2E_MODE_HOLD && P->task == B2E_TASK_GRASP,
+                 mode == B2E_MODE_IK_POSE || (mode == B2E_MODE_ACTION && P->use_ik));
     if (mode == B2E_MODE_ACTION) {
       /* _termination() inside apply_action (:239-242): counter only advances when not terminated */
       fk_t fk;

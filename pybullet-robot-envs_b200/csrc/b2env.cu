@@ -866,7 +866,7 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
 template <int NSG, bool GB>   // GB: some group of the warp keeps its big system in GLOBAL scratch (no slot was free)
 __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restrict__ M, const DevModelU& U,
                                             const b2e_params& P, unsigned hm, int sh, int lane, int nd, int nlim, int nc,
-                                            float my_q, float my_target, float my_kp, float cpx, float cpy, float cpz,
+                                            float my_q, float my_target, float my_kp, float my_mv, float cpx, float cpy, float cpz,
                                             int big_off, float* gscratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp g = {hm, sh, lane};
@@ -895,7 +895,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     const bool isd = lane < nd;
     const int d = isd ? lane : 0;
     float desired = my_kp * (my_target - my_q) * inv_dt;
-    const float mv = __ldg(&M->max_vel[d]);
+    const float mv = my_mv;
     if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
     const float diag = isd ? sm.Minv[d][d] : 1.f;
     m.diag = diag;
@@ -1721,7 +1721,11 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       // a warp whose first group has no environment leaves (block barriers count the warps that are left); a second group
       // without one shadows the first (stores masked)
       const int slot_a = warp * (int)gridDim.x + (int)blockIdx.x;
-      if (slot_a >= n_slots) return;
+      if (slot_a >= n_slots) {   // (after zeroing this thread's share of the block's overflow slots, see below)
+        float4* s4 = reinterpret_cast<float4*>(smem_raw + sizeof(EnvSmem) * 2 * wpb);
+        for (int k = threadIdx.x; k < (int)(sizeof(BigSlot) / 16) * nslot; k += blockDim.x) s4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
       env = sched[SCHED_TAIL(pp, B) + (slot < n_slots ? slot : slot_a)];
     } else {
       int cnt[NBK_MAIN];
@@ -1778,8 +1782,13 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   float my_hp = (IK && lane < 6) ? st.hand_pose[env * 6 + lane] : 0.f;   // commanded hand pose (lane = component)
   const float my_lower = is_dof ? __ldg(&M->lower[lane]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[lane]) : 0.f;
   const bool ctrl_gains = !IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE;
-  const float my_kp = (ctrl_gains && lane < P.n_ctrl) ? P.kp_ctrl
-                      : ((ctrl_gains && P.task == B2E_TASK_GRASP && lane >= P.n_ctrl) ? P.kp_grip : P.kp_hold);
+  // Cartesian control with a velocity cap (robot.apply_action(action, max_vel), panda_env.py:285-291): the controlled joints
+  // run with PyBullet's default position gain and maxVelocity = max_vel
+  const bool ik_cap = IK && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE) && P.ik_max_vel > 0.f && lane < P.n_ctrl;
+  const float my_kp = ik_cap ? P.kp_ik_max_vel
+                      : ((ctrl_gains && lane < P.n_ctrl) ? P.kp_ctrl
+                         : ((ctrl_gains && P.task == B2E_TASK_GRASP && lane >= P.n_ctrl) ? P.kp_grip : P.kp_hold));
+  const float my_mv = ik_cap ? P.ik_max_vel : (is_dof ? __ldg(&M->max_vel[lane]) : -1.f);
   const float grip_cmd = SHF(my_act, P.n_ctrl & (GL - 1));   // GRASP: action[n_ctrl] = gripper command
   int iters = 0, nc = 0, R = 0;
 #ifdef PROFILE_CYCLES
@@ -2116,7 +2125,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const long long t_solve0 = clock64();
 #endif
     const int big_off = got < 0 ? -1 : slots_off + (int)sizeof(BigSlot) * got;
-#define B2E_SOLVE(N, G) build_and_solve<N, G>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, cpos[0], cpos[1], cpos[2], big_off, gscratch)
+#define B2E_SOLVE(N, G) build_and_solve<N, G>(sm, M, U, P, g.hm, g.sh, lane, nd, nlim, nc, my_q, my_target, my_kp, my_mv, cpos[0], cpos[1], cpos[2], big_off, gscratch)
     if (RGw <= GL) iters = B2E_SOLVE(1, false);
     else if (!need_global) iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, false) : B2E_SOLVE(3, false);
     else iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, true) : B2E_SOLVE(3, true);

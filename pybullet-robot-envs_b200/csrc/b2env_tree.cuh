@@ -554,7 +554,9 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
   const float my_lower = is_dof ? __ldg(&M->lower[li]) : 0.f, my_upper = is_dof ? __ldg(&M->upper[li]) : 0.f;
   const float my_home = is_dof ? __ldg(&M->home[li]) : 0.f;
   const bool ctrl_gains = !IK && mode != B2E_MODE_HOLD && mode != B2E_MODE_IK_POSE;
-  const float my_kp = (ctrl_gains && is_ctrl) ? P.kp_ctrl : P.kp_hold;
+  // Cartesian control with a velocity cap (icub_env.py:331-337): every joint keeps its gain, maxVelocity = max_vel
+  const bool ik_cap = IK && (mode == B2E_MODE_ACTION || mode == B2E_MODE_IK_POSE) && P.ik_max_vel > 0.f && is_dof;
+  const float my_kp = ik_cap ? P.kp_ik_max_vel : ((ctrl_gains && is_ctrl) ? P.kp_ctrl : P.kp_hold);
   int iters = 0, nc = 0, R = 0;
   bool stop = false;
   __syncwarp();
@@ -950,7 +952,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     MotorRegs m;
     {
       float desired = my_kp * (my_target - my_q) * inv_dt;
-      const float mv = __ldg(&M->max_vel[li]);
+      const float mv = ik_cap ? P.ik_max_vel : __ldg(&M->max_vel[li]);
       if (mv > 0) desired = fminf(fmaxf(desired, -mv), mv);
       const float diag = is_dof ? sm.Mi[MI(lane, lane)] : 1.f;
       m.diag = diag;

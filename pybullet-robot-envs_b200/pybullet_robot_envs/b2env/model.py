@@ -87,6 +87,7 @@ class B2EParams(C.Structure):
         ("n_obs_joints", _i), ("obs_dof", _i * 16), ("ctrl_dof", _i * 16), ("ctrl_mask", C.c_uint32),
         ("ik_link_offset", _f * 3), ("reward_kind", _i), ("max_contacts", _i),
         ("n_sboxes", _i), ("sbox_c", (_f * 3) * MAX_SBOXES), ("sbox_h", (_f * 3) * MAX_SBOXES), ("sbox_mu", _f * MAX_SBOXES),
+        ("ik_max_vel", _f), ("kp_ik_max_vel", _f),
     ]
 
 
@@ -339,6 +340,8 @@ def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orie
             p.sbox_c[k][j] = c[j]
             p.sbox_h[k][j] = h[j]
         p.sbox_mu[k] = 1.0
+    p.ik_max_vel = -1.0
+    p.kp_ik_max_vel = 0.1
     p.cube_half = 0.025
     p.cube_mass = 0.1
     p.cube_inertia = 0.1 * (0.05 ** 2) / 6.0

@@ -10,6 +10,7 @@ from pybullet_robot_envs.b2env import binding
 from pybullet_robot_envs.b2env.client import B2Client, squeeze1
 from pybullet_robot_envs.b2env.model import (ICUB_CTRL_GROUPS, ICUB_EU_LIM, ICUB_HAND_OFFSET, ICUB_HOME,
                                              ICUB_HOME_HAND_POSE, icub_ctrl_dofs, load_icub_arm)
+from pybullet_robot_envs.envs.utils import euler_from_quaternion
 from pybullet_robot_envs.gym_compat import seeding
 
 
@@ -139,8 +140,6 @@ class iCubEnv:
                                      '\n- 6: (dx,dy,dz,droll,dpitch,dyaw)'
                                      '\n- 7: (dx,dy,dz,qx,qy,qz,w)'
                                      '\ninstead it is: ', action.shape[1])
-            if action.shape[1] == 7:
-                raise NotImplementedError("quaternion hand-pose commands (control_eu_or_quat=1) are not built")
             # the pose is stored; workspace / rotation clamps, COM -> link frame, IK, blocked joints and the 32
             # position targets (reference :274-326) happen inside the next physics launch (MODE_IK_POSE)
             hp = self._client.get("hand_pose")
@@ -150,9 +149,20 @@ class iCubEnv:
             if action.shape[1] == 6 and self._control_orientation:
                 for k in range(3):
                     hp[:, 3 + k] = np.clip(action[:, 3 + k], self._eu_lim[k][0], self._eu_lim[k][1])
+            elif action.shape[1] == 7 and self._control_orientation:
+                # quaternion command: kept as Euler angles on the device, converted back there (same rotation up to rounding)
+                hp[:, 3:6] = euler_from_quaternion(action[:, 3:7])
             else:
                 hp[:, 3:6] = np.asarray(self._home_hand_pose[3:6], np.float32)
             self._client.set("hand_pose", hp)
+            # max_vel != -1 (reference :331-337): every joint keeps the gain 0.2, maxVelocity = max_vel, until the next call
+            prm = self._client.params
+            want = float(max_vel) if max_vel != -1 else -1.0
+            if prm is not None and prm.ik_max_vel != want:
+                prm.ik_max_vel = want
+                prm.kp_ik_max_vel = prm.kp_hold
+                if self._client.sim is not None:
+                    self._client.sim.set_params(prm)
             self._client.pending_mode = binding.MODE_IK_POSE
             return
         if action.shape[1] != len(self._joints_to_control):

@@ -9,6 +9,8 @@ import numpy as np
 from pybullet_robot_envs.b2env import binding
 from pybullet_robot_envs.b2env.client import B2Client, squeeze1
 from pybullet_robot_envs.b2env.model import PANDA_HOME, load_panda
+from pybullet_robot_envs.b2env.proxies import KEY_BOX_CUBE, KEY_CAP_CUBE, KEY_SPHERE_CUBE
+from pybullet_robot_envs.envs.utils import euler_from_quaternion, quaternion_from_euler
 from pybullet_robot_envs.gym_compat import seeding
 
 
@@ -90,7 +92,7 @@ class pandaEnv:
         return 3
 
     def get_observation_dim(self):
-        return 18
+        return 18 + (1 if self._control_eu_or_quat == 1 else 0) - (0 if self._include_vel_obs else 3)
 
     def get_workspace(self):
         return [i[:] for i in self._workspace_lim]
@@ -116,8 +118,13 @@ class pandaEnv:
     def get_observation(self):
         """EE pose (link 11 COM), standardised EE linear velocity, joint positions
         (reference :141-193) -> (obs [B,18], limits)."""
-        raw = self._client.observe()[3]
-        return squeeze1(raw[:, :18].astype(np.float64), self._client.num_envs), self.observation_limits()
+        raw = self._client.observe()[3][:, :18].astype(np.float64)
+        if self._control_eu_or_quat == 1:   # hand orientation as a quaternion (reference :165-167): 19 entries
+            raw = np.concatenate([raw[:, :3], quaternion_from_euler(raw[:, 3:6]), raw[:, 6:]], axis=1)
+        if not self._include_vel_obs:
+            k = 7 if self._control_eu_or_quat == 1 else 6
+            raw = np.concatenate([raw[:, :k], raw[:, k + 3:]], axis=1)
+        return squeeze1(raw, self._client.num_envs), self.observation_limits()
 
     # ------------------------------------------------------------------ control
     def pre_grasp(self):
@@ -147,16 +154,24 @@ class pandaEnv:
                                      '\n- 6: (dx,dy,dz,droll,dpitch,dyaw)'
                                      '\n- 7: (dx,dy,dz,qx,qy,qz,w)'
                                      '\ninstead it is: ', action.shape[1])
-            if action.shape[1] == 7:
-                raise NotImplementedError("quaternion hand-pose commands (control_eu_or_quat=1) are not built")
             # Cartesian command: the pose is stored; IK + motor targets happen inside the next physics
             # launch (B2Client.step_simulation picks MODE_IK_POSE), like calculateInverseKinematics +
             # setJointMotorControlArray(kp 0.2) at reference :269-282
             hp = self._client.get("hand_pose")
-            hp[:, :action.shape[1]] = action
-            if action.shape[1] == 3:
+            hp[:, :3] = action[:, :3]
+            if not self._control_orientation or action.shape[1] == 3:
+                # orientation not under control: the home orientation (reference :247-248).  [A 3-wide command with
+                # control_orientation=1 keeps the CURRENT orientation in the reference (:264-266); here it keeps the
+                # commanded one, which the task envs never let drift]
                 hp[:, 3:6] = np.asarray(self._home_hand_pose[3:6], np.float32)
+            elif action.shape[1] == 6:
+                hp[:, 3:6] = np.clip(action[:, 3:6], -m.pi, m.pi)                      # reference :251-257
+            else:
+                # quaternion command (reference :260-261): the device keeps the commanded pose as Euler angles and converts
+                # back with getQuaternionFromEuler, the same rotation up to rounding
+                hp[:, 3:6] = euler_from_quaternion(action[:, 3:7])
             self._client.set("hand_pose", hp)
+            self._set_ik_max_vel(max_vel)
             self._client.pending_mode = binding.MODE_IK_POSE
             return
         assert action.shape[1] == self.joint_action_space, \
@@ -167,18 +182,30 @@ class pandaEnv:
         self._client.set("mtarget", mt)
         self._client.pending_mode = binding.MODE_TARGETS
 
+    def _set_ik_max_vel(self, max_vel):
+        """``max_vel != -1`` (reference :285-291): the 7 arm joints run through setJointMotorControl2(maxVelocity=max_vel)
+        with PyBullet's default position gain; it stays in force until the next apply_action, like a motor setting."""
+        prm = self._client.params
+        want = float(max_vel) if max_vel != -1 else -1.0
+        if prm is not None and abs(prm.ik_max_vel - want) > 0:
+            prm.ik_max_vel = want
+            prm.kp_ik_max_vel = 0.1
+            if self._client.sim is not None:
+                self._client.sim.set_params(prm)
+
     def check_collision(self, obj_id=None):
-        """True where the robot touches the object somewhere else than with the finger pads."""
+        """True where the robot touches the object somewhere else than with the finger pads (sphere and capsule proxies
+        of link4 .. hand; the pads are the box proxies)."""
         keys = self._client.get("cache_key")
-        body = (keys >= 16) & (keys < 16 + 8)       # sphere-cube contacts of link4..hand proxies
+        body = ((keys >= KEY_SPHERE_CUBE) & (keys < KEY_SPHERE_CUBE + 16)) | ((keys >= KEY_CAP_CUBE) & (keys < KEY_CAP_CUBE + 4))
         return squeeze1(body.any(axis=1), self._client.num_envs)
 
     def check_contact_fingertips(self, obj_id=None):
         keys = self._client.get("cache_key")
         lam = self._client.get("cache_lam").reshape(keys.shape[0], keys.shape[1], 3)
         dt = self._client.params.dt
-        left = (keys >= 16 + 8) & (keys < 16 + 11)
-        right = (keys >= 16 + 11) & (keys < 16 + 14)
+        left = (keys >= KEY_BOX_CUBE) & (keys < KEY_BOX_CUBE + 1024)               # pad 0 = panda_leftfinger
+        right = (keys >= KEY_BOX_CUBE + 1024) & (keys < KEY_BOX_CUBE + 2048)       # pad 1 = panda_rightfinger
         n = left.any(axis=1).astype(int) + right.any(axis=1).astype(int)
         f0 = np.where(left, lam[:, :, 0] / dt, 0).sum(axis=1) / np.maximum(left.sum(axis=1), 1)
         f1 = np.where(right, lam[:, :, 0] / dt, 0).sum(axis=1) / np.maximum(right.sum(axis=1), 1)
