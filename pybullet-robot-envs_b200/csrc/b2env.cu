@@ -1324,6 +1324,81 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
     s_c[0] = sm.T[s_link][9] + oo[0]; s_c[1] = sm.T[s_link][10] + oo[1]; s_c[2] = sm.T[s_link][11] + oo[2];
   }
   scr[lane * 4 + 0] = s_c[0]; scr[lane * 4 + 1] = s_c[1]; scr[lane * 4 + 2] = s_c[2]; scr[lane * 4 + 3] = s_r;
+  // finger-pad boxes: world pose (lanes 0..n_boxes-1 own a box; every lane can read them from scratch)
+  const int nbx = U.n_boxes;
+  float* bscr = scr + 64;     // per box: centre (3) | bounding radius | R (9) | half extents (3)
+  if (lane < nbx) {
+    const int li = __ldg(&M->box_link[lane]);
+    const float lc[3] = {__ldg(&M->box_c[lane][0]), __ldg(&M->box_c[lane][1]), __ldg(&M->box_c[lane][2])};
+    float Rl[9], oo[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
+    m3vec(Rl, lc, oo);
+    const float h[3] = {__ldg(&M->box_h[lane][0]), __ldg(&M->box_h[lane][1]), __ldg(&M->box_h[lane][2])};
+    float* bs = bscr + 16 * lane;
+    bs[0] = sm.T[li][9] + oo[0]; bs[1] = sm.T[li][10] + oo[1]; bs[2] = sm.T[li][11] + oo[2];
+    bs[3] = sqrtf(dot3(h, h));
+#pragma unroll
+    for (int k = 0; k < 9; k++) bs[4 + k] = Rl[k];
+    bs[13] = h[0]; bs[14] = h[1]; bs[15] = h[2];
+  }
+  gsync(g);
+  // capsules: world end points (lanes 0..n_caps-1 own one; every lane can read them from scratch), then capsule vs cube:
+  // lane = capsule, GJK / EPA on the segment core behind a bounding-sphere cull
+  const int ncap = U.n_caps;
+  float* cscr = bscr + 16 * B2E_MAX_BOXES;   // per capsule: p0 (3) | radius | p1 (3) | friction
+  if (lane < ncap) {
+    const int li = __ldg(&M->cap_link[lane]);
+    float Rl[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
+    float* cs = cscr + 8 * lane;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float lc[3] = {e ? __ldg(&M->cap_p1[lane][0]) : __ldg(&M->cap_p0[lane][0]), e ? __ldg(&M->cap_p1[lane][1]) : __ldg(&M->cap_p0[lane][1]),
+                           e ? __ldg(&M->cap_p1[lane][2]) : __ldg(&M->cap_p0[lane][2])};
+      float oo[3];
+      m3vec(Rl, lc, oo);
+      cs[4 * e + 0] = sm.T[li][9] + oo[0]; cs[4 * e + 1] = sm.T[li][10] + oo[1]; cs[4 * e + 2] = sm.T[li][11] + oo[2];
+    }
+    cs[3] = __ldg(&M->cap_r[lane]); cs[7] = __ldg(&M->cap_mu[lane]);
+  }
+  gsync(g);
+  // ---- conservative votes of the warp (both environments): does ANY robot proxy come within the margin of the bounding
+  //      sphere of the cube / of the top of the static world (every static box and the ground plane lie at z <= ztop)?  If
+  //      not, no test of section 2 / section 3 can report a contact (sphere: dist >= gap; box-box: a face axis separates by
+  //      more than the margin; GJK: distance >= gap), and the section is skipped — the common case of a rollout ----
+  float ztop = 0.f;
+  for (int k = 0; k < nsb; k++) {
+    float bc[3], bh[3];
+    sbox_get(P, k, bc, bh);
+    ztop = fmaxf(ztop, bc[2] + bh[2]);
+  }
+  bool near_cube = false, near_static = false;
+  {
+    const float rc = rb + margin;
+    if (s_world) {
+      const float d[3] = {s_c[0] - cpos[0], s_c[1] - cpos[1], s_c[2] - cpos[2]};
+      near_cube = near_cube || !(dot3(d, d) > (rc + s_r) * (rc + s_r));
+      near_static = near_static || !(s_c[2] - s_r - ztop > margin);
+    }
+    if (lane < nbx) {
+      const float* bs = bscr + 16 * lane;
+      const float d[3] = {bs[0] - cpos[0], bs[1] - cpos[1], bs[2] - cpos[2]};
+      near_cube = near_cube || !(dot3(d, d) > (rc + bs[3]) * (rc + bs[3]));
+      near_static = near_static || !(bs[2] - bs[3] - ztop > margin);
+    }
+    if (lane < ncap) {
+      const float* cs = cscr + 8 * lane;
+      const float mid[3] = {0.5f * (cs[0] + cs[4]) - cpos[0], 0.5f * (cs[1] + cs[5]) - cpos[1], 0.5f * (cs[2] + cs[6]) - cpos[2]};
+      const float ax[3] = {cs[4] - cs[0], cs[5] - cs[1], cs[6] - cs[2]};
+      const float rr = rc + cs[3] + 0.5f * sqrtf(dot3(ax, ax)) * 1.0001f;
+      near_cube = near_cube || !(dot3(mid, mid) > rr * rr);
+      near_static = near_static || !(fminf(cs[2], cs[6]) - cs[3] - ztop > margin);
+    }
+  }
+  const bool any_cube = __any_sync(FULL, near_cube), any_static = __any_sync(FULL, near_static);
+  if (any_cube) {
   // ---- 2. robot vs cube: spheres (closest point on the box) ----
   {
     bool hit = false;
@@ -1375,25 +1450,6 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
     }
     base += __popc(b);
   }
-  // finger-pad boxes: world pose (lanes 0..n_boxes-1 own a box; every lane can read them from scratch)
-  const int nbx = U.n_boxes;
-  float* bscr = scr + 64;     // per box: centre (3) | bounding radius | R (9) | half extents (3)
-  if (lane < nbx) {
-    const int li = __ldg(&M->box_link[lane]);
-    const float lc[3] = {__ldg(&M->box_c[lane][0]), __ldg(&M->box_c[lane][1]), __ldg(&M->box_c[lane][2])};
-    float Rl[9], oo[3];
-#pragma unroll
-    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
-    m3vec(Rl, lc, oo);
-    const float h[3] = {__ldg(&M->box_h[lane][0]), __ldg(&M->box_h[lane][1]), __ldg(&M->box_h[lane][2])};
-    float* bs = bscr + 16 * lane;
-    bs[0] = sm.T[li][9] + oo[0]; bs[1] = sm.T[li][10] + oo[1]; bs[2] = sm.T[li][11] + oo[2];
-    bs[3] = sqrtf(dot3(h, h));
-#pragma unroll
-    for (int k = 0; k < 9; k++) bs[4 + k] = Rl[k];
-    bs[13] = h[0]; bs[14] = h[1]; bs[15] = h[2];
-  }
-  gsync(g);
   if (__any_sync(FULL, nbx > 0)) {  // robot boxes vs cube: lane = box, box-box behind a bounding-sphere cull
     int cnt = 0;
     float nrm[3] = {0.f, 0.f, 1.f};
@@ -1419,27 +1475,6 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
     }
     base += total;
   }
-  // capsules: world end points (lanes 0..n_caps-1 own one; every lane can read them from scratch), then capsule vs cube:
-  // lane = capsule, GJK / EPA on the segment core behind a bounding-sphere cull
-  const int ncap = U.n_caps;
-  float* cscr = bscr + 16 * B2E_MAX_BOXES;   // per capsule: p0 (3) | radius | p1 (3) | friction
-  if (lane < ncap) {
-    const int li = __ldg(&M->cap_link[lane]);
-    float Rl[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) Rl[k] = sm.T[li][k];
-    float* cs = cscr + 8 * lane;
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const float lc[3] = {e ? __ldg(&M->cap_p1[lane][0]) : __ldg(&M->cap_p0[lane][0]), e ? __ldg(&M->cap_p1[lane][1]) : __ldg(&M->cap_p0[lane][1]),
-                           e ? __ldg(&M->cap_p1[lane][2]) : __ldg(&M->cap_p0[lane][2])};
-      float oo[3];
-      m3vec(Rl, lc, oo);
-      cs[4 * e + 0] = sm.T[li][9] + oo[0]; cs[4 * e + 1] = sm.T[li][10] + oo[1]; cs[4 * e + 2] = sm.T[li][11] + oo[2];
-    }
-    cs[3] = __ldg(&M->cap_r[lane]); cs[7] = __ldg(&M->cap_mu[lane]);
-  }
-  gsync(g);
   if (__any_sync(FULL, ncap > 0)) {
     bool hit = false;
     if (lane < ncap) {
@@ -1470,6 +1505,8 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
     }
     base += __popc(b);
   }
+  }
+  if (any_static) {
   // ---- 3. robot vs static world: spheres vs static boxes (lane = sphere, at most three boxes each), vs the ground plane ----
   {
     int cnt = 0, kk[3] = {0, 0, 0};
@@ -1651,6 +1688,7 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
       }
       base += __popc(b);
     }
+  }
   }
   // ---- 4. robot self-collision (URDF_USE_SELF_COLLISION, panda_env.py:53): sphere pairs of non-neighbouring links ----
   {

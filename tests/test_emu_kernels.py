@@ -269,3 +269,48 @@ def test_panda_contact_families_parity(emu_lib, oracle_lib):
         assert seen == set(FAMILIES), set(FAMILIES) - seen
     finally:
         sim.close()
+
+
+def test_panda_robot_quaternion_command_and_velocity_cap(emu_lib, monkeypatch):
+    """pandaEnv.apply_action on the emulated kernels: a 7-wide (x, y, z, qx, qy, qz, w) command drives the arm like the 6-wide
+    Euler command of the same rotation (panda_env.py:251-261); max_vel != -1 caps the joint speeds (:285-291); the robot
+    observation carries a quaternion when control_eu_or_quat = 1 (:165-167)."""
+    from pybullet_robot_envs.b2env import binding
+    monkeypatch.setattr(binding, "_lib", emu_lib)
+    from pybullet_robot_envs.b2env.client import B2Client
+    from pybullet_robot_envs.b2env.model import TASK_REACH, panda_task_setup as setup
+    from pybullet_robot_envs.envs.panda_envs.panda_env import pandaEnv
+    from pybullet_robot_envs.envs.utils import quaternion_from_euler
+    eu = np.array([3.0, 0.2, -0.3])
+    pos = [0.45, 0.1, 0.8]
+    finals = []
+    for kind in (0, 1):
+        c = B2Client(num_envs=1)
+        robot = pandaEnv(c, use_IK=1, control_eu_or_quat=kind)
+        m, p = setup(TASK_REACH, use_ik=1)
+        c.configure(robot.model, p)
+        pose = sample_object_poses(1, 0)
+        c.ensure().reset_host(pose, targets_for(pose))
+        robot.reset()
+        assert robot.get_action_dim() == (7 if kind else 6)
+        cmd = np.concatenate([pos, quaternion_from_euler(eu)]) if kind else np.concatenate([pos, eu])
+        for i in range(40):
+            robot.apply_action(cmd)
+            c.step_simulation(1)
+        obs, lim = robot.get_observation()
+        assert len(obs) == (19 if kind else 18) == len(lim) == robot.get_observation_dim()
+        if kind:
+            np.testing.assert_allclose(np.linalg.norm(obs[3:7]), 1.0, atol=1e-6)
+        finals.append(c.get("q")[0].copy())
+        if kind:
+            # velocity cap: a far command, no arm joint faster than 0.2 rad/s
+            robot.apply_action(np.concatenate([[0.6, -0.25, 0.7], quaternion_from_euler(eu)]), max_vel=0.2)
+            worst = 0.0
+            for i in range(10):
+                c.step_simulation(1, binding.MODE_IK_POSE)
+                worst = max(worst, float(np.abs(c.get("qd")[0, :7]).max()))
+            assert worst <= 0.2 * 1.02, worst
+            robot.apply_action(np.concatenate([[0.6, -0.25, 0.7], quaternion_from_euler(eu)]))    # cap off again
+            assert c.params.ik_max_vel == -1.0
+        c.close()
+    np.testing.assert_allclose(finals[0], finals[1], atol=2e-4)

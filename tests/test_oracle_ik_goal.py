@@ -118,3 +118,39 @@ def test_grasp_task_rules(oracle_lib):
     o.state["obj_pose"][:, 2] = 0.65 + 0.11
     obs, rew, done = o.step(a, 1, 0)
     assert np.all(done == 1) and np.all(rew == 1000)
+
+
+def test_cartesian_velocity_cap(oracle_lib):
+    """robot.apply_action(action, max_vel) with max_vel != -1 (panda_env.py:285-291): the 7 arm motors run with PyBullet's default
+    position gain and maxVelocity = max_vel, so a far Cartesian command moves no arm joint faster than the cap; without the
+    cap the same command does."""
+    B = 2
+    peak = {}
+    for cap in (-1.0, 0.3):
+        m, p = panda_task_setup(TASK_PUSH, use_ik=1)
+        p.ik_max_vel = cap
+        o = oracle_lib.Oracle(m, p, B, nthreads=2)
+        pose = sample_object_poses(B, 1)
+        o.reset(pose, targets_for(pose, z=0.65))
+        o.step(None, 1, 3, want_obs=False)
+        o.step(None, 100, 3, want_obs=False)                       # hold the home hand pose through the IK mode
+        o.state["hand_pose"][:, :3] = [0.55, 0.25, 0.75]           # a far command
+        worst = 0.0
+        for i in range(30):
+            o.step(None, 1, 3, want_obs=False)
+            worst = max(worst, float(np.abs(o.state["qd"][:, :7]).max()))
+        peak[cap] = worst
+    assert peak[0.3] <= 0.3 * 1.02, peak
+    assert peak[-1.0] > 0.6, peak
+
+
+def test_quaternion_helpers_round_trip():
+    from pybullet_robot_envs.envs.utils import euler_from_quaternion, quaternion_from_euler
+    rng = np.random.RandomState(0)
+    e = rng.uniform(-1.5, 1.5, (200, 3))
+    q = quaternion_from_euler(e)
+    np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(euler_from_quaternion(q), e, atol=1e-9)
+    np.testing.assert_allclose(quaternion_from_euler([math.pi, 0, 0]), [1, 0, 0, 0], atol=1e-12)   # the home hand orientation
+    for k in range(5):   # same numbers as the oracle's conversions
+        np.testing.assert_allclose(quaternion_from_euler(e[k]), _e2q(*e[k]), atol=1e-6)
