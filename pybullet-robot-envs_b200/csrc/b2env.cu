@@ -606,18 +606,19 @@ struct RowRegs {
 // tables of the block at its start; the global scratch is zeroed at create), so 0 * entry = 0.
 template <int NSG>
 __device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
-                                           const float* W, const float* WT, int AS, int i, bool active) {
+                                           const float* WT, int AS, int i, float lo2, float hi2) {
+  // delta form (see generic_step; motor rows have no cfm): dlambda = clamp(u invd, lo - lambda, hi - lambda) with the two
+  // bounds prepared once per sweep by the caller (a row is visited once per sweep); a group that does not sweep its motor
+  // rows in this pass has lo2 = hi2 = 0 and broadcasts 0
   const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
   const float cm = Minv[i * (NDMAX + 1) + lc];
   float cg[NSG];   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
 #pragma unroll
   for (int s = 0; s < NSG; s++) cg[s] = WT[i * AS + GL * s + g.lane];
-  float nl = fmaf(m.u, m.invd, m.lam);
-  nl = fminf(fmaxf(nl, m.lo), m.hi);
-  const float dl = active ? nl - m.lam : 0.f;   // `active`: this group sweeps its motor rows in this pass
+  const float dl = fminf(fmaxf(m.u * m.invd, lo2), hi2);
   const float dli = SHF(dl, i);
-  m.lam = (g.lane == i && active) ? nl : m.lam;
   m.u = fmaf(-cm, dli, m.u);                    // inactive: dli = 0 and the tables are finite (zeroed at kernel start)
+  if (g.lane == i) m.lam += dl;
 #pragma unroll
   for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-cg[s], dli, r.u[s]);
 }
@@ -643,16 +644,19 @@ __device__ __forceinline__ void rows_prepare(const Grp& g, RowRegs<NSG>& r, unsi
 template <int NSG, int SI>
 __device__ __forceinline__ void generic_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Arow,
                                              const float* Wrow, int li) {
+  // Arow / Wrow already point at this lane's column of the row
   float ca[NSG];
 #pragma unroll
-  for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s + g.lane];
-  const float cw = Wrow[g.lane];
+  for (int s = 0; s < NSG; s++) ca[s] = Arow[GL * s];
+  const float cw = Wrow[0];
   const float dl = fminf(fmaxf(fmaf(r.u[SI], r.invd[SI], r.cc[SI]), r.lo2[SI]), r.hi2[SI]);
   const float dli = SHF(dl, li);
-  r.lam[SI] += (g.lane == li) ? dl : 0.f;
+  r.u[SI] = fmaf(-ca[SI], dli, r.u[SI]);        // the running error the next rows of this set wait for: first
+  if (g.lane == li) r.lam[SI] += dl;
   m.u = fmaf(-cw, dli, m.u);                    // m.u of a finished arm island is dead
 #pragma unroll
-  for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
+  for (int s = 0; s < NSG; s++)
+    if (s != SI) r.u[s] = fmaf(-ca[s], dli, r.u[s]);
 }
 
 // Visit the rows of one 16-row set whose bits are set in `mk`, in ascending order.  The loop is a counted loop
@@ -665,8 +669,8 @@ __device__ __forceinline__ void sweep_set(const Grp& g, MotorRegs& m, RowRegs<NS
   // w: union of the two groups' row masks of this set (__reduce_or_sync: provably warp-uniform trip count)
   if (w == 0u) return;
   const int lo = __ffs(w) - 1, hi = 32 - __clz(w);
-  const float* Arow = A + (GL * SI + lo) * AS;
-  const float* Wrow = W + (GL * SI + lo) * WSTRIDE;
+  const float* Arow = A + (GL * SI + lo) * AS + g.lane;
+  const float* Wrow = W + (GL * SI + lo) * WSTRIDE + g.lane;
   B2E_UNROLL(SWEEP_UNROLL)
   for (int i = lo; i < hi; i++) {
     generic_step<NSG, SI>(g, m, r, Arow, Wrow, i);
@@ -724,6 +728,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     dA0 = b0 & 1u; dB0 = (b0 >> GL) & 1u; dA1 = b1 & 1u; dB1 = (b1 >> GL) & 1u;
   }
   int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
+  bool serial_motor = false;
   unsigned wn[3] = {0, 0, 0}, wf[3] = {0, 0, 0};
   bool fresh = true;
   for (int it = 0; it < max_iters; it++) {
@@ -742,12 +747,18 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     for (int s = 0; s < NSG; s++) r.prev[s] = r.lam[s];
     if (!(dA0 && dB0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
       float dl = 0.f;
-      B2E_UNROLL(MOTOR_UNROLL)
-      for (int j = 0; j < NDMAX; j++) dl = fmaf(TL[j * GL + g.lane], SHF(m.u, j), dl);
-      const float nl = m.lam + dl;
-      const bool viol = !done0 && g.lane < nd && !(nl >= m.lo && nl <= m.hi);
-      if (__any_sync(FULL, viol)) {
-        for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, W, WT, AS, i, !done0);
+      if (!serial_motor) {   // (warp-uniform) block form, unless a bound activated in an earlier sweep of this solve
+        B2E_UNROLL(MOTOR_UNROLL)
+        for (int j = 0; j < NDMAX; j++) dl = fmaf(TL[j * GL + g.lane], SHF(m.u, j), dl);
+        const float nl = m.lam + dl;
+        const bool viol = !done0 && g.lane < nd && !(nl >= m.lo && nl <= m.hi);
+        // a saturated motor (an arm pressed onto the table) stays saturated sweep after sweep: once a bound has activated
+        // the remaining sweeps of the solve take the serial rows directly instead of trying the block form first
+        serial_motor = __any_sync(FULL, viol);
+      }
+      if (serial_motor) {
+        const float mlo2 = done0 ? 0.f : m.lo - m.lam, mhi2 = done0 ? 0.f : m.hi - m.lam;
+        for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, WT, AS, i, mlo2, mhi2);
       } else {
         dl = done0 ? 0.f : dl;
         m.lam += dl;
@@ -874,7 +885,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   // up to 16 generic rows live in the environment's own shared memory; a bigger system uses `big`
   // (an overflow slot of the block, or the env's global scratch), which also carries W^T
   const bool use_big = (NSG > 1) && (nlim + 3 * nc > GL);
-  const int AS = use_big ? BIGS : GL;
+  // row stride; passed through a shuffle (identity: source lane = own lane) so that ptxas keeps it in a register — it
+  // otherwise re-selects between the two constants in every row-loop iteration (three dependent instructions on the pointer)
+  const int AS = SHF(use_big ? BIGS : GL, lane);
   // the slot address is formed here from the shared-memory base so that, in the GB = false instantiations,
   // every table access is a shared-memory access (no generic loads in the row loops)
   float* big = reinterpret_cast<float*>(smem_raw + (big_off < 0 ? 0 : big_off));   // byte offset of the claimed overflow slot
