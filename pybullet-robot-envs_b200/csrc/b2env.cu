@@ -902,6 +902,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   const float dt = P.dt, inv_dt = 1.0f / P.dt;
   const float cinv_m = 1.0f / P.cube_mass, cinv_I = 1.0f / P.cube_inertia;
 
+#ifdef PROFILE_STAGES
+  const long long t_bs0 = clock64();
+#endif
   // ---- motor row of dof `lane` (btMultiBodyJointMotor: velocity target kp*(target-q)/dt, kd = 1, erp = 1) ----
   MotorRegs m;
   {
@@ -1049,6 +1052,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     }
   }
   gsync(g);
+#ifdef PROFILE_STAGES
+  if (lane == 0) sm.cost[1] = (float)(clock64() - t_bs0);   // rows + W built
+#endif
   // generic x generic block: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
 #pragma unroll
   for (int s = 0; s < NSG; s++) {
@@ -1098,6 +1104,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       m.u = fmaf(-W[c * WSTRIDE + lane], l0, m.u);
     }
   }
+#ifdef PROFILE_STAGES
+  if (lane == 0) sm.cost[2] = (float)(clock64() - t_bs0);   // + Delassus block, warm start
+#endif
   int iters_arm = -1;
   bool arm_sweep = true;
   const bool arm_simple = !coupled && !arm_generic;
@@ -1110,6 +1119,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
+#ifdef PROFILE_STAGES
+  if (lane == 0) sm.cost[3] = (float)(clock64() - t_bs0);   // + affine arm solve
+#endif
 #ifdef PROFILE_CYCLES
   const long long t_pgs0 = clock64();
 #endif
@@ -1847,7 +1859,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 #endif
   bool stop = false;
 #ifdef PROFILE_STAGES   // instrumentation build only: cycle stamps of the stages of the last sub-step -> B2E_F_CONTACTS[env][0..7]
-  long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_T(k) prof_t[k] = clock64()
 #else
 #define PROF_T(k) do { } while (0)
@@ -2259,8 +2271,10 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
                      isfinite(cv[2]) && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]));
       if (gany(g, bad)) flags |= B2E_ST_NAN;
     }
+    PROF_T(7);   // integrate + cache done
 
   }
+  PROF_T(8);   // final FK + termination done
 
   if (role != ROLE_PLAIN) {   // file this environment under its cost class for the next full-batch step
     int cls = -1, rank = 0;
@@ -2285,6 +2299,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       sched[(cls == NBK_MAIN ? SCHED_TAIL(seq & 1, B) : SCHED_LIST(seq & 1, cls, B)) + pos] = env;
     }
   }
+  PROF_T(9);   // filed under a cost class
   // ---- store state (padding groups shadow the last env: they keep pace but store nothing) ----
   if (is_dof && live_env) {
     st.q[env * nd + lane] = my_q;
@@ -2305,6 +2320,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     for (int j = 0; j < 3; j++) st.cache_lam[(env * B2E_CACHE_SLOTS + lane) * 3 + j] = sm.clam[lane][j];
   }
 
+  PROF_T(10);  // state stored
   // ---- observation / termination / reward (panda_push_gym_env.py:249-253) ----
   if (mode == B2E_MODE_ACTION || obs_out) {
     const float* R2 = Rm;   // kinematics of the final q (computed at the top of the last loop pass)
@@ -2430,6 +2446,8 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     for (int k = 1; k < 7; k++) o[k - 1] = (float)(prof_t[k] - prof_t[0]);
     o[6] = (float)(t_end - prof_t[0]);
     o[7] = (float)blockIdx.x;
+    for (int k = 7; k < 11; k++) o[13 + k - 7] = (float)(prof_t[k] - prof_t[0]);   // [13..16]: finer stamps of the `rest`
+    o[17] = sm.cost[1]; o[18] = sm.cost[2]; o[19] = sm.cost[3];                    // [17..19]: parts of the solve (cycles)
   }
 #endif
   if (lane == 0 && mode != B2E_MODE_OBSERVE && live_env) {

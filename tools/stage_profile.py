@@ -51,6 +51,14 @@ for D in depths:
     for k, n in enumerate(names):
         v = t[:, k]
         print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % (n, v.mean(), np.percentile(v, 50), np.percentile(v, 99), v.max()))
+    cf = sim.get("contacts").reshape(B, -1)[:, 13:20].astype(np.float64)
+    if cf.any():   # finer stamps of this build: parts of `rest` and of `solve`
+        fin = {"rest: integrate+cache": cf[:, 0] - c[:, 5], "rest: final FK+termination": cf[:, 1] - cf[:, 0],
+               "rest: cost-class filing": cf[:, 2] - cf[:, 1], "rest: state store": cf[:, 3] - cf[:, 2],
+               "rest: observation+reward": c[:, 6] - cf[:, 3], "solve: rows + W": cf[:, 4], "solve: A + warm start": cf[:, 5] - cf[:, 4],
+               "solve: affine arm": cf[:, 6] - cf[:, 5], "solve: sweeps + store": t[:, 4] - cf[:, 6]}
+        for n, v in fin.items():
+            print("   %-28s mean %8.0f  p50 %8.0f  p99 %8.0f" % (n, v.mean(), np.percentile(v, 50), np.percentile(v, 99)))
     tot = c[:, 6]
     print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % ("block lifetime", tot.mean(), np.percentile(tot, 50), np.percentile(tot, 99), tot.max()))
     top = np.argsort(-t[:, 4])[:6]
