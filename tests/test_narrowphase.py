@@ -401,3 +401,47 @@ def test_gjk_degenerate_configurations(lib):
     assert k == 1 and abs(out[6] + 0.01) < 1e-5 and np.isfinite(n).all()
     k, n, out = convex_contact(lib, _shape(B2N_POINT, [0.5, 0, 0], r=0.01), box, margin=0.01)       # far: no contact
     assert k == 0
+
+
+def test_narrowphase_symmetries(lib):
+    """Size-independent properties: swapping the two shapes negates the normal and keeps the depth (box-box and GJK / EPA);
+    a rigid motion of both shapes moves the contact with it."""
+    rng = np.random.RandomState(7)
+    n_bb = n_cc = 0
+    for it in range(200):
+        hA, hB = rng.uniform(0.01, 0.05, 3), rng.uniform(0.01, 0.2, 3)
+        RA = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        RB = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        g0 = _support_gap(np.zeros(3), RA, hA, np.zeros(3), RB, hB, u)
+        cA = u * (-g0 + rng.uniform(-0.01, 0.006))
+        # rigid motion (rotation Q, translation t)
+        Q = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        t = rng.uniform(-0.3, 0.3, 3)
+        k1, n1, p1 = box_box(lib, cA, RA, hA, np.zeros(3), RB, hB)
+        k2, n2, p2 = box_box(lib, np.zeros(3), RB, hB, cA, RA, hA)
+        k3, n3, p3 = box_box(lib, Q @ cA + t, Q @ RA, hA, t, Q @ RB, hB)
+        if k1 and k2:
+            n_bb += 1
+            assert abs(p1[:, 6].min() - p2[:, 6].min()) < 2e-4, (it, p1[:, 6], p2[:, 6])      # same deepest penetration
+            assert np.dot(n1, n2) < -0.7 or abs(p1[:, 6].min()) < 2e-3, (it, n1, n2)       # opposite normals (face / edge choice may differ near ties)
+        if k1 and k3 and abs(p1[:, 6].min()) > 1e-4:
+            assert abs(p1[:, 6].min() - p3[:, 6].min()) < 1e-4, (it, p1[:, 6], p3[:, 6])
+            assert np.linalg.norm(Q @ n1.astype(np.float64) - n3) < 2e-2 or k1 != k3, (it, n1, n3)
+        # GJK / EPA: capsule vs box, swapped and moved
+        Rs = _rot(rng.normal(size=3), rng.uniform(0, np.pi))
+        cap = _shape(B2N_SEGMENT, cA, Rs, (0, 0, 0.08), 0.03)
+        box = _shape(B2N_BOX, np.zeros(3), RB, hB)
+        ka, na, oa = convex_contact(lib, cap, box, margin=0.05)
+        kb, nb, ob = convex_contact(lib, box, cap, margin=0.05)
+        kc, nc, oc = convex_contact(lib, _shape(B2N_SEGMENT, Q @ cA + t, Q @ Rs, (0, 0, 0.08), 0.03), _shape(B2N_BOX, t, Q @ RB, hB), margin=0.05)
+        assert ka == kb == kc
+        if ka:
+            n_cc += 1
+            assert abs(oa[6] - ob[6]) < 1e-4 and abs(oa[6] - oc[6]) < 1e-4, (it, oa[6], ob[6], oc[6])
+            if abs(oa[6] + 0.03) > 2e-3:      # away from the cores just touching (normal undefined there)
+                assert np.linalg.norm(na + nb) < 2e-2, (it, na, nb)
+                assert np.linalg.norm(Q @ na - nc) < 2e-2, (it, na, nc)
+                np.testing.assert_allclose(Q @ oa[0:3] + t, oc[0:3], atol=2e-3)
+    assert n_bb >= 15 and n_cc > 60, (n_bb, n_cc)

@@ -25,6 +25,26 @@ for kw, A in ((dict(), 7), (dict(use_ik=1), 6)):
     st = sim.get("status")
     print(kw, "rows max", st[:, 3].max(), "nan", (st[:, 0] & 1).sum(), "finite", np.isfinite(o).all())
     sim.close()
+# every contact family of the collision stage (box-box at the rim / legs, finger pads, capsule through GJK / EPA, self pairs),
+# stepped through the scheduled path as well (tail launch: B2ENV_SCHED_MIN lowered)
+import os
+m, p = panda_task_setup(TASK_PUSH)
+qs, poses, fam = family_states(b2oracle, m, p, list(FAMILIES), per_family=6, seed=5)
+for sched_min in ("1", "100000"):
+    os.environ["B2ENV_SCHED_MIN"] = sched_min
+    B = len(fam)
+    sim = B2Sim(m, p, B, 0)
+    sim.reset_host(poses, targets_for(poses))
+    sim.set("q", qs); sim.set("mtarget", qs)
+    rng = np.random.RandomState(1)
+    for i in range(6):
+        o, r, d = sim.step_host(rng.uniform(-1, 1, (B, 7)).astype(np.float32), 1, 0)
+    st = sim.get("status")
+    keys = sim.get("cache_key")
+    seen = sorted(f for f, (lo, hi) in FAMILIES.items() if ((keys >= lo) & (keys < hi)).any())
+    print("families, sched_min", sched_min, "rows max", st[:, 3].max(), "nan", (st[:, 0] & 1).sum(), "finite", np.isfinite(o).all(), "seen", len(seen))
+    sim.close()
+del os.environ["B2ENV_SCHED_MIN"]
 # iCub tree kernel (one warp per env): joint mode, Cartesian mode, hand pressed onto the cube (coupled islands)
 import icub_cases
 from pybullet_robot_envs.b2env.model import icub_task_setup
