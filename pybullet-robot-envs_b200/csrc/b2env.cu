@@ -2690,14 +2690,17 @@ static int launch_step(b2e_sim* s, const float* action, float* obs, float* rewar
   if (ordered) ORDER_BEGIN(s, stream);
   if (s->tree) {
     const int tb = (n + TREE_WPB - 1) / TREE_WPB;
+    // cost-ordered blocks only for physics launches over the whole batch
+    int* tsched = (!env_ids && env_offset == 0 && n == s->B && n_substeps > 0 && s->d_sched) ? s->d_sched : nullptr;
+    const int tseq = tsched ? s->sched_seq++ : 0;
     if (s->params.use_ik)
       B2E_LAUNCH(tree_step_kernel<true>, tb, 32 * TREE_WPB, TREE_SMEM_BYTES, stream,
           s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-          env_offset);
+          env_offset, tsched, tseq);
     else
       B2E_LAUNCH(tree_step_kernel<false>, tb, 32 * TREE_WPB, TREE_SMEM_BYTES, stream,
           s->d_model, s->umodel, s->params, s->st, action, obs, reward, done, n_substeps, mode, s->record_contacts, env_ids, n,
-          env_offset);
+          env_offset, tsched, tseq);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     if (ordered) ORDER_END(s, stream);
@@ -2831,7 +2834,7 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
   {
     const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches cost-ordered scheduling off (A/B measurements)
     const char* mn = getenv("B2ENV_SCHED_MIN");   // smallest batch that is scheduled (tests lower it)
-    if (!tree && num_envs >= (mn ? atoi(mn) : 2048) && !(e && e[0] == '0')) {
+    if (num_envs >= (mn ? atoi(mn) : 2048) && !(e && e[0] == '0')) {   // group kernel: class lists + tail launch; tree kernel: class lists
       // every environment starts in class 0, in index order (as the lists of "step 1", read by the first step, seq = 2)
       const size_t ni = (size_t)SCHED_INTS(num_envs);
       int* h = (int*)calloc(ni, sizeof(int));

@@ -495,14 +495,43 @@ __global__ void __launch_bounds__(32 * TREE_WPB, TREE_MINB)
 tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P,
                  DevState st, const float* __restrict__ action, float* __restrict__ obs_out, float* __restrict__ reward_out,
                  float* __restrict__ done_out, int nsub, int mode, int record_contacts, const int* __restrict__ env_ids,
-                 int n_ids, int env_offset) {
+                 int n_ids, int env_offset, int* sched, int seq) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_slots = n_ids;
+  int n_slots = n_ids;
   const int slot = blockIdx.x * TREE_WPB + warp;
-  const bool live_env = slot < n_slots;   // padding warps of the last block shadow the last slot, stores masked
-  const int slot_c = live_env ? slot : n_slots - 1;
-  const int env = env_ids ? env_ids[slot_c] : env_offset + slot_c;
+  int env;
+  if (sched) {
+    // Cost-ordered blocks (full-batch physics launches): the warps of a block advance in phase (stage barriers, block-shared
+    // IK loop), so a block lasts as long as its slowest environment.  Every environment files itself, at the end of a step,
+    // under a class given by its solver sweep count; the next step takes slot -> environment from the class lists, heaviest
+    // class first, so that the four environments of a block cost about the same.  Results do not depend on the slot
+    // (tests/test_emu_kernels.py::test_icub_cost_ordered_blocks_are_transparent).  Same list layout as the group kernel's.
+    const int qp = (seq - 1) & 3, pp = (seq - 1) & 1, B = st.B;
+    if (blockIdx.x == 0 && (int)threadIdx.x < NBK) sched[SCHED_CNT((seq + 1) & 3, threadIdx.x)] = 0;   // the next step's counters
+    int rem = slot, cls = 0, tot = 0;
+    bool found = false;
+    for (int b = NBK_MAIN - 1; b >= 0; b--) {
+      const int c = sched[SCHED_CNT(qp, b)];
+      tot += c;
+      if (!found) {
+        if (rem < c) { cls = b; found = true; }
+        else rem -= c;
+      }
+    }
+    n_slots = tot;
+    if (!found) {   // padding warp of the last block: shadow the last environment of the lightest populated class
+      for (int b = 0; b < NBK_MAIN; b++) {
+        const int c = sched[SCHED_CNT(qp, b)];
+        if (c > 0) { cls = b; rem = c - 1; break; }
+      }
+    }
+    env = sched[SCHED_LIST(pp, cls, B) + rem];
+  } else {
+    const int sc = slot < n_slots ? slot : n_slots - 1;
+    env = env_ids ? env_ids[sc] : env_offset + sc;
+  }
+  const bool live_env = slot < n_slots;   // padding warps of the last block shadow another slot, stores masked
   TreeSmem& sm = reinterpret_cast<TreeSmem*>(smem_raw)[warp];
   const int nd = U.n_dof, nl = U.n_links;   // nl == nd: body index == dof index
   const float dt = P.dt;
@@ -1378,5 +1407,10 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       st.status[env * 4 + 2] = nc;
       st.status[env * 4 + 3] = R;
     }
+  }
+  if (sched && lane == 0 && live_env) {   // file this environment under its cost class for the next full-batch step
+    const int cls = min(NBK_MAIN - 1, iters / 10);
+    const int pos = atomicAdd(&sched[SCHED_CNT(seq & 3, cls)], 1);
+    sched[SCHED_LIST(seq & 1, cls, st.B) + pos] = env;
   }
 }

@@ -314,3 +314,44 @@ def test_panda_robot_quaternion_command_and_velocity_cap(emu_lib, monkeypatch):
             assert c.params.ik_max_vel == -1.0
         c.close()
     np.testing.assert_allclose(finals[0], finals[1], atol=2e-4)
+
+
+def test_icub_cost_ordered_blocks_are_transparent(oracle_lib, emu_lib):
+    """iCub tree kernel, cost-ordered blocks (full-batch launches take slot -> environment from per-sweep-count class lists):
+    which block steps an environment, and next to which three others, must not change a bit of its results.  Same batch
+    stepped with scheduling on and off, Cartesian control, some hands pressed towards the table so that the sweep counts
+    (the classes) differ; the class lists must hold every environment exactly once after every step."""
+    from pybullet_robot_envs.b2env.model import icub_task_setup
+    B = 11   # three blocks of four, the last one with a padding warp
+    m, p = icub_task_setup(TASK_PUSH, use_ik=1)
+    sims = [_mk_sched(emu_lib, m, p, B, True), _mk_sched(emu_lib, m, p, B, False)]
+    try:
+        pose = icub_cases.object_poses(B, 2)
+        pose[:, 2] = 0.651
+        tg = (pose[:, :3] + np.array([0.05, 0.05, 0.0], np.float32)).astype(np.float32)
+        for sim in sims:
+            sim.reset_host(pose, tg)
+            sim.set("shaping", np.ones((B, 2), np.float32))
+            sim.step_host(None, 1, 3, want_obs=False)       # robot.reset(): IK of the home hand pose
+            hp = sim.get("hand_pose")
+            hp[::3, 2] = 0.66                               # every third hand is sent down onto the table
+            hp[::3, 0] = pose[::3, 0]
+            hp[::3, 1] = pose[::3, 1] + 0.08
+            sim.set("hand_pose", hp)
+            sim.step_host(None, 12, 3, want_obs=False)
+        rng = np.random.RandomState(5)
+        classes = set()
+        for i in range(4):
+            a = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+            outs = [sim.step_host(a, 1, 0) for sim in sims]
+            for x, y in zip(outs[0], outs[1]):
+                np.testing.assert_array_equal(x, y, err_msg="step %d" % i)
+            for f in ("q", "qd", "obj_pose", "obj_vel", "mtarget", "counters", "cache_key", "cache_lam", "status", "raw_obs", "hand_pose"):
+                np.testing.assert_array_equal(sims[0].get(f), sims[1].get(f), err_msg="%s step %d" % (f, i))
+            envs, n_tail = sims[0].debug_sched_lists()
+            assert sorted(envs) == list(range(B)) and n_tail == 0, (i, sorted(envs), n_tail)
+            classes |= set(np.minimum(15, sims[0].get("status")[:, 1] // 10).tolist())
+        assert len(classes) >= 2, classes      # the batch really was spread over several classes
+    finally:
+        for sim in sims:
+            sim.close()
