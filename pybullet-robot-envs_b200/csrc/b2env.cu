@@ -104,6 +104,7 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #define ROLE_MAIN 1
 #define ROLE_TAIL 2
 #define SCRATCH_PER_ENV (BIGS * BIGS + BIGS * WSTRIDE + NDMAX * BIGS)   // A | W | W^T(arm part), same layout as a slot
+#define SCRATCH_PAD 64
 #define NDMAX 9           // dofs handled by the warp kernel (Panda: 7 arm + 2 fingers)
 #define NLMAX 32          // links (lanes)
 
@@ -2829,8 +2830,11 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
   s->st.status = (int*)s->fields[B2E_F_STATUS]; s->st.raw_obs = (float*)s->fields[B2E_F_RAW_OBS];
   s->st.contacts = (float*)s->fields[B2E_F_CONTACTS];
   s->st.shaping = (float*)s->fields[B2E_F_SHAPING];
-  CUDA_TRY(cudaMalloc(&s->st.scratch, (size_t)num_envs * SCRATCH_PER_ENV * 4));
-  CUDA_TRY(cudaMemset(s->st.scratch, 0, (size_t)num_envs * SCRATCH_PER_ENV * 4));   // tables are finite from the start
+  // + SCRATCH_PAD floats: the lanes of the third row set read W^T up to 7 entries past a system's end (BigSlot carries the same
+  // pad); for every environment but the last that is the neighbour's scratch, for the last one it must still be allocated
+  // (found by compute-sanitizer on a 70-env batch whose last block had more big systems than overflow slots)
+  CUDA_TRY(cudaMalloc(&s->st.scratch, ((size_t)num_envs * SCRATCH_PER_ENV + SCRATCH_PAD) * 4));
+  CUDA_TRY(cudaMemset(s->st.scratch, 0, ((size_t)num_envs * SCRATCH_PER_ENV + SCRATCH_PAD) * 4));   // tables are finite from the start
   {
     const char* e = getenv("B2ENV_SCHED");   // B2ENV_SCHED=0 switches cost-ordered scheduling off (A/B measurements)
     const char* mn = getenv("B2ENV_SCHED_MIN");   // smallest batch that is scheduled (tests lower it)
