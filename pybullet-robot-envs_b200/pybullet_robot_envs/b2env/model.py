@@ -288,8 +288,12 @@ def load_panda(base_position=(0.0, 0.0, 0.625), urdf_path=None, dt=1.0 / 240.0):
     else:
         with open(PANDA_JSON) as f:
             d = json.load(f)
-    m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES, boxes=PANDA_BOXES,
-                                  self_pairs=PANDA_SELF_PAIRS, capsules=PANDA_CAPSULES)
+    if os.environ.get("B2ENV_CONTACT_MODEL") == "r1":   # round 1's proxies, for like-for-like measurements only
+        from .proxies import PANDA_SPHERES_R1
+        m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES_R1)
+    else:
+        m = descriptor_from_urdf_dict(d, base_position, PANDA_HOME, ee_link=11, spheres=PANDA_SPHERES, boxes=PANDA_BOXES,
+                                      self_pairs=PANDA_SELF_PAIRS, capsules=PANDA_CAPSULES)
     # soft finger contacts: <stiffness>/<damping> (URDF:256-263) -> per-contact erp/cfm the way
     # Bullet derives them: denom = dt*k + d, erp = dt*k/denom, cfm = 1/(denom*dt) [EXT-recalled]
     names = [l["name"] for l in d["links"]]
@@ -334,6 +338,8 @@ def default_params(task, obs_low, obs_high, n_act=7, n_ctrl=7, use_ik=0, ik_orie
     # static boxes: [0] the top slab, [1..4] the legs 0.1 x 0.1 x 0.58 at (0.85 +- 0.65, +- 0.4, 0.29) [EXT-recalled, App. B.3]
     boxes = [((0.85, 0.0, 0.6), (0.75, 0.5, 0.025))]
     boxes += [((0.85 + sx * 0.65, sy * 0.4, 0.29), (0.05, 0.05, 0.29)) for sx in (-1, 1) for sy in (-1, 1)]
+    if os.environ.get("B2ENV_CONTACT_MODEL") == "r1":
+        boxes = boxes[:1]           # round 1: the table top only
     p.n_sboxes = len(boxes)
     for k, (c, h) in enumerate(boxes):
         for j in range(3):
