@@ -75,9 +75,6 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #ifndef SWEEP_UNROLL
 #define SWEEP_UNROLL 1
 #endif
-#ifndef MOTOR_UNROLL
-#define MOTOR_UNROLL 3
-#endif
 #define B2E_PRAGMA(x) _Pragma(#x)
 #define B2E_UNROLL(n) B2E_PRAGMA(unroll n)
 // Cost-ordered scheduling (full-batch launches of the group kernel).  The environments of a block advance in phase
@@ -348,8 +345,8 @@ struct EnvSmem {
   float WT[NDMAX * GL];        // WT[d][g] = W[g][d]: what a motor row reads (unit stride over g).  A 16-row system
                                // solved in a 2/3-set instantiation (its warp mate is big) reads up to 31 floats past
                                // the end for its non-existent rows: T follows, which nobody writes during the solve
-  float T[TLMAX][12];          // link world transforms: R (9) + p (3); dead after collision detection: pgs_solve keeps
-                               // (D+L)^-1 of the motor block here, TL[k][row] = T[k*16 + row] (NDMAX*GL = TLMAX*12 floats)
+  float T[TLMAX][12];          // link world transforms: R (9) + p (3); dead after collision detection: pgs_solve stages the
+                               // impulses of the generic rows here for the friction bounds (3 * GL <= TLMAX * 12 floats)
   float S[NDMAX][6];           // world spatial axes about O=base: (w, v_O)
   float Minv[NDMAX][NDMAX + 1];
   float vstar[16];             // unconstrained velocities (9 arm + 6 cube)
@@ -374,7 +371,7 @@ struct BigSlot {
                              // third row set run to g = 47)
 };
 
-static_assert(NDMAX * GL <= TLMAX * 12, "pgs_solve keeps its 9 x 16 triangular table in EnvSmem::T");
+static_assert(3 * GL <= TLMAX * 12, "pgs_solve stages the generic-row impulses in EnvSmem::T");
 static_assert(sizeof(BigSlot) % 16 == 0, "BigSlot is zeroed with 16-byte stores");
 // ------------------------------------------------------------------------------------------
 // forward kinematics: lane = link.  Composition along the tree by pointer jumping.
@@ -606,16 +603,16 @@ struct RowRegs {
 // broadcasts a zero impulse change; its table entries may be stale but are always finite (step_kernel zeroes the
 // tables of the block at its start; the global scratch is zeroed at create), so 0 * entry = 0.
 template <int NSG>
-__device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Minv,
-                                           const float* WT, int AS, int i, float lo2, float hi2) {
+__device__ __forceinline__ void motor_step(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* Mrow,
+                                           const float* WTr, int i, float lo2, float hi2) {
   // delta form (see generic_step; motor rows have no cfm): dlambda = clamp(u invd, lo - lambda, hi - lambda) with the two
   // bounds prepared once per sweep by the caller (a row is visited once per sweep); a group that does not sweep its motor
   // rows in this pass has lo2 = hi2 = 0 and broadcasts 0
-  const int lc = g.lane < NDMAX ? g.lane : NDMAX;  // rows of Minv are padded to NDMAX + 1 (pad = 0)
-  const float cm = Minv[i * (NDMAX + 1) + lc];
+  // Mrow / WTr: this lane's column of row i of M^-1 (padded to NDMAX + 1, pad = 0) and of the transposed W table
+  const float cm = Mrow[0];
   float cg[NSG];   // A[generic g][motor i] = W_g[i], read from the transposed table (unit stride over g)
 #pragma unroll
-  for (int s = 0; s < NSG; s++) cg[s] = WT[i * AS + GL * s + g.lane];
+  for (int s = 0; s < NSG; s++) cg[s] = WTr[GL * s];
   const float dl = fminf(fmaxf(m.u * m.invd, lo2), hi2);
   const float dli = SHF(dl, i);
   m.u = fmaf(-cm, dli, m.u);                    // inactive: dli = 0 and the tables are finite (zeroed at kernel start)
@@ -694,19 +691,22 @@ __device__ __forceinline__ void sweep_generic(const Grp& g, MotorRegs& m, RowReg
 
 template <int NSG>
 __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG>& r, const float* A, const float* W,
-                                         const float* WT, int AS, const float* Minv, float* TL, int nd, int RG, int fric_start,
-                                         bool coupled, bool has_cube_rows, bool arm_sweep, int max_iters, float tol) {
-  // The motor rows have no active bound in practice (|lambda| <= 1e5 dt), so their part of a sweep — n_dof serial,
-  // shuffle-dependent row updates — is the triangular solve dlambda = (D+L)^-1 u followed by u -= M^-1 dlambda (and
-  // the same for the generic rows' u through W^T): two 9-wide mat-vecs.  Same iterates in exact arithmetic; a sweep in
-  // which a bound WOULD activate (the 10 N finger rows of the grasp task) takes the serial rows instead.
-  if (__any_sync(FULL, arm_sweep)) {
-    float Ar[NDMAX], T[NDMAX];
-    motor_block_T(g, Minv, nd, m.invd, Ar, T);
-#pragma unroll
-    for (int k = 0; k < NDMAX; k++) TL[k * GL + g.lane] = T[k];
-    gsync(g);
-  }
+                                         const float* WT, int AS, const float* Minv, float* stage, int nd, int RG, int fric_start,
+                                         bool coupled, bool has_cube_rows, bool arm_sweep, int max_iters, float tol,
+                                         float* prof = nullptr) {   // prof (-DPROFILE_SWEEP builds): cycles per part of the sweeps
+#ifdef PROFILE_SWEEP
+  float pacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#define PSW(k) { const long long t_ = clock64(); pacc[k] += (float)(t_ - t_psw); t_psw = t_; }
+#else
+#define PSW(k) do { } while (0)
+#endif
+  // The motor rows of a coupled / limit-carrying arm island are swept serially, in delta form (motor_step).  Round 1 solved them
+  // as one block per sweep (dlambda = (D+L)^-1 u, then u -= M^-1 dlambda: two 9-wide mat-vecs over shuffles, falling back to
+  // the serial rows when a bound would activate); measured in round 2 with cycle stamps inside the sweep (tools/stage_profile.py,
+  // -DPROFILE_SWEEP): for the lone warp of a sweep-capped solve the block form cost ~1700 cycles per sweep against ~650 for the
+  // nine serial rows (ptxas interleaves its shuffles with their consumers on reused registers, so they complete one by one),
+  // and whole-batch throughput went 36.6 M -> 40.4 M env-steps/s with the serial rows alone.  `stage` (the dead link-transform
+  // table) stages the impulses for the friction bounds.
   // generic-row masks per set: island (arm / cube) x phase (non-friction, friction)
   unsigned arm_nf[3] = {0, 0, 0}, arm_f[3] = {0, 0, 0}, cube_nf[3] = {0, 0, 0}, cube_f[3] = {0, 0, 0};
 #pragma unroll
@@ -729,7 +729,6 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     dA0 = b0 & 1u; dB0 = (b0 >> GL) & 1u; dA1 = b1 & 1u; dB1 = (b1 >> GL) & 1u;
   }
   int my_it = (done0 && done1) ? 0 : -1;   // sweep count of this group (the loop itself is shared by the warp)
-  bool serial_motor = false;
   unsigned wn[3] = {0, 0, 0}, wf[3] = {0, 0, 0};
   bool fresh = true;
   for (int it = 0; it < max_iters; it++) {
@@ -743,56 +742,47 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
       }
       fresh = false;
     }
+#ifdef PROFILE_SWEEP
+    long long t_psw = clock64();
+#endif
     m.prev = m.lam;
 #pragma unroll
     for (int s = 0; s < NSG; s++) r.prev[s] = r.lam[s];
     if (!(dA0 && dB0)) {  // motor rows first (Bullet: non-contact constraints, then normals, then frictions)
-      float dl = 0.f;
-      if (!serial_motor) {   // (warp-uniform) block form, unless a bound activated in an earlier sweep of this solve
-        B2E_UNROLL(MOTOR_UNROLL)
-        for (int j = 0; j < NDMAX; j++) dl = fmaf(TL[j * GL + g.lane], SHF(m.u, j), dl);
-        const float nl = m.lam + dl;
-        const bool viol = !done0 && g.lane < nd && !(nl >= m.lo && nl <= m.hi);
-        // a saturated motor (an arm pressed onto the table) stays saturated sweep after sweep: once a bound has activated
-        // the remaining sweeps of the solve take the serial rows directly instead of trying the block form first
-        serial_motor = __any_sync(FULL, viol);
-      }
-      if (serial_motor) {
-        const float mlo2 = done0 ? 0.f : m.lo - m.lam, mhi2 = done0 ? 0.f : m.hi - m.lam;
-        for (int i = 0; i < nd; i++) motor_step<NSG>(g, m, r, Minv, WT, AS, i, mlo2, mhi2);
-      } else {
-        dl = done0 ? 0.f : dl;
-        m.lam += dl;
-        const int lc = g.lane < NDMAX ? g.lane : NDMAX;
-        B2E_UNROLL(MOTOR_UNROLL)
-        for (int i = 0; i < NDMAX; i++) {
-          const float di = SHF(dl, i);
-          m.u = fmaf(-Minv[i * (NDMAX + 1) + lc], di, m.u);
-#pragma unroll
-          for (int s = 0; s < NSG; s++) r.u[s] = fmaf(-WT[i * AS + GL * s + g.lane], di, r.u[s]);
-        }
+      PSW(5);   // (profiling builds) previous-impulse copies
+      const float mlo2 = done0 ? 0.f : m.lo - m.lam, mhi2 = done0 ? 0.f : m.hi - m.lam;
+      const float* Mrow = Minv + (g.lane < NDMAX ? g.lane : NDMAX);
+      const float* WTr = WT + g.lane;
+      B2E_UNROLL(SWEEP_UNROLL)
+      for (int i = 0; i < nd; i++) {
+        motor_step<NSG>(g, m, r, Mrow, WTr, i, mlo2, mhi2);
+        Mrow += NDMAX + 1;
+        WTr += AS;
       }
     }
+    PSW(0);   // masks + motor rows
     sweep_generic<NSG>(g, m, r, A, W, AS, (arm_nf[0] & a0) | (cube_nf[0] & c0), (arm_nf[1] & a0) | (cube_nf[1] & c0),
                        (arm_nf[2] & a0) | (cube_nf[2] & c0), wn[0], wn[1], wn[2]);
+    PSW(1);   // non-friction rows
     if ((wf[0] | wf[1] | wf[2]) != 0u) {
-      // friction bounds from the current normal impulses (mu * lambda_n)
+      // friction bounds from the current normal impulses (mu * lambda_n): every lane stages its impulses, a friction row reads
+      // its contact's normal impulse back (3 stores + 3 loads instead of NSG^2 shuffles with their selects)
+#pragma unroll
+      for (int s = 0; s < NSG; s++) stage[GL * s + g.lane] = r.lam[s];
+      gsync(g);
 #pragma unroll
       for (int s = 0; s < NSG; s++) {
-        const int ni = r.nidx[s];
-        float v = 0.f;
-#pragma unroll
-        for (int t = 0; t < NSG; t++) {
-          const float vt = SHF(r.lam[t], ni & (GL - 1));
-          if ((ni >> 4) == t) v = vt;
-        }
+        const float v = stage[r.nidx[s]];
         if (r.type[s] == ROW_FRICTION) {
           const float lim = r.mu[s] * v;
           r.lo[s] = -lim; r.hi[s] = lim;
         }
       }
+      gsync(g);
+      PSW(2);   // friction bounds
       sweep_generic<NSG>(g, m, r, A, W, AS, (arm_f[0] & a0) | (cube_f[0] & c0), (arm_f[1] & a0) | (cube_f[1] & c0),
                          (arm_f[2] & a0) | (cube_f[2] & c0), wf[0], wf[1], wf[2]);
+      PSW(3);   // friction rows
     }
     float ra = 0.f, rc = 0.f;
     if (!done0 && g.lane < nd) {
@@ -815,7 +805,13 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
     done0 = g.sh ? dB0 : dA0;
     done1 = g.sh ? dB1 : dA1;
     if (my_it < 0 && done0 && done1) my_it = it + 1;
+    PSW(4);   // residual + control
   }
+#ifdef PROFILE_SWEEP
+  if (prof && g.lane == 0)
+    for (int k = 0; k < 6; k++) prof[k] = pacc[k];
+#endif
+#undef PSW
   return my_it < 0 ? max_iters : my_it;
 }
 
@@ -1126,8 +1122,13 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 #ifdef PROFILE_CYCLES
   const long long t_pgs0 = clock64();
 #endif
+#ifdef PROFILE_SWEEP   // the environment's global scratch is free while its system lives in a slot: its last 8 floats carry the profile
+  float* prof = (use_big && big != gscratch) || !use_big ? gscratch + SCRATCH_PER_ENV - 8 : nullptr;
+#else
+  float* prof = nullptr;
+#endif
   int iters = pgs_solve<NSG>(g, m, rr, A, W, WT, AS, Minv, &sm.T[0][0], nd, RG, fric_start, coupled, has_cube, arm_sweep, P.solver_iters,
-                            P.residual_tol);
+                            P.residual_tol, prof);
 #ifdef PROFILE_CYCLES
   if (lane == 0) sm.lim_dist[3] = (float)(clock64() - t_pgs0);   // instrumentation build only: cycles of the sweeps
 #endif
@@ -1861,6 +1862,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   bool stop = false;
 #ifdef PROFILE_STAGES   // instrumentation build only: cycle stamps of the stages of the last sub-step -> B2E_F_CONTACTS[env][0..7]
   long long prof_t[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int prof_slot = -2;
 #define PROF_T(k) prof_t[k] = clock64()
 #else
 #define PROF_T(k) do { } while (0)
@@ -2185,6 +2187,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const bool need_global = __any_sync(FULL, RG > GL && got < 0);   // rare: more big systems in the block than slots
     const float* big = (RG > GL && got < 0) ? gscratch : reinterpret_cast<const float*>(&slots[got < 0 ? 0 : got]);
     PROF_T(4);   // past the pre-solve barrier
+#ifdef PROFILE_STAGES
+    prof_slot = RG > GL ? got : -3;   // overflow slot of this environment's system (-1: global scratch, -3: no big system)
+#endif
 #ifdef PROFILE_CYCLES
     const long long t_solve0 = clock64();
 #endif
@@ -2449,6 +2454,11 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     o[7] = (float)blockIdx.x;
     for (int k = 7; k < 11; k++) o[13 + k - 7] = (float)(prof_t[k] - prof_t[0]);   // [13..16]: finer stamps of the `rest`
     o[17] = sm.cost[1]; o[18] = sm.cost[2]; o[19] = sm.cost[3];                    // [17..19]: parts of the solve (cycles)
+    o[21] = (float)(role * 100 + prof_slot);                                        // [21]: launch role x 100 + overflow slot
+#ifdef PROFILE_SWEEP
+    for (int k = 0; k < 5; k++) o[8 + k] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + k];   // [8..12]: parts of the sweeps
+    o[20] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + 5];                                   // [20]: before the serial motor rows
+#endif
   }
 #endif
   if (lane == 0 && mode != B2E_MODE_OBSERVE && live_env) {

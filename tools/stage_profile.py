@@ -69,6 +69,11 @@ for D in depths:
     if cs.any():   # -DPROFILE_SWEEP build: cycles per part of the sweeps
         for e in top[:4]:
             n = max(1, st[e, 1])
+            code = sim.get("contacts").reshape(B, -1)[e, 21]
+            print("   env %d: launch role %d (1 main, 2 tail), system storage %d (>= 0 overflow slot, -1 global scratch, -3 own block), block %d" % (
+                e, int(round(code / 100.0)), int(code - 100 * round(code / 100.0)), c[e, 7]))
+            pre = sim.get("contacts").reshape(B, -1)[e, 20]
+            print("   env %d: of motor+masks, before the serial motor rows (copies, block-form attempt): %.0f cycles per sweep" % (e, pre / n))
             print("   env %d sweep parts, cycles per sweep: motor+masks %.0f | non-friction rows %.0f | friction bounds %.0f | friction rows %.0f | residual %.0f  (rows %d, nc %d)" % (
                 e, cs[e, 0] / n, cs[e, 1] / n, cs[e, 2] / n, cs[e, 3] / n, cs[e, 4] / n, st[e, 3], st[e, 2]))
         simple_e = np.nonzero(st[:, 3] == 21)[0][:3]
