@@ -901,6 +901,12 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
 
 #ifdef PROFILE_STAGES
   const long long t_bs0 = clock64();
+#ifdef PROFILE_WARM   // probe build (with -DPROFILE_STAGES): the three solve-part outputs carry ACTIVE-LANE counts instead of cycles,
+  // cost[1] = entry + 100 x after rows/W + 10000 x after the Delassus block, cost[2] = after the cache look-up / the warm-start
+  // apply / the sweeps, cost[3] = (kernel body) after the collision stage / before / after the overflow-slot claim.  32 everywhere
+  // = the warp is converged; 31 = a straggler lane, every shuffle takes the divergent path (WARPSYNC.COLLECTIVE)
+  int am0 = __popc(__activemask()), am1 = 0, am2 = 0, am3 = 0, am4 = 0, am5 = 0;
+#endif
 #endif
   // ---- motor row of dof `lane` (btMultiBodyJointMotor: velocity target kp*(target-q)/dt, kd = 1, erp = 1) ----
   MotorRegs m;
@@ -1049,8 +1055,11 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     }
   }
   gsync(g);
-#ifdef PROFILE_STAGES
+#if defined(PROFILE_STAGES) && !defined(PROFILE_WARM)
   if (lane == 0) sm.cost[1] = (float)(clock64() - t_bs0);   // rows + W built
+#endif
+#ifdef PROFILE_WARM
+  am1 = __popc(__activemask());
 #endif
   // generic x generic block: A[c][r] = J_r . W_c  (symmetric; stored so that row c is contiguous in r)
 #pragma unroll
@@ -1059,20 +1068,29 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
     const bool valid = gi < RG;
     const float* J = Jall[s];
     for (int c = 0; c < RG; c++) {
+      // row c of W as four 16-byte loads issued together (rows are 64-byte aligned).  With scalar loads placed next to their
+      // FFMAs behind the two branches, the 15-term dot product ran load -> FFMA -> load -> FFMA: ~1250 cycles per (set, c) for
+      // the lone warp of a big system, 137 k cycles for a 36-row block (cycle stamps, -DPROFILE_STAGES).  Same terms, same order.
+      const float4* w4 = reinterpret_cast<const float4*>(W + c * WSTRIDE);
+      const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
+      const float w[16] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w};
+      // branch-free: the arm part of a cube-table column is dropped by a select (its W entries are zero anyway, but J of this
+      // lane's row need not be), the cube part of a limit column multiplies zeros (W[c][9..14] = 0 for c < nlim)
+      const int cc = c < nlim ? 0 : (c < fric_start ? c - nlim : (c - fric_start) >> 1);
+      const bool cube_only = (c >= nlim) && sm.con[cc].type == CT_CUBE_STATIC;
       float acc = 0.f;
-      const bool cube_only = (c >= nlim) && sm.con[c < fric_start ? c - nlim : (c - fric_start) >> 1].type == CT_CUBE_STATIC;
-      if (!cube_only) {
 #pragma unroll
-        for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
-      }
-      if (c >= nlim) {
+      for (int k = 0; k < NDMAX; k++) acc = fmaf(J[k], w[k], acc);
+      acc = cube_only ? 0.f : acc;
 #pragma unroll
-        for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], W[c * WSTRIDE + k], acc);
-      }
+      for (int k = NDMAX; k < 15; k++) acc = fmaf(J[k], w[k], acc);
       if (valid) A[c * AS + gi] = acc;
     }
   }
   gsync(g);
+#ifdef PROFILE_WARM
+  am2 = __popc(__activemask());
+#endif
   // warm start (contact rows): lambda0 = cached impulse * factor, u -= A lambda0
 #pragma unroll
   for (int s = 0; s < NSG; s++) {
@@ -1088,6 +1106,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       rr.lam[s] = l0;
     }
   }
+#ifdef PROFILE_WARM
+  am3 = __popc(__activemask());
+#endif
   for (int c = 0; c < RGw; c++) {
     float l0 = 0.f;
 #pragma unroll
@@ -1101,7 +1122,9 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       m.u = fmaf(-W[c * WSTRIDE + lane], l0, m.u);
     }
   }
-#ifdef PROFILE_STAGES
+#ifdef PROFILE_WARM
+  am4 = __popc(__activemask());
+#elif defined(PROFILE_STAGES)
   if (lane == 0) sm.cost[2] = (float)(clock64() - t_bs0);   // + Delassus block, warm start
 #endif
   int iters_arm = -1;
@@ -1116,7 +1139,7 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
       arm_sweep = false;
     }
   }
-#ifdef PROFILE_STAGES
+#if defined(PROFILE_STAGES) && !defined(PROFILE_WARM)
   if (lane == 0) sm.cost[3] = (float)(clock64() - t_bs0);   // + affine arm solve
 #endif
 #ifdef PROFILE_CYCLES
@@ -1137,6 +1160,10 @@ __device__ __noinline__ int build_and_solve(EnvSmem& sm, const DevModel* __restr
   if (lane == 0)
     sm.cost[0] = 20000.f + 150.f * (float)(iters_arm > 0 ? iters_arm : 0) +
                  (float)iters * ((arm_sweep ? 400.f : 0.f) + 55.f * (float)RG);
+#ifdef PROFILE_WARM   // probe build: active lanes at entry / after rows+W / after the Delassus block | after look-up / apply / the sweeps
+  am5 = __popc(__activemask());
+  if (lane == 0) { sm.cost[1] = (float)(am0 + 100 * am1 + 10000 * am2); sm.cost[2] = (float)(am3 + 100 * am4 + 10000 * am5); sm.cost[3] = 0.f; }
+#endif
   if (iters_arm > iters) iters = iters_arm;
   sm.mlam[lane] = lane < nd ? m.lam : 0.f;
 #pragma unroll
@@ -1862,7 +1889,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
   bool stop = false;
 #ifdef PROFILE_STAGES   // instrumentation build only: cycle stamps of the stages of the last sub-step -> B2E_F_CONTACTS[env][0..7]
   long long prof_t[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  int prof_slot = -2;
+  int prof_slot = -2, prof_mate = -1, prof_glob = 0, prof_rgw = 0;
 #define PROF_T(k) prof_t[k] = clock64()
 #else
 #define PROF_T(k) do { } while (0)
@@ -2150,6 +2177,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
       nc = cr & 255;
       if (cr & 256) flags |= B2E_ST_CONTACT_OVERFLOW;
     }
+#ifdef PROFILE_WARM
+    const int amA = __popc(__activemask());
+#endif
     const unsigned lt = (1u << lane) - 1u;
     // joint-limit rows near a limit (lane = dof): order (dof, lower) then (dof, upper)
     const float dlo = my_q - my_lower, dup = my_upper - my_q;
@@ -2178,17 +2208,29 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     const int RGw = (int)__reduce_max_sync(FULL, (unsigned)RG);
     // storage of a big system (> 16 generic rows): an overflow slot of the block if one is free, else global scratch
     float* gscratch = st.scratch + (size_t)env * SCRATCH_PER_ENV;
+    // (the claim loop is warp-uniform: a lane looping on its own over the slots left the warp diverged for the whole build --
+    // every shuffle of it through the divergent path -- until the first ballot of the sweeps; active-lane probes, DESIGN.md 4c')
     int got = -1;
-    if (lane == 0 && RG > GL) {
-      for (int k = 0; k < nslot && got < 0; k++)
-        if (atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
+#ifdef PROFILE_WARM
+    const int amB = __popc(__activemask());
+#endif
+    for (int k = 0; k < nslot; k++) {
+      const bool want = lane == 0 && RG > GL && got < 0;
+      if (!__any_sync(FULL, want)) break;
+      if (want && atomicCAS(&slot_owner[k], -1, warp * 2 + half) == -1) got = k;
     }
+#ifdef PROFILE_WARM
+    const int amC = __popc(__activemask());
+#endif
     got = SHF(got, 0);
     const bool need_global = __any_sync(FULL, RG > GL && got < 0);   // rare: more big systems in the block than slots
     const float* big = (RG > GL && got < 0) ? gscratch : reinterpret_cast<const float*>(&slots[got < 0 ? 0 : got]);
     PROF_T(4);   // past the pre-solve barrier
 #ifdef PROFILE_STAGES
     prof_slot = RG > GL ? got : -3;   // overflow slot of this environment's system (-1: global scratch, -3: no big system)
+    prof_mate = __shfl_sync(FULL, env, 16 * (1 - half));   // the environment of the other half of the warp
+    prof_glob = need_global ? 1 : 0;
+    prof_rgw = RGw;
 #endif
 #ifdef PROFILE_CYCLES
     const long long t_solve0 = clock64();
@@ -2200,6 +2242,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     else iters = (RGw <= 2 * GL) ? B2E_SOLVE(2, true) : B2E_SOLVE(3, true);
 #undef B2E_SOLVE
     PROF_T(5);   // solve done (this warp)
+#ifdef PROFILE_WARM
+    if (lane == 0) sm.cost[3] = (float)(amA + 100 * amB + 10000 * amC);   // active lanes after the collision stage / before / after the slot claim
+#endif
 
 #ifdef PROFILE_CYCLES
     R = (int)((clock64() - t_solve0) >> 6) * 64 + (RG > GL ? (got < 0 ? 2 : 1) : 0);   // cycles (multiple of 64) + storage code
@@ -2455,6 +2500,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     for (int k = 7; k < 11; k++) o[13 + k - 7] = (float)(prof_t[k] - prof_t[0]);   // [13..16]: finer stamps of the `rest`
     o[17] = sm.cost[1]; o[18] = sm.cost[2]; o[19] = sm.cost[3];                    // [17..19]: parts of the solve (cycles)
     o[21] = (float)(role * 100 + prof_slot);                                        // [21]: launch role x 100 + overflow slot
+    o[22] = (float)prof_mate; o[23] = (float)(prof_glob * 1000 + prof_rgw); o[24] = (float)n_slots;
 #ifdef PROFILE_SWEEP
     for (int k = 0; k < 5; k++) o[8 + k] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + k];   // [8..12]: parts of the sweeps
     o[20] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + 5];                                   // [20]: before the serial motor rows

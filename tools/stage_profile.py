@@ -69,6 +69,14 @@ for D in depths:
     if cs.any():   # -DPROFILE_SWEEP build: cycles per part of the sweeps
         for e in top[:4]:
             n = max(1, st[e, 1])
+            cfe = sim.get("contacts").reshape(B, -1)[e, 13:20].astype(np.float64)
+            print("   env %d: stage cycles fk %.0f dyn %.0f coll %.0f | solve %.0f = rows+W %.0f, A+warm start %.0f, affine %.0f, sweeps+store %.0f | "
+                  "integrate+cache %.0f final FK %.0f filing %.0f store %.0f obs %.0f" % (
+                      e, t[e, 0], t[e, 1], t[e, 2], t[e, 4], cfe[4], cfe[5] - cfe[4], cfe[6] - cfe[5], t[e, 4] - cfe[6],
+                      cfe[0] - c[e, 5], cfe[1] - cfe[0], cfe[2] - cfe[1], cfe[3] - cfe[2], c[e, 6] - cfe[3]))
+            ex = sim.get("contacts").reshape(B, -1)[e, 22:25]
+            print("   env %d: warp mate env %d (rows %d, sweeps %d), warp runs the %s instantiation for %d generic rows, slots of the launch %d" % (
+                e, int(ex[0]), st[int(ex[0]), 3], st[int(ex[0]), 1], "global-scratch" if ex[1] >= 1000 else "slot", int(ex[1]) % 1000, int(ex[2])))
             code = sim.get("contacts").reshape(B, -1)[e, 21]
             print("   env %d: launch role %d (1 main, 2 tail), system storage %d (>= 0 overflow slot, -1 global scratch, -3 own block), block %d" % (
                 e, int(round(code / 100.0)), int(code - 100 * round(code / 100.0)), c[e, 7]))
