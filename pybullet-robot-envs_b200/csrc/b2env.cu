@@ -1890,7 +1890,12 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
 #ifdef PROFILE_STAGES   // instrumentation build only: cycle stamps of the stages of the last sub-step -> B2E_F_CONTACTS[env][0..7]
   long long prof_t[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int prof_slot = -2, prof_mate = -1, prof_glob = 0, prof_rgw = 0;
+#ifdef PROFILE_WARM   // + active lanes at every stamp -> B2E_F_CONTACTS[env][32..45]
+  int prof_am[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_T(k) do { prof_t[k] = clock64(); prof_am[k] = __popc(__activemask()); } while (0)
+#else
 #define PROF_T(k) prof_t[k] = clock64()
+#endif
 #else
 #define PROF_T(k) do { } while (0)
 #endif
@@ -2491,6 +2496,7 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     }
   }
 #ifdef PROFILE_STAGES
+  PROF_T(11);   // observation / reward done
   if (lane == 0 && live_env && nsub > 0) {
     const long long t_end = clock64();
     float* o = st.contacts + (size_t)env * B2E_MAX_CONTACTS * 8;
@@ -2501,6 +2507,9 @@ step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U,
     o[17] = sm.cost[1]; o[18] = sm.cost[2]; o[19] = sm.cost[3];                    // [17..19]: parts of the solve (cycles)
     o[21] = (float)(role * 100 + prof_slot);                                        // [21]: launch role x 100 + overflow slot
     o[22] = (float)prof_mate; o[23] = (float)(prof_glob * 1000 + prof_rgw); o[24] = (float)n_slots;
+#ifdef PROFILE_WARM
+    for (int k = 0; k < 14; k++) o[32 + k] = (float)prof_am[k];
+#endif
 #ifdef PROFILE_SWEEP
     for (int k = 0; k < 5; k++) o[8 + k] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + k];   // [8..12]: parts of the sweeps
     o[20] = st.scratch[(size_t)env * SCRATCH_PER_ENV + SCRATCH_PER_ENV - 8 + 5];                                   // [20]: before the serial motor rows

@@ -51,6 +51,21 @@ for D in depths:
     for k, n in enumerate(names):
         v = t[:, k]
         print("   %-16s mean %8.0f  p50 %8.0f  p99 %8.0f  max %8.0f" % (n, v.mean(), np.percentile(v, 50), np.percentile(v, 99), v.max()))
+    am = sim.get("contacts").reshape(B, -1)[:, 32:46].astype(np.int64)
+    if am.any():   # -DPROFILE_WARM build: active lanes of the warp at every stamp, over all environments (32 = converged)
+        stamps = ["start", "after FK", "dynamics", "collision", "pre-solve barrier", "solve", "post-solve barrier", "integrate+cache",
+                  "final FK", "filing", "state store", "obs+reward"]
+        for k, n in enumerate(stamps):
+            u, cnt = np.unique(am[:, k], return_counts=True)
+            print("   active lanes at %-20s %s" % (n, ", ".join("%d: %d envs" % (a, b) for a, b in zip(u, cnt))))
+        packs = sim.get("contacts").reshape(B, -1)[:, 17:20].astype(np.int64)
+        labels = [("build entry", "rows + W", "Delassus block"), ("cache look-up", "warm-start apply", "sweeps"),
+                  ("collision stage", "before slot claim", "after slot claim")]
+        for j in range(3):
+            for q in range(3):
+                u, cnt = np.unique((packs[:, j] // (100 ** q)) % 100, return_counts=True)
+                print("   active lanes after %-18s %s" % (labels[j][q], ", ".join("%d: %d envs" % (a, b) for a, b in zip(u, cnt))))
+        continue
     cf = sim.get("contacts").reshape(B, -1)[:, 13:20].astype(np.float64)
     if cf.any():   # finer stamps of this build: parts of `rest` and of `solve`
         fin = {"rest: integrate+cache": cf[:, 0] - c[:, 5], "rest: final FK+termination": cf[:, 1] - cf[:, 0],
