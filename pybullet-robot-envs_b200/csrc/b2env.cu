@@ -47,6 +47,13 @@ __thread unsigned char smem_raw[232448] __attribute__((aligned(128)));
 #endif
 
 #define FULL 0xffffffffu
+#ifdef PROFILE_WARM   // probe build: per code site, visits of a warp and visits with fewer than 32 active lanes (b2e_debug_lane_sites)
+__device__ unsigned long long g_lane_site[16][2];
+#define LANE_SITE(k) do { const unsigned am_ = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am_) - 1) { \
+    atomicAdd(&g_lane_site[k][0], 1ull); if (am_ != FULL) atomicAdd(&g_lane_site[k][1], 1ull); } } while (0)
+#else
+#define LANE_SITE(k) do { } while (0)
+#endif
 #ifndef PHASE_SYNC
 #define PHASE_SYNC 1       // block barriers between stages keep the warps of a block on the same code
 #endif
@@ -473,6 +480,7 @@ __device__ __noinline__ float ik_solve(float* scr, const DevModel* __restrict__ 
   float qv = my_q;
   bool fin = false;   // this group reached the residual (the loop is shared by both groups of the warp)
   for (int it = 0; it < max_iters; it++) {
+    LANE_SITE(2);
     float R[9], p[3];
     const float qi = SHF(qv, my_dof < 0 ? 0 : my_dof);
     fk_lanes(M, U, g, (lane < nl && my_dof >= 0) ? qi : 0.f, R, p);
@@ -732,6 +740,7 @@ __device__ __forceinline__ int pgs_solve(const Grp& g, MotorRegs& m, RowRegs<NSG
   unsigned wn[3] = {0, 0, 0}, wf[3] = {0, 0, 0};
   bool fresh = true;
   for (int it = 0; it < max_iters; it++) {
+    LANE_SITE(0);
     if (dA0 && dB0 && dA1 && dB1) break;
     const unsigned a0 = done0 ? 0u : 0xffffffffu, c0 = done1 ? 0u : 0xffffffffu;
     if (fresh) {
@@ -843,6 +852,7 @@ __device__ __forceinline__ int arm_affine_solve(const Grp& g, const float* Minv,
   int my_it = -1;          // >= 0: converged after that many sweeps; -2: a bound would activate (fallback)
   bool openA = true, openB = true;   // warp-uniform: group A / B still iterating (two ballots per sweep)
   for (int it = 0; it < max_iters; it++) {
+    LANE_SITE(1);
     if (!openA && !openB) break;   // the loop is shared by both groups of the warp
     float a0 = c, a1 = 0.f;
 #pragma unroll
@@ -3198,3 +3208,12 @@ int b2e_timer_stop(b2e_sim* s, void* stream, float* ms_out) {
 }
 
 }  // extern "C"
+
+#ifdef PROFILE_WARM
+extern "C" int b2e_debug_lane_sites(unsigned long long* out32, int reset) {   // probe build only (not part of include/b2env.h)
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out32, g_lane_site, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_lane_site, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -170,6 +170,7 @@ __device__ __noinline__ float tree_ik(float* scr, const DevModel* __restrict__ M
 #else
   for (int it = 0; it < max_iters; it++) {
 #endif
+    LANE_SITE(6);
     float R[9], p[3];
     tree_fk(M, U, lane, lane < nl ? qv : 0.f, R, p);
     float pe[3], Re[9];
@@ -272,6 +273,7 @@ __device__ __forceinline__ int tree_affine_sweeps(float* pb, int lane, bool row,
   bool clamp = false;
   const float INF = __int_as_float(0x7f800000);
   for (; it < max_iters; it++) {
+    LANE_SITE(5);
     __syncwarp();
     pb[lane] = p;
     __syncwarp();
@@ -438,6 +440,7 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
   int it = 0;
   for (; it < max_iters; it++) {
     if (done0 && done1) break;
+    LANE_SITE(4);
     m.prev = m.lam;
     r.prev = r.lam;
     r.base = r.lam * r.gg;
@@ -537,6 +540,12 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
   const float dt = P.dt;
   const int maxc = (P.max_contacts > 0 && P.max_contacts < TREE_MAXC) ? P.max_contacts : TREE_MAXC;
 
+#ifdef PROFILE_WARM   // probe build: active lanes of the warp at the stage boundaries -> B2E_F_CONTACTS[env][32..47] (32 = converged)
+  int tp_am[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TREE_PROBE(k) tp_am[k] = __popc(__activemask())
+#else
+#define TREE_PROBE(k) do { } while (0)
+#endif
   // ---- load state ----
   const bool is_dof = lane < nd;
   const int li = is_dof ? lane : 0;
@@ -658,6 +667,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
                               tq[1], tq[2], tq[3]);
       if (is_dof && !ghost) my_target = (P.n_obs_joints > 0 && !is_ctrl) ? my_home : t;
     }
+    TREE_PROBE(1);   // after the action / IK stage
     TREE_BARRIER();
     if (is_dof) {
 #pragma unroll
@@ -667,6 +677,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     }
 
     // ---- dynamics in world coordinates about O = base position ----
+    TREE_PROBE(2);
     float S[6] = {0, 0, 0, 0, 0, 0};
     float Iw[16];   // f(6) | m | h(3) | I_O(6): summed over the subtree below
     {
@@ -837,6 +848,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     TREE_BARRIER();
 
     // ---- collision detection (pre-step poses): same canonical order and keys as the Panda kernel ----
+    TREE_PROBE(3);   // dynamics done
     float Rc[9];
     quat_to_mat(cquat, Rc);
     const float ca = P.cube_half, margin = P.contact_margin;
@@ -973,6 +985,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     TREE_BARRIER();
 
     // ---- constraint rows: motor row of dof `lane`, generic row `lane` ----
+    TREE_PROBE(4);   // collision done
     const int fric_start = nlim + nc;
     const int RG = nlim + 3 * nc;
     R = nd + RG;
@@ -1159,6 +1172,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
     TREE_BARRIER();
     bool arm_done = false;
     int iters_arm = 0;
+    TREE_PROBE(5);   // rows, Delassus block, warm start done
     {
       // arm island = motor rows + limit rows only (no proxy contact): affine Gauss-Seidel
       if (!coupled && !arm_contact) {
@@ -1174,7 +1188,9 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
         }
       }
     }
+    TREE_PROBE(6);   // affine arm island done
     iters = tree_pgs(sm, lane, m, rr, nd, RG, fric_start, coupled, has_cube, arm_done, P.solver_iters, P.residual_tol);
+    TREE_PROBE(7);   // sweeps done
     if (iters_arm > iters) iters = iters_arm;
     sm.mlam[lane] = is_dof ? m.lam : 0.f;
     sm.glam[lane] = lane < RG ? rr.lam : 0.f;
@@ -1185,6 +1201,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
 #endif
 
     // ---- delta velocities dv = sum_r W_r lambda_r ----
+    TREE_PROBE(8);
     float dvk = 0.f, dvc = 0.f;
     for (int g2 = 0; g2 < RG; g2++) {
       const float lg = sm.glam[g2];
@@ -1220,6 +1237,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       for (int k = 0; k < 4; k++) cquat[k] = nq[k] * nn;
     }
     // ---- contact cache for the next step's warm start ----
+    TREE_PROBE(9);   // integrated
     {
       int key = -1;
       float l3[3] = {0.f, 0.f, 0.f};
@@ -1256,6 +1274,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
   }
 
   // ---- store state ----
+  TREE_PROBE(10);
   if (is_dof && live_env) {
     st.q[env * nd + lane] = my_q;
     st.qd[env * nd + lane] = my_qd;
@@ -1276,6 +1295,7 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
   }
 
   // ---- observation / termination / reward (icub_push_gym_env.py:276-282) ----
+  TREE_PROBE(11);
   if (mode == B2E_MODE_ACTION || obs_out) {
     const int ee = U.ee_link;
     const float cm[3] = {U.ee_com[0], U.ee_com[1], U.ee_com[2]};
@@ -1408,6 +1428,11 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       st.status[env * 4 + 3] = R;
     }
   }
+  TREE_PROBE(12);   // observation / reward done
+#ifdef PROFILE_WARM
+  if (lane == 0 && live_env && nsub > 0)
+    for (int k = 0; k < 16; k++) st.contacts[(size_t)env * B2E_MAX_CONTACTS * 8 + 32 + k] = (float)tp_am[k];
+#endif
   if (sched && lane == 0 && live_env) {   // file this environment under its cost class for the next full-batch step
     const int cls = min(NBK_MAIN - 1, iters / 10);
     const int pos = atomicAdd(&sched[SCHED_CNT(seq & 3, cls)], 1);

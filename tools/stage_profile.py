@@ -111,3 +111,13 @@ for D in depths:
         A = np.stack([its, np.ones_like(its)], axis=1).astype(np.float64)
         coef = np.linalg.lstsq(A, cyc, rcond=None)[0]
         print("   resting-cube envs (21 rows): solve cycles ~ %.0f + %.1f * sweeps  (=> %.1f cycles per row update over 12 cube rows)" % (coef[1], coef[0], coef[0] / 12))
+try:   # -DPROFILE_WARM build: loop sites, visits / visits with a split warp
+    import ctypes as C
+    out = (C.c_ulonglong * 32)()
+    sim.lib.b2e_debug_lane_sites.argtypes = [C.c_void_p, C.c_int]
+    if sim.lib.b2e_debug_lane_sites(out, 1) == 0:
+        for k, n in enumerate(["Panda sweep", "Panda affine arm iteration", "Panda IK pass"]):
+            if out[2 * k]:
+                print("   loop site %-28s %d warp visits, %d with fewer than 32 active lanes" % (n, out[2 * k], out[2 * k + 1]))
+except AttributeError:
+    pass
