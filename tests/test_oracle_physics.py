@@ -117,3 +117,54 @@ def test_termination_and_reward_semantics(oracle_lib):
     o.state["counters"][:, 0] = 1001
     _, _, done = o.step(np.zeros((4, 7), np.float32), 1, 0)
     assert np.all(done == 1)                                            # counter > max_steps (:313)
+
+
+def _christoffel_bias(o, q, qd, h=2e-3):
+    """c_i = sum_jk 1/2 (dM_ij/dq_k + dM_ik/dq_j - dM_jk/dq_i) qd_j qd_k from central differences of the oracle's own
+    mass matrix M(q) = (M^-1(q))^-1 — the velocity-dependent forces every rigid-body system must show, computed
+    without the recursive algorithm under test."""
+    nd = len(q)
+    M = lambda qq: np.linalg.inv(o.minv(qq.astype(np.float32)).astype(np.float64))
+    dM = np.zeros((nd, nd, nd))
+    for k in range(nd):
+        e = np.zeros(nd); e[k] = h
+        qp, qm = (q + e).astype(np.float32).astype(np.float64), (q - e).astype(np.float32).astype(np.float64)
+        dM[:, :, k] = (M(qp) - M(qm)) / (qp[k] - qm[k])
+    c = np.zeros(nd)
+    for i in range(nd):
+        G = 0.5 * (dM[i, :, :] + dM[i, :, :].T - dM[:, :, i])
+        c[i] = qd @ G @ qd
+    return c, M(q)
+
+
+@pytest.mark.parametrize("robot", ["panda", "icub"])
+def test_bias_forces_are_the_christoffel_symbols_of_the_mass_matrix(oracle_lib, robot):
+    """Pins the Coriolis / centrifugal part of the articulated-body algorithm (chain and branching tree) on first principles:
+    with tau = 0, M (qdd(q, qd) - qdd(q, 0)) must equal -c(q, qd), c built from derivatives of the mass matrix (which
+    tests/test_oracle_kat.py pins on SURVEY App. C.3).  Independent of the recursion: a wrong velocity-product term, a wrong
+    frame for the spatial cross products or a missing branch contribution shows here."""
+    from pybullet_robot_envs.b2env.model import default_params, load_icub, TASK_REACH
+    if robot == "panda":
+        m, p = panda_task_setup(TASK_PUSH)
+    else:
+        m, _ = load_icub()
+        p = default_params(TASK_REACH, [0] * 31, [1] * 31)
+    nd = m.n_dof
+    o = oracle_lib.Oracle(m, p, 1, double=True)
+    rng = np.random.RandomState(3)
+    lo = np.array([m.lower[d] for d in range(nd)], np.float64)
+    hi = np.array([m.upper[d] for d in range(nd)], np.float64)
+    z = np.zeros(nd, np.float32)
+    worst = 0.0
+    for trial in range(2 if robot == "icub" else 4):
+        q = (lo + (hi - lo) * rng.uniform(0.2, 0.8, nd)).astype(np.float32).astype(np.float64)
+        qd = rng.uniform(-1.5, 1.5, nd)
+        c, M = _christoffel_bias(o, q, qd)
+        a_v = o.forward_dynamics(q.astype(np.float32), qd.astype(np.float32), z).astype(np.float64)
+        a_0 = o.forward_dynamics(q.astype(np.float32), z, z).astype(np.float64)
+        lhs = M @ (a_v - a_0)
+        scale = max(1.0, np.abs(c).max())
+        assert np.abs(c).max() > 0.05                       # the configuration does exercise the velocity products
+        np.testing.assert_allclose(lhs, -c, atol=4e-3 * scale)
+        worst = max(worst, np.abs(lhs + c).max() / scale)
+    assert worst < 4e-3
