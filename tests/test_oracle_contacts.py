@@ -147,3 +147,46 @@ def test_self_collision_keeps_the_hand_off_the_upper_arm(oracle_lib):
         gaps[with_pairs] = np.array(g)
     assert gaps[True].min() > -3e-3, gaps[True]                    # pushed out to (almost) touching
     assert gaps[True].min() > gaps[False].min() + 1e-3 or gaps[False].min() > -3e-3, (gaps[True], gaps[False])
+
+
+def test_sliding_cube_decelerates_at_mu_g_per_friction_direction(oracle_lib):
+    """Coulomb friction through the solver rows, closed form: a cube sliding on the table top loses mu g dt of speed per step
+    along each of the two friction directions of the contact (Bullet's friction pyramid: the rows are bounded by mu x normal
+    impulse separately, so a diagonal slide is braked sqrt(2) harder than an axis-aligned one), on top of the base damping
+    v <- v (1 - dt (k1 + k2 |v|)); the normal rows carry m g dt in total, the cube neither lifts nor sinks nor turns."""
+    mu, v0, n = 0.3, 0.3, 10
+    m, p = panda_task_setup(TASK_PUSH)
+    p.cube_mu = mu                                   # table friction 1.0: combined coefficient = mu (product rule)
+    orc = oracle_lib.Oracle(m, p, 3, nthreads=1)
+    poses = np.zeros((3, 7), np.float32)
+    poses[:, 6] = 1.0
+    poses[:, :3] = [0.8, 0.0, 0.65]                  # far from the arm and the rim
+    _place(orc, poses)
+    orc.step(None, 40, 1, want_obs=False)            # settle on the four-point manifold
+    z0 = orc.state["obj_pose"][:, 2].copy()
+    v = orc.state["obj_vel"].copy()
+    v[0, 0] = v0                                     # along x (a friction direction of a z-normal contact)
+    v[1, 1] = -v0                                    # along -y (the other one)
+    v[2, 0] = v[2, 1] = v0 / np.sqrt(2.0)            # diagonal, same speed
+    orc.state["obj_vel"][:] = v
+    dt, g = p.dt, 9.81
+    ex = np.array([v0, v0, v0 / np.sqrt(2.0)])       # per-axis speeds
+    speed = np.array([v0, v0, v0])
+    for _ in range(n):
+        orc.step(None, 1, 1, want_obs=False)
+        damp = 1.0 - dt * (p.damp_lin_k1 + p.damp_lin_k2 * speed)
+        ex = ex * damp - mu * g * dt
+        speed = np.array([ex[0], ex[1], ex[2] * np.sqrt(2.0)])
+    got = orc.state["obj_vel"]
+    np.testing.assert_allclose(got[0, 0], ex[0], atol=1e-3)
+    np.testing.assert_allclose(got[1, 1], -ex[1], atol=1e-3)
+    np.testing.assert_allclose(got[2, :2], [ex[2], ex[2]], atol=1e-3)
+    assert abs(ex[0] - (v0 - n * mu * g * dt)) < 2e-3                     # (the damping terms are a small correction)
+    assert np.abs(got[0, 1:3]).max() < 2e-3 and np.abs(got[1, [0, 2]]).max() < 2e-3     # no sideways or vertical drift
+    assert np.abs(orc.state["obj_pose"][:, 2] - z0).max() < 2e-4
+    lam = orc.state["cache_lam"].reshape(3, -1, 3)                                        # [B, slots, 3]: normal, friction 1, friction 2
+    np.testing.assert_allclose(lam[:, :, 0].sum(axis=1), p.cube_mass * g * dt, rtol=2e-2)   # the normal rows carry the weight
+    # every friction row of the sliding cubes sits on its bound mu x normal impulse
+    np.testing.assert_allclose(np.abs(lam[0, :, 1:]).max(axis=1), mu * lam[0, :, 0], atol=1e-6)
+    orc.step(None, 40, 1, want_obs=False)
+    assert np.abs(orc.state["obj_vel"][:, :3]).max() < 1e-3                              # friction brings all three to rest
