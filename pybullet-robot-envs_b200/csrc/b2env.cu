@@ -1298,7 +1298,7 @@ __device__ __noinline__ int collide_stage(EnvSmem& sm, const DevModel* __restric
                                           float cqz, float cqw) {
   const Grp g = {hm, sh, lane};
   const unsigned lt = (1u << lane) - 1u;
-  const int maxc = B2E_MAX_CONTACTS;
+  const int maxc = (P.max_contacts > 0 && P.max_contacts < B2E_MAX_CONTACTS) ? P.max_contacts : B2E_MAX_CONTACTS;   // b2e_params.max_contacts
   const float cpos[3] = {cpx, cpy, cpz}, cquat[4] = {cqx, cqy, cqz, cqw};
   float Rc[9];
   quat_to_mat(cquat, Rc);

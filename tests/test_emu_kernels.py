@@ -271,6 +271,40 @@ def test_panda_contact_families_parity(emu_lib, oracle_lib):
         sim.close()
 
 
+def test_panda_contact_list_truncation_parity(emu_lib, oracle_lib):
+    """`b2e_params.max_contacts` below the candidate count: both sides keep the first `max_contacts` points of the canonical
+    contact order, raise B2E_ST_CONTACT_OVERFLOW for the same environments and solve the same truncated system."""
+    from common import FAMILIES, family_states
+    m, p = panda_task_setup(TASK_PUSH)
+    p.max_contacts = 5
+    qs, poses, fam = family_states(oracle_lib, m, panda_task_setup(TASK_PUSH)[1], list(FAMILIES), per_family=2, seed=7)
+    B = len(fam)
+    from pybullet_robot_envs.b2env.binding import B2Sim
+    sim = B2Sim(m, p, B, 0, lib=emu_lib)
+    try:
+        orc = oracle_lib.Oracle(m, p, B, nthreads=4)
+        orc.reset(poses, targets_for(poses))
+        orc.state["q"][:] = qs
+        orc.state["mtarget"][:] = qs
+        overflowed = 0
+        for i in range(3):
+            copy_state_to_gpu(orc, sim)
+            orc.step(None, 1, 1, want_obs=False)
+            sim.step_host(None, 1, 1, want_obs=False)
+            g_st, o_st = sim.get("status"), orc.state["status"]
+            np.testing.assert_array_equal(g_st[:, 2:], o_st[:, 2:], err_msg="n_contacts / n_rows, step %d" % i)
+            np.testing.assert_array_equal(g_st[:, 0] & 6, o_st[:, 0] & 6, err_msg="overflow flags, step %d" % i)
+            np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="contact keys, step %d" % i)
+            assert g_st[:, 2].max() <= 5
+            overflowed += int(((g_st[:, 0] & 2) > 0).sum())
+            conv = o_st[:, 1] < 150
+            assert np.abs(sim.get("q") - orc.state["q"])[conv].max() < 2e-4
+            assert np.abs(sim.get("obj_pose") - orc.state["obj_pose"])[conv].max() < 2e-4
+        assert overflowed > 0   # the families with 8- and 12-point manifolds do overflow a 5-point list
+    finally:
+        sim.close()
+
+
 def test_panda_robot_quaternion_command_and_velocity_cap(emu_lib, monkeypatch):
     """pandaEnv.apply_action on the emulated kernels: a 7-wide (x, y, z, qx, qy, qz, w) command drives the arm like the 6-wide
     Euler command of the same rotation (panda_env.py:251-261); max_vel != -1 caps the joint speeds (:285-291); the robot
