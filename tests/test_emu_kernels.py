@@ -305,6 +305,37 @@ def test_panda_contact_list_truncation_parity(emu_lib, oracle_lib):
         sim.close()
 
 
+def test_unsupported_parameter_combinations_are_refused(emu_lib):
+    """Parameters a kernel does not implement are refused by b2e_create / b2e_set_params (B2E_EUNSUPPORTED), never ignored:
+    iCub-only semantics on the Panda kernel, Panda-only semantics on the tree kernel."""
+    from pybullet_robot_envs.b2env.binding import B2EError, B2Sim
+    from pybullet_robot_envs.b2env.model import icub_task_setup, TASK_GRASP
+    import ctypes as C
+    m, p = panda_task_setup(TASK_PUSH)
+    for field, value in (("reward_kind", 2), ("n_obs_joints", 3)):
+        m2, p2 = panda_task_setup(TASK_PUSH)
+        setattr(p2, field, value)
+        with pytest.raises(B2EError, match="tree kernel"):
+            B2Sim(m2, p2, 2, 0, lib=emu_lib)
+    m2, p2 = panda_task_setup(TASK_PUSH)
+    p2.ik_link_offset[1] = 0.01
+    with pytest.raises(B2EError, match="ik_link_offset"):
+        B2Sim(m2, p2, 2, 0, lib=emu_lib)
+    sim = B2Sim(m, p, 2, 0, lib=emu_lib)
+    try:   # the same checks guard b2e_set_params; a refused update leaves the parameters as they were
+        bad = type(p).from_buffer_copy(p)
+        bad.reward_kind = 3
+        assert emu_lib.b2e_set_params(sim.h, C.byref(bad)) < 0
+        assert b"tree kernel" in emu_lib.b2e_last_error()
+        assert emu_lib.b2e_set_params(sim.h, C.byref(p)) == 0
+    finally:
+        sim.close()
+    mi, pi = icub_task_setup(TASK_PUSH, use_ik=1)
+    pi.task = TASK_GRASP
+    with pytest.raises(B2EError, match="grasp"):
+        B2Sim(mi, pi, 2, 0, lib=emu_lib)
+
+
 def test_panda_robot_quaternion_command_and_velocity_cap(emu_lib, monkeypatch):
     """pandaEnv.apply_action on the emulated kernels: a 7-wide (x, y, z, qx, qy, qz, w) command drives the arm like the 6-wide
     Euler command of the same rotation (panda_env.py:251-261); max_vel != -1 caps the joint speeds (:285-291); the robot
