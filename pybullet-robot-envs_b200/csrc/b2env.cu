@@ -2857,8 +2857,7 @@ static int create_impl(b2e_sim* s, const DevModel& hm, const b2e_params* params,
 
 // Parameters one of the two kernels does not implement are refused, never ignored (the oracle is generic; a silent difference
 // would be a parity hole): joint lists / iCub rewards / the hand-frame IK offset need the tree kernel, the grasp task needs the
-// Panda kernel.  (Known and documented exception, DESIGN.md 4e: the tree kernel collides against the table TOP and the ground
-// plane only; the static boxes of the descriptor matter to it through table_min / table_max.)
+// Panda kernel.
 static int check_params(const char* who, const b2e_params* p, int tree) {
   if (!tree) {
     if (p->n_obs_joints > 0) return fail(B2E_EUNSUPPORTED, "%s: joint lists (n_obs_joints > 0) need the tree kernel", who);

@@ -493,6 +493,146 @@ __device__ __forceinline__ int tree_pgs(TreeSmem& sm, int lane, MotorRegs& m, Tr
   return it;
 }
 
+__device__ __forceinline__ void tree_emit(TreeSmem& sm, int slot, int maxc, int key, int type, int link, const float* pA,
+                                          const float* pB, const float* n, float dist, float mu, float erp, float cfm) {
+  if (slot >= maxc) return;
+  Contact& c = sm.con[slot];
+  c.key = key; c.type = type; c.link = link; c.link2 = -1;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { c.pA[j] = pA[j]; c.pB[j] = pB[j]; c.n[j] = n[j]; }
+  c.dist = dist; c.mu = mu; c.erp = erp;
+  sm.con_cfm[slot] = cfm;
+}
+
+// General collision path of the tree kernel: the static world of round 2 (rim and sides of the top slab, table legs, ground
+// plane) for the cube and the sphere proxies, family by family in the order and with the keys of oracle collide()
+// (b2oracle.c: cube vs table top | cube vs static boxes through b2n_box_box | cube vs plane | sphere vs cube | sphere vs static
+// boxes, at most three each | sphere vs plane).  Taken by a warp (= an environment) only when its cube is not wholly over the
+// table top or one of its spheres is near anything but the top face: rare, warp-uniform, so the common path keeps the closed
+// forms of the caller.  v: this lane's cube vertex (lane < 8); s_*: this lane's sphere (lane < ns) and its sphere-cube result.
+// Returns the contact count (<= maxc) | overflow << 8.
+__device__ __noinline__ int tree_collide_general(TreeSmem& sm, const DevModel* __restrict__ M, const b2e_params& P, int lane, int ns,
+                                                 int maxc, float cpx, float cpy, float cpz, float cqx, float cqy, float cqz, float cqw,
+                                                 bool cube_fast, float vx, float vy, float vz, float scx, float scy, float scz,
+                                                 float s_r, int s_link, bool sc_hit, float sc_dist, float scnx, float scny,
+                                                 float scnz, float scbx, float scby, float scbz) {
+  const unsigned lt = (1u << lane) - 1u;
+  const float margin = P.contact_margin, ca = P.cube_half, top = P.table_max[2];
+  const float cpos[3] = {cpx, cpy, cpz}, cquat[4] = {cqx, cqy, cqz, cqw};
+  const float v[3] = {vx, vy, vz}, s_c[3] = {scx, scy, scz};
+  const float up[3] = {0.f, 0.f, 1.f};
+  const float rb = ca * 1.7320508075688772f;
+  const int nsb = P.n_sboxes > 0 ? P.n_sboxes : 1;
+  float Rc[9];
+  quat_to_mat(cquat, Rc);
+  int base = 0;
+  {  // cube wholly over the table top: vertex-face manifold
+    const bool hit = cube_fast && lane < 8 && (v[2] - top) < margin;
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (hit) {
+      const float pB[3] = {v[0], v[1], top};
+      tree_emit(sm, base + __popc(b & lt), maxc, KEY_CUBE_TABLE + lane, CT_CUBE_STATIC, -1, v, pB, up, v[2] - top, P.cube_mu * P.table_mu, P.erp, 0.f);
+    }
+    base += __popc(b);
+  }
+  {  // rim of the top slab, legs: lane = static box, general box-box behind a bounding-sphere cull
+    int cnt = 0;
+    float nrm[3] = {0.f, 0.f, 1.f};
+    b2n_contact pts[B2N_MAX_POINTS];
+    const int k = lane;
+    if (k < nsb && k >= (cube_fast ? 1 : 0)) {
+      const float chh[3] = {ca, ca, ca};
+      const float ident[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+      float bc[3], bh[3];
+      sbox_get(P, k, bc, bh);
+      const float d[3] = {cpos[0] - bc[0], cpos[1] - bc[1], cpos[2] - bc[2]};
+      if (!(sqrtf(dot3(d, d)) - (rb + sqrtf(dot3(bh, bh))) >= margin)) cnt = b2n_box_box(cpos, Rc, chh, bc, ident, bh, margin, nrm, pts);
+    }
+    __syncwarp();
+    int off = 0, total = 0;
+    for (int j = 0; j < nsb; j++) {
+      const int cj = __shfl_sync(FULL, cnt, j);
+      if (j < lane) off += cj;
+      total += cj;
+    }
+    for (int q = 0; q < cnt; q++)
+      tree_emit(sm, base + off + q, maxc, B2E_KEY_CUBE_SBOX + B2N_ID_STRIDE * k + pts[q].id, CT_CUBE_STATIC, -1, pts[q].pa, pts[q].pb, nrm,
+                pts[q].dist, P.cube_mu * (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu), P.erp, 0.f);
+    base += total;
+  }
+  {  // ground plane z = 0
+    const bool hit = !cube_fast && lane < 8 && v[2] < margin;
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (hit) {
+      const float pB[3] = {v[0], v[1], 0.f};
+      tree_emit(sm, base + __popc(b & lt), maxc, KEY_CUBE_PLANE + lane, CT_CUBE_STATIC, -1, v, pB, up, v[2], P.cube_mu * P.plane_mu, P.erp, 0.f);
+    }
+    base += __popc(b);
+  }
+  const bool s_world = lane < ns && !(__ldg(&M->sph_flags[lane < ns ? lane : 0]) & 1);
+  const float s_mu = lane < ns ? __ldg(&M->sph_mu[lane]) : 0.f, s_cfm = lane < ns ? __ldg(&M->sph_cfm[lane]) : 0.f;
+  const float serp = lane < ns ? __ldg(&M->sph_erp[lane]) : -1.f;
+  const float s_erp = serp >= 0.f ? serp : P.erp;
+  {  // sphere proxies vs the cube (closed form of the caller)
+    const bool hit = s_world && sc_hit;
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (hit) {
+      const float n[3] = {scnx, scny, scnz}, pB[3] = {scbx, scby, scbz};
+      const float pA[3] = {s_c[0] - n[0] * s_r, s_c[1] - n[1] * s_r, s_c[2] - n[2] * s_r};
+      tree_emit(sm, base + __popc(b & lt), maxc, KEY_SPHERE_CUBE + lane, CT_SPHERE_CUBE, s_link, pA, pB, n, sc_dist, P.cube_mu * s_mu, s_erp, s_cfm);
+    }
+    base += __popc(b);
+  }
+  {  // sphere proxies vs the static boxes (lane = sphere, at most three boxes each)
+    int cnt = 0, kk[3] = {0, 0, 0};
+    float nn[3][3], pb[3][3], dd[3] = {0.f, 0.f, 0.f};
+    bool tp[3] = {false, false, false};
+    if (s_world) {
+      for (int k = 0; k < nsb && cnt < 3; k++) {
+        float bc[3], bh[3], n[3], pB[3], dist;
+        bool is_top;
+        sbox_get(P, k, bc, bh);
+        const float d[3] = {s_c[0] - bc[0], s_c[1] - bc[1], s_c[2] - bc[2]};
+        if (sqrtf(dot3(d, d)) - (s_r + sqrtf(dot3(bh, bh))) >= margin) continue;
+        if (!sphere_aabox(s_c, s_r, bc, bh, margin, n, pB, dist, is_top)) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          if (c == cnt) {
+            kk[c] = k; dd[c] = dist; tp[c] = is_top;
+#pragma unroll
+            for (int j = 0; j < 3; j++) { nn[c][j] = n[j]; pb[c][j] = pB[j]; }
+          }
+        cnt++;
+      }
+    }
+    __syncwarp();
+    const unsigned b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2);
+    const int off = __popc(b0 & lt) + 2 * __popc(b1 & lt), total = __popc(b0) + 2 * __popc(b1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (c < cnt) {
+        const int k = kk[c];
+        const float pA[3] = {s_c[0] - nn[c][0] * s_r, s_c[1] - nn[c][1] * s_r, s_c[2] - nn[c][2] * s_r};
+        tree_emit(sm, base + off + c, maxc, (k == 0 && tp[c]) ? KEY_SPHERE_TABLE + lane : B2E_KEY_SPHERE_SBOX + 8 * lane + k, CT_SPHERE_STATIC,
+                  s_link, pA, pb[c], nn[c], dd[c], (P.n_sboxes > 0 ? P.sbox_mu[k] : P.table_mu) * s_mu, s_erp, s_cfm);
+      }
+    }
+    base += total;
+  }
+  {  // sphere proxies vs the ground plane
+    const float dist = s_c[2] - s_r;
+    const bool hit = s_world && dist < margin;
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (hit) {
+      const float pA[3] = {s_c[0], s_c[1], dist}, pB[3] = {s_c[0], s_c[1], 0.f};
+      tree_emit(sm, base + __popc(b & lt), maxc, B2E_KEY_SPHERE_PLANE + lane, CT_SPHERE_STATIC, s_link, pA, pB, up, dist, P.plane_mu * s_mu, s_erp, s_cfm);
+    }
+    base += __popc(b);
+  }
+  __syncwarp();
+  return (base > maxc ? maxc : base) | (base > maxc ? 256 : 0);
+}
+
 template <bool IK>
 __global__ void __launch_bounds__(32 * TREE_WPB, TREE_MINB)
 tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevModelU U, const __grid_constant__ b2e_params P,
@@ -922,49 +1062,77 @@ tree_step_kernel(const DevModel* __restrict__ M, const __grid_constant__ DevMode
       st_dist = s_c[2] - s_r - P.table_max[2];
       st_hit = over && (st_dist < margin);
     }
-    const unsigned bv = __ballot_sync(FULL, v_hit), bsc = __ballot_sync(FULL, sc_hit), bst = __ballot_sync(FULL, st_hit);
+    // The static world beyond the table top (rim and sides of the slab, legs, ground plane) is the general path: an environment
+    // takes it when its cube is not wholly over the top (bounding sphere, as the oracle decides) or when one of its spheres is
+    // near anything but the top face (the oracle's own bounding culls).  Otherwise the closed forms above are exactly what
+    // oracle collide() produces: vertices on the top plane, spheres over the top face.
     const unsigned lt = (1u << lane) - 1u;
-    const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
-    const int total = n_v + n_sc + n_st;
-    if (total > maxc) flags |= B2E_ST_CONTACT_OVERFLOW;
-    nc = total > maxc ? maxc : total;
-    if (v_hit) {
-      const int cs = __popc(bv & lt);
-      if (cs < maxc) {
-        Contact& c = sm.con[cs];
-        c.key = v_key; c.type = CT_CUBE_STATIC; c.link = -1;
-        c.pA[0] = v_pos[0]; c.pA[1] = v_pos[1]; c.pA[2] = v_pos[2];
-        c.pB[0] = v_pos[0]; c.pB[1] = v_pos[1]; c.pB[2] = v_top;
-        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
-        c.dist = v_dist; c.mu = v_mu; c.erp = P.erp;
-        sm.con_cfm[cs] = 0.f;
+    const float rb_c = ca * 1.7320508075688772f;
+    const bool cube_fast = cpos[0] - rb_c >= P.table_min[0] && cpos[0] + rb_c <= P.table_max[0] && cpos[1] - rb_c >= P.table_min[1] &&
+                           cpos[1] + rb_c <= P.table_max[1] && cpos[2] >= P.table_max[2];
+    bool sph_general = false;
+    if (lane < ns) {
+      const int nsb = P.n_sboxes > 0 ? P.n_sboxes : 1;
+      for (int k = 0; k < nsb; k++) {
+        float bc[3], bh[3];
+        sbox_get(P, k, bc, bh);
+        const float d[3] = {s_c[0] - bc[0], s_c[1] - bc[1], s_c[2] - bc[2]};
+        if (sqrtf(dot3(d, d)) - (s_r + sqrtf(dot3(bh, bh))) >= margin) continue;   // culled by the oracle as well
+        const bool over_top = k == 0 && fabsf(d[0]) <= bh[0] && fabsf(d[1]) <= bh[1] && d[2] > bh[2];
+        if (!over_top) sph_general = true;
       }
+      if (s_c[2] - s_r < margin) sph_general = true;   // ground plane
     }
-    if (sc_hit) {
-      const int cs = n_v + __popc(bsc & lt);
-      if (cs < maxc) {
-        Contact& c = sm.con[cs];
-        const float serp = __ldg(&M->sph_erp[lane]);
-        c.key = KEY_SPHERE_CUBE + lane; c.type = CT_SPHERE_CUBE; c.link = s_link;
-#pragma unroll
-        for (int j = 0; j < 3; j++) { c.n[j] = sc_n[j]; c.pB[j] = sc_pB[j]; c.pA[j] = s_c[j] - sc_n[j] * s_r; }
-        c.dist = sc_dist; c.mu = P.cube_mu * __ldg(&M->sph_mu[lane]);
-        c.erp = serp >= 0 ? serp : P.erp;
-        sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+    if (!cube_fast || __any_sync(FULL, sph_general)) {
+      const int cr = tree_collide_general(sm, M, P, lane, ns, maxc, cpos[0], cpos[1], cpos[2], cquat[0], cquat[1], cquat[2], cquat[3],
+                                          cube_fast, v_pos[0], v_pos[1], v_pos[2], s_c[0], s_c[1], s_c[2], s_r, s_link, sc_hit, sc_dist,
+                                          sc_n[0], sc_n[1], sc_n[2], sc_pB[0], sc_pB[1], sc_pB[2]);
+      nc = cr & 255;
+      if (cr & 256) flags |= B2E_ST_CONTACT_OVERFLOW;
+    } else {
+      const unsigned bv = __ballot_sync(FULL, v_hit), bsc = __ballot_sync(FULL, sc_hit), bst = __ballot_sync(FULL, st_hit);
+      const int n_v = __popc(bv), n_sc = __popc(bsc), n_st = __popc(bst);
+      const int total = n_v + n_sc + n_st;
+      if (total > maxc) flags |= B2E_ST_CONTACT_OVERFLOW;
+      nc = total > maxc ? maxc : total;
+      if (v_hit) {
+        const int cs = __popc(bv & lt);
+        if (cs < maxc) {
+          Contact& c = sm.con[cs];
+          c.key = v_key; c.type = CT_CUBE_STATIC; c.link = -1;
+          c.pA[0] = v_pos[0]; c.pA[1] = v_pos[1]; c.pA[2] = v_pos[2];
+          c.pB[0] = v_pos[0]; c.pB[1] = v_pos[1]; c.pB[2] = v_top;
+          c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+          c.dist = v_dist; c.mu = v_mu; c.erp = P.erp;
+          sm.con_cfm[cs] = 0.f;
+        }
       }
-    }
-    if (st_hit) {
-      const int cs = n_v + n_sc + __popc(bst & lt);
-      if (cs < maxc) {
-        Contact& c = sm.con[cs];
-        const float serp = __ldg(&M->sph_erp[lane]);
-        c.key = KEY_SPHERE_TABLE + lane; c.type = CT_SPHERE_STATIC; c.link = s_link;
-        c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
-        c.pA[0] = s_c[0]; c.pA[1] = s_c[1]; c.pA[2] = s_c[2] - s_r;
-        c.pB[0] = s_c[0]; c.pB[1] = s_c[1]; c.pB[2] = P.table_max[2];
-        c.dist = st_dist; c.mu = P.table_mu * __ldg(&M->sph_mu[lane]);
-        c.erp = serp >= 0 ? serp : P.erp;
-        sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+      if (sc_hit) {
+        const int cs = n_v + __popc(bsc & lt);
+        if (cs < maxc) {
+          Contact& c = sm.con[cs];
+          const float serp = __ldg(&M->sph_erp[lane]);
+          c.key = KEY_SPHERE_CUBE + lane; c.type = CT_SPHERE_CUBE; c.link = s_link;
+  #pragma unroll
+          for (int j = 0; j < 3; j++) { c.n[j] = sc_n[j]; c.pB[j] = sc_pB[j]; c.pA[j] = s_c[j] - sc_n[j] * s_r; }
+          c.dist = sc_dist; c.mu = P.cube_mu * __ldg(&M->sph_mu[lane]);
+          c.erp = serp >= 0 ? serp : P.erp;
+          sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+        }
+      }
+      if (st_hit) {
+        const int cs = n_v + n_sc + __popc(bst & lt);
+        if (cs < maxc) {
+          Contact& c = sm.con[cs];
+          const float serp = __ldg(&M->sph_erp[lane]);
+          c.key = KEY_SPHERE_TABLE + lane; c.type = CT_SPHERE_STATIC; c.link = s_link;
+          c.n[0] = 0.f; c.n[1] = 0.f; c.n[2] = 1.f;
+          c.pA[0] = s_c[0]; c.pA[1] = s_c[1]; c.pA[2] = s_c[2] - s_r;
+          c.pB[0] = s_c[0]; c.pB[1] = s_c[1]; c.pB[2] = P.table_max[2];
+          c.dist = st_dist; c.mu = P.table_mu * __ldg(&M->sph_mu[lane]);
+          c.erp = serp >= 0 ? serp : P.erp;
+          sm.con_cfm[cs] = __ldg(&M->sph_cfm[lane]);
+        }
       }
     }
     // joint-limit rows near a limit (lane = dof): order (dof, lower) then (dof, upper)

@@ -117,3 +117,54 @@ def hand_contact_parity(make_sim, oracle_lib, n_check=6):
         check_state(orc, sim, "contact %d" % i, tol_q=1e-4, tol_qd=3e-2, tol_obj=1e-4, tol_vel=3e-2, ik=True)
     assert seen, "the approach produced no hand-cube contact"
     return orc, sim
+
+
+def static_world_parity(make_sim, oracle_lib, rounds=5):
+    """The static world beyond the table top (the tree kernel's general collision path): cubes at the rim of the top slab, tipping
+    over it, on the floor next to a table leg, and hands driven to the table edge so that sphere proxies touch the rim from the
+    side — next to ordinary environments in the same launch.  The oracle runs the scenario; every few steps the kernel restarts
+    from the oracle's state and one step is compared: contact counts and keys exact, states to solver tolerances (most of these
+    systems are sweep-capped)."""
+    B = 10
+    m, p = icub_task_setup(TASK_PUSH, use_ik=1)
+    sim = make_sim(m, p, B)
+    orc = oracle_lib.Oracle(m, p, B, nthreads=4)
+    pose = object_poses(B, 0)
+    pose[:, 2] = 0.651
+    orc.reset(pose, pose[:, :3].copy())
+    orc.state["shaping"][:] = 1
+    orc.step(None, 1, 3, want_obs=False)
+    hp = orc.state["hand_pose"].copy()
+    for e, t in enumerate([(0.1, 0.25, 0.63), (0.1, 0.3, 0.66), (0.12, 0.1, 0.63), (0.1, 0.0, 0.64), (0.2, 0.3, 0.63), (0.1, -0.1, 0.63)]):
+        hp[e, :3] = t                                   # hands towards the near rim of the table (x = 0.1)
+    orc.state["hand_pose"][:] = hp
+    op = orc.state["obj_pose"].copy()
+    op[6, :3] = [0.11, 0.0, 0.651]                      # cube 1 cm inside the rim: clipped rim manifold (box-box against the slab)
+    op[7, :3] = [0.092, -0.2, 0.651]                    # cube overhanging the rim: tips over it
+    op[8, :3] = [0.2, -0.4 + 0.08, 0.026]               # cube on the floor, 0.5 cm from a table leg's face
+    op[9, :3] = [0.115, 0.2, 0.651]                     # rim again, yawed 45 degrees
+    op[9, 3:] = [0.0, 0.0, np.sin(np.pi / 8), np.cos(np.pi / 8)]
+    orc.state["obj_pose"][:] = op
+    orc.state["obj_vel"][8, 1] = -0.3                   # sliding towards the leg
+    seen = set()
+    for r in range(rounds):
+        orc.step(None, 12 if r else 2, 3, want_obs=False)
+        sync(orc, sim)
+        orc.step(None, 1, 3, want_obs=False)
+        sim.step_host(None, 1, 3, want_obs=False)
+        g, o = sim.get("status"), orc.state["status"]
+        np.testing.assert_array_equal(g[:, 2:], o[:, 2:], err_msg="n_contacts / n_rows, round %d" % r)
+        np.testing.assert_array_equal(g[:, 0] & 6, o[:, 0] & 6, err_msg="overflow flags, round %d" % r)
+        np.testing.assert_array_equal(sim.get("cache_key"), orc.state["cache_key"], err_msg="contact keys (order included), round %d" % r)
+        keys = orc.state["cache_key"]
+        for name, lo, hi in (("cube-plane", 8, 16), ("sphere-sbox", 128, 256), ("sphere-plane", 256, 512), ("cube-sbox", 4096, 12288)):
+            if ((keys >= lo) & (keys < hi)).any():
+                seen.add(name)
+        # converged systems whose IK loop stopped at the same iteration on both sides (see check_state)
+        conv = (o[:, 1] < 150) & (np.abs(sim.get("mtarget") - orc.state["mtarget"]).max(axis=1) <= 2e-4)
+        for f, tol in (("q", 2e-4), ("obj_pose", 2e-4)):
+            err = np.abs(sim.get(f) - orc.state[f])
+            assert err[conv].max() <= tol, (r, f, err[conv].max())
+            assert np.isfinite(sim.get(f)).all() and err.max() < 5e-3, (r, f, err.max())
+    assert {"cube-sbox", "cube-plane", "sphere-sbox"} <= seen, seen
+    return orc, sim
