@@ -2722,6 +2722,12 @@ static int build_dev_model(const b2e_model* m, DevModel* d, DevModelU* u, int* t
   if (m->n_boxes < 0 || m->n_boxes > B2E_MAX_BOXES || m->n_self_pairs < 0 || m->n_self_pairs > B2E_MAX_SELF_PAIRS)
     return fail(B2E_EINVAL, "bad n_boxes / n_self_pairs%s", "");
   if (!tree && m->n_boxes > 2) return fail(B2E_EUNSUPPORTED, "group kernel: at most two box proxies%s", "");
+  if (tree) {   // the tree kernel collides sphere proxies only: other proxies are refused, not dropped (the oracle would use them)
+    bool flagged = false;
+    for (int s = 0; s < m->n_spheres; s++) flagged = flagged || m->sph_flags[s] != 0;
+    if (m->n_boxes > 0 || m->n_self_pairs > 0 || m->n_caps > 0 || flagged)
+      return fail(B2E_EUNSUPPORTED, "tree kernel: box / capsule proxies, self-collision pairs and sphere flags need the group kernel%s", "");
+  }
   d->n_boxes = u->n_boxes = tree ? 0 : m->n_boxes;
   d->n_self_pairs = u->n_self_pairs = tree ? 0 : m->n_self_pairs;
   for (int b = 0; b < m->n_boxes; b++) {

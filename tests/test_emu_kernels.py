@@ -340,6 +340,11 @@ def test_unsupported_parameter_combinations_are_refused(emu_lib):
     pi.task = TASK_GRASP
     with pytest.raises(B2EError, match="grasp"):
         B2Sim(mi, pi, 2, 0, lib=emu_lib)
+    mi, pi = icub_task_setup(TASK_PUSH, use_ik=1)
+    mi.n_self_pairs = 1                                  # proxies the tree kernel does not collide are refused, not dropped
+    mi.self_a[0], mi.self_b[0] = 0, 4
+    with pytest.raises(B2EError, match="group kernel"):
+        B2Sim(mi, pi, 2, 0, lib=emu_lib)
 
 
 def test_panda_robot_quaternion_command_and_velocity_cap(emu_lib, monkeypatch):
