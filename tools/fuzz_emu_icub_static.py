@@ -2,7 +2,10 @@
 """Fuzz of the EMULATED iCub tree kernel (general collision path: cube near the rim of the table top, near a leg, on the floor,
 random orientations and velocities) against the oracle: every step restarts from the oracle state; contact counts, keys (order
 included) and overflow flags must be exact, converged environments within 2e-4.  Round 2: 864 env-steps, no mismatch
-(518 with cube-vs-static-box manifolds, 333 with ground-plane vertices).    python tools/fuzz_emu_icub_static.py"""
+(518 with cube-vs-static-box manifolds, 333 with ground-plane vertices).  Second part: random arm postures (hands and forearms
+anywhere between home and the joint limits: over the table, at its rim, pressed into it): 768 env-steps, no mismatch (55 with
+sphere-vs-slab-side contacts, 70 sphere-table, 18 sphere-cube, the contact-list overflow once).
+    python tools/fuzz_emu_icub_static.py"""
 import sys
 import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [ROOT, os.path.join(ROOT, 'pybullet-robot-envs_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np
@@ -47,3 +50,38 @@ for seed in range(6):
         tot += B
         orc.step(None, 3, 1, want_obs=False)
 print("iCub static-world fuzz:", tot, "env-steps, keys / counts / flags exact;", fams, "overflowed", int(((orc.state['status'][:,0]&2)>0).sum()))
+sim.close()
+
+# ---- part 2: random arm postures (sphere proxies against the static world) ----
+m, p = icub_task_setup(TASK_PUSH, use_ik=0)
+B = 32
+nd = m.n_dof
+lo = np.array([m.lower[d] for d in range(nd)], np.float32); hi = np.array([m.upper[d] for d in range(nd)], np.float32)
+home = np.array([m.home[d] for d in range(nd)], np.float32)
+sim = B2Sim(m, p, B, 0, lib=lib)
+orc = b2oracle.Oracle(m, p, B, nthreads=4)
+tot = 0; fams = {}
+for seed in range(8):
+    rng = np.random.RandomState(200 + seed)
+    pose = icub_cases.object_poses(B, seed); pose[:, 2] = 0.651
+    orc.reset(pose, pose[:, :3].copy()); sim.reset_host(pose, pose[:, :3].copy())
+    w = rng.uniform(0, 1, (B, 1)).astype(np.float32)
+    q = (home + w * ((lo + (hi - lo) * rng.uniform(0.05, 0.95, (B, nd))) - home)).astype(np.float32)
+    orc.state["q"][:] = q; orc.state["mtarget"][:] = q
+    for i in range(3):
+        icub_cases.sync(orc, sim)
+        orc.step(None, 1, 1, want_obs=False); sim.step_host(None, 1, 1, want_obs=False)
+        g, o = sim.get("status"), orc.state["status"]
+        assert np.array_equal(g[:, 2:], o[:, 2:]), (seed, i, np.where((g[:, 2:] != o[:, 2:]).any(axis=1)))
+        assert np.array_equal(g[:, 0] & 6, o[:, 0] & 6), (seed, i)
+        assert np.array_equal(sim.get("cache_key"), orc.state["cache_key"]), (seed, i)
+        assert np.isfinite(sim.get("q")).all()
+        conv = o[:, 1] < 150
+        if conv.any():
+            err = np.abs(sim.get("q") - orc.state["q"])[conv].max()
+            assert err < 5e-4, (seed, i, err)
+        k = orc.state["cache_key"]
+        for name, a, b in (("sphere-cube", 16, 32), ("sphere-table", 32, 64), ("sphere-sbox", 128, 256), ("sphere-plane", 256, 512)):
+            fams[name] = fams.get(name, 0) + int(((k >= a) & (k < b)).any(axis=1).sum())
+        tot += B
+print("iCub random-posture fuzz:", tot, "env-steps exact;", fams, "overflow env-steps", int(((orc.state['status'][:,0]&2)>0).sum()))
