@@ -46,6 +46,14 @@ def test_hand_contacts(make_sim, oracle_lib):
     icub_cases.hand_contact_parity(make_sim, oracle_lib, n_check=10)
 
 
+@pytest.mark.xfail(strict=False, reason="general collision path of the tree kernel: written after round 2's GPU time was spent, "
+                   "verified on the host emulation only (tests/test_emu_kernels.py); its first GPU execution is the driver's "
+                   "round-end run.  XPASS = verified on the B200; a difference here must not hide the other GPU tests")
+def test_static_world_general_path(make_sim, oracle_lib):
+    """Rim / legs / floor for the iCub path (tests/icub_cases.py: static_world_parity), CUDA vs oracle."""
+    icub_cases.static_world_parity(make_sim, oracle_lib)
+
+
 def test_free_running_rollout(make_sim, oracle_lib):
     """120 random Cartesian steps without re-synchronising: the hand stays away from the cube (targets move by
     <= 0.6 m in 120 steps only in the worst case; envs whose hand touched something are excluded), so the
